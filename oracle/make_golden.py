@@ -1,0 +1,222 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, via oracle/ref_harness.py) on CPU in the build container.
+
+    python oracle/make_golden.py            # rewrites every fixture
+
+The fixtures are what pins oracle/port.py (and through it the CUDA path) to the reference:
+the reference itself ships no tests or golden vectors.  Each fixture
+carries its own weights and inputs, so nothing here has to be regenerated on the GPU box.
+"""
+from __future__ import annotations
+
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import ref_harness as H  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+TINY = dict(d_model=32, nheads=4, d_inner=64, enc_layers=2, dec_layers=2)
+
+
+def synth_batch(g, B, T_list, L_list, idim=83):
+    """Synthetic batch in the collate_fn layout (src/io/dataset.py:21-33): zero padded,
+    sorted by ilen descending, labels uniform in [1, 365]."""
+    Tm = max(T_list)
+    x = torch.zeros(B, Tm, idim)
+    for b, t in enumerate(T_list):
+        x[b, :t] = torch.randn(t, idim, generator=g)
+    ilens = torch.tensor(T_list, dtype=torch.int64)
+    ys = [torch.randint(1, 366, (l,), generator=g, dtype=torch.int64) for l in L_list]
+    olens = torch.tensor(L_list, dtype=torch.int64)
+    return x, ilens, ys, olens
+
+
+def pack_batch(prefix, batch, out):
+    x, ilens, ys, olens = batch
+    out[prefix + "x"] = x.numpy()
+    out[prefix + "ilens"] = ilens.numpy()
+    out[prefix + "olens"] = olens.numpy()
+    out[prefix + "ys_cat"] = torch.cat(ys).numpy()
+
+
+def sd_to_np(prefix, sd, out, skip_pe=True):
+    for n, t in sd.items():
+        if skip_pe and n == "pos_encoder.pe":
+            continue
+        out[prefix + n] = t.detach().cpu().numpy().copy()
+
+
+def summarize(prefix, sd, out, skip_pe=True, nsample=384):
+    """Compact pin of a dict of tensors: a strided sample + float64 sum and L2 norm each."""
+    for n, t in sd.items():
+        if skip_pe and n == "pos_encoder.pe":
+            continue
+        a = t.detach().cpu().numpy().reshape(-1)
+        stride = max(1, a.size // nsample)
+        out[prefix + n + "#sample"] = a[::stride][:nsample].copy()
+        out[prefix + n + "#sum"] = np.float64(a.astype(np.float64).sum())
+        out[prefix + n + "#l2"] = np.float64(np.sqrt((a.astype(np.float64) ** 2).sum()))
+
+
+def clone_batch(b):
+    x, ilens, ys, olens = b
+    return x.clone(), ilens.clone(), [y.clone() for y in ys], olens.clone()
+
+
+def golden_run_batch():
+    """One run_batch(train=True) on a ragged batch: logits, targets, masks, loss, acc, grads."""
+    cfg = H.base_config(**TINY, dropout=0.0)
+    solver = H.build_reference_solver(cfg, H.make_paras("fomaml"))
+    from src.nets_utils import make_bool_pad_mask, generate_square_subsequent_mask
+    g = torch.Generator().manual_seed(1)
+    batch = synth_batch(g, 3, [37, 30, 22], [5, 3, 4])
+    out = {}
+    pack_batch("in.", batch, out)
+    w = {}
+    sd_to_np("", solver.asr_model.state_dict(), w)
+    np.savez_compressed(GOLD / "weights_tiny.npz", **w)
+    out["pe_head"] = solver.asr_model.state_dict()["pos_encoder.pe"][:64, 0].numpy().copy()
+
+    m = solver.asr_model
+    m.train()
+    x, ilens, ys, olens = clone_batch(batch)
+    # a throw-away optimizer: run_batch calls self.asr_opt.zero_grad() (trainer :91)
+    solver.asr_opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    logit, gold = m(x, ilens, ys, olens.clone())
+    out["logit"] = logit.detach().numpy().copy()
+    out["gold"] = gold.numpy().copy()
+    enc_lens = torch.floor(ilens.to(dtype=torch.float32) / 4).to(dtype=torch.int64)
+    out["enc_lens"] = enc_lens.numpy()
+    out["enc_pad_mask"] = make_bool_pad_mask(enc_lens).numpy()
+    out["causal_mask"] = generate_square_subsequent_mask(gold.shape[1]).numpy()
+    ol = olens.clone()
+    info = solver.run_batch(0, x, ilens, ys, ol, train=True)
+    out["olens_after"] = ol.numpy()
+    out["loss"] = np.float64(info["loss"])
+    out["acc"] = np.float64(info["acc"])
+    summarize("g.", {n: p.grad for n, p in m.named_parameters()}, out)
+    # greedy decode (f-1 row): ids [L, B]
+    m.eval()
+    with torch.no_grad():
+        out["greedy"] = m.recog(x, ilens).numpy().copy()
+    np.savez_compressed(GOLD / "run_batch_tiny.npz", **out)
+    print("run_batch_tiny: loss", info["loss"], "acc", info["acc"])
+
+
+def golden_fomaml():
+    """Two FOMAML meta-steps, 2 accents, meta_k=2, through the reference's own
+    run_task/_train/_partial_meta_update/_final_meta_update (SURVEY App. A recipe)."""
+    from torch import nn
+    cfg = H.base_config(**TINY, dropout=0.0, warmup_steps=4, k=0.02)
+    solver = H.build_reference_solver(cfg, H.make_paras("fomaml", meta_k=2))
+    g = torch.Generator().manual_seed(2)
+    out = {"meta_k": 2, "n_accents": 2, "n_meta_steps": 2, "warmup_steps": 4, "k": 0.02}
+    w = np.load(GOLD / "weights_tiny.npz")
+    for n, t in solver._original.items():        # same seed, same net -> same init
+        if n != "pos_encoder.pe":
+            assert np.array_equal(w[n], t.detach().numpy()), n
+    shapes = [([24, 24], [4, 2]), ([31, 31, 31], [3, 5, 2]), ([40], [6])]
+    for step in range(2):
+        for acc in range(2):
+            tr = [synth_batch(g, len(s[0]), *s) for s in (shapes[(step + acc) % 3], shapes[(step + acc + 1) % 3])]
+            te = synth_batch(g, 2, [28, 20], [4, 3])
+            for j, b in enumerate(tr):
+                pack_batch(f"s{step}.a{acc}.tr{j}.", b, out)
+            pack_batch(f"s{step}.a{acc}.te.", te, out)
+            solver.run_task([(acc, clone_batch(b)) for b in tr])
+            info = solver._train(acc, *clone_batch(te), accent_idx=acc)
+            gn = nn.utils.clip_grad_norm_(solver.asr_model.parameters(), 5)
+            assert not math.isnan(gn)
+            out[f"s{step}.a{acc}.te_loss"] = np.float64(info["loss"])
+            out[f"s{step}.a{acc}.te_gnorm"] = np.float64(float(gn))
+            solver._partial_meta_update()
+        # capture the averaged meta-gradient the reference feeds to Adam
+        cnt = solver._counter
+        summarize(f"s{step}.mg.", {n: u / cnt for n, u in solver._updates.items()}, out)
+        solver._final_meta_update()
+        out[f"s{step}.lr"] = np.float64(solver.meta_opt.lr)
+        summarize(f"s{step}.w.", solver._original, out)
+    summarize("fast.", solver.asr_model.state_dict(), out)
+    out["inner_lr"] = np.float64(solver.inner_lr)
+    np.savez_compressed(GOLD / "fomaml_tiny.npz", **out)
+    print("fomaml_tiny: lr", solver.meta_opt.lr, "inner_lr", solver.inner_lr)
+
+
+def golden_multi():
+    """Three multi-task steps (multi_interface.py:100-114): run_batch, clip, noam-Adam."""
+    from torch import nn
+    cfg = H.base_config(**TINY, dropout=0.0, warmup_steps=4, k=0.02, meta=False)
+    solver = H.build_reference_solver(cfg, H.make_paras("multi"))
+    g = torch.Generator().manual_seed(3)
+    out = {"n_steps": 3, "warmup_steps": 4, "k": 0.02}
+    w = np.load(GOLD / "weights_tiny.npz")
+    for n, t in solver.asr_model.state_dict().items():
+        if n != "pos_encoder.pe":
+            assert np.array_equal(w[n], t.detach().numpy()), n
+    for step in range(3):
+        b = synth_batch(g, 3, [33, 33, 26], [4, 6, 2])
+        pack_batch(f"s{step}.", b, out)
+        info = solver._train(0, *clone_batch(b), accent_idx=0)
+        gn = nn.utils.clip_grad_norm_(solver.asr_model.parameters(), 5)
+        summarize(f"s{step}.g.", {n: p.grad for n, p in solver.asr_model.named_parameters()}, out)
+        solver.asr_opt.step()
+        out[f"s{step}.loss"] = np.float64(info["loss"])
+        out[f"s{step}.gnorm"] = np.float64(float(gn))
+        summarize(f"s{step}.w.", solver.asr_model.state_dict(), out)
+    np.savez_compressed(GOLD / "multi_tiny.npz", **out)
+    print("multi_tiny done")
+
+
+def golden_ctc():
+    """The CTC call site of src/blstm_trainer.py:55-70 on synthetic encoder outputs:
+    targets [366]+y+[366], blank 0, reduction='mean', zero_infinity=True.  Cases: ragged
+    input lengths, repeated labels, an infeasible utterance (S > T), and L=0."""
+    H.install_stubs()
+    import torch.nn.functional as F
+    ctc = torch.nn.CTCLoss(blank=0, reduction='mean', zero_infinity=True)
+    g = torch.Generator().manual_seed(4)
+    out = {}
+    cases = {
+        "a": dict(T=[20, 17, 12, 9], ys=[[5, 5, 7], [9], [3, 4, 4, 4, 2], [1, 2, 3, 4, 5, 6, 7, 8]], C=40),
+        "b": dict(T=[33, 33], ys=[[11, 12, 13, 14, 15, 16], [2, 2, 2]], C=367),
+    }
+    for name, c in cases.items():
+        B, Tm, C = len(c["T"]), max(c["T"]), c["C"]
+        eos = C - 1
+        logits = torch.randn(B, Tm, C, generator=g) * 2.0
+        ys = [torch.tensor(y, dtype=torch.int64) for y in c["ys"]]
+        ys_out = [torch.cat([torch.tensor([eos]), y, torch.tensor([eos])]) for y in ys]
+        y_true = torch.cat(ys_out)
+        olens = torch.tensor([len(y) for y in ys_out], dtype=torch.int64)
+        enc_lens = torch.tensor(c["T"], dtype=torch.int64)
+        lg = logits.clone().requires_grad_(True)
+        pred = F.log_softmax(lg, dim=-1)
+        loss = ctc(pred.transpose(0, 1).contiguous(), y_true, enc_lens, olens)
+        loss.backward()
+        nll = F.ctc_loss(pred.detach().transpose(0, 1).contiguous(), y_true, enc_lens, olens,
+                         blank=0, reduction='none', zero_infinity=True)
+        out[f"{name}.logits"] = logits.numpy()
+        out[f"{name}.targets"] = y_true.numpy()
+        out[f"{name}.in_lens"] = enc_lens.numpy()
+        out[f"{name}.tgt_lens"] = olens.numpy()
+        out[f"{name}.loss"] = np.float64(float(loss))
+        out[f"{name}.nll"] = nll.numpy()
+        out[f"{name}.grad_logits"] = lg.grad.numpy().copy()
+        print(f"ctc case {name}: loss {float(loss):.6f} nll {nll.tolist()}")
+    np.savez_compressed(GOLD / "ctc.npz", **out)
+
+
+if __name__ == "__main__":
+    assert H.reference_available(), "needs /root/reference (build container only)"
+    GOLD.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    golden_run_batch()
+    golden_fomaml()
+    golden_multi()
+    golden_ctc()
