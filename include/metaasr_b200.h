@@ -1,0 +1,206 @@
+/*
+ * metaasr_b200 -- C ABI of the B200-native meta-training hot path.
+ *
+ * The reference (sunprinceS/MetaASR-CrossAccent) is pure Python on stock PyTorch and has no
+ * FFI of its own; every entry point below names the reference call site (file:line relative
+ * to the reference root) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success or a negative MASR_E_* code; masr_last_error()
+ *     returns a thread-local message for the last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller; `stream` is a cudaStream_t
+ *     passed as void*; calls are asynchronous on that stream.
+ *   - dtype codes: MASR_F32 = 0, MASR_BF16 = 1 ("act" tensors use the given dtype; statistics,
+ *     losses, logits of the CE kernel and all weight gradients are always fp32).
+ *   - activations are row-major, batch-first: [rows, features]; conv tensors are NHWC
+ *     (H = time, W = frequency).
+ */
+#ifndef METAASR_B200_H_
+#define METAASR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MASR_OK 0
+#define MASR_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define MASR_E_CUDA (-2)      /* CUDA runtime or driver error     */
+#define MASR_E_NOGPU (-3)     /* no sm_100 device                 */
+
+#define MASR_F32 0
+#define MASR_BF16 1
+
+#define MASR_ABI_VERSION 1
+
+int masr_abi_version(void);
+const char* masr_last_error(void);
+/* Fails (MASR_E_NOGPU) unless `device` is an sm_100 GPU: there is no CPU fallback. */
+int masr_init(int device);
+
+/* ------------------------------------------------------------------ kernel 1: CTC
+ * Replaces F.log_softmax + nn.CTCLoss(blank, reduction='mean', zero_infinity) forward+backward,
+ * src/blstm_trainer.py:22,65-70.  One CTA per utterance.
+ *   acts        [T, B, C] fp32 (act_is_logprob=0: un-normalised logits, log-softmax fused;
+ *               act_is_logprob=1: log-probabilities as nn.CTCLoss receives them)
+ *   targets     int64, concatenated; tgt_offsets [B] int64 start of each utterance's labels
+ *   in_lens     [B] int64, tgt_lens [B] int64
+ *   nll         [B] fp32 out (0 where infeasible and zero_infinity)
+ *   loss        [1] fp32 out = mean_b(nll_b / max(tgt_len_b, 1))      (may be NULL)
+ *   grad        [T, B, C] fp32 out = d loss / d acts * grad_scale; frames >= in_len get 0
+ *               (may be NULL for forward only)
+ */
+int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_is_logprob,
+                     const int64_t* targets, const int64_t* tgt_offsets,
+                     const int64_t* in_lens, const int64_t* tgt_lens, int max_tgt_len,
+                     int blank, int zero_infinity, float grad_scale,
+                     float* nll, float* loss, float* grad,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* Bytes of global workspace masr_ctc_fwd_bwd needs for this shape (0: tables fit in shared memory). */
+size_t masr_ctc_workspace_bytes(int T, int B, int C, int max_tgt_len);
+
+/* ------------------------------------------------------------------ kernel 2: GEMM family
+ * C[M,N] = op(sum_k A(m,k) * B(n,k) + bias[n]),  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk].
+ * Covers nn.Linear forward (torch/nn/functional.py linear, called from
+ * mono_transformer_torch.py:62,66,120,206 and nn.Transformer*Layer), its dgrad and wgrad.
+ *   flags: bit0 relu, bit1 accumulate into C (C += ...), bit2 split-K with fp32 atomics
+ *          (C must be fp32 and pre-initialised)
+ *   path : 0 = fp32-accumulate SIMT kernel (any dtype / stride),
+ *          1 = tcgen05/TMEM/TMA kernel (bf16 operands; see masr_umma_* for constraints)
+ */
+#define MASR_GEMM_RELU 1
+#define MASR_GEMM_ACCUM 2
+#define MASR_GEMM_SPLITK 4
+int masr_gemm(const void* A, int a_dtype, int64_t sam, int64_t sak,
+              const void* B, int b_dtype, int64_t sbn, int64_t sbk,
+              void* C, int c_dtype, int64_t ldc, const float* bias,
+              int M, int N, int K, int flags, int splitk, void* stream);
+
+/* tcgen05 GEMM: A [M,K] bf16 and B [N,K] bf16 both K-major ("TN"), C [M,N] bf16 or fp32. */
+int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
+                      void* C, int c_dtype, int64_t ldc, const float* bias,
+                      int M, int N, int K, int flags, void* stream);
+
+/* ------------------------------------------------------------------ conv front end
+ * nn.Conv2d(3x3, stride 1, pad 1) + ReLU + MaxPool2d(2,2), mono_transformer_torch.py:49-60,116.
+ */
+/* conv1: Cin = 1.  x [B,H,W] fp32 -> y [B,H,W,Cout] act, bias+ReLU fused.  w [Cout,9] fp32. */
+int masr_conv1_fwd(const float* x, const float* w, const float* bias, void* y, int y_dtype,
+                   int B, int H, int W, int Cout, void* stream);
+/* dw [Cout,9] += sum_p dy[p,co] * x[p+tap]; db [Cout] += sum_p dy[p,co]   (dy already ReLU-masked) */
+int masr_conv1_wgrad(const float* x, const void* dy, int dy_dtype, float* dw, float* db,
+                     int B, int H, int W, int Cout, void* stream);
+/* im2col for the SIMT path: col[p, tap*Cin+ci] = x[b, h+dh, w+dw, ci] (0 outside). */
+int masr_im2col3x3(const void* x, void* col, int dtype, int B, int H, int W, int Cin, void* stream);
+/* dx[q, ci] (=|+=) sum_tap dcol[q-(dh,dw), tap*Cin+ci]; optional ReLU mask: dx *= (mask_src > 0) */
+int masr_col2im3x3(const void* dcol, void* dx, int dtype, const void* relu_src,
+                   int B, int H, int W, int Cin, void* stream);
+/* weight layout prep: w [Cout,Cin,3,3] fp32 -> wp [Cout, 9*Cin] (k = tap*Cin+ci) of dtype */
+int masr_conv_w_prep(const float* w, void* wp, int dtype, int Cout, int Cin, void* stream);
+/* dw [Cout,Cin,3,3] += dwp [Cout, 9*Cin] (fp32) */
+int masr_conv_w_unprep_add(const float* dwp, float* dw, int Cout, int Cin, void* stream);
+/* 2x2/2 floor-mode max pool, NHWC */
+int masr_maxpool2x2_fwd(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream);
+/* dx = scatter(dy) to the first arg-max of each window, times (x > 0) when relu_mask != 0 */
+int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int dtype, int relu_mask,
+                        int B, int H, int W, int C, void* stream);
+/* dx *= (y > 0), elementwise */
+int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ attention
+ * softmax(Q K^T / sqrt(hd) + mask) V with the masks built from lengths inside the kernel:
+ * key-padding (src_key_padding_mask / memory_key_padding_mask of make_bool_pad_mask,
+ * src/nets_utils.py:85-94) via klens[B] (NULL = none) and the causal mask of
+ * generate_square_subsequent_mask (:9-15) via causal != 0.  Replaces
+ * torch/nn/functional.py multi_head_attention_forward's SDPA call.
+ * q/k/v/out rows are [b*L + l], head h occupies columns [h*hd, (h+1)*hd); ld* are row strides
+ * in elements.  lse [B,H,Lq] fp32.  Attention-probability dropout (p_drop, seed, site) uses the
+ * library's counter-based generator and is replayed in backward.
+ */
+int masr_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                  void* out, int64_t ldo, float* lse, int dtype,
+                  int B, int H, int Lq, int Lk, int hd, const int64_t* klens, int causal,
+                  float p_drop, uint64_t seed, uint32_t site, void* stream);
+int masr_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                  const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                  float* dsum_ws /* [B*H*Lq] fp32 scratch */, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int dtype,
+                  int B, int H, int Lq, int Lk, int hd, const int64_t* klens, int causal,
+                  float p_drop, uint64_t seed, uint32_t site, void* stream);
+
+/* ------------------------------------------------------------------ kernel 3: fused elementwise
+ * residual + dropout + LayerNorm (post-norm TransformerEncoder/DecoderLayer, eps 1e-5):
+ *   s = res + dropout(x)   (written back over x; res may be NULL)
+ *   y = LN(s) * gamma + beta ; mean/rstd [rows] fp32 saved for backward.
+ */
+int masr_add_layernorm_fwd(void* x_inout, const void* res, const float* gamma, const float* beta,
+                           void* y, float* mean, float* rstd, int dtype, int rows, int d, float eps,
+                           float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* ds = LN'(dy) (written to ds; if ds_accum != 0: ds += ...), dgamma/dbeta += ;
+ * dx (the sub-layer output branch) = ds * dropmask/(1-p) when dx != NULL */
+int masr_add_layernorm_bwd(const void* dy, const void* s, const float* mean, const float* rstd,
+                           const float* gamma, void* ds, int ds_accum, void* dx,
+                           float* dgamma, float* dbeta, int dtype, int rows, int d,
+                           float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* x = dropout(x + pe[row % L]) in place (PositionalEncoding, mono_transformer_torch.py:30-32) */
+int masr_add_pe_dropout(void* x, const float* pe, int dtype, int rows, int L, int d,
+                        float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* out[r] = dropout(E[ids[r]] + pe[r % L]) (preprocess(), :131-133); ids int64 */
+int masr_embed_pe_fwd(const int64_t* ids, const float* E, const float* pe, void* out, int dtype,
+                      int rows, int L, int d, float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* dE[ids[r]] += dropmask * dout[r]  (fp32 atomics) */
+int masr_embed_bwd(const int64_t* ids, const void* dout, int dtype, float* dE, int rows, int L, int d,
+                   float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* x = dropout(x) in place / dx = dropout'(dx) in place with the same (seed, site) */
+int masr_dropout(void* x, int dtype, int64_t n, float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* out[n] += sum_m x[m, n]  (bias gradients) */
+int masr_colsum_add(const void* x, int dtype, int64_t ldx, float* out, int M, int N, void* stream);
+/* dst = cast(src) */
+int masr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* dst[r, f*C + c] = src[r, c*F + f]   (vgg2enc column permutation, (c,f) -> (f,c)); with add != 0
+ * and the roles swapped it un-permutes a gradient: dst[r, c*F+f] += src[r, f*C+c] (fp32 only) */
+int masr_permute_cf(const void* src, int src_dtype, void* dst, int dst_dtype, int rows, int C, int F,
+                    int inverse_add, void* stream);
+
+/* label-smoothed cross entropy + accuracy + gradient, src/transformer_torch_trainer.py:64-92.
+ *   logits [N, C] fp32, gold [N] int64 (IGNORE_ID = -1 rows are skipped)
+ *   stats  [4] double: {sum of row losses, n_correct, n_non_pad, 0} (accumulated; zero it first)
+ *   argmax [N] int64 out (may be NULL); dlogits [N, C] fp32 out = d(mean loss)/d logits given
+ *   inv_n = 1 / n_non_pad (may be NULL)
+ */
+int masr_ls_ce_fwd_bwd(const float* logits, const int64_t* gold, int N, int C, float eps, float inv_n,
+                       double* stats, int64_t* argmax, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------ kernel 4: flat multi-tensor ops
+ * All operate on flat fp32 arenas of n elements (parameters laid out back to back).
+ */
+/* out[0] (double) = sum g^2 ; must be zeroed by the caller (or zero_first != 0) */
+int masr_mt_sumsq(const float* g, int64_t n, double* out, int zero_first, void* stream);
+/* clip_grad_norm_(max_norm) + SGD(momentum, nesterov) in one pass, fo_meta_interface.py:242-248.
+ * Reads sum-of-squares from sumsq[0]; if it is NaN the step is skipped (math.isnan guard).
+ * g is scaled in place by the clip coefficient (as clip_grad_norm_ does). first_step: buf = g. */
+int masr_mt_clip_sgd(float* p, float* g, float* buf, int64_t n, const double* sumsq, float max_norm,
+                     float lr, float momentum, int nesterov, int first_step, void* stream);
+/* g *= min(1, max_norm / (sqrt(sumsq) + 1e-6)) */
+int masr_mt_clip(float* g, int64_t n, const double* sumsq, float max_norm, void* stream);
+/* FOMAML: upd += g * clipcoef(sumsq)   (fo_meta_interface.py:148-149,192-196); sumsq may be NULL */
+int masr_mt_accumulate(float* upd, const float* g, int64_t n, const double* sumsq, float max_norm,
+                       void* stream);
+/* Reptile: upd += theta - phi */
+int masr_mt_reptile_delta(float* upd, const float* theta, const float* phi, int64_t n, void* stream);
+/* average + Adam: g = upd / count; m,v,p updated (torch/optim/adam.py single-tensor form);
+ * bias corrections are passed pre-computed in double by the host.  skip_if_nan (may be NULL):
+ * sumsq whose NaN skips the step (multi-task path, multi_interface.py:111-114). */
+int masr_mt_adam(float* p, float* m, float* v, const float* upd, int64_t n, float count,
+                 float lr, float beta1, float beta2, float eps, double bc1, double bc2,
+                 const double* skip_if_nan, const double* clip_sumsq, float max_norm, void* stream);
+/* Reptile interpolation outer update: theta -= eps * upd * inv_count */
+int masr_mt_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METAASR_B200_H_ */

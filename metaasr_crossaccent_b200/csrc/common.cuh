@@ -1,0 +1,89 @@
+// Shared device/host helpers for the metaasr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <algorithm>
+
+#include "../../include/metaasr_b200.h"
+
+namespace masr {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define MASR_CHECK_CUDA(expr)                                              \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess) return ::masr::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define MASR_LAUNCH_CHECK() MASR_CHECK_CUDA(cudaGetLastError())
+
+#define MASR_REQUIRE(cond, msg)                                            \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      ::masr::set_error(std::string("invalid argument: ") + (msg) + " [" #cond "]"); \
+      return MASR_E_INVALID;                                               \
+    }                                                                      \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------ dtype helpers
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// dispatch a templated functor on a runtime dtype code
+#define MASR_DISPATCH_DTYPE(code, T, ...)                                   \
+  do {                                                                      \
+    if ((code) == MASR_F32) { using T = float; __VA_ARGS__; }               \
+    else if ((code) == MASR_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { ::masr::set_error("bad dtype code"); return MASR_E_INVALID; }    \
+  } while (0)
+
+// ------------------------------------------------------------------ counter-based dropout RNG
+// keep(seed, site, idx) is a pure function, so the backward pass regenerates the forward mask.
+// 64-bit mix (splitmix64 finaliser) of (seed, site, element index) -> 24-bit uniform.
+__device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t site, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t(site) + 1) + idx * 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return uint32_t(z >> 40);   // 24 bits
+}
+// returns the multiplier applied to a kept/dropped element: 1/(1-p) or 0
+__device__ __forceinline__ float drop_scale(float p, float inv_keep, uint64_t seed, uint32_t site, uint64_t idx) {
+  if (p <= 0.f) return 1.f;
+  float u = float(mix_hash(seed, site, idx)) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.f;
+}
+
+// ------------------------------------------------------------------ warp / block reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+int sm_count();
+
+}  // namespace masr

@@ -1,0 +1,320 @@
+// VGG front end helpers (mono_transformer_torch.py:49-60): the Cin=1 first conv (HBM-bound,
+// direct), im2col/col2im for the fp32 SIMT path, weight layout prep, 2x2 max-pool and ReLU
+// backward.  All activation tensors are NHWC (H = time, W = frequency).
+#include "common.cuh"
+
+namespace masr {
+
+// ------------------------------------------------------------------ conv1 (Cin = 1)
+// One thread computes 8 output channels of one pixel: 8 threads cover a pixel's 64 channels, so a
+// warp writes 4 pixels x 64 channels contiguously (coalesced); the 9 input taps come from L1.
+template <typename T>
+__global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ bias, T* __restrict__ y,
+                                 int B, int H, int W, int Cout) {
+  extern __shared__ float sw[];            // [Cout][9] weights then [Cout] bias
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * 9 + i] = bias[i];
+  __syncthreads();
+  const int groups = Cout / 8;
+  const int64_t total = int64_t(B) * H * W * groups;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int cg = int(idx % groups);
+    const int64_t p = idx / groups;
+    const int wv = int(p % W);
+    const int hv = int((p / W) % H);
+    const int64_t b = p / (int64_t(W) * H);
+    float tap[9];
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int hh = hv + dh, ww = wv + dw;
+        tap[(dh + 1) * 3 + (dw + 1)] =
+            (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(b * H + hh) * W + ww] : 0.f;
+      }
+    T* dst = y + p * Cout + cg * 8;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float* wc = sw + (cg * 8 + c) * 9;
+      float acc = sw[Cout * 9 + cg * 8 + c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc = fmaf(tap[t], wc[t], acc);
+      dst[c] = from_f<T>(fmaxf(acc, 0.f));
+    }
+  }
+}
+
+// dw[co][tap] += sum_p dy[p][co] x[p+tap], db[co] += sum_p dy[p][co].  Block = Cout x PL threads;
+// thread (co, lane) walks pixels lane, lane+PL, ... of the block's slice, so reads of dy are
+// contiguous over co.  Partials are combined in shared memory, then one atomicAdd per output.
+template <typename T>
+__global__ void conv1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                   float* __restrict__ dw, float* __restrict__ db,
+                                   int B, int H, int W, int Cout, int64_t pix_per_block) {
+  extern __shared__ float red[];           // [PL][Cout][10]
+  const int co = threadIdx.x % Cout;
+  const int lane = threadIdx.x / Cout;
+  const int PL = blockDim.x / Cout;
+  const int64_t P = int64_t(B) * H * W;
+  const int64_t p0 = blockIdx.x * pix_per_block;
+  const int64_t p1 = min(P, p0 + pix_per_block);
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  for (int64_t p = p0 + lane; p < p1; p += PL) {
+    const float g = to_f<T>(dy[p * Cout + co]);
+    if (g == 0.f) continue;                // ReLU-masked gradients are mostly exact zeros
+    const int wv = int(p % W);
+    const int hv = int((p / W) % H);
+    const int64_t b = p / (int64_t(W) * H);
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+      for (int dw_ = -1; dw_ <= 1; ++dw_) {
+        const int hh = hv + dh, ww = wv + dw_;
+        const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(b * H + hh) * W + ww] : 0.f;
+        acc[(dh + 1) * 3 + (dw_ + 1)] = fmaf(g, xv, acc[(dh + 1) * 3 + (dw_ + 1)]);
+      }
+    acc[9] += g;
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) red[(lane * Cout + co) * 10 + i] = acc[i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < Cout * 10; o += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += red[l * Cout * 10 + o];
+    const int c = o / 10, t = o % 10;
+    if (t < 9) atomicAdd(&dw[c * 9 + t], s); else atomicAdd(&db[c], s);
+  }
+}
+
+// ------------------------------------------------------------------ im2col / col2im (SIMT path)
+template <typename T>
+__global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col,
+                                 int B, int H, int W, int C) {
+  const int64_t total = int64_t(B) * H * W * 9 * C;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % C);
+    const int tap = int((idx / C) % 9);
+    const int64_t p = idx / (9 * int64_t(C));
+    const int wv = int(p % W);
+    const int hv = int((p / W) % H);
+    const int64_t b = p / (int64_t(W) * H);
+    const int hh = hv + tap / 3 - 1, ww = wv + tap % 3 - 1;
+    T v = from_f<T>(0.f);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((b * H + hh) * W + ww) * C + c];
+    col[idx] = v;
+  }
+}
+
+template <typename T>
+__global__ void col2im3x3_kernel(const T* __restrict__ dcol, T* __restrict__ dx,
+                                 const T* __restrict__ relu_src, int B, int H, int W, int C) {
+  const int64_t total = int64_t(B) * H * W * C;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % C);
+    const int64_t q = idx / C;
+    const int wv = int(q % W);
+    const int hv = int((q / W) % H);
+    const int64_t b = q / (int64_t(W) * H);
+    float s = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      // col[p][tap] = x[p + (dh,dw)]  =>  x[q] feeds col[q - (dh,dw)][tap]
+      const int hh = hv - (tap / 3 - 1), ww = wv - (tap % 3 - 1);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        s += to_f<T>(dcol[(((b * H + hh) * W + ww) * 9 + tap) * C + c]);
+    }
+    if (relu_src != nullptr && !(to_f<T>(relu_src[idx]) > 0.f)) s = 0.f;
+    dx[idx] = from_f<T>(s);
+  }
+}
+
+// w [Cout][Cin][3][3] fp32 -> wp [Cout][tap][Cin]
+template <typename T>
+__global__ void conv_w_prep_kernel(const float* __restrict__ w, T* __restrict__ wp, int Cout, int Cin) {
+  const int total = Cout * Cin * 9;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ci = idx % Cin;
+    const int tap = (idx / Cin) % 9;
+    const int co = idx / (9 * Cin);
+    wp[idx] = from_f<T>(w[(co * Cin + ci) * 9 + tap]);
+  }
+}
+__global__ void conv_w_unprep_add_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin) {
+  const int total = Cout * Cin * 9;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ci = idx % Cin;
+    const int tap = (idx / Cin) % 9;
+    const int co = idx / (9 * Cin);
+    dw[(co * Cin + ci) * 9 + tap] += dwp[idx];
+  }
+}
+
+// ------------------------------------------------------------------ max pool 2x2 / 2, floor mode
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = int64_t(B) * Ho * Wo * C;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % C);
+    const int wo = int((idx / C) % Wo);
+    const int ho = int((idx / (int64_t(C) * Wo)) % Ho);
+    const int64_t b = idx / (int64_t(C) * Wo * Ho);
+    const T* base = x + ((b * H + 2 * ho) * W + 2 * wo) * C + c;
+    float m = to_f<T>(base[0]);
+    m = fmaxf(m, to_f<T>(base[C]));
+    m = fmaxf(m, to_f<T>(base[int64_t(W) * C]));
+    m = fmaxf(m, to_f<T>(base[int64_t(W) * C + C]));
+    y[idx] = from_f<T>(m);
+  }
+}
+
+// One thread per INPUT element: gradient goes to the first maximum of its window in (h, w) scan
+// order (ATen's strict '>' update), zero elsewhere and in the floor-dropped last row/column.
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                   int relu_mask, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = int64_t(B) * H * W * C;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % C);
+    const int wv = int((idx / C) % W);
+    const int hv = int((idx / (int64_t(C) * W)) % H);
+    const int64_t b = idx / (int64_t(C) * W * H);
+    const int ho = hv / 2, wo = wv / 2;
+    float g = 0.f;
+    if (ho < Ho && wo < Wo) {
+      const T* base = x + ((b * H + 2 * ho) * W + 2 * wo) * C + c;
+      const float v0 = to_f<T>(base[0]), v1 = to_f<T>(base[C]);
+      const float v2 = to_f<T>(base[int64_t(W) * C]), v3 = to_f<T>(base[int64_t(W) * C + C]);
+      int arg = 0; float m = v0;
+      if (v1 > m) { m = v1; arg = 1; }
+      if (v2 > m) { m = v2; arg = 2; }
+      if (v3 > m) { m = v3; arg = 3; }
+      const int mine = (hv & 1) * 2 + (wv & 1);
+      if (arg == mine && (!relu_mask || m > 0.f))
+        g = to_f<T>(dy[((b * Ho + ho) * Wo + wo) * C + c]);
+    }
+    dx[idx] = from_f<T>(g);
+  }
+}
+
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ y, T* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    if (!(to_f<T>(y[i]) > 0.f)) dx[i] = from_f<T>(0.f);
+}
+
+static inline int grid_for(int64_t total, int threads) {
+  int64_t blocks = ceil_div64(total, threads);
+  int64_t cap = int64_t(sm_count()) * 16;
+  return int(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+}  // namespace masr
+
+using namespace masr;
+
+extern "C" int masr_conv1_fwd(const float* x, const float* w, const float* bias, void* y, int y_dtype,
+                              int B, int H, int W, int Cout, void* stream) {
+  MASR_REQUIRE(Cout % 8 == 0 && Cout <= 256, "conv1: Cout must be a multiple of 8");
+  const int64_t total = int64_t(B) * H * W * (Cout / 8);
+  if (total == 0) return MASR_OK;
+  const size_t smem = size_t(Cout) * 10 * sizeof(float);
+  MASR_DISPATCH_DTYPE(y_dtype, T,
+      conv1_fwd_kernel<T><<<grid_for(total, 256), 256, smem, as_stream(stream)>>>(
+          x, w, bias, static_cast<T*>(y), B, H, W, Cout));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_conv1_wgrad(const float* x, const void* dy, int dy_dtype, float* dw, float* db,
+                                int B, int H, int W, int Cout, void* stream) {
+  MASR_REQUIRE(Cout > 0 && Cout <= 256 && 256 % Cout == 0, "conv1_wgrad: Cout must divide 256");
+  const int64_t P = int64_t(B) * H * W;
+  if (P == 0) return MASR_OK;
+  const int threads = 256, PL = threads / Cout;
+  int blocks = int(std::min<int64_t>(ceil_div64(P, 256), int64_t(sm_count()) * 4));
+  const int64_t ppb = ceil_div64(P, blocks);
+  blocks = int(ceil_div64(P, ppb));
+  const size_t smem = size_t(PL) * Cout * 10 * sizeof(float);
+  MASR_DISPATCH_DTYPE(dy_dtype, T,
+      conv1_wgrad_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
+          x, static_cast<const T*>(dy), dw, db, B, H, W, Cout, ppb));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_im2col3x3(const void* x, void* col, int dtype, int B, int H, int W, int Cin, void* stream) {
+  const int64_t total = int64_t(B) * H * W * 9 * Cin;
+  if (total == 0) return MASR_OK;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      im2col3x3_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+          static_cast<const T*>(x), static_cast<T*>(col), B, H, W, Cin));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_col2im3x3(const void* dcol, void* dx, int dtype, const void* relu_src,
+                              int B, int H, int W, int Cin, void* stream) {
+  const int64_t total = int64_t(B) * H * W * Cin;
+  if (total == 0) return MASR_OK;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      col2im3x3_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+          static_cast<const T*>(dcol), static_cast<T*>(dx), static_cast<const T*>(relu_src), B, H, W, Cin));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_conv_w_prep(const float* w, void* wp, int dtype, int Cout, int Cin, void* stream) {
+  const int total = Cout * Cin * 9;
+  if (total == 0) return MASR_OK;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      conv_w_prep_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, static_cast<T*>(wp), Cout, Cin));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_conv_w_unprep_add(const float* dwp, float* dw, int Cout, int Cin, void* stream) {
+  const int total = Cout * Cin * 9;
+  if (total == 0) return MASR_OK;
+  conv_w_unprep_add_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dwp, dw, Cout, Cin);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_maxpool2x2_fwd(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream) {
+  const int64_t total = int64_t(B) * (H / 2) * (W / 2) * C;
+  if (total == 0) return MASR_OK;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+          static_cast<const T*>(x), static_cast<T*>(y), B, H, W, C));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int dtype, int relu_mask,
+                                   int B, int H, int W, int C, void* stream) {
+  const int64_t total = int64_t(B) * H * W * C;
+  if (total == 0) return MASR_OK;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+          static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), relu_mask, B, H, W, C));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, void* stream) {
+  if (n == 0) return MASR_OK;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      relu_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(static_cast<const T*>(y), static_cast<T*>(dx), n));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}

@@ -1,0 +1,403 @@
+// Kernel family 3: fused elementwise / row-reduction kernels -- residual+dropout+LayerNorm
+// (forward and backward), positional encoding, embedding, label-smoothed CE with accuracy and
+// gradient, bias-gradient column sums, casts.  All of them are HBM-bound: one pass over the data,
+// 128-bit accesses where the row length allows, fp32 math.
+#include "common.cuh"
+
+namespace masr {
+
+static inline int grid_for(int64_t total, int threads) {
+  int64_t blocks = ceil_div64(total, threads);
+  int64_t cap = int64_t(sm_count()) * 16;
+  return int(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+// ------------------------------------------------------------------ residual + dropout + LayerNorm
+// One warp per row; the row (d <= 32 * LN_MAX_PER_LANE) lives in registers between the two passes.
+constexpr int LN_MAX_PER_LANE = 32;     // d <= 1024
+
+template <typename T>
+__global__ void add_layernorm_fwd_kernel(T* __restrict__ x, const T* __restrict__ res,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                         int rows, int d, float eps, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int per = (d + 31) / 32;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    float v[LN_MAX_PER_LANE];
+    float sum = 0.f;
+    const int64_t base = int64_t(row) * d;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      if (i < per) {
+        const int c = lane + i * 32;
+        float s = 0.f;
+        if (c < d) {
+          s = to_f<T>(x[base + c]) * drop_scale(p, inv_keep, seed, site, uint64_t(base + c));
+          if (res != nullptr) s += to_f<T>(res[base + c]);
+          s = to_f<T>(from_f<T>(s));       // the stored (possibly bf16-rounded) value is what backward sees
+          x[base + c] = from_f<T>(s);
+        }
+        v[i] = s;
+        sum += s;
+      }
+    }
+    const float mean = warp_sum(sum) / float(d);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i)
+      if (i < per) { const int c = lane + i * 32; if (c < d) { const float t = v[i] - mean; var += t * t; } }
+    const float rstd = rsqrtf(warp_sum(var) / float(d) + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i)
+      if (i < per) {
+        const int c = lane + i * 32;
+        if (c < d) y[base + c] = from_f<T>((v[i] - mean) * rstd * gamma[c] + beta[c]);
+      }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
+// Backward.  ds = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.
+// dgamma/dbeta: per-thread column partials across the block's rows, combined through shared
+// memory, then one atomicAdd per column per block.
+template <typename T>
+__global__ void add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s,
+                                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                         const float* __restrict__ gamma, T* __restrict__ ds, int ds_accum,
+                                         T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                         int rows, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  extern __shared__ float red[];      // [warps][2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int per = (d + 31) / 32;
+  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  for (int row = blockIdx.x * warps_per_block + warp; row < rows; row += gridDim.x * warps_per_block) {
+    const int64_t base = int64_t(row) * d;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i)
+      if (i < per) {
+        const int c = lane + i * 32;
+        g[i] = 0.f; xh[i] = 0.f;
+        if (c < d) {
+          const float dyv = to_f<T>(dy[base + c]);
+          xh[i] = (to_f<T>(s[base + c]) - mean) * rstd;
+          g[i] = dyv * gamma[c];
+          dg[i] += dyv * xh[i];
+          db[i] += dyv;
+          s1 += g[i];
+          s2 += g[i] * xh[i];
+        }
+      }
+    s1 = warp_sum(s1) / float(d);
+    s2 = warp_sum(s2) / float(d);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i)
+      if (i < per) {
+        const int c = lane + i * 32;
+        if (c < d) {
+          const float v = rstd * (g[i] - s1 - xh[i] * s2);
+          if (dx != nullptr) dx[base + c] = from_f<T>(v * drop_scale(p, inv_keep, seed, site, uint64_t(base + c)));
+          float o = v;
+          if (ds_accum) o += to_f<T>(ds[base + c]);
+          ds[base + c] = from_f<T>(o);
+        }
+      }
+  }
+  float* rg = red + size_t(warp) * 2 * d;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i)
+    if (i < per) { const int c = lane + i * 32; if (c < d) { rg[c] = dg[i]; rg[d + c] = db[i]; } }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) t += red[size_t(w) * 2 * d + c];
+    if (c < d) atomicAdd(&dgamma[c], t); else atomicAdd(&dbeta[c - d], t);
+  }
+}
+
+// ------------------------------------------------------------------ positional encoding / embedding / dropout
+template <typename T>
+__global__ void add_pe_dropout_kernel(T* __restrict__ x, const float* __restrict__ pe, int64_t n, int L, int d,
+                                      float p, float inv_keep, uint64_t seed, uint32_t site) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % d);
+    const int l = int((i / d) % L);
+    const float v = (to_f<T>(x[i]) + pe[int64_t(l) * d + c]) * drop_scale(p, inv_keep, seed, site, uint64_t(i));
+    x[i] = from_f<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E,
+                                    const float* __restrict__ pe, T* __restrict__ out, int64_t n, int L, int d,
+                                    float p, float inv_keep, uint64_t seed, uint32_t site) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % d);
+    const int64_t r = i / d;
+    const int l = int(r % L);
+    const float v = (E[ids[r] * d + c] + pe[int64_t(l) * d + c]) * drop_scale(p, inv_keep, seed, site, uint64_t(i));
+    out[i] = from_f<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout, float* __restrict__ dE,
+                                 int64_t n, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % d);
+    const int64_t r = i / d;
+    const float g = to_f<T>(dout[i]) * drop_scale(p, inv_keep, seed, site, uint64_t(i));
+    if (g != 0.f) atomicAdd(&dE[ids[r] * d + c], g);
+  }
+}
+
+template <typename T>
+__global__ void dropout_kernel(T* __restrict__ x, int64_t n, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    x[i] = from_f<T>(to_f<T>(x[i]) * drop_scale(p, inv_keep, seed, site, uint64_t(i)));
+}
+
+// out[n] += sum_m x[m, n].  Block (32 x 8): thread column n = blockIdx.x*32 + tx, rows strided by
+// (8 * gridDim.y); partials reduced over ty in shared memory; one atomicAdd per column per block.
+template <typename T>
+__global__ void colsum_add_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out, int M, int N) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int n = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (n < N)
+    for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) acc += to_f<T>(x[int64_t(m) * ldx + n]);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(&out[n], t);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    dst[i] = from_f<TD>(to_f<TS>(src[i]));
+}
+
+// forward: dst[r, f*C + c] = src[r, c*F + f]; inverse_add: dst[r, c*F + f] += src[r, f*C + c]
+template <typename TS, typename TD>
+__global__ void permute_cf_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t rows, int C, int F, int inverse_add) {
+  const int64_t n = rows * C * F;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / (int64_t(C) * F);
+    const int j = int(i % (int64_t(C) * F));
+    if (!inverse_add) {
+      const int f = j / C, c = j % C;            // i indexes dst (f-major)
+      dst[i] = from_f<TD>(to_f<TS>(src[r * C * F + int64_t(c) * F + f]));
+    } else {
+      const int c = j / F, f = j % F;            // i indexes dst (c-major)
+      dst[i] = from_f<TD>(to_f<TD>(dst[i]) + to_f<TS>(src[r * C * F + int64_t(f) * C + c]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ label-smoothed CE + accuracy + grad
+// src/transformer_torch_trainer.py:64-84.  One warp per row of C logits.
+//   q_c = (1-eps) for the gold class, eps/C otherwise (sums to 1 - eps/C)
+//   loss_row = -sum_c q_c (z_c - logZ);   d loss_row / d z_c = (sum q) softmax_c - q_c
+__global__ void ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ gold, int N, int C,
+                             float eps, float inv_n, double* __restrict__ stats, int64_t* __restrict__ argmax_out,
+                             float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  double loss_acc = 0.0;
+  int correct = 0, nonpad = 0;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < N; row += gridDim.x * warps_per_block) {
+    const float* z = logits + int64_t(row) * C;
+    const int64_t g = gold[row];
+    float mx = -INFINITY; int am = 0;
+    for (int c = lane; c < C; c += 32) { const float v = z[c]; if (v > mx) { mx = v; am = c; } }
+    // warp arg-max with first-index tie-break (torch.max(1) on CPU/CUDA returns the first maximum)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+      if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    }
+    float se = 0.f, sz = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = z[c]; se += expf(v - mx); sz += v; }
+    se = warp_sum(se); sz = warp_sum(sz);
+    const float logZ = mx + logf(se);
+    if (argmax_out != nullptr && lane == 0) argmax_out[row] = am;
+    const bool valid = (g >= 0);
+    if (valid) {
+      const float q_on = 1.f - eps, q_off = eps / float(C);
+      const float zg = z[g];
+      // -[(1-eps)(zg - logZ) + q_off * (sum_{c != g} z_c - (C-1) logZ)]
+      const float row_loss = -(q_on * (zg - logZ) + q_off * ((sz - zg) - float(C - 1) * logZ));
+      if (lane == 0) { loss_acc += double(row_loss); nonpad += 1; correct += (am == int(g)); }
+    }
+    if (dlogits != nullptr) {
+      float* dz = dlogits + int64_t(row) * C;
+      if (valid) {
+        const float q_on = 1.f - eps, q_off = eps / float(C);
+        const float qsum = q_on + float(C - 1) * q_off;
+        for (int c = lane; c < C; c += 32) {
+          const float sm = expf(z[c] - logZ);
+          dz[c] = (qsum * sm - (c == int(g) ? q_on : q_off)) * inv_n;
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) dz[c] = 0.f;
+      }
+    }
+  }
+  if (lane == 0 && nonpad > 0) {
+    atomicAdd(&stats[0], loss_acc);
+    atomicAdd(&stats[1], double(correct));
+    atomicAdd(&stats[2], double(nonpad));
+  }
+}
+
+}  // namespace masr
+
+using namespace masr;
+
+extern "C" int masr_add_layernorm_fwd(void* x_inout, const void* res, const float* gamma, const float* beta,
+                                      void* y, float* mean, float* rstd, int dtype, int rows, int d, float eps,
+                                      float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  MASR_REQUIRE(d > 0 && d <= 32 * LN_MAX_PER_LANE, "layernorm: d must be <= 1024");
+  if (rows == 0) return MASR_OK;
+  const int threads = 256, wpb = threads / 32;
+  const int blocks = int(std::min<int64_t>(ceil_div64(rows, wpb), int64_t(sm_count()) * 8));
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      add_layernorm_fwd_kernel<T><<<blocks, threads, 0, as_stream(stream)>>>(
+          static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd,
+          rows, d, eps, p_drop, inv_keep, seed, site));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_add_layernorm_bwd(const void* dy, const void* s, const float* mean, const float* rstd,
+                                      const float* gamma, void* ds, int ds_accum, void* dx,
+                                      float* dgamma, float* dbeta, int dtype, int rows, int d,
+                                      float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  MASR_REQUIRE(d > 0 && d <= 32 * LN_MAX_PER_LANE, "layernorm: d must be <= 1024");
+  if (rows == 0) return MASR_OK;
+  const int threads = 256, wpb = threads / 32;
+  const int blocks = int(std::min<int64_t>(ceil_div64(rows, wpb), int64_t(sm_count()) * 2));
+  const size_t smem = size_t(wpb) * 2 * d * sizeof(float);
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      add_layernorm_bwd_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
+          static_cast<const T*>(dy), static_cast<const T*>(s), mean, rstd, gamma, static_cast<T*>(ds), ds_accum,
+          static_cast<T*>(dx), dgamma, dbeta, rows, d, p_drop, inv_keep, seed, site));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_add_pe_dropout(void* x, const float* pe, int dtype, int rows, int L, int d,
+                                   float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  const int64_t n = int64_t(rows) * d;
+  if (n == 0) return MASR_OK;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      add_pe_dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+          static_cast<T*>(x), pe, n, L, d, p_drop, inv_keep, seed, site));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_embed_pe_fwd(const int64_t* ids, const float* E, const float* pe, void* out, int dtype,
+                                 int rows, int L, int d, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  const int64_t n = int64_t(rows) * d;
+  if (n == 0) return MASR_OK;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      embed_pe_fwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+          ids, E, pe, static_cast<T*>(out), n, L, d, p_drop, inv_keep, seed, site));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_embed_bwd(const int64_t* ids, const void* dout, int dtype, float* dE, int rows, int L, int d,
+                              float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  (void)L;
+  const int64_t n = int64_t(rows) * d;
+  if (n == 0) return MASR_OK;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      embed_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+          ids, static_cast<const T*>(dout), dE, n, d, p_drop, inv_keep, seed, site));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_dropout(void* x, int dtype, int64_t n, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  if (n == 0 || p_drop <= 0.f) return MASR_OK;
+  const float inv_keep = 1.f / (1.f - p_drop);
+  MASR_DISPATCH_DTYPE(dtype, T,
+      dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(static_cast<T*>(x), n, p_drop, inv_keep, seed, site));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_colsum_add(const void* x, int dtype, int64_t ldx, float* out, int M, int N, void* stream) {
+  if (M == 0 || N == 0) return MASR_OK;
+  dim3 block(32, 8);
+  const int gy = int(std::min<int64_t>(ceil_div64(M, 8 * 8), 64));
+  dim3 grid(unsigned(ceil_div64(N, 32)), unsigned(gy));
+  MASR_DISPATCH_DTYPE(dtype, T,
+      colsum_add_kernel<T><<<grid, block, 0, as_stream(stream)>>>(static_cast<const T*>(x), ldx, out, M, N));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+  if (n == 0) return MASR_OK;
+  cudaStream_t st = as_stream(stream);
+  const int g = grid_for(n, 256);
+  if (src_dtype == MASR_F32 && dst_dtype == MASR_BF16)
+    cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
+  else if (src_dtype == MASR_BF16 && dst_dtype == MASR_F32)
+    cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
+  else if (src_dtype == MASR_F32 && dst_dtype == MASR_F32)
+    cast_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), n);
+  else if (src_dtype == MASR_BF16 && dst_dtype == MASR_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n);
+  else { set_error("masr_cast: bad dtype"); return MASR_E_INVALID; }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_permute_cf(const void* src, int src_dtype, void* dst, int dst_dtype, int rows, int C, int F,
+                               int inverse_add, void* stream) {
+  const int64_t n = int64_t(rows) * C * F;
+  if (n == 0) return MASR_OK;
+  cudaStream_t st = as_stream(stream);
+  const int g = grid_for(n, 256);
+  if (src_dtype == MASR_F32 && dst_dtype == MASR_F32)
+    permute_cf_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), rows, C, F, inverse_add);
+  else if (src_dtype == MASR_F32 && dst_dtype == MASR_BF16 && !inverse_add)
+    permute_cf_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), rows, C, F, 0);
+  else { set_error("masr_permute_cf: unsupported dtype combination"); return MASR_E_INVALID; }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_ls_ce_fwd_bwd(const float* logits, const int64_t* gold, int N, int C, float eps, float inv_n,
+                                  double* stats, int64_t* argmax, float* dlogits, void* stream) {
+  MASR_REQUIRE(C > 0, "ls_ce: C must be positive");
+  if (N == 0) return MASR_OK;
+  const int threads = 128, wpb = threads / 32;
+  const int blocks = int(std::min<int64_t>(ceil_div64(N, wpb), int64_t(sm_count()) * 8));
+  ls_ce_kernel<<<blocks, threads, 0, as_stream(stream)>>>(logits, gold, N, C, eps, inv_n, stats, argmax, dlogits);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}

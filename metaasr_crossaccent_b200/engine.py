@@ -1,0 +1,531 @@
+"""Forward + backward of the transformer_pytorch ASR model as an explicit schedule of C-ABI kernel
+calls over flat parameter / gradient arenas (no autograd, no torch ops on the path).
+
+Mirrors MyTransformer.forward (reference src/model/transformer_pytorch/mono_transformer_torch.py:
+113-141,178-208) and the loss of TransformerTrainer.run_batch (src/transformer_torch_trainer.py:
+59-92), including the reference's quirks: padded frames are not re-masked in the
+conv stack, floor-mode pooling, enc_lens = floor(ilens/4), no target key-padding in decoder
+self-attention, no sqrt(d) embedding scale, label smoothing over n_class, tied output projection.
+
+Layout decisions (B200-first):
+  * every trainable tensor is a view into ONE flat fp32 arena (state-dict order, tied matrix once),
+    gradients into a second arena of the same layout -> clip / SGD / FOMAML accumulate / Adam /
+    all-reduce are single streaming passes (ops.mt_*);
+  * activations are batch-first [B*T, d]; conv tensors NHWC so that (a) the implicit-GEMM K dim
+    (tap, Cin) is contiguous and (b) the pooled conv4 output IS the [B*T', 2560] vgg2enc input
+    (the (c,f)->(f,c) flattening difference is folded into a column permutation of vgg2enc.weight);
+  * masks are never materialised: kernels take lengths.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+IGNORE_ID = -1
+LN_EPS = 1e-5
+ARENA_ALIGN = 64          # elements (256 B): keeps every tensor 16 B aligned for 128-bit / TMA access
+
+
+class NetConfig:
+    """asr_model block of the reference YAMLs (config/transformer/pretrain/fometa-hkust.yaml:13-26)."""
+
+    def __init__(self, idim=83, d_model=512, nheads=8, d_inner=2048, enc_layers=2, dec_layers=4,
+                 odim=367, dropout=0.1, pos_dropout=0.1, tie=True):
+        self.idim, self.d_model, self.nheads, self.d_inner = idim, d_model, nheads, d_inner
+        self.enc_layers, self.dec_layers, self.odim = enc_layers, dec_layers, odim
+        self.dropout, self.pos_dropout, self.tie = float(dropout), float(pos_dropout), bool(tie)
+        self.sos_id, self.eos_id = 0, odim - 1
+        self.vgg_ch = 128
+        self.f4 = idim // 4
+        self.vgg_o_dim = self.vgg_ch * self.f4
+        assert d_model % nheads == 0 and d_model // nheads <= 64
+
+    @staticmethod
+    def from_yaml(am: dict, odim: int):
+        return NetConfig(am["idim"], am["d_model"], am["nheads"], am["d_inner"], am["encoder"]["nlayers"],
+                         am["decoder"]["nlayers"], odim, am.get("dropout", 0.0), am.get("pos_dropout", 0.0),
+                         am.get("tgt_share_weight", 1) != 0)
+
+
+def param_shapes(cfg: NetConfig) -> "OrderedDict[str, tuple]":
+    """state_dict key -> shape in the reference's registration order (114 entries for the hkust net)."""
+    d, ff = cfg.d_model, cfg.d_inner
+    s = OrderedDict()
+    for i, (co, ci) in zip((0, 2, 5, 7), ((64, 1), (64, 64), (128, 64), (128, 128))):
+        s[f"feat_extractor.{i}.weight"] = (co, ci, 3, 3)
+        s[f"feat_extractor.{i}.bias"] = (co,)
+    s["vgg2enc.weight"] = (d, cfg.vgg_o_dim)
+    s["vgg2enc.bias"] = (d,)
+    s["pos_encoder.pe"] = (3000, 1, d)
+    s["char_trans.weight"] = (cfg.odim, d)
+    s["char_trans.bias"] = (cfg.odim,)
+    s["pre_embed.weight"] = (cfg.odim, d)
+
+    def attn(p):
+        s[p + ".in_proj_weight"] = (3 * d, d)
+        s[p + ".in_proj_bias"] = (3 * d,)
+        s[p + ".out_proj.weight"] = (d, d)
+        s[p + ".out_proj.bias"] = (d,)
+
+    def ffn_norms(p, n_norm):
+        s[p + ".linear1.weight"] = (ff, d)
+        s[p + ".linear1.bias"] = (ff,)
+        s[p + ".linear2.weight"] = (d, ff)
+        s[p + ".linear2.bias"] = (d,)
+        for j in range(1, n_norm + 1):
+            s[p + f".norm{j}.weight"] = (d,)
+            s[p + f".norm{j}.bias"] = (d,)
+
+    for l in range(cfg.enc_layers):
+        attn(f"encoder.layers.{l}.self_attn")
+        ffn_norms(f"encoder.layers.{l}", 2)
+    s["encoder.norm.weight"] = (d,)
+    s["encoder.norm.bias"] = (d,)
+    for l in range(cfg.dec_layers):
+        attn(f"decoder.layers.{l}.self_attn")
+        attn(f"decoder.layers.{l}.multihead_attn")
+        ffn_norms(f"decoder.layers.{l}", 3)
+    s["decoder.norm.weight"] = (d,)
+    s["decoder.norm.bias"] = (d,)
+    return s
+
+
+def positional_table(max_len, d_model):
+    """PositionalEncoding buffer, computed exactly as mono_transformer_torch.py:21-27 (fp32, CPU)."""
+    pe = torch.zeros(max_len, d_model)
+    position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.unsqueeze(0).transpose(0, 1).contiguous()      # [max_len, 1, d]
+
+
+class ArenaLayout:
+    """Offsets of the unique trainable tensors inside the flat arenas."""
+
+    def __init__(self, cfg: NetConfig):
+        self.shapes = param_shapes(cfg)
+        self.offsets = OrderedDict()
+        off = 0
+        for name, shape in self.shapes.items():
+            if name == "pos_encoder.pe" or (cfg.tie and name == "pre_embed.weight"):
+                continue
+            self.offsets[name] = off
+            n = 1
+            for v in shape:
+                n *= v
+            off += (n + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+        self.total = off
+        self.n_unique_elems = sum(int(torch.Size(self.shapes[n]).numel()) for n in self.offsets)
+
+    def view(self, arena: torch.Tensor, name: str) -> torch.Tensor:
+        shape = self.shapes[name]
+        off = self.offsets[name]
+        return arena[off:off + int(torch.Size(shape).numel())].view(shape)
+
+
+class TransformerEngine:
+    """Owns arenas + workspaces and runs forward / backward through a kernel backend."""
+
+    def __init__(self, cfg: NetConfig, backend, device, label_smoothing=0.2, seed=531):
+        self.cfg, self.be, self.device = cfg, backend, torch.device(device)
+        self.eps_ls = float(label_smoothing)
+        self.act_dtype = backend.act_dtype
+        self.layout = ArenaLayout(cfg)
+        n = self.layout.total
+        self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.pe = positional_table(3000, cfg.d_model).to(self.device)               # [3000,1,d]
+        self.pe2d = self.pe.view(3000, cfg.d_model)
+        self.P = OrderedDict((nm, self.layout.view(self.params, nm)) for nm in self.layout.offsets)
+        self.G = OrderedDict((nm, self.layout.view(self.grads, nm)) for nm in self.layout.offsets)
+        if cfg.tie:
+            self.P["pre_embed.weight"] = self.P["char_trans.weight"]
+            self.G["pre_embed.weight"] = self.G["char_trans.weight"]
+        # compute-dtype shadow of the parameter arena (bf16 mode) and re-laid-out conv / vgg2enc weights
+        self.shadow = None
+        if self.act_dtype != torch.float32:
+            self.shadow = torch.zeros(n, dtype=self.act_dtype, device=self.device)
+        self.W = OrderedDict()      # name -> compute-dtype weight used by GEMMs
+        self.wp = {}                # conv idx -> [Cout, 9*Cin] compute dtype
+        self.dwp = {}               # conv idx -> fp32 gradient in the same layout
+        for i, (co, ci) in zip((2, 5, 7), ((64, 64), (128, 64), (128, 128))):
+            self.wp[i] = torch.zeros(co, 9 * ci, dtype=self.act_dtype, device=self.device)
+            self.dwp[i] = torch.zeros(co, 9 * ci, dtype=torch.float32, device=self.device)
+        self.vgg2enc_p = torch.zeros(cfg.d_model, cfg.vgg_o_dim, dtype=self.act_dtype, device=self.device)
+        self.d_vgg2enc_p = torch.zeros(cfg.d_model, cfg.vgg_o_dim, dtype=torch.float32, device=self.device)
+        self.weights_dirty = True
+        self.stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.step_seed = int(seed) * 1000003
+        self._ws = {}
+        self._sites = {}
+        self.training = True
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, sd):
+        """Copy a reference-layout state dict (114 keys) into the arena; with tied weights the
+        pre_embed.weight entry is written last, as nn.Module.load_state_dict does."""
+        for name in self.layout.shapes:
+            if name == "pos_encoder.pe" or name not in sd:
+                continue
+            self.P[name].copy_(sd[name].to(self.device, torch.float32))
+        self.weights_dirty = True
+
+    def state_dict(self):
+        """Reference-compatible state dict (same keys / shapes / fp32), tensors are arena views."""
+        out = OrderedDict()
+        for name in self.layout.shapes:
+            out[name] = self.pe if name == "pos_encoder.pe" else self.P[name]
+        return out
+
+    def prep_weights(self):
+        """Refresh the derived weight copies after the fp32 master arena changed."""
+        if not self.weights_dirty:
+            return
+        be = self.be
+        src = self.P
+        if self.shadow is not None:
+            be.cast(self.params, self.shadow)
+            src = OrderedDict((nm, self.layout.view(self.shadow, nm)) for nm in self.layout.offsets)
+        self.W = src
+        for i in (2, 5, 7):
+            be.conv_w_prep(self.P[f"feat_extractor.{i}.weight"], self.wp[i])
+        be.permute_cf(self.P["vgg2enc.weight"], self.vgg2enc_p, self.cfg.vgg_ch, self.cfg.f4, False)
+        self.weights_dirty = False
+
+    # ------------------------------------------------------------------ helpers
+    def site(self, name):
+        if name not in self._sites:
+            self._sites[name] = len(self._sites) + 1
+        return self._sites[name]
+
+    def _buf(self, ws, name, shape, dtype=None):
+        t = ws.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype or self.act_dtype, device=self.device)
+            ws[name] = t
+        return t
+
+    def workspace(self, B, T, L1):
+        key = (B, T, L1)
+        if key not in self._ws:
+            if len(self._ws) > 8:
+                self._ws.clear()
+            self._ws[key] = {}
+        return self._ws[key]
+
+    # ------------------------------------------------------------------ batch preparation (host)
+    def prepare_batch(self, xs_pad, ilens, ys, olens=None):
+        """Host-side bookkeeping of MyTransformer.forward/preprocess (:117,124-141): enc_lens,
+        ys_in (sos + y, eos padded), ys_out (y + eos, IGNORE padded); olens += 1 in place."""
+        cfg = self.cfg
+        B = xs_pad.shape[0]
+        assert B == ilens.shape[0] == len(ys), "Batch size mismatch"
+        enc_lens = torch.floor(ilens.to(dtype=torch.float32) / 4).to(dtype=torch.int64)
+        L1 = max(int(y.numel()) for y in ys) + 1
+        ys_in = torch.full((B, L1), cfg.eos_id, dtype=torch.int64)
+        ys_out = torch.full((B, L1), IGNORE_ID, dtype=torch.int64)
+        for b, y in enumerate(ys):
+            n = int(y.numel())
+            ys_in[b, 0] = cfg.sos_id
+            ys_in[b, 1:n + 1] = y
+            ys_out[b, :n] = y
+            ys_out[b, n] = cfg.eos_id
+        if olens is not None:
+            olens += 1
+        n_total = int(ys_out.ne(IGNORE_ID).sum())
+        return {"x": xs_pad, "enc_lens": enc_lens, "ys_in": ys_in, "ys_out": ys_out, "n_total": n_total,
+                "B": B, "T": xs_pad.shape[1], "L1": L1}
+
+    def to_device(self, hb):
+        """H2D of one prepared batch (pinned host memory when available, non-blocking)."""
+        dev = {}
+        for k in ("x", "enc_lens", "ys_in", "ys_out"):
+            t = hb[k]
+            if self.device.type == "cuda" and not t.is_pinned():
+                t = t.pin_memory()
+            dev[k] = t.to(self.device, non_blocking=True)
+        dev.update({k: hb[k] for k in ("n_total", "B", "T", "L1")})
+        return dev
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, db, want_grad=True):
+        """Runs the network on a device batch; fills ws['logits'] [B*L1, C] fp32 and the loss
+        statistics; with want_grad also d(mean loss)/d logits."""
+        cfg, be = self.cfg, self.be
+        self.prep_weights()
+        B, T, L1 = db["B"], db["T"], db["L1"]
+        F0 = cfg.idim
+        T2, F2 = T // 2, F0 // 2
+        T4, F4 = T2 // 2, F2 // 2
+        d, ff, H, C = cfg.d_model, cfg.d_inner, cfg.nheads, cfg.odim
+        Me, Md = B * T4, B * L1
+        ws = self.workspace(B, T, L1)
+        ws["dims"] = (B, T, L1, T2, F2, T4, F4, Me, Md)
+        buf = lambda n, shape, dt=None: self._buf(ws, n, shape, dt)
+        f32 = torch.float32
+        seed = self.step_seed
+        pd = cfg.dropout if self.training else 0.0
+        ppd = cfg.pos_dropout if self.training else 0.0
+        P, W = self.P, self.W
+
+        # ---- VGG front end (NHWC)
+        a1 = buf("a1", (B, T, F0, 64))
+        be.conv1_fwd(db["x"], P["feat_extractor.0.weight"], P["feat_extractor.0.bias"], a1)
+        a2 = buf("a2", (B, T, F0, 64))
+        be.conv3x3_fwd(a1, self.wp[2], P["feat_extractor.2.bias"], a2)
+        p1 = buf("p1", (B, T2, F2, 64))
+        be.maxpool_fwd(a2, p1)
+        a3 = buf("a3", (B, T2, F2, 128))
+        be.conv3x3_fwd(p1, self.wp[5], P["feat_extractor.5.bias"], a3)
+        a4 = buf("a4", (B, T2, F2, 128))
+        be.conv3x3_fwd(a3, self.wp[7], P["feat_extractor.7.bias"], a4)
+        p2 = buf("p2", (B, T4, F4, 128))
+        be.maxpool_fwd(a4, p2)
+        h = buf("h0", (Me, d))
+        be.linear_fwd(p2.view(Me, F4 * 128), self.vgg2enc_p, P["vgg2enc.bias"], h)
+        be.add_pe_dropout(h, self.pe2d, T4, ppd, seed, self.site("enc.pe"))
+
+        # ---- encoder (post-norm)
+        for l in range(cfg.enc_layers):
+            pre = f"encoder.layers.{l}"
+            qkv = buf(f"e{l}.qkv", (Me, 3 * d))
+            be.linear_fwd(h, W[pre + ".self_attn.in_proj_weight"], P[pre + ".self_attn.in_proj_bias"], qkv)
+            ctx = buf(f"e{l}.ctx", (Me, d))
+            lse = buf(f"e{l}.lse", (B * H * T4,), f32)
+            be.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, lse, B, H, T4, T4, db["enc_lens"], False,
+                        pd, seed, self.site(pre + ".sa"))
+            s1 = buf(f"e{l}.s1", (Me, d))
+            be.linear_fwd(ctx, W[pre + ".self_attn.out_proj.weight"], P[pre + ".self_attn.out_proj.bias"], s1)
+            h1 = buf(f"e{l}.h1", (Me, d))
+            be.add_layernorm_fwd(s1, h, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1,
+                                 buf(f"e{l}.m1", (Me,), f32), buf(f"e{l}.r1", (Me,), f32), pd, seed, self.site(pre + ".d1"))
+            f1 = buf(f"e{l}.f1", (Me, ff))
+            be.linear_fwd(h1, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True)
+            be.dropout(f1, pd, seed, self.site(pre + ".df"))
+            s2 = buf(f"e{l}.s2", (Me, d))
+            be.linear_fwd(f1, W[pre + ".linear2.weight"], P[pre + ".linear2.bias"], s2)
+            h2 = buf(f"e{l}.h2", (Me, d))
+            be.add_layernorm_fwd(s2, h1, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], h2,
+                                 buf(f"e{l}.m2", (Me,), f32), buf(f"e{l}.r2", (Me,), f32), pd, seed, self.site(pre + ".d2"))
+            h = h2
+        ws["enc_last"] = h
+        mem = buf("mem", (Me, d))
+        be.add_layernorm_fwd(h, None, P["encoder.norm.weight"], P["encoder.norm.bias"], mem,
+                             buf("enc.m", (Me,), f32), buf("enc.r", (Me,), f32), 0.0, seed, 0)
+
+        # ---- decoder
+        x = buf("d.x0", (Md, d))
+        be.embed_pe_fwd(db["ys_in"].view(-1), P["pre_embed.weight"], self.pe2d, x, L1, ppd, seed, self.site("dec.pe"))
+        for l in range(cfg.dec_layers):
+            pre = f"decoder.layers.{l}"
+            ws[f"d{l}.in"] = x
+            qkv = buf(f"d{l}.qkv", (Md, 3 * d))
+            be.linear_fwd(x, W[pre + ".self_attn.in_proj_weight"], P[pre + ".self_attn.in_proj_bias"], qkv)
+            ctx1 = buf(f"d{l}.ctx1", (Md, d))
+            lse1 = buf(f"d{l}.lse1", (B * H * L1,), f32)
+            be.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx1, lse1, B, H, L1, L1, None, True,
+                        pd, seed, self.site(pre + ".sa"))
+            s1 = buf(f"d{l}.s1", (Md, d))
+            be.linear_fwd(ctx1, W[pre + ".self_attn.out_proj.weight"], P[pre + ".self_attn.out_proj.bias"], s1)
+            h1 = buf(f"d{l}.h1", (Md, d))
+            be.add_layernorm_fwd(s1, x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1,
+                                 buf(f"d{l}.m1", (Md,), f32), buf(f"d{l}.r1", (Md,), f32), pd, seed, self.site(pre + ".d1"))
+            Wc, bc = W[pre + ".multihead_attn.in_proj_weight"], P[pre + ".multihead_attn.in_proj_bias"]
+            q2 = buf(f"d{l}.q2", (Md, d))
+            be.linear_fwd(h1, Wc[:d], bc[:d], q2)
+            kv2 = buf(f"d{l}.kv2", (Me, 2 * d))
+            be.linear_fwd(mem, Wc[d:], bc[d:], kv2)
+            ctx2 = buf(f"d{l}.ctx2", (Md, d))
+            lse2 = buf(f"d{l}.lse2", (B * H * L1,), f32)
+            be.attn_fwd(q2, kv2[:, :d], kv2[:, d:], ctx2, lse2, B, H, L1, T4, db["enc_lens"], False,
+                        pd, seed, self.site(pre + ".ca"))
+            s2 = buf(f"d{l}.s2", (Md, d))
+            be.linear_fwd(ctx2, W[pre + ".multihead_attn.out_proj.weight"], P[pre + ".multihead_attn.out_proj.bias"], s2)
+            h2 = buf(f"d{l}.h2", (Md, d))
+            be.add_layernorm_fwd(s2, h1, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], h2,
+                                 buf(f"d{l}.m2", (Md,), f32), buf(f"d{l}.r2", (Md,), f32), pd, seed, self.site(pre + ".d2"))
+            f1 = buf(f"d{l}.f1", (Md, ff))
+            be.linear_fwd(h2, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True)
+            be.dropout(f1, pd, seed, self.site(pre + ".df"))
+            s3 = buf(f"d{l}.s3", (Md, d))
+            be.linear_fwd(f1, W[pre + ".linear2.weight"], P[pre + ".linear2.bias"], s3)
+            h3 = buf(f"d{l}.h3", (Md, d))
+            be.add_layernorm_fwd(s3, h2, P[pre + ".norm3.weight"], P[pre + ".norm3.bias"], h3,
+                                 buf(f"d{l}.m3", (Md,), f32), buf(f"d{l}.r3", (Md,), f32), pd, seed, self.site(pre + ".d3"))
+            x = h3
+        ws["dec_last"] = x
+        dout = buf("d.out", (Md, d))
+        be.add_layernorm_fwd(x, None, P["decoder.norm.weight"], P["decoder.norm.bias"], dout,
+                             buf("dec.m", (Md,), f32), buf("dec.r", (Md,), f32), 0.0, seed, 0)
+        logits = buf("logits", (Md, C), f32)
+        be.linear_fwd(dout, W["char_trans.weight"], P["char_trans.bias"], logits)
+
+        # ---- label-smoothed CE, accuracy, d logits
+        be.zero_(self.stats)
+        argmax = buf("argmax", (Md,), torch.int64)
+        dlogits = buf("dlogits", (Md, C), f32) if want_grad else None
+        be.ls_ce(logits, db["ys_out"].view(-1), self.eps_ls, 1.0 / max(db["n_total"], 1), self.stats, argmax, dlogits)
+        return ws
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, db, ws):
+        """Back-propagates ws['dlogits'] through the whole network; gradients are ACCUMULATED into
+        self.grads (zeroed here first, as run_batch's asr_opt.zero_grad() does)."""
+        cfg, be = self.cfg, self.be
+        B, T, L1, T2, F2, T4, F4, Me, Md = ws["dims"]
+        F0 = cfg.idim
+        d, ff, H, C = cfg.d_model, cfg.d_inner, cfg.nheads, cfg.odim
+        buf = lambda n, shape, dt=None: self._buf(ws, n, shape, dt)
+        f32 = torch.float32
+        seed = self.step_seed
+        pd = cfg.dropout if self.training else 0.0
+        ppd = cfg.pos_dropout if self.training else 0.0
+        P, W, G = self.P, self.W, self.G
+        be.zero_(self.grads)
+
+        def ffn_bwd(pre, g_s, f1, h_in, g_res, Mrows, tag):
+            """g_s: grad wrt linear2 output; accumulates the FFN input gradient into g_res."""
+            be.linear_wgrad(f1, g_s, G[pre + ".linear2.weight"], G[pre + ".linear2.bias"])
+            g_f1 = buf(tag + ".g_f1", (Mrows, ff))
+            be.linear_dgrad(g_s, W[pre + ".linear2.weight"], g_f1)
+            be.dropout(g_f1, pd, seed, self.site(pre + ".df"))
+            be.relu_bwd(f1, g_f1)
+            be.linear_wgrad(h_in, g_f1, G[pre + ".linear1.weight"], G[pre + ".linear1.bias"])
+            be.linear_dgrad(g_f1, W[pre + ".linear1.weight"], g_res, accumulate=True)
+
+        def self_attn_bwd(pre, g_o, qkv, ctx, lse, x_in, g_res, Mrows, L, klens, causal, tag, site):
+            be.linear_wgrad(ctx, g_o, G[pre + ".self_attn.out_proj.weight"], G[pre + ".self_attn.out_proj.bias"])
+            g_ctx = buf(tag + ".g_ctx", (Mrows, d))
+            be.linear_dgrad(g_o, W[pre + ".self_attn.out_proj.weight"], g_ctx)
+            g_qkv = buf(tag + ".g_qkv", (Mrows, 3 * d))
+            dsum = buf(tag + ".dsum", (B * H * L,), f32)
+            be.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, g_ctx, lse, dsum,
+                        g_qkv[:, :d], g_qkv[:, d:2 * d], g_qkv[:, 2 * d:], B, H, L, L, klens, causal, pd, seed, site)
+            be.linear_wgrad(x_in, g_qkv, G[pre + ".self_attn.in_proj_weight"], G[pre + ".self_attn.in_proj_bias"])
+            be.linear_dgrad(g_qkv, W[pre + ".self_attn.in_proj_weight"], g_res, accumulate=True)
+
+        # ---- output projection + final decoder norm
+        dlogits = ws["dlogits"]
+        be.linear_wgrad(ws["d.out"], dlogits, G["char_trans.weight"], G["char_trans.bias"])
+        g_out = buf("g.out", (Md, d))
+        be.linear_dgrad(dlogits, W["char_trans.weight"], g_out)
+        gd = [buf("g.dA", (Md, d)), buf("g.dB", (Md, d))]
+        g_br = buf("g.dBr", (Md, d))                       # gradient of the sub-layer (branch) output
+        cur = 0
+        be.add_layernorm_bwd(g_out, ws["dec_last"], ws["dec.m"], ws["dec.r"], P["decoder.norm.weight"], gd[cur], False,
+                             None, G["decoder.norm.weight"], G["decoder.norm.bias"])
+        g_mem = buf("g.mem", (Me, d))
+        first_mem = True
+        for l in reversed(range(cfg.dec_layers)):
+            pre = f"decoder.layers.{l}"
+            # norm3 / FFN
+            nxt = 1 - cur
+            be.add_layernorm_bwd(gd[cur], ws[f"d{l}.s3"], ws[f"d{l}.m3"], ws[f"d{l}.r3"], P[pre + ".norm3.weight"],
+                                 gd[nxt], False, g_br, G[pre + ".norm3.weight"], G[pre + ".norm3.bias"],
+                                 pd, seed, self.site(pre + ".d3"))
+            ffn_bwd(pre, g_br, ws[f"d{l}.f1"], ws[f"d{l}.h2"], gd[nxt], Md, "gd")
+            cur = nxt
+            # norm2 / cross attention
+            nxt = 1 - cur
+            be.add_layernorm_bwd(gd[cur], ws[f"d{l}.s2"], ws[f"d{l}.m2"], ws[f"d{l}.r2"], P[pre + ".norm2.weight"],
+                                 gd[nxt], False, g_br, G[pre + ".norm2.weight"], G[pre + ".norm2.bias"],
+                                 pd, seed, self.site(pre + ".d2"))
+            be.linear_wgrad(ws[f"d{l}.ctx2"], g_br, G[pre + ".multihead_attn.out_proj.weight"],
+                            G[pre + ".multihead_attn.out_proj.bias"])
+            g_ctx = buf("gd.g_ctx", (Md, d))
+            be.linear_dgrad(g_br, W[pre + ".multihead_attn.out_proj.weight"], g_ctx)
+            g_q2 = buf("gd.g_q2", (Md, d))
+            g_kv2 = buf("gd.g_kv2", (Me, 2 * d))
+            dsum = buf("gd.dsum", (B * H * L1,), f32)
+            kv2 = ws[f"d{l}.kv2"]
+            be.attn_bwd(ws[f"d{l}.q2"], kv2[:, :d], kv2[:, d:], ws[f"d{l}.ctx2"], g_ctx, ws[f"d{l}.lse2"], dsum,
+                        g_q2, g_kv2[:, :d], g_kv2[:, d:], B, H, L1, T4, db["enc_lens"], False,
+                        pd, seed, self.site(pre + ".ca"))
+            Wc = W[pre + ".multihead_attn.in_proj_weight"]
+            Gw, Gb = G[pre + ".multihead_attn.in_proj_weight"], G[pre + ".multihead_attn.in_proj_bias"]
+            be.linear_wgrad(ws[f"d{l}.h1"], g_q2, Gw[:d], Gb[:d])
+            be.linear_dgrad(g_q2, Wc[:d], gd[nxt], accumulate=True)
+            be.linear_wgrad(ws["mem"], g_kv2, Gw[d:], Gb[d:])
+            be.linear_dgrad(g_kv2, Wc[d:], g_mem, accumulate=not first_mem)
+            first_mem = False
+            cur = nxt
+            # norm1 / causal self attention
+            nxt = 1 - cur
+            be.add_layernorm_bwd(gd[cur], ws[f"d{l}.s1"], ws[f"d{l}.m1"], ws[f"d{l}.r1"], P[pre + ".norm1.weight"],
+                                 gd[nxt], False, g_br, G[pre + ".norm1.weight"], G[pre + ".norm1.bias"],
+                                 pd, seed, self.site(pre + ".d1"))
+            self_attn_bwd(pre, g_br, ws[f"d{l}.qkv"], ws[f"d{l}.ctx1"], ws[f"d{l}.lse1"], ws[f"d{l}.in"], gd[nxt],
+                          Md, L1, None, True, "gd", self.site(pre + ".sa"))
+            cur = nxt
+        be.embed_bwd(db["ys_in"].view(-1), gd[cur], G["pre_embed.weight"], L1, ppd, seed, self.site("dec.pe"))
+
+        # ---- encoder
+        ge = [buf("g.eA", (Me, d)), buf("g.eB", (Me, d))]
+        g_ebr = buf("g.eBr", (Me, d))
+        cur = 0
+        if cfg.dec_layers == 0:
+            be.zero_(g_mem)
+        be.add_layernorm_bwd(g_mem, ws["enc_last"], ws["enc.m"], ws["enc.r"], P["encoder.norm.weight"], ge[cur], False,
+                             None, G["encoder.norm.weight"], G["encoder.norm.bias"])
+        for l in reversed(range(cfg.enc_layers)):
+            pre = f"encoder.layers.{l}"
+            nxt = 1 - cur
+            be.add_layernorm_bwd(ge[cur], ws[f"e{l}.s2"], ws[f"e{l}.m2"], ws[f"e{l}.r2"], P[pre + ".norm2.weight"],
+                                 ge[nxt], False, g_ebr, G[pre + ".norm2.weight"], G[pre + ".norm2.bias"],
+                                 pd, seed, self.site(pre + ".d2"))
+            ffn_bwd(pre, g_ebr, ws[f"e{l}.f1"], ws[f"e{l}.h1"], ge[nxt], Me, "ge")
+            cur = nxt
+            nxt = 1 - cur
+            be.add_layernorm_bwd(ge[cur], ws[f"e{l}.s1"], ws[f"e{l}.m1"], ws[f"e{l}.r1"], P[pre + ".norm1.weight"],
+                                 ge[nxt], False, g_ebr, G[pre + ".norm1.weight"], G[pre + ".norm1.bias"],
+                                 pd, seed, self.site(pre + ".d1"))
+            x_in = ws["h0"] if l == 0 else ws[f"e{l - 1}.h2"]
+            self_attn_bwd(pre, g_ebr, ws[f"e{l}.qkv"], ws[f"e{l}.ctx"], ws[f"e{l}.lse"], x_in, ge[nxt],
+                          Me, T4, db["enc_lens"], False, "ge", self.site(pre + ".sa"))
+            cur = nxt
+        g_h0 = ge[cur]
+        be.dropout(g_h0, ppd, seed, self.site("enc.pe"))
+
+        # ---- vgg2enc + VGG front end
+        p2f = ws["p2"].view(Me, F4 * 128)
+        be.zero_(self.d_vgg2enc_p)
+        be.linear_wgrad(p2f, g_h0, self.d_vgg2enc_p, G["vgg2enc.bias"])
+        be.permute_cf(self.d_vgg2enc_p, G["vgg2enc.weight"], cfg.vgg_ch, cfg.f4, True)
+        g_p2 = buf("g.p2", (B, T4, F4, 128))
+        be.linear_dgrad(g_h0, self.vgg2enc_p, g_p2.view(Me, F4 * 128))
+        g_a4 = buf("g.a4", (B, T2, F2, 128))
+        be.maxpool_bwd(ws["a4"], g_p2, g_a4, True)
+        for i in (2, 5, 7):
+            be.zero_(self.dwp[i])
+        be.conv3x3_wgrad(ws["a3"], g_a4, self.dwp[7], G["feat_extractor.7.bias"])
+        g_a3 = buf("g.a3", (B, T2, F2, 128))
+        be.conv3x3_dgrad(g_a4, self.wp[7], g_a3, ws["a3"])
+        be.conv3x3_wgrad(ws["p1"], g_a3, self.dwp[5], G["feat_extractor.5.bias"])
+        g_p1 = buf("g.p1", (B, T2, F2, 64))
+        be.conv3x3_dgrad(g_a3, self.wp[5], g_p1, None)
+        g_a2 = buf("g.a2", (B, T, F0, 64))
+        be.maxpool_bwd(ws["a2"], g_p1, g_a2, True)
+        be.conv3x3_wgrad(ws["a1"], g_a2, self.dwp[2], G["feat_extractor.2.bias"])
+        g_a1 = buf("g.a1", (B, T, F0, 64))
+        be.conv3x3_dgrad(g_a2, self.wp[2], g_a1, ws["a1"])
+        be.conv1_wgrad(db["x"], g_a1, G["feat_extractor.0.weight"], G["feat_extractor.0.bias"])
+        for i in (2, 5, 7):
+            be.conv_w_unprep_add(self.dwp[i], G[f"feat_extractor.{i}.weight"])
+
+    # ------------------------------------------------------------------ public step
+    def forward_backward(self, db):
+        """One run_batch(train=True) worth of device work.  Returns the workspace; the loss
+        statistics stay on the device in self.stats = [sum of row losses, n_correct, n_non_pad]."""
+        self.step_seed += 1
+        ws = self.forward(db, want_grad=True)
+        self.backward(db, ws)
+        return ws
+
+    def read_stats(self):
+        """The single device->host read of a step: {'loss', 'acc'} like run_batch's info dict."""
+        s = self.stats.tolist()
+        n = max(s[2], 1.0)
+        return {"loss": s[0] / n, "acc": s[1] / n}

@@ -1,0 +1,242 @@
+"""Thin Python binding of the C ABI: each method forwards torch CUDA tensors (data_ptr, sizes,
+strides) and the current CUDA stream to one `masr_*` entry point.  PyTorch is used for device
+memory and streams only -- no torch op runs on this path, and there is no fallback: constructing
+the backend fails unless libmetaasr_b200.so is built and an sm_100 GPU is present.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+GEMM_RELU, GEMM_ACCUM, GEMM_SPLITK = 1, 2, 4
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaBackend:
+    """Kernel dispatch object used by engine.TransformerEngine (the test suite swaps in a torch
+    implementation of the same interface on CPU to check the orchestration against the oracle)."""
+
+    name = "cuda"
+
+    def __init__(self, device, act_dtype=torch.float32, gemm="simt"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.MetaASRLibraryError("metaasr_b200 kernels run on an sm_100 GPU only (no CPU fallback)")
+        self.device = device
+        self.lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+        self.act_dtype = act_dtype
+        self.gemm_path = gemm          # "simt" | "umma"
+        self.launches = 0              # our kernels launched through this backend (bench: gpu_launches)
+        self._scratch = {}
+
+    # -------------------------------------------------------------- plumbing
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _call(self, name, *args, n_kernels=1):
+        rc = getattr(self.lib, name)(*args)
+        if rc != 0:
+            _lib.check(rc, name)
+        self.launches += n_kernels
+
+    def scratch(self, key, numel, dtype):
+        t = self._scratch.get(key)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(int(numel), dtype=dtype, device=self.device)
+            self._scratch[key] = t
+        return t[:numel]
+
+    # -------------------------------------------------------------- GEMM family
+    def gemm(self, A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, flags=0, splitk=1):
+        self._call("masr_gemm", _p(A), _dt(A), sam, sak, _p(B), _dt(B), sbn, sbk, _p(C), _dt(C), ldc, _p(bias),
+                   M, N, K, flags, splitk, self.stream)
+
+    def linear_fwd(self, x, w, bias, y, relu=False):
+        """y[M,N] = x[M,K] @ w[N,K]^T + bias (nn.Linear forward)."""
+        M, K = x.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and y.shape == (M, N) and x.stride(1) == 1 and w.stride(1) == 1 and y.stride(1) == 1
+        self.gemm(x, x.stride(0), 1, w, w.stride(0), 1, y, y.stride(0), bias, M, N, K, GEMM_RELU if relu else 0)
+
+    def linear_dgrad(self, dy, w, dx, accumulate=False):
+        """dx[M,K] (+)= dy[M,N] @ w[N,K]."""
+        M, N = dy.shape
+        K = w.shape[1]
+        assert dx.shape == (M, K) and dy.stride(1) == 1 and w.stride(1) == 1 and dx.stride(1) == 1
+        self.gemm(dy, dy.stride(0), 1, w, 1, w.stride(0), dx, dx.stride(0), None, M, K, N,
+                  GEMM_ACCUM if accumulate else 0)
+
+    def linear_wgrad(self, x, dy, dw, db):
+        """dw[N,K] += dy[M,N]^T @ x[M,K] (fp32, split-K atomics); db[N] += column sums of dy."""
+        M, K = x.shape
+        N = dy.shape[1]
+        assert dw.shape == (N, K) and dw.dtype == torch.float32 and dw.stride(1) == 1
+        tiles = ((N + 127) // 128) * ((K + 127) // 128)
+        splitk = max(1, min((M + 255) // 256, (4 * 148 + tiles - 1) // tiles))
+        self.gemm(dy, 1, dy.stride(0), x, 1, x.stride(0), dw, dw.stride(0), None, N, K, M, GEMM_SPLITK, splitk)
+        if db is not None:
+            self.colsum_add(dy, db)
+
+    # -------------------------------------------------------------- conv front end
+    def conv1_fwd(self, x, w, bias, y):
+        B, H, W = x.shape
+        self._call("masr_conv1_fwd", _p(x), _p(w), _p(bias), _p(y), _dt(y), B, H, W, w.shape[0], self.stream)
+
+    def conv1_wgrad(self, x, dy, dw, db):
+        B, H, W = x.shape
+        self._call("masr_conv1_wgrad", _p(x), _p(dy), _dt(dy), _p(dw), _p(db), B, H, W, dw.shape[0], self.stream)
+
+    def conv_w_prep(self, w, wp):
+        self._call("masr_conv_w_prep", _p(w), _p(wp), _dt(wp), w.shape[0], w.shape[1], self.stream)
+
+    def conv_w_unprep_add(self, dwp, dw):
+        self._call("masr_conv_w_unprep_add", _p(dwp), _p(dw), dw.shape[0], dw.shape[1], self.stream)
+
+    def _im2col(self, x):
+        B, H, W, Cin = x.shape
+        col = self.scratch("col", B * H * W * 9 * Cin, x.dtype).view(B * H * W, 9 * Cin)
+        self._call("masr_im2col3x3", _p(x), _p(col), _dt(x), B, H, W, Cin, self.stream)
+        return col
+
+    def conv3x3_fwd(self, x, wp, bias, y):
+        """y = relu(conv3x3(x) + bias), NHWC; wp [Cout, 9*Cin]."""
+        B, H, W, Cin = x.shape
+        Cout = wp.shape[0]
+        col = self._im2col(x)
+        self.gemm(col, 9 * Cin, 1, wp, 9 * Cin, 1, y, Cout, bias, B * H * W, Cout, 9 * Cin, GEMM_RELU)
+
+    def conv3x3_dgrad(self, dy, wp, dx, relu_src=None):
+        """dx = conv3x3^T(dy) (times (relu_src > 0) when given)."""
+        B, H, W, Cout = dy.shape
+        Cin = dx.shape[3]
+        P = B * H * W
+        dcol = self.scratch("col", P * 9 * Cin, dy.dtype).view(P, 9 * Cin)
+        self.gemm(dy, Cout, 1, wp, 1, 9 * Cin, dcol, 9 * Cin, None, P, 9 * Cin, Cout, 0)
+        self._call("masr_col2im3x3", _p(dcol), _p(dx), _dt(dx), _p(relu_src), B, H, W, Cin, self.stream)
+
+    def conv3x3_wgrad(self, x, dy, dwp, db):
+        """dwp[Cout, 9*Cin] += dy^T @ im2col(x) (fp32); db += column sums of dy."""
+        B, H, W, Cin = x.shape
+        Cout = dy.shape[3]
+        P = B * H * W
+        col = self._im2col(x)
+        tiles = ((Cout + 127) // 128) * ((9 * Cin + 127) // 128)
+        splitk = max(1, min((P + 511) // 512, (4 * 148 + tiles - 1) // tiles))
+        self.gemm(dy, 1, Cout, col, 1, 9 * Cin, dwp, 9 * Cin, None, Cout, 9 * Cin, P, GEMM_SPLITK, splitk)
+        self.colsum_add(dy.view(P, Cout), db)
+
+    def maxpool_fwd(self, x, y):
+        B, H, W, Cc = x.shape
+        self._call("masr_maxpool2x2_fwd", _p(x), _p(y), _dt(x), B, H, W, Cc, self.stream)
+
+    def maxpool_bwd(self, x, dy, dx, relu_mask=True):
+        B, H, W, Cc = x.shape
+        self._call("masr_maxpool2x2_bwd", _p(x), _p(dy), _p(dx), _dt(x), int(relu_mask), B, H, W, Cc, self.stream)
+
+    def relu_bwd(self, y, dx):
+        self._call("masr_relu_bwd", _p(y), _p(dx), _dt(y), y.numel(), self.stream)
+
+    # -------------------------------------------------------------- attention
+    def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
+        hd = out.shape[1] // H
+        self._call("masr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                   _p(lse), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site, self.stream)
+
+    def attn_bwd(self, q, k, v, out, dout, lse, dsum, dq, dk, dv, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
+        hd = out.shape[1] // H
+        self._call("masr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                   _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
+                   _p(dv), dv.stride(0), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site,
+                   self.stream, n_kernels=2)
+
+    # -------------------------------------------------------------- fused elementwise
+    def add_layernorm_fwd(self, x, res, gamma, beta, y, mean, rstd, p=0.0, seed=0, site=0, eps=1e-5):
+        rows, d = x.shape
+        self._call("masr_add_layernorm_fwd", _p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), _dt(x),
+                   rows, d, eps, float(p), seed, site, self.stream)
+
+    def add_layernorm_bwd(self, dy, s, mean, rstd, gamma, ds, ds_accum, dx, dgamma, dbeta, p=0.0, seed=0, site=0):
+        rows, d = dy.shape
+        self._call("masr_add_layernorm_bwd", _p(dy), _p(s), _p(mean), _p(rstd), _p(gamma), _p(ds), int(ds_accum),
+                   _p(dx), _p(dgamma), _p(dbeta), _dt(dy), rows, d, float(p), seed, site, self.stream)
+
+    def add_pe_dropout(self, x, pe, L, p=0.0, seed=0, site=0):
+        rows, d = x.shape
+        self._call("masr_add_pe_dropout", _p(x), _p(pe), _dt(x), rows, L, d, float(p), seed, site, self.stream)
+
+    def embed_pe_fwd(self, ids, E, pe, out, L, p=0.0, seed=0, site=0):
+        rows, d = out.shape
+        self._call("masr_embed_pe_fwd", _p(ids), _p(E), _p(pe), _p(out), _dt(out), rows, L, d, float(p), seed, site,
+                   self.stream)
+
+    def embed_bwd(self, ids, dout, dE, L, p=0.0, seed=0, site=0):
+        rows, d = dout.shape
+        self._call("masr_embed_bwd", _p(ids), _p(dout), _dt(dout), _p(dE), rows, L, d, float(p), seed, site, self.stream)
+
+    def dropout(self, x, p, seed, site):
+        if p > 0.0:
+            self._call("masr_dropout", _p(x), _dt(x), x.numel(), float(p), seed, site, self.stream)
+
+    def colsum_add(self, x, out):
+        M, N = x.shape
+        self._call("masr_colsum_add", _p(x), _dt(x), x.stride(0), _p(out), M, N, self.stream)
+
+    def cast(self, src, dst):
+        self._call("masr_cast", _p(src), _dt(src), _p(dst), _dt(dst), src.numel(), self.stream)
+
+    def permute_cf(self, src, dst, Cc, Fq, inverse_add=False):
+        rows = src.shape[0]
+        self._call("masr_permute_cf", _p(src), _dt(src), _p(dst), _dt(dst), rows, Cc, Fq, int(inverse_add), self.stream)
+
+    def ls_ce(self, logits, gold, eps, inv_n, stats, argmax, dlogits):
+        N, Cc = logits.shape
+        self._call("masr_ls_ce_fwd_bwd", _p(logits), _p(gold), N, Cc, float(eps), float(inv_n), _p(stats), _p(argmax),
+                   _p(dlogits), self.stream)
+
+    def zero_(self, t):
+        """Device memset through the CUDA runtime (stream-ordered); counts as plumbing, not a kernel of ours."""
+        t.zero_()
+
+    # -------------------------------------------------------------- kernel 4: flat arena ops
+    def mt_sumsq(self, g, out, zero_first=True):
+        self._call("masr_mt_sumsq", _p(g), g.numel(), _p(out), int(zero_first), self.stream, n_kernels=2 if zero_first else 1)
+
+    def mt_clip_sgd(self, p, g, buf, sumsq, max_norm, lr, momentum, nesterov, first_step):
+        self._call("masr_mt_clip_sgd", _p(p), _p(g), _p(buf), p.numel(), _p(sumsq), float(max_norm), float(lr),
+                   float(momentum), int(nesterov), int(first_step), self.stream)
+
+    def mt_clip(self, g, sumsq, max_norm):
+        self._call("masr_mt_clip", _p(g), g.numel(), _p(sumsq), float(max_norm), self.stream)
+
+    def mt_accumulate(self, upd, g, sumsq=None, max_norm=0.0):
+        self._call("masr_mt_accumulate", _p(upd), _p(g), g.numel(), _p(sumsq), float(max_norm), self.stream)
+
+    def mt_reptile_delta(self, upd, theta, phi):
+        self._call("masr_mt_reptile_delta", _p(upd), _p(theta), _p(phi), upd.numel(), self.stream)
+
+    def mt_adam(self, p, m, v, upd, count, lr, beta1, beta2, eps, bc1, bc2, skip_if_nan=None, clip_sumsq=None, max_norm=0.0):
+        self._call("masr_mt_adam", _p(p), _p(m), _p(v), _p(upd), p.numel(), float(count), float(lr), float(beta1),
+                   float(beta2), float(eps), float(bc1), float(bc2), _p(skip_if_nan), _p(clip_sumsq), float(max_norm),
+                   self.stream)
+
+    def mt_axpy(self, y, x, a):
+        self._call("masr_mt_axpy", _p(y), _p(x), float(a), y.numel(), self.stream)
+
+    def copy_(self, dst, src):
+        """Flat device-to-device copy (cudaMemcpyAsync under torch); replaces the 114 per-tensor
+        copies of load_state_dict(_original), fo_meta_interface.py:226."""
+        dst.copy_(src, non_blocking=True)
