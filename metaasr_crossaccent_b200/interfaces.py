@@ -1,0 +1,410 @@
+"""Fused meta-learning interfaces: drop-ins for the reference's training loops
+
+    FOMetaASRInterface  (src/fo_meta_interface.py:18-302)   FOMAML  (+ Reptile, which the
+                         reference accepts on the CLI but raises on, :195-198 -- SURVEY 8a row R)
+    MultiASRInterface   (src/multi_interface.py:17-192)     multi-task
+
+They keep the reference's hook names and behaviour (`load_model`, `run_task`,
+`_partial_meta_update`, `_final_meta_update`, `train`, `save_per_steps`, `_original`,
+`_updates`, `_counter`, `meta_opt`, `inner_lr`) but run every parameter-space step as ONE fused
+kernel over the flat arenas of engine.py and combine the ranks' meta-gradients with a single
+all-reduce (dist.py).  Two ways to use them:
+
+  * inside the reference tree: `fused(FOMetaMixin, src.fo_meta_interface.FOMetaASRInterface)`
+    keeps the reference's __init__/logging/eval/checkpoint code and swaps only the hot hooks
+    (INTEGRATION.md);
+  * standalone (bench, tests, GPU box without the reference): FOMetaASRInterface /
+    MultiASRInterface below, built on the small PretrainHost base.
+"""
+from __future__ import annotations
+
+import math
+import pickle
+import random
+from collections import OrderedDict
+from functools import partial
+from pathlib import Path
+
+import torch
+
+from . import dist as D
+from .optim import FlatAdamState, FlatInnerSGD, FlatNoamAdam, noam_lr
+
+GRAD_CLIP = 5                  # src/marcos.py:7
+LOG_DIR = 'testing-logs'       # src/marcos.py:4
+INIT_BEST_ER = 200.0           # src/marcos.py:5
+SOS_SYMBOL, EOS_SYMBOL = '<s>', '</s>'
+
+
+class RunningAvgDict(dict):
+    """Stand-in for torchexp.stat.RunningAvgDict (pretrain_interface.py:12): decay 1.0 ->
+    count-weighted mean, else exponential moving average.  Picklable (info_dict.latest)."""
+
+    def __init__(self, decay_rate=0.99):
+        super().__init__()
+        self.decay_rate = decay_rate
+        self._n = {}
+
+    def add(self, info, n=1):
+        for k, v in info.items():
+            v = float(v)
+            if k not in self:
+                self[k], self._n[k] = v, n
+            elif self.decay_rate >= 1.0:
+                tot = self._n[k] + n
+                self[k] = (self[k] * self._n[k] + v * n) / tot
+                self._n[k] = tot
+            else:
+                self[k] = self.decay_rate * self[k] + (1 - self.decay_rate) * v
+
+
+class _NullDashboard:
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
+class PretrainHost:
+    """Minimal stand-alone equivalent of PretrainInterface (src/pretrain_interface.py:16-138):
+    config fields, vocabulary (<s> + units + </s>), log-dir layout, text logs.  Data comes from
+    `self.data_container` (anything with get_item(accent_idx=None, num=1), io/dataset.py:248)."""
+
+    def __init__(self, config, paras, id2accent):
+        self.config, self.paras = config, paras
+        self.train_type = 'pretrain'
+        s = config['solver']
+        self.eval_ival, self.log_ival, self.save_ival = s['eval_ival'], s['log_ival'], s['save_ival']
+        self.half_batch_ilen, self.dev_max_ilen = s.get('half_batch_ilen'), s.get('dev_max_ilen')
+        self.sample_strategy = getattr(paras, 'sample_strategy', 'normal')
+        self.best_cer = self.best_wer = INIT_BEST_ER
+        units = [SOS_SYMBOL]
+        mapping = Path(s.get('spm_mapping', ''))
+        if mapping.is_file():
+            with open(mapping) as fin:
+                units += [line.rstrip().split(' ')[0] for line in fin.readlines()]
+        else:                                     # synthetic runs: unigram150 has 365 units -> odim 367
+            units += [f"<u{i}>" for i in range(1, int(s.get('n_units', 365)) + 1)]
+        units.append(EOS_SYMBOL)
+        self.id2units = units
+        self.id2ch = units
+        self.metric_observer = None               # CER/WER stays host-side and out of scope
+        self.accents = [id2accent[a] for a in paras.pretrain_accents]
+        self.num_pretrain = paras.num_pretrain
+        self.tgt_accent = id2accent.get(getattr(paras, 'tgt_accent', None), 'none')
+        self.max_step = paras.max_step if paras.max_step > 0 else s['total_steps']
+        assert self.num_pretrain == len(self.accents)
+        self.log_dir = None
+        if getattr(paras, 'log_root', None) is not None and D.rank() == 0:
+            self.log_dir = Path(paras.log_root, LOG_DIR, self.train_type, s['setting'], paras.algo,
+                                paras.pretrain_suffix, self.tgt_accent, str(paras.runs))
+            self.log_dir.mkdir(parents=True, exist_ok=True)
+        self.train_info = RunningAvgDict(decay_rate=0.99)
+        self.global_step = 1
+        self.dashboard = _NullDashboard()
+        self.data_container = None
+
+    def load_data(self):
+        pass
+
+    def write_log(self, k, v):
+        if self.log_dir is not None:
+            with open(self.log_dir.joinpath(k), 'a') as fout:
+                print(f"{self.global_step} {v}", file=fout)
+
+    def log_msg(self, lr=None):
+        pass
+
+    def write_tr_logs(self):
+        for k, v in self.train_info.items():
+            self.write_log(f"train_{k}", float(v))
+
+    def check_evaluate(self):
+        if self.global_step % self.eval_ival == 0:
+            self.evaluate()
+
+    def evaluate(self):
+        self.write_tr_logs()
+
+    def save_per_steps(self):
+        """snapshot.latest / snapshot.step.N / info_dict.latest / global_step, rank 0 only
+        (fo_meta_interface.py:70-88); what is saved is asr_model = last task's fast weights."""
+        if self.log_dir is None:
+            return
+        sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.asr_model.state_dict().items())
+        torch.save(sd, self.log_dir.joinpath("snapshot.latest"))
+        with open(self.log_dir.joinpath("info_dict.latest"), 'wb') as f:
+            pickle.dump(self.train_info, f)
+        with open(self.log_dir.joinpath("global_step"), 'w') as f:
+            print(self.global_step, file=f)
+        torch.save(sd, self.log_dir.joinpath(f"snapshot.step.{self.global_step}"))
+
+
+# ======================================================================================= FOMAML / Reptile
+class FOMetaMixin:
+    """Hot hooks of FOMetaASRInterface on flat arenas."""
+
+    def _fo_init(self):
+        paras, config = self.paras, self.config
+        assert paras.meta_k is not None
+        self.meta_k = paras.meta_k
+        self.meta_batch_size = paras.meta_batch_size if paras.meta_batch_size is not None else self.num_pretrain
+        self.asr_model, self.asr_opt = None, None
+        self._train = partial(self.run_batch, train=True)
+        self._eval = partial(self.run_batch, train=False)
+        self._updates, self._counter = None, 0
+        am = config['asr_model']
+        opt = am['meta']['optimizer_opt']
+        self.inner_lr = am['d_model'] ** (-0.5) * opt['k'] * (opt['warmup_steps'] ** (-0.5))   # :42-45
+        self.reptile_outer = am.get('reptile_outer', 'adam')       # 'adam' (row R default) | 'interp'
+        self.reptile_eps = float(am.get('reptile_eps', 1.0))
+
+    # -- fo_meta_interface.py:90-111
+    def load_model(self):
+        eng = self.asr_model.engine
+        if getattr(self.paras, 'resume', False):
+            self.asr_model.load_state_dict(torch.load(self.resume_model_path))
+        am = self.config['asr_model']
+        if am['meta_opt_cls'] != 'noam':
+            raise NotImplementedError("Should use noam optimizer in outer loop transformer learning")
+        # the META weights: a detached flat clone.  The reference's clone breaks weight tying into two
+        # tensors that receive identical gradients and identical Adam states, i.e. stay bit-identical
+        # forever -> one copy is exact.
+        self._original_flat = eng.params.clone()
+        self._original = OrderedDict()
+        for name in eng.layout.shapes:
+            if name == "pos_encoder.pe":
+                self._original[name] = eng.pe
+            else:
+                src = "char_trans.weight" if (eng.cfg.tie and name == "pre_embed.weight") else name
+                self._original[name] = eng.layout.view(self._original_flat, src)
+        opt = am['meta']['optimizer_opt']
+        self.meta_opt = _MetaNoamAdam(eng.be, self._original_flat, opt['k'], am['d_model'], opt['warmup_steps'])
+        # update arena: [n params | 1 slot for the task counter] -> a single all-reduce carries both
+        self._upd_flat = torch.zeros(eng.layout.total + 64, dtype=torch.float32, device=eng.device)
+        self._gnorm = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        io = am.get('inner_optimizer_opt', {})
+        if am.get('inner_optimizer_cls', 'SGD') != 'SGD':
+            raise NotImplementedError("fused inner loop implements torch.optim.SGD (fometa-hkust.yaml:2-6)")
+        self.asr_opt = FlatInnerSGD(eng, self.inner_lr, io.get('momentum', 0.0), io.get('nesterov', False))
+        self._stats_ring = torch.zeros(max(self.num_pretrain, 1), 4, dtype=torch.float64, device=eng.device)
+        self._ring_sizes = []
+
+    # -- fo_meta_interface.py:223-250
+    def run_task(self, batches):
+        eng = self.asr_model.engine
+        be = eng.be
+        self._counter += 1
+        be.copy_(eng.params, self._original_flat)              # load_state_dict(_original): one flat copy
+        eng.weights_dirty = True
+        self.asr_model.train()
+        self.asr_opt.reset()                                   # fresh SGD per task
+        for (idx, (x, ilens, ys, olens)) in batches:
+            self.run_batch(idx, x, ilens, ys, olens, train=True, sync=False)
+            be.mt_sumsq(eng.grads[:eng.layout.total], self._gnorm)          # clip_grad_norm_ (device-side norm)
+            self.asr_opt.step(self._gnorm, GRAD_CLIP)                        # NaN norm -> kernel skips the step
+
+    # -- fo_meta_interface.py:145-154 (inner-loop test) + :180-198
+    def inner_test(self, val_batch):
+        eng = self.asr_model.engine
+        be = eng.be
+        idx, (x, ilens, ys, olens) = val_batch
+        if self.paras.algo == 'fomaml':
+            self.run_batch(idx, x, ilens, ys, olens, train=True, accent_idx=idx, sync=False)
+            be.mt_sumsq(eng.grads[:eng.layout.total], self._gnorm)
+        else:   # reptile: the held-out batch only produces logging statistics (no gradient needed)
+            hb = eng.prepare_batch(x, ilens, ys, olens)
+            eng.forward(eng.to_device(hb), want_grad=False)
+        slot = len(self._ring_sizes)
+        self._stats_ring[slot].copy_(eng.stats)
+        self._ring_sizes.append(len(ys))
+        self._partial_meta_update()
+
+    def _partial_meta_update(self):
+        eng = self.asr_model.engine
+        n = eng.layout.total
+        self._updates = self._upd_flat
+        if self.paras.algo == 'fomaml':       # _updates[n] += clip(p.grad)
+            eng.be.mt_accumulate(self._upd_flat[:n], eng.grads[:n], self._gnorm, GRAD_CLIP)
+        elif self.paras.algo == 'reptile':    # _updates[n] += theta - phi
+            eng.be.mt_reptile_delta(self._upd_flat[:n], self._original_flat[:n], eng.params[:n])
+        else:
+            raise ValueError(f"Not support meta algo {self.paras.algo}")
+
+    # -- fo_meta_interface.py:200-221 (+ the one collective of the path)
+    def _final_meta_update(self):
+        eng = self.asr_model.engine
+        n = eng.layout.total
+        if D.is_dist():
+            self._upd_flat[n] = float(self._counter)
+            D.all_reduce_sum_(self._upd_flat)
+            count = float(self._global_task_count) if self._global_task_count else float(self._upd_flat[n].item())
+        else:
+            count = float(self._counter)
+        if self.paras.algo == 'reptile' and self.reptile_outer == 'interp':
+            eng.be.mt_axpy(self._original_flat[:n], self._upd_flat[:n], -self.reptile_eps / max(count, 1.0))
+            self.meta_opt.lr = self.reptile_eps
+        else:
+            self.meta_opt.step(self._upd_flat[:n], max(count, 1.0))
+        eng.be.zero_(self._upd_flat)
+        self._counter, self._updates = 0, None
+
+    _global_task_count = 0       # tasks of the meta-batch over ALL ranks (0: read it from the all-reduce)
+
+    def meta_step_on_tasks(self, tasks, global_task_count=None):
+        """One meta-step given this rank's tasks = [(train_batches, test_batch), ...]; batches are
+        (accent_idx, (x, ilens, ys, olens)) tuples as DataContainer.get_item yields them."""
+        if global_task_count is not None:
+            self._global_task_count = global_task_count
+        self._ring_sizes = []
+        for tr_batches, val_batch in tasks:
+            self.run_task(tr_batches)
+            self.inner_test(val_batch)
+        self._final_meta_update()
+
+    def flush_train_info(self):
+        """The single device->host read of a meta-step: per-task inner-test loss/acc."""
+        k = len(self._ring_sizes)
+        infos = []
+        if k:
+            for row, bs in zip(self._stats_ring[:k].tolist(), self._ring_sizes):
+                nn_ = max(row[2], 1.0)
+                info = {'loss': row[0] / nn_, 'acc': row[1] / nn_}
+                infos.append(info)
+                self.train_info.add(info, bs)
+        self._ring_sizes = []
+        return infos
+
+    # -- fo_meta_interface.py:128-177
+    def train(self):
+        task_ids = list(range(self.num_pretrain))
+        world = D.world_size()
+        try:
+            while self.global_step < self.max_step:
+                for _ in range(self.eval_ival):
+                    random.shuffle(task_ids)           # identical on every rank (same seed, pretrain.py:62)
+                    mine = D.partition_tasks(task_ids, self.meta_batch_size)
+                    self._global_task_count = min(self.meta_batch_size, len(task_ids))
+                    tasks = []
+                    for accent_id in mine:
+                        tr = self.data_container.get_item(accent_id, self.meta_k)
+                        te = self.data_container.get_item(accent_id)[0]
+                        tasks.append((tr, te))
+                    self.meta_step_on_tasks(tasks)
+                    self.flush_train_info()
+                    self.log_msg(self.meta_opt.lr)
+                    self.check_evaluate()
+                    self.global_step += 1
+                    self.dashboard.step()
+                    if self.global_step % self.save_ival == 0:
+                        self.save_per_steps()
+                    self.dashboard.check()
+                    if world > 1 and self.global_step >= self.max_step:
+                        break
+        except KeyboardInterrupt:
+            self.save_per_steps()
+            self.dashboard.set_status('pretrained(SIGINT)')
+        else:
+            self.dashboard.set_status('pretrained')
+
+
+class _MetaNoamAdam:
+    """meta_opt: noam schedule + Adam(0.9, 0.98, 1e-9) on the flat meta weights; averaging by the
+    task count (`_updates /= _counter`) is fused into the Adam kernel."""
+
+    def __init__(self, backend, original_flat, k, d_model, warmup_steps):
+        self.k, self.d_model, self.warmup_steps = k, d_model, warmup_steps
+        self.n = None
+        self.state = FlatAdamState(backend, original_flat)
+        self.step_num, self.lr = 0, d_model ** (-0.5)
+
+    def step(self, upd_flat, count):
+        self.step_num += 1
+        self.lr = noam_lr(self.step_num, self.k, self.d_model, self.warmup_steps)
+        n = upd_flat.numel()
+        st = self.state
+        st.t += 1
+        bc1, bc2 = 1.0 - st.b1 ** st.t, 1.0 - st.b2 ** st.t
+        st.be.mt_adam(st.p[:n], st.m[:n], st.v[:n], upd_flat, count, self.lr, st.b1, st.b2, st.eps, bc1, bc2)
+
+    def zero_grad(self):
+        pass
+
+
+# ======================================================================================= multi-task
+class MultiMixin:
+    """Hot hooks of MultiASRInterface (multi_interface.py:94-140) on flat arenas."""
+
+    def _multi_init(self):
+        self.asr_model, self.asr_opt = None, None
+        self._train = partial(self.run_batch, train=True)
+        self._eval = partial(self.run_batch, train=False)
+
+    def load_model(self):
+        if getattr(self.paras, 'resume', False):
+            self.asr_model.load_state_dict(torch.load(self.resume_model_path))
+        eng = self.asr_model.engine
+        self._gnorm = torch.zeros(1, dtype=torch.float64, device=eng.device)
+
+    def multi_step(self, item, sync=True):
+        """run_batch -> clip_grad_norm_ -> optimizer step (NaN norm skips the step on the device)."""
+        eng = self.asr_model.engine
+        idx, (x, ilens, ys, olens) = item
+        info = self.run_batch(idx, x, ilens, ys, olens, train=True, accent_idx=idx, sync=sync)
+        n = eng.layout.total
+        world = D.world_size()
+        if world > 1:                       # data-parallel variant: mean of the ranks' gradients
+            D.all_reduce_sum_(eng.grads)
+        eng.be.mt_sumsq(eng.grads[:n], self._gnorm)
+        if isinstance(self.asr_opt, FlatNoamAdam):
+            if world > 1:
+                self.asr_opt.step_num += 1
+                self.asr_opt.lr = noam_lr(self.asr_opt.step_num, self.asr_opt.k, self.asr_opt.d_model,
+                                          self.asr_opt.warmup_steps)
+                self.asr_opt.state.step(eng.grads, float(world), self.asr_opt.lr, skip_if_nan=self._gnorm,
+                                        clip_sumsq=self._gnorm, max_norm=GRAD_CLIP * world)
+                eng.weights_dirty = True
+            else:
+                self.asr_opt.step(self._gnorm, GRAD_CLIP)
+        else:                               # any torch optimizer (fine-tuning configs): reference semantics
+            eng.be.mt_clip(eng.grads[:n], self._gnorm, GRAD_CLIP)
+            if not math.isnan(float(self._gnorm.item())):
+                self.asr_opt.step()
+            eng.weights_dirty = True
+        return info
+
+    def train(self):
+        try:
+            while self.global_step < self.max_step:
+                for _ in range(self.eval_ival):
+                    item = self.data_container.get_item()[0]
+                    info = self.multi_step(item)
+                    self.train_info.add(info, len(item[1][2]))
+                    self.log_msg(getattr(self.asr_opt, 'lr', None))
+                    self.check_evaluate()
+                    self.global_step += 1
+                    self.dashboard.step()
+                    if self.global_step % self.save_ival == 0:
+                        self.save_per_steps()
+                    self.dashboard.check()
+        except KeyboardInterrupt:
+            self.save_per_steps()
+            self.dashboard.set_status('pretrained(SIGINT)')
+        else:
+            self.dashboard.set_status('pretrained')
+
+
+def fused(mixin, base):
+    """Graft the fused hot hooks onto an interface base class (the reference's own
+    FOMetaASRInterface / MultiASRInterface, or PretrainHost)."""
+    init_name = '_fo_init' if mixin is FOMetaMixin else '_multi_init'
+
+    class Fused(mixin, base):
+        def __init__(self, config, paras, id2accent):
+            base.__init__(self, config, paras, id2accent)
+            getattr(self, init_name)()
+
+    Fused.__name__ = f"Fused{base.__name__}"
+    return Fused
+
+
+FOMetaASRInterface = fused(FOMetaMixin, PretrainHost)
+MultiASRInterface = fused(MultiMixin, PretrainHost)

@@ -69,7 +69,10 @@ def check_adam_weights(z, wprefix, gprefixes, name, t, lr, tol_lr=3e-2, gmin=1e-
     gs = z[wprefix + name + "#sample"].astype(np.float64)
     mask = np.ones_like(gs, dtype=bool)
     for gp in gprefixes:
-        mask &= np.abs(z[gp + name + "#sample"]) > gmin
+        ga = np.abs(z[gp + name + "#sample"])
+        # a gradient below the fp32 re-ordering noise of its tensor (~1 % of the largest entry after
+        # two inner SGD steps through ReLU / max-pool switches) can flip sign -> +-2 lr under Adam
+        mask &= ga > max(gmin, 0.05 * float(ga.max()))
     err = np.abs(s - gs)[mask]
     assert mask.sum() == 0 or err.max() <= tol_lr * lr, \
         f"{wprefix}{name}: max err {err.max():.3e} = {err.max() / lr:.3f} lr over {mask.sum()} elems"
