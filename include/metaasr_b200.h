@@ -80,7 +80,14 @@ int masr_gemm(const void* A, int a_dtype, int64_t sam, int64_t sak,
               void* C, int c_dtype, int64_t ldc, const float* bias,
               int M, int N, int K, int flags, int splitk, void* stream);
 
-/* tcgen05 GEMM: A [M,K] bf16 and B [N,K] bf16 both K-major ("TN"), C [M,N] bf16 or fp32. */
+/* tcgen05 GEMM, bf16 operands, fp32 accumulation in TMEM, C [M,N] bf16 or fp32 (bias / ReLU / accumulate
+ * flags as above).  a_mn = 0: A is [M,K] K-major (lda); a_mn = 1: A is stored transposed, At[K,M] (M
+ * contiguous).  Same for B with N.  Forward: (0,0); dgrad: (0,1) with B = w[N,K] read as Bt[K'=N, N'=K];
+ * wgrad: (1,1).  Requires 16-byte aligned bases and leading dimensions that are multiples of 8. */
+int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                   void* C, int c_dtype, int64_t ldc, const float* bias,
+                   int M, int N, int K, int flags, int splitk, void* stream);
+/* Convenience form of the above: A [M,K] and B [N,K] both K-major ("TN"). */
 int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
                       void* C, int c_dtype, int64_t ldc, const float* bias,
                       int M, int N, int K, int flags, void* stream);

@@ -32,6 +32,8 @@ SIGNATURES = {
     "masr_ctc_fwd_bwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p,
                          c_p, c_sz, c_p],
     "masr_gemm": [c_p, c_i, c_i64, c_i64, c_p, c_i, c_i64, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_umma_gemm": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_umma_gemm_tn": [c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_conv1_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_conv1_wgrad": [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_im2col3x3": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],

@@ -1,0 +1,293 @@
+// Kernel family 2: bf16 GEMMs on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in
+// TMEM), operands staged by TMA into 128B-swizzled shared memory through an mbarrier ring.
+//
+// One CTA computes a 128 x BN tile of C.  Warp roles (192 threads):
+//   warp 0    TMA producer   : one elected lane issues cp.async.bulk.tensor loads, STAGES deep
+//   warp 1    MMA issuer     : allocates TMEM, one lane issues tcgen05.mma (4 x K=16 per 64-wide k-block),
+//                              tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2-5 epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> bias / ReLU / accumulate ->
+//                              global (each thread owns one output row: 64-128 B contiguous per store burst)
+// Operand forms (template): K-major ("TN" forward GEMM: x[M,K] w[N,K]) or MN-major (dgrad: w[N,K] read as
+// B[K_out, N_red]; wgrad: dy[M,N], x[M,K] reduced over M) -- the latter only changes the TMA box, the smem
+// descriptor (LBO/SBO) and two bits of the instruction descriptor, the data are never transposed in memory.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace masr {
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool swizzle128) {
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MASR_E_CUDA; }
+  cuuint64_t gdim[5]; cuuint64_t gstr[5]; cuuint32_t bx[5]; cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];       // stride of dim i+1
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu] stride %llu box [%u,%u]", int(r), rank,
+             (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0);
+    set_error(buf);
+    return MASR_E_CUDA;
+  }
+  return MASR_OK;
+}
+
+// ------------------------------------------------------------------ kernel
+constexpr int UG_BM = 128;         // UMMA M
+constexpr int UG_BK = 64;          // k-block: 64 bf16 = one 128 B swizzle row
+constexpr int UG_THREADS = 192;
+
+struct UmmaGemmParams {
+  int M, N, K;                     // C[M,N] = sum_k A(m,k) B(n,k)
+  void* C; int64_t ldc; int c_is_f32;
+  const float* bias;
+  int flags;
+  int kb_per_split;                // k-blocks per blockIdx.z slice (split-K: fp32 atomics into C)
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaGemmParams p) {
+  using namespace umma;
+  constexpr uint32_t A_BYTES = UG_BM * UG_BK * 2;          // 16 KB
+  constexpr uint32_t B_BYTES = BN * UG_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024 B alignment is required by the 128 B swizzle atom
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
+  const int total_kb = (p.K + UG_BK - 1) / UG_BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int num_kb = min(total_kb - kb_begin, p.kb_per_split);      // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* sa = smem + s * STAGE_BYTES;
+        unsigned char* sb = sa + A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int k0 = (kb_begin + kb) * UG_BK;
+        if (!A_MN) {
+          tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);               // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int c = 0; c < UG_BM / 64; ++c)                          // box {64 m, 64 k} per 64-wide chunk
+            tma_load_2d(sa + c * (64 * UG_BK * 2), &map_a, &full_bar[s], m0 + c * 64, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sb + c * (64 * UG_BK * 2), &map_b, &full_bar[s], n0 + c * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < UG_BK / 16; ++k) {
+          // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 k-rows = +2048 B
+          const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sa + k * 32);
+          const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sb + k * 32);
+          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs have read it
+      }
+      mma_commit(tmem_full_bar);             // accumulator complete
+    }
+  } else {
+    // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const bool relu = p.flags & MASR_GEMM_RELU, accum = p.flags & MASR_GEMM_ACCUM, splitk = p.flags & MASR_GEMM_SPLITK;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+      tmem_ld_wait();
+      if (m < p.M) {
+        const int nbase = n0 + c0;
+        if (p.c_is_f32) {
+          float* crow = static_cast<float*>(p.C) + int64_t(m) * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nbase + j;
+            if (n < p.N) {
+              float x = v[j];
+              if (p.bias != nullptr && (!splitk || blockIdx.z == 0)) x += p.bias[n];
+              if (splitk) { atomicAdd(crow + n, x); continue; }
+              if (accum) x += crow[n];
+              if (relu) x = fmaxf(x, 0.f);
+              crow[n] = x;
+            }
+          }
+        } else {
+          __nv_bfloat16* crow = static_cast<__nv_bfloat16*>(p.C) + int64_t(m) * p.ldc;
+          const bool vec_ok = (nbase + 32 <= p.N) && ((p.ldc & 7) == 0) && ((nbase & 7) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nbase + j;
+            float t = v[j];
+            if (n < p.N) {
+              if (p.bias != nullptr) t += p.bias[n];
+              if (accum) t += __bfloat162float(crow[n]);
+              if (relu) t = fmaxf(t, 0.f);
+            }
+            x[j] = t;
+          }
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(x[j], x[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(x[j + 2], x[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j + 4], x[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(x[j + 6], x[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(crow + nbase + j) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nbase + j;
+              if (n < p.N) crow[n] = __float2bfloat16_rn(x[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaGemmParams& p, cudaStream_t st) {
+  constexpr size_t smem = size_t(STAGES) * (UG_BM * UG_BK * 2 + BN * UG_BK * 2) + 1024 + 256;
+  auto kern = umma_gemm_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_set = true;
+  }
+  const int total_kb = int(ceil_div64(p.K, UG_BK));
+  const int nsplit = int(ceil_div64(total_kb, p.kb_per_split));
+  dim3 grid(unsigned(ceil_div64(p.N, BN)), unsigned(ceil_div64(p.M, UG_BM)), unsigned(nsplit));
+  kern<<<grid, UG_THREADS, smem, st>>>(ma, mb, p);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+// operand map: K-major  -> dims {K, rows}, box {64, tile_rows};  MN-major -> dims {rows(MN), K}, box {64, 64}
+static int operand_map(CUtensorMap* out, const void* base, int64_t ld_elems, int rows_mn, int K, bool mn_major, int tile_rows) {
+  MASR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "umma: operand base must be 16-byte aligned");
+  MASR_REQUIRE(ld_elems % 8 == 0, "umma: operand leading dimension must be a multiple of 8 elements");
+  uint64_t dims[2]; uint64_t strides[1]; uint32_t box[2];
+  if (!mn_major) { dims[0] = uint64_t(K); dims[1] = uint64_t(rows_mn); box[0] = 64; box[1] = uint32_t(tile_rows); }
+  else           { dims[0] = uint64_t(rows_mn); dims[1] = uint64_t(K); box[0] = 64; box[1] = 64; }
+  strides[0] = uint64_t(ld_elems) * 2;
+  return make_tmap_bf16(out, base, 2, dims, strides, box, true);
+}
+
+}  // namespace masr
+
+using namespace masr;
+
+// C[M,N] = A[M,K] B[N,K]^T  (a_mn / b_mn = 0) or with MN-major operands:
+//   a_mn: A is stored as At[K, M] (M contiguous, leading dimension lda)
+//   b_mn: B is stored as Bt[K, N] (N contiguous, leading dimension ldb)
+extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                              void* C, int c_dtype, int64_t ldc, const float* bias,
+                              int M, int N, int K, int flags, int splitk, void* stream) {
+  MASR_REQUIRE(M > 0 && N > 0 && K > 0, "umma gemm: empty problem");
+  MASR_REQUIRE(!(flags & MASR_GEMM_SPLITK) || c_dtype == MASR_F32, "umma gemm: split-K needs an fp32 C");
+  MASR_REQUIRE(!((flags & MASR_GEMM_SPLITK) && (flags & MASR_GEMM_RELU)), "umma gemm: split-K cannot fuse ReLU");
+  const int BN = (N <= 64) ? 64 : 128;
+  const int total_kb = (K + UG_BK - 1) / UG_BK;
+  int kb_per_split = total_kb;
+  if ((flags & MASR_GEMM_SPLITK) && splitk > 1) kb_per_split = (total_kb + splitk - 1) / splitk;
+  CUtensorMap ma, mb;
+  int rc = operand_map(&ma, A, lda, M, K, a_mn != 0, UG_BM);
+  if (rc != MASR_OK) return rc;
+  rc = operand_map(&mb, B, ldb, N, K, b_mn != 0, BN);
+  if (rc != MASR_OK) return rc;
+  UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, kb_per_split};
+  cudaStream_t st = as_stream(stream);
+  const int key = (BN == 64 ? 0 : 4) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
+  switch (key) {
+    case 0: return launch_umma<64, 4, false, false>(ma, mb, p, st);
+    case 1: return launch_umma<64, 4, false, true>(ma, mb, p, st);
+    case 2: return launch_umma<64, 4, true, false>(ma, mb, p, st);
+    case 3: return launch_umma<64, 4, true, true>(ma, mb, p, st);
+    case 4: return launch_umma<128, 4, false, false>(ma, mb, p, st);
+    case 5: return launch_umma<128, 4, false, true>(ma, mb, p, st);
+    case 6: return launch_umma<128, 4, true, false>(ma, mb, p, st);
+    default: return launch_umma<128, 4, true, true>(ma, mb, p, st);
+  }
+}
+
+extern "C" int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
+                                 void* C, int c_dtype, int64_t ldc, const float* bias,
+                                 int M, int N, int K, int flags, void* stream) {
+  return masr_umma_gemm(A, lda, 0, B, ldb, 0, C, c_dtype, ldc, bias, M, N, K, flags, 1, stream);
+}

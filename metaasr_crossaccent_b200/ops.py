@@ -65,11 +65,32 @@ class CudaBackend:
         self._call("masr_gemm", _p(A), _dt(A), sam, sak, _p(B), _dt(B), sbn, sbk, _p(C), _dt(C), ldc, _p(bias),
                    M, N, K, flags, splitk, self.stream)
 
+    def _umma_ok(self, *ts):
+        """tcgen05 path: bf16 operands, 16 B aligned bases, leading dimensions multiple of 8."""
+        if self.gemm_path != "umma":
+            return False
+        for t in ts:
+            if t.dtype != torch.bfloat16 or t.data_ptr() % 16 or t.stride(0) % 8 or t.stride(1) != 1:
+                return False
+        return True
+
+    def umma_gemm(self, A, a_mn, B, b_mn, C, bias, M, N, K, flags=0, splitk=1):
+        self._call("masr_umma_gemm", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), _dt(C),
+                   C.stride(0), _p(bias), M, N, K, flags, int(splitk), self.stream)
+
+    @staticmethod
+    def _wgrad_splitk(rows_out, cols_out, k_red):
+        """Split the reduction so that ~2 waves of 128x128 tiles cover the 148 SMs."""
+        tiles = ((rows_out + 127) // 128) * ((cols_out + 127) // 128)
+        return max(1, min((k_red + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+
     def linear_fwd(self, x, w, bias, y, relu=False):
         """y[M,N] = x[M,K] @ w[N,K]^T + bias (nn.Linear forward)."""
         M, K = x.shape
         N = w.shape[0]
         assert w.shape[1] == K and y.shape == (M, N) and x.stride(1) == 1 and w.stride(1) == 1 and y.stride(1) == 1
+        if self._umma_ok(x, w):
+            return self.umma_gemm(x, 0, w, 0, y, bias, M, N, K, GEMM_RELU if relu else 0)
         self.gemm(x, x.stride(0), 1, w, w.stride(0), 1, y, y.stride(0), bias, M, N, K, GEMM_RELU if relu else 0)
 
     def linear_dgrad(self, dy, w, dx, accumulate=False):
@@ -77,17 +98,23 @@ class CudaBackend:
         M, N = dy.shape
         K = w.shape[1]
         assert dx.shape == (M, K) and dy.stride(1) == 1 and w.stride(1) == 1 and dx.stride(1) == 1
+        if self._umma_ok(dy, w):
+            return self.umma_gemm(dy, 0, w, 1, dx, None, M, K, N, GEMM_ACCUM if accumulate else 0)
         self.gemm(dy, dy.stride(0), 1, w, 1, w.stride(0), dx, dx.stride(0), None, M, K, N,
                   GEMM_ACCUM if accumulate else 0)
 
     def linear_wgrad(self, x, dy, dw, db):
-        """dw[N,K] += dy[M,N]^T @ x[M,K] (fp32, split-K atomics); db[N] += column sums of dy."""
+        """dw[N,K] += dy[M,N]^T @ x[M,K] (fp32); db[N] += column sums of dy."""
         M, K = x.shape
         N = dy.shape[1]
         assert dw.shape == (N, K) and dw.dtype == torch.float32 and dw.stride(1) == 1
-        tiles = ((N + 127) // 128) * ((K + 127) // 128)
-        splitk = max(1, min((M + 255) // 256, (4 * 148 + tiles - 1) // tiles))
-        self.gemm(dy, 1, dy.stride(0), x, 1, x.stride(0), dw, dw.stride(0), None, N, K, M, GEMM_SPLITK, splitk)
+        if self._umma_ok(dy, x):
+            sk = self._wgrad_splitk(N, K, M)
+            self.umma_gemm(dy, 1, x, 1, dw, None, N, K, M, GEMM_SPLITK if sk > 1 else GEMM_ACCUM, sk)
+        else:
+            tiles = ((N + 127) // 128) * ((K + 127) // 128)
+            splitk = max(1, min((M + 255) // 256, (4 * 148 + tiles - 1) // tiles))
+            self.gemm(dy, 1, dy.stride(0), x, 1, x.stride(0), dw, dw.stride(0), None, N, K, M, GEMM_SPLITK, splitk)
         if db is not None:
             self.colsum_add(dy, db)
 
@@ -117,6 +144,9 @@ class CudaBackend:
         B, H, W, Cin = x.shape
         Cout = wp.shape[0]
         col = self._im2col(x)
+        y2 = y.view(B * H * W, Cout)
+        if self._umma_ok(col, wp):
+            return self.umma_gemm(col, 0, wp, 0, y2, bias, B * H * W, Cout, 9 * Cin, GEMM_RELU)
         self.gemm(col, 9 * Cin, 1, wp, 9 * Cin, 1, y, Cout, bias, B * H * W, Cout, 9 * Cin, GEMM_RELU)
 
     def conv3x3_dgrad(self, dy, wp, dx, relu_src=None):
@@ -125,7 +155,11 @@ class CudaBackend:
         Cin = dx.shape[3]
         P = B * H * W
         dcol = self.scratch("col", P * 9 * Cin, dy.dtype).view(P, 9 * Cin)
-        self.gemm(dy, Cout, 1, wp, 1, 9 * Cin, dcol, 9 * Cin, None, P, 9 * Cin, Cout, 0)
+        dy2 = dy.view(P, Cout)
+        if self._umma_ok(dy2, wp):
+            self.umma_gemm(dy2, 0, wp, 1, dcol, None, P, 9 * Cin, Cout, 0)
+        else:
+            self.gemm(dy, Cout, 1, wp, 1, 9 * Cin, dcol, 9 * Cin, None, P, 9 * Cin, Cout, 0)
         self._call("masr_col2im3x3", _p(dcol), _p(dx), _dt(dx), _p(relu_src), B, H, W, Cin, self.stream)
 
     def conv3x3_wgrad(self, x, dy, dwp, db):
@@ -134,9 +168,14 @@ class CudaBackend:
         Cout = dy.shape[3]
         P = B * H * W
         col = self._im2col(x)
-        tiles = ((Cout + 127) // 128) * ((9 * Cin + 127) // 128)
-        splitk = max(1, min((P + 511) // 512, (4 * 148 + tiles - 1) // tiles))
-        self.gemm(dy, 1, Cout, col, 1, 9 * Cin, dwp, 9 * Cin, None, Cout, 9 * Cin, P, GEMM_SPLITK, splitk)
+        dy2 = dy.view(P, Cout)
+        if self._umma_ok(dy2, col):
+            sk = self._wgrad_splitk(Cout, 9 * Cin, P)
+            self.umma_gemm(dy2, 1, col, 1, dwp, None, Cout, 9 * Cin, P, GEMM_SPLITK if sk > 1 else GEMM_ACCUM, sk)
+        else:
+            tiles = ((Cout + 127) // 128) * ((9 * Cin + 127) // 128)
+            splitk = max(1, min((P + 511) // 512, (4 * 148 + tiles - 1) // tiles))
+            self.gemm(dy, 1, Cout, col, 1, 9 * Cin, dwp, 9 * Cin, None, Cout, 9 * Cin, P, GEMM_SPLITK, splitk)
         self.colsum_add(dy.view(P, Cout), db)
 
     def maxpool_fwd(self, x, y):

@@ -1,0 +1,99 @@
+"""GPU parity of kernel 1 (CTC alpha-beta) through the C ABI: against the committed goldens of the
+reference call site (nn.CTCLoss as configured in src/blstm_trainer.py:22), against the oracle port,
+against F.ctc_loss on seeded inputs incl. the BASELINE shape, and the domain's size-independent
+properties (gradient rows sum to zero; zero gradient beyond the input length)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import port
+from tests.helpers import GOLD
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda", 0)
+
+
+def test_ctc_golden_reference_call_site(dev):
+    from metaasr_crossaccent_b200.ctc import ctc_fwd_bwd
+    z = np.load(GOLD / "ctc.npz")
+    for c in ("a", "b"):
+        logits = torch.from_numpy(z[f"{c}.logits"].copy()).transpose(0, 1).contiguous().to(dev)   # [T,B,C]
+        tg, il, tl = (torch.from_numpy(z[f"{c}.{k}"].copy()) for k in ("targets", "in_lens", "tgt_lens"))
+        loss, nll, grad = ctc_fwd_bwd(logits, tg, il, tl, blank=0, zero_infinity=True, is_logprob=False)
+        assert np.allclose(nll.cpu().numpy(), z[f"{c}.nll"], rtol=1e-5, atol=1e-4)
+        ref = float(z[f"{c}.loss"])
+        assert abs(float(loss) - ref) <= 1e-5 * abs(ref)
+        g_ref = z[f"{c}.grad_logits"]
+        g = grad.transpose(0, 1).cpu().numpy()
+        assert np.abs(g - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
+        assert (g[g_ref == 0] == 0).all()                      # zero pattern exact
+        # log-prob input mode == nn.CTCLoss contract
+        lp = torch.log_softmax(logits, -1)
+        loss2, nll2, grad2 = ctc_fwd_bwd(lp.contiguous(), tg, il, tl, is_logprob=True)
+        assert abs(float(loss2) - ref) <= 1e-5 * abs(ref)
+        assert np.abs(grad2.transpose(0, 1).cpu().numpy() - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
+
+
+@pytest.mark.parametrize("T,B,C,L", [(128, 32, 367, 32), (50, 5, 40, 70), (375, 4, 367, 100), (20, 3, 10, 0)])
+def test_ctc_vs_torch_and_properties(dev, T, B, C, L):
+    from metaasr_crossaccent_b200.ctc import B200CTCLoss, ctc_fwd_bwd
+    g = torch.Generator().manual_seed(T * 1000 + L)
+    logits = (torch.randn(T, B, C, generator=g) * 2).to(dev)
+    in_lens = torch.tensor([T - (3 * b) % max(T // 2, 1) for b in range(B)], dtype=torch.int64)
+    tgt_lens = torch.tensor([max(0, L - b) for b in range(B)], dtype=torch.int64)
+    ys = [torch.randint(1, C - 1, (int(l),), generator=g) for l in tgt_lens]
+    if L >= 3:
+        ys[0][1] = ys[0][0]                                  # repeated label
+    e = torch.tensor([C - 1])
+    ys_out = [torch.cat([e, y, e]) for y in ys]              # [366]+y+[366] (blstm_trainer.py:56-58)
+    targets = torch.cat(ys_out)
+    tl = torch.tensor([len(y) for y in ys_out], dtype=torch.int64)
+    lg = logits.clone().requires_grad_(True)
+    lp = F.log_softmax(lg, -1)
+    ref = F.ctc_loss(lp, targets.to(dev), in_lens, tl, blank=0, reduction='mean', zero_infinity=True)
+    ref.backward()
+    loss, nll, grad = ctc_fwd_bwd(logits, targets, in_lens, tl)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-7
+    scale = float(lg.grad.abs().max())
+    assert float((grad - lg.grad).abs().max()) <= 2e-4 * scale + 1e-9
+    # properties: rows of d/dlogits sum to 0; nothing beyond the input length
+    assert float(grad.sum(-1).abs().max()) <= 1e-5 * scale * C
+    for b in range(B):
+        assert float(grad[int(in_lens[b]):, b].abs().max() if int(in_lens[b]) < T else 0.0) == 0.0
+    # autograd module drop-in for nn.CTCLoss(blank=0, reduction='mean', zero_infinity=True)
+    lg2 = logits.clone().requires_grad_(True)
+    l2 = B200CTCLoss()(F.log_softmax(lg2, -1), targets, in_lens, tl)
+    l2.backward()
+    assert float((lg2.grad - lg.grad).abs().max()) <= 2e-4 * scale + 1e-9
+    # small case also against the pure-python oracle in float64
+    if T * B * max(L, 1) <= 50 * 5 * 70:
+        onll, oloss, ograd = port.ctc_alpha_beta(logits.cpu(), targets, in_lens, tl)
+        assert abs(float(loss) - float(oloss)) <= 1e-5 * abs(float(oloss)) + 1e-7
+        assert float((grad.cpu().double() - ograd).abs().max()) <= 2e-4 * scale + 1e-9
+
+
+def test_ctc_infeasible_and_large_workspace(dev):
+    from metaasr_crossaccent_b200.ctc import ctc_fwd_bwd
+    # S > T: infeasible -> nll 0 and zero gradient under zero_infinity
+    logits = torch.randn(4, 2, 12, device=dev)
+    targets = torch.tensor([1, 2, 3, 4, 5, 6, 7, 1], dtype=torch.int64)
+    loss, nll, grad = ctc_fwd_bwd(logits, targets, torch.tensor([4, 4]), torch.tensor([7, 1]))
+    assert float(nll[0]) == 0.0 and float(grad[:, 0].abs().max()) == 0.0 and float(nll[1]) > 0
+    # long utterances: tables go to the global workspace (T'=750, L=150)
+    T, B, C, L = 750, 3, 367, 150
+    g = torch.Generator().manual_seed(5)
+    lg = (torch.randn(T, B, C, generator=g)).to(dev).requires_grad_(True)
+    tg = torch.randint(1, C, (B * L,), generator=g)
+    il, tl = torch.tensor([750, 700, 600]), torch.tensor([L] * B)
+    ref = F.ctc_loss(F.log_softmax(lg, -1), tg.to(dev), il, tl, blank=0, reduction='mean', zero_infinity=True)
+    ref.backward()
+    loss, nll, grad = ctc_fwd_bwd(lg.detach(), tg, il, tl)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert float((grad - lg.grad).abs().max()) <= 3e-4 * float(lg.grad.abs().max())

@@ -1,0 +1,158 @@
+"""GPU end-to-end parity of the hot path through the drop-in boundary (get_trainer + fused
+interfaces + C ABI) against (a) the committed goldens of the live reference (tiny net) and (b) the
+oracle port on seeded inputs at the hkust network size.  fp32: loss 1e-5, ids bit-exact; bf16: 2e-2."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests.helpers import GOLD, check_adam_weights, check_summary, load_batch, load_weights, tiny_cfg
+
+pytestmark = pytest.mark.gpu
+ID2ACCENT = {"ca": "canada", "en": "england", "hk": "hongkong"}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda", 0)
+
+
+def make_config(meta=True, k=0.02, warmup=4, dtype="fp32", tiny=True, gemm="simt"):
+    am = {"idim": 83, "dropout": 0.0, "tgt_share_weight": 1, "pos_dropout": 0.0, "dtype": dtype, "gemm": gemm}
+    if tiny:
+        am.update({"nheads": 4, "d_model": 32, "d_inner": 64, "encoder": {"nlayers": 2}, "decoder": {"nlayers": 2}})
+    else:
+        am.update({"nheads": 8, "d_model": 512, "d_inner": 2048, "encoder": {"nlayers": 2}, "decoder": {"nlayers": 4}})
+    if meta:
+        am.update({"inner_optimizer_cls": "SGD", "inner_optimizer_opt": {"momentum": 0.9, "nesterov": True},
+                   "meta_opt_cls": "noam", "meta": {"optimizer_opt": {"k": k, "warmup_steps": warmup}}})
+    else:
+        am.update({"optimizer_cls": "noam", "optimizer_opt": {"k": k, "warmup_steps": warmup}})
+    solver = {"setting": "t", "total_steps": 10, "label_smoothing": 0.2, "eval_ival": 100000, "log_ival": 100000,
+              "save_ival": 100000, "spm_mapping": "/nonexistent"}
+    return {"asr_model": am, "solver": solver}
+
+
+def make_solver(algo, meta=True, **kw):
+    from metaasr_crossaccent_b200 import interfaces as I
+    from metaasr_crossaccent_b200.trainer import get_trainer
+    paras = argparse.Namespace(pretrain_accents=["ca", "en"], num_pretrain=2, tgt_accent="hk", runs=0, seed=531,
+                               meta_k=2, meta_batch_size=2, sample_strategy="normal", max_step=0, resume=False,
+                               algo=algo, pretrain_suffix="t", log_root=None)
+    cls = I.MultiASRInterface if algo == "multi" else I.FOMetaASRInterface
+    s = get_trainer(cls, make_config(meta, **kw), paras, ID2ACCENT)
+    s.set_model()
+    return s
+
+
+def load_tiny(s):
+    s.asr_model.load_state_dict(load_weights(tiny_cfg()))
+    if hasattr(s, "_original_flat"):
+        s._original_flat.copy_(s.asr_model.engine.params)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_run_batch_vs_reference_golden(dev, dtype):
+    z = np.load(GOLD / "run_batch_tiny.npz")
+    s = make_solver("fomaml", dtype=dtype)
+    load_tiny(s)
+    x, ilens, ys, olens = load_batch(z, "in.")
+    info = s.run_batch(0, x, ilens, ys, olens, train=True)
+    tol = 1e-5 if dtype == "fp32" else 2e-2
+    assert abs(info["loss"] - float(z["loss"])) <= tol * abs(float(z["loss"])), info
+    assert np.array_equal(olens.numpy(), z["olens_after"])
+    ws = s.asr_model.engine.workspace(3, 37, z["gold"].shape[1])
+    logit = ws["logits"].view(3, -1, 367).cpu().numpy()
+    if dtype == "fp32":
+        assert np.abs(logit - z["logit"]).max() < 5e-5
+        assert np.array_equal(ws["argmax"].view(3, -1).cpu().numpy(), z["logit"].argmax(-1))   # ids bit-exact
+        assert info["acc"] == float(z["acc"])
+        for n, p in s.asr_model.named_parameters():
+            check_summary(z, "g.", n, p.grad, rtol_l2=2e-3, atol_sample=2e-3)
+    else:
+        assert np.abs(logit - z["logit"]).max() < 2e-2 * np.abs(z["logit"]).max()
+        # ids exact wherever the reference's top-2 margin exceeds the bf16 error bound
+        srt = np.sort(z["logit"], -1)
+        safe = (srt[..., -1] - srt[..., -2]) > 4e-2 * np.abs(z["logit"]).max()
+        am = ws["argmax"].view(3, -1).cpu().numpy()
+        assert np.array_equal(am[safe], z["logit"].argmax(-1)[safe])
+        for n, p in s.asr_model.named_parameters():
+            gl2 = float(z["g." + n + "#l2"])
+            l2 = float(p.grad.double().norm())
+            assert abs(l2 - gl2) <= 0.1 * gl2 + 1e-6, (n, l2, gl2)
+
+
+def test_fomaml_meta_step_vs_reference_golden(dev):
+    z = np.load(GOLD / "fomaml_tiny.npz")
+    s = make_solver("fomaml")
+    load_tiny(s)
+    eng = s.asr_model.engine
+    tasks = []
+    for acc in range(2):
+        tr = [(acc, load_batch(z, f"s0.a{acc}.tr{j}.")) for j in range(2)]
+        tasks.append((tr, (acc, load_batch(z, f"s0.a{acc}.te."))))
+    captured = {}
+    orig = s.meta_opt.step
+
+    def spy(upd, count):
+        captured["mg"] = (upd / count).clone()
+        return orig(upd, count)
+    s.meta_opt.step = spy
+    s.meta_step_on_tasks(tasks)
+    infos = s.flush_train_info()
+    for acc, info in enumerate(infos):
+        ref = float(z[f"s0.a{acc}.te_loss"])
+        assert abs(info["loss"] - ref) <= 2e-4 * abs(ref)
+    assert abs(s.meta_opt.lr - float(z["s0.lr"])) < 1e-12
+    for n in eng.layout.offsets:
+        check_summary(z, "s0.mg.", n, eng.layout.view(captured["mg"], n), rtol_l2=5e-3, atol_sample=3e-2)
+        check_adam_weights(z, "s0.w.", ["s0.mg."], n, s._original[n], s.meta_opt.lr)
+
+
+def test_multi_step_vs_reference_golden(dev):
+    z = np.load(GOLD / "multi_tiny.npz")
+    s = make_solver("multi", meta=False)
+    load_tiny(s)
+    for step in range(2):
+        info = s.multi_step((0, load_batch(z, f"s{step}.")))
+        ref = float(z[f"s{step}.loss"])
+        assert abs(info["loss"] - ref) <= (1e-5 if step == 0 else 5e-3) * abs(ref)
+    lr = port.noam_lr(1, 0.02, 32, 4)
+
+
+def synth_batch(g, B, T, L):
+    x = torch.randn(B, T, 83, generator=g)
+    ilens = torch.full((B,), T, dtype=torch.int64)
+    ys = [torch.randint(1, 366, (L,), generator=g) for _ in range(B)]
+    return x, ilens, ys, torch.full((B,), L, dtype=torch.int64)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_hkust_run_batch_vs_oracle_port(dev, dtype):
+    """Full-size network (d512/h8/ff2048/2e4d, C=367), B=4, T=128: CUDA path vs torch-CPU oracle on
+    identical seeded inputs and weights."""
+    s = make_solver("fomaml", dtype=dtype, tiny=False)
+    cfg = port.NetCfg()
+    sd = port.init_state_dict(cfg, seed=7)
+    s.asr_model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(11)
+    x, ilens, ys, olens = synth_batch(g, 4, 128, 8)
+    oinfo, ograds, ologit, _ = port.run_batch(sd, cfg, x.clone(), ilens.clone(), [y.clone() for y in ys], olens.clone(), 0.2)
+    info = s.run_batch(0, x, ilens, ys, olens, train=True)
+    tol = 1e-5 if dtype == "fp32" else 2e-2
+    assert abs(info["loss"] - oinfo["loss"]) <= tol * abs(oinfo["loss"]), (info, oinfo)
+    eng = s.asr_model.engine
+    ws = eng.workspace(4, 128, 9)
+    if dtype == "fp32":
+        assert torch.equal(ws["argmax"].view(4, 9).cpu(), ologit.argmax(-1))
+    worst = 0.0
+    for n, og in ograds.items():
+        gg = eng.G[n].cpu()
+        rel = float((gg - og).norm() / (og.norm() + 1e-12))
+        worst = max(worst, rel)
+        assert rel <= (2e-3 if dtype == "fp32" else 1e-1), (n, rel)
+    print(f"[{dtype}] loss {info['loss']:.6f} vs oracle {oinfo['loss']:.6f}; worst grad rel-L2 {worst:.2e}")
