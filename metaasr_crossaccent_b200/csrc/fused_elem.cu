@@ -294,6 +294,10 @@ extern "C" int masr_add_layernorm_bwd(const void* dy, const void* s, const float
   const int blocks = int(std::min<int64_t>(ceil_div64(rows, wpb), int64_t(sm_count()) * 2));
   const size_t smem = size_t(wpb) * 2 * d * sizeof(float);
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  if (smem > 48 * 1024) {       // d > 768: opt in to more than the default 48 KB of dynamic shared memory
+    MASR_CHECK_CUDA(cudaFuncSetAttribute(add_layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    MASR_CHECK_CUDA(cudaFuncSetAttribute(add_layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  }
   MASR_DISPATCH_DTYPE(dtype, T,
       add_layernorm_bwd_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
           static_cast<const T*>(dy), static_cast<const T*>(s), mean, rstd, gamma, static_cast<T*>(ds), ds_accum,

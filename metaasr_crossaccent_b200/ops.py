@@ -40,6 +40,7 @@ class CudaBackend:
         self.act_dtype = act_dtype
         self.gemm_path = gemm          # "simt" | "umma"
         self.launches = 0              # our kernels launched through this backend (bench: gpu_launches)
+        self.prof = None               # dict -> per-launch CUDA events of the tensor-core GEMMs (bench.py)
         self._scratch = {}
 
     # -------------------------------------------------------------- plumbing
@@ -75,8 +76,16 @@ class CudaBackend:
         return True
 
     def umma_gemm(self, A, a_mn, B, b_mn, C, bias, M, N, K, flags=0, splitk=1):
+        prof = self.prof
+        if prof is not None:        # bench.py: CUDA events around every launch, on the launching stream
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         self._call("masr_umma_gemm", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), _dt(C),
                    C.stride(0), _p(bias), M, N, K, flags, int(splitk), self.stream)
+        if prof is not None:
+            e1.record()
+            kind = ("fwd", "dgrad", "a_mn", "wgrad")[int(a_mn) * 2 + int(b_mn)]
+            prof.setdefault((kind, M, N, K), []).append((e0, e1))
 
     @staticmethod
     def _wgrad_splitk(rows_out, cols_out, k_red):

@@ -65,8 +65,11 @@ def get_trainer(cls, config, paras, id2accent):
             {'loss','acc'}; sync=False (fused interfaces) skips the device->host read and returns None,
             the statistics staying in engine.stats."""
             eng = self.asr_model.engine
-            hb = eng.prepare_batch(x, ilens, ys, olens)
-            db = eng.to_device(hb)
+            if isinstance(x, dict):                  # an already prepared, device-resident batch
+                hb = db = x
+            else:
+                hb = eng.prepare_batch(x, ilens, ys, olens)
+                db = eng.to_device(hb)
             if train:
                 eng.weights_dirty = True
                 ws = eng.forward_backward(db)

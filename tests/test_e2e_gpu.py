@@ -131,11 +131,11 @@ def synth_batch(g, B, T, L):
     return x, ilens, ys, torch.full((B,), L, dtype=torch.int64)
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_hkust_run_batch_vs_oracle_port(dev, dtype):
+@pytest.mark.parametrize("dtype,gemm", [("fp32", "simt"), ("bf16", "simt"), ("bf16", "umma")])
+def test_hkust_run_batch_vs_oracle_port(dev, dtype, gemm):
     """Full-size network (d512/h8/ff2048/2e4d, C=367), B=4, T=128: CUDA path vs torch-CPU oracle on
     identical seeded inputs and weights."""
-    s = make_solver("fomaml", dtype=dtype, tiny=False)
+    s = make_solver("fomaml", dtype=dtype, tiny=False, gemm=gemm)
     cfg = port.NetCfg()
     sd = port.init_state_dict(cfg, seed=7)
     s.asr_model.load_state_dict(sd)
@@ -155,4 +155,4 @@ def test_hkust_run_batch_vs_oracle_port(dev, dtype):
         rel = float((gg - og).norm() / (og.norm() + 1e-12))
         worst = max(worst, rel)
         assert rel <= (2e-3 if dtype == "fp32" else 1e-1), (n, rel)
-    print(f"[{dtype}] loss {info['loss']:.6f} vs oracle {oinfo['loss']:.6f}; worst grad rel-L2 {worst:.2e}")
+    print(f"[{dtype}/{gemm}] loss {info['loss']:.6f} vs oracle {oinfo['loss']:.6f}; worst grad rel-L2 {worst:.2e}")
