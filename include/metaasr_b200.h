@@ -95,6 +95,15 @@ int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
 /* ------------------------------------------------------------------ conv front end
  * nn.Conv2d(3x3, stride 1, pad 1) + ReLU + MaxPool2d(2,2), mono_transformer_torch.py:49-60,116.
  */
+/* Implicit-GEMM 3x3 convolution on tcgen05 (bf16 NHWC, channels 64 or 128): the 9 shifted input boxes are
+ * fetched by 4-D TMA (out-of-bounds zero fill = padding), nothing is unfolded in memory.
+ * wp is the [Cout, 9*Cin] bf16 layout of masr_conv_w_prep; dwp the same layout in fp32 (accumulated). */
+int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float* bias, void* y,
+                          int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx, const void* relu_src,
+                            int B, int H, int W, int Cin, int Cout, void* stream);
+int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp,
+                            int B, int H, int W, int Cin, int Cout, void* stream);
 /* conv1: Cin = 1.  x [B,H,W] fp32 -> y [B,H,W,Cout] act, bias+ReLU fused.  w [Cout,9] fp32. */
 int masr_conv1_fwd(const float* x, const float* w, const float* bias, void* y, int y_dtype,
                    int B, int H, int W, int Cout, void* stream);

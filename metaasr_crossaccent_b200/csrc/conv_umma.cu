@@ -1,0 +1,415 @@
+// 3x3 convolution (stride 1, pad 1) of the VGG front end as IMPLICIT GEMM on tcgen05 tensor cores.
+// mono_transformer_torch.py:49-60 (nn.Conv2d + ReLU); 72 % of the model FLOPs live here.
+//
+// Activations are NHWC bf16.  Nothing is ever unfolded in memory: for each of the 9 taps the TMA engine
+// fetches the SHIFTED [th x tw pixels, 64 channels] box of the input with a 4-D tensor map
+// {C, W, H, B}; coordinates may be -1 or run past W/H, and the hardware's out-of-bounds zero fill IS
+// the convolution's zero padding.  Each box lands in shared memory as th*tw rows of 128 B (one
+// swizzle row per pixel) and is consumed directly as a K-major (fwd/dgrad) or MN-major (wgrad) UMMA
+// operand.  Weights stay in the [Cout, tap*Cin + ci] layout produced by masr_conv_w_prep:
+//   fwd  : D[pix, co] = sum_{tap,ci} X[pix+tap, ci] * Wp[co, tap*Cin+ci]      A K-major (4-D), B K-major
+//   dgrad: D[pix, ci] = sum_{tap,co} dY[pix-tap, co] * Wp[co, tap*Cin+ci]     A K-major (4-D), B MN-major
+//   wgrad: D_tap[co, ci] = sum_pix dY[pix, co] * X[pix+tap, ci]               A, B MN-major (4-D), split over
+//          pixel tiles across CTAs, 3 taps (one kernel row) accumulate side by side in TMEM, fp32 atomics out
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace masr {
+
+constexpr int CV_THREADS = 192;
+
+struct ConvTile { int tw, th, nw, nh; };
+
+// choose the pixel rectangle (tw x th <= max_rows) maximising useful MMA rows
+static ConvTile pick_tile(int H, int W, int max_rows) {
+  ConvTile best{0, 0, 0, 0};
+  double best_eff = -1.0;
+  for (int nw = 1; nw <= 16; ++nw) {
+    const int tw = (W + nw - 1) / nw;
+    if (tw > max_rows || tw > 256) continue;
+    const int th = std::min(std::min(max_rows / tw, 256), H);
+    if (th < 1) continue;
+    const int nh = (H + th - 1) / th;
+    const double eff = (double(W) / (nw * tw)) * (double(tw * th) / max_rows) * (double(H) / (nh * th));
+    if (eff > best_eff) { best_eff = eff; best = ConvTile{tw, th, nw, nh}; }
+  }
+  return best;
+}
+
+static int act_map(CUtensorMap* out, const void* base, int B, int H, int W, int C, int tw, int th) {
+  MASR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 64 == 0, "conv: NHWC tensor must be 16 B aligned, C % 64 == 0");
+  uint64_t dims[4] = {uint64_t(C), uint64_t(W), uint64_t(H), uint64_t(B)};
+  uint64_t strides[3] = {uint64_t(C) * 2, uint64_t(W) * C * 2, uint64_t(H) * W * C * 2};
+  uint32_t box[4] = {64, uint32_t(tw), uint32_t(th), 1};
+  return make_tmap_bf16(out, base, 4, dims, strides, box, true);
+}
+
+struct ConvParams {
+  int B, H, W;
+  int Cred;          // reduction channels (fwd: Cin, dgrad: Cout)
+  int Cn;            // output channels of this GEMM (fwd: Cout, dgrad: Cin) == BN
+  int Cin;           // the conv's Cin (column stride of a tap inside Wp)
+  int tw, th, nw, nh;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* relu_src;   // dgrad: multiply by (relu_src > 0)
+  const float* bias;               // fwd
+  int relu;                        // fwd
+};
+
+// MODE 0 = forward, 1 = dgrad
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+  using namespace umma;
+  constexpr uint32_t A_BYTES = 128 * 128;                 // up to 128 pixel rows of 128 B
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int iw = tile % p.nw;
+  const int ih = (tile / p.nw) % p.nh;
+  const int b = tile / (p.nw * p.nh);
+  const int h0 = ih * p.th, w0 = iw * p.tw;
+  const int rows = p.th * p.tw;
+  const int cpb = p.Cred / 64;
+  const int num_kb = 9 * cpb;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = uint32_t(rows) * 128 + B_BYTES;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* sa = smem + s * STAGE_BYTES;
+        unsigned char* sb = sa + A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        const int tap = kb / cpb, cc = kb % cpb;
+        const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+        if (MODE == 0) {
+          tma_load_4d(sa, &map_a, &full_bar[s], cc * 64, w0 + dw, h0 + dh, b);
+          tma_load_2d(sb, &map_w, &full_bar[s], tap * p.Cin + cc * 64, 0);          // box {64 k, BN rows(co)}
+        } else {
+          tma_load_4d(sa, &map_a, &full_bar[s], cc * 64, w0 - dw, h0 - dh, b);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)                                          // box {64 ci, 64 rows(co)}
+            tma_load_2d(sb + c * 8192, &map_w, &full_bar[s], tap * p.Cin + c * 64, cc * 64);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, MODE == 1 ? 1 : 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = desc_kmajor_sw128(sa + k * 32);
+          const uint64_t db = (MODE == 1) ? desc_mnmajor_sw128(sb + k * 2048, 8192) : desc_kmajor_sw128(sb + k * 32);
+          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[s]);
+      }
+      mma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int r = q * 32 + lane;
+    const int h = h0 + r / p.tw, w = w0 + r % p.tw;
+    const bool valid = (r < rows) && (h < p.H) && (w < p.W);
+    const int64_t pix = (int64_t(b) * p.H + h) * p.W + w;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+      tmem_ld_wait();
+      if (valid) {
+        __nv_bfloat16* orow = p.out + pix * p.Cn + c0;
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = v[j] + (p.bias != nullptr ? p.bias[c0 + j] : 0.f);
+            v[j] = p.relu ? fmaxf(t, 0.f) : t;
+          }
+        } else if (p.relu_src != nullptr) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.relu_src + pix * p.Cn + c0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 u = src[j / 8];
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h2[e]);
+              if (!(f.x > 0.f)) v[j + 2 * e] = 0.f;
+              if (!(f.y > 0.f)) v[j + 2 * e + 1] = 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+          __nv_bfloat162 a1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+          __nv_bfloat162 a3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+          pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+          reinterpret_cast<uint4*>(orow)[j / 8] = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+// ------------------------------------------------------------------ wgrad
+struct WgradParams {
+  int B, H, W, Cout, Cin;
+  int tw, th, nw, nh;
+  float* dwp;          // [Cout, 9*Cin] fp32, accumulated with atomics
+};
+
+// One CTA: kernel row dh = blockIdx.y - 1, pixel tiles blockIdx.x, +gridDim.x, ...  (split-K over pixels).
+// Per stage: dY tile (A, MN-major, rows = pixels) and the three dw-shifted X tiles (B, MN-major).
+template <int CI, int STAGES>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgradParams p) {
+  using namespace umma;
+  constexpr uint32_t A_BYTES = 2 * 8192;                  // 2 chunks of 64 co x 64 pixel rows
+  constexpr uint32_t B_BYTES = (CI / 64) * 8192;          // per dw
+  constexpr uint32_t STAGE_BYTES = A_BYTES + 3 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = (3 * CI <= 256) ? 256 : 512;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dh = int(blockIdx.y) - 1;
+  const int rows = p.th * p.tw;                            // <= 64 pixel rows per stage
+  const int ntiles = p.B * p.nh * p.nw;
+  const int my_tiles = (ntiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int co_chunks = p.Cout / 64;
+
+  // rows [th*tw, 64) of every chunk are never written by TMA: zero the ring once so they contribute 0
+  for (uint32_t i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += CV_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_dy);
+    prefetch_tmap(&map_x);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = uint32_t(rows) * 128 * uint32_t(co_chunks + 3 * (CI / 64));
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = int(blockIdx.x) + it * int(gridDim.x);
+        const int iw = tile % p.nw, ih = (tile / p.nw) % p.nh, b = tile / (p.nw * p.nh);
+        const int h0 = ih * p.th, w0 = iw * p.tw;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* sa = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * 8192, &map_dy, &full_bar[s], c * 64, w0, h0, b);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int c = 0; c < CI / 64; ++c)
+            tma_load_4d(sa + A_BYTES + j * B_BYTES + c * 8192, &map_x, &full_bar[s], c * 64, w0 + (j - 1), h0 + dh, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, CI, 1, 1);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint32_t sb = sa + A_BYTES + j * B_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = desc_mnmajor_sw128(sa + k * 2048, 8192);
+            const uint64_t db = desc_mnmajor_sw128(sb + k * 2048, 8192);
+            mma_f16_ss(tmem_base + uint32_t(j * CI), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        mma_commit(&empty_bar[s]);
+      }
+      mma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    if (my_tiles > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int co = q * 32 + lane;
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const int tap = (dh + 1) * 3 + j;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CI; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(j * CI + c0), v);
+          tmem_ld_wait();
+          if (co < p.Cout) {
+            float* dst = p.dwp + int64_t(co) * (9 * p.Cin) + tap * p.Cin + c0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) atomicAdd(dst + e, v[e]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+template <typename K>
+static int set_smem(K kern, size_t smem) {
+  MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  return MASR_OK;
+}
+
+}  // namespace masr
+
+using namespace masr;
+
+// y[B,H,W,Cout] = relu?(conv3x3(x[B,H,W,Cin]) + bias); wp [Cout, 9*Cin] bf16 (masr_conv_w_prep layout)
+extern "C" int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float* bias, void* y,
+                                     int B, int H, int W, int Cin, int Cout, int relu, void* stream) {
+  MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
+  if (B * H * W == 0) return MASR_OK;
+  const ConvTile t = pick_tile(H, W, 128);
+  CUtensorMap ma, mw;
+  int rc = act_map(&ma, x, B, H, W, Cin, t.tw, t.th);
+  if (rc != MASR_OK) return rc;
+  uint64_t wd[2] = {uint64_t(9 * Cin), uint64_t(Cout)};
+  uint64_t ws[1] = {uint64_t(9 * Cin) * 2};
+  uint32_t wb[2] = {64, uint32_t(Cout)};
+  rc = make_tmap_bf16(&mw, wp, 2, wd, ws, wb, true);
+  if (rc != MASR_OK) return rc;
+  ConvParams p{B, H, W, Cin, Cout, Cin, t.tw, t.th, t.nw, t.nh, static_cast<__nv_bfloat16*>(y), nullptr, bias, relu};
+  const unsigned grid = unsigned(B * t.nh * t.nw);
+  cudaStream_t st = as_stream(stream);
+  constexpr int ST = 4;
+  if (Cout == 64) {
+    const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256;
+    rc = set_smem(umma_conv_kernel<64, ST, 0>, smem); if (rc) return rc;
+    umma_conv_kernel<64, ST, 0><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
+  } else {
+    const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256;
+    rc = set_smem(umma_conv_kernel<128, ST, 0>, smem); if (rc) return rc;
+    umma_conv_kernel<128, ST, 0><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
+  }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+// dx[B,H,W,Cin] = conv3x3^T(dy[B,H,W,Cout]) (times (relu_src > 0) when relu_src != NULL)
+extern "C" int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx, const void* relu_src,
+                                       int B, int H, int W, int Cin, int Cout, void* stream) {
+  MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
+  if (B * H * W == 0) return MASR_OK;
+  const ConvTile t = pick_tile(H, W, 128);
+  CUtensorMap ma, mw;
+  int rc = act_map(&ma, dy, B, H, W, Cout, t.tw, t.th);
+  if (rc != MASR_OK) return rc;
+  uint64_t wd[2] = {uint64_t(9 * Cin), uint64_t(Cout)};
+  uint64_t ws[1] = {uint64_t(9 * Cin) * 2};
+  uint32_t wb[2] = {64, 64};
+  rc = make_tmap_bf16(&mw, wp, 2, wd, ws, wb, true);
+  if (rc != MASR_OK) return rc;
+  ConvParams p{B, H, W, Cout, Cin, Cin, t.tw, t.th, t.nw, t.nh, static_cast<__nv_bfloat16*>(dx),
+               static_cast<const __nv_bfloat16*>(relu_src), nullptr, 0};
+  const unsigned grid = unsigned(B * t.nh * t.nw);
+  cudaStream_t st = as_stream(stream);
+  constexpr int ST = 4;
+  if (Cin == 64) {
+    const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256;
+    rc = set_smem(umma_conv_kernel<64, ST, 1>, smem); if (rc) return rc;
+    umma_conv_kernel<64, ST, 1><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
+  } else {
+    const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256;
+    rc = set_smem(umma_conv_kernel<128, ST, 1>, smem); if (rc) return rc;
+    umma_conv_kernel<128, ST, 1><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
+  }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+// dwp[Cout, 9*Cin] (fp32) += sum_pix dy[pix, co] * x[pix+tap, ci]
+extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp,
+                                       int B, int H, int W, int Cin, int Cout, void* stream) {
+  MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
+  if (B * H * W == 0) return MASR_OK;
+  const ConvTile t = pick_tile(H, W, 64);
+  CUtensorMap mdy, mx;
+  int rc = act_map(&mdy, dy, B, H, W, Cout, t.tw, t.th);
+  if (rc != MASR_OK) return rc;
+  rc = act_map(&mx, x, B, H, W, Cin, t.tw, t.th);
+  if (rc != MASR_OK) return rc;
+  WgradParams p{B, H, W, Cout, Cin, t.tw, t.th, t.nw, t.nh, dwp};
+  const int ntiles = B * t.nh * t.nw;
+  const int gx = std::max(1, std::min(ntiles, sm_count() / 3));
+  dim3 grid(unsigned(gx), 3, 1);
+  cudaStream_t st = as_stream(stream);
+  if (Cin == 64) {
+    constexpr int ST = 4;
+    const size_t smem = ST * (16384 + 3 * 8192) + 1024 + 256;
+    rc = set_smem(umma_conv_wgrad_kernel<64, ST>, smem); if (rc) return rc;
+    umma_conv_wgrad_kernel<64, ST><<<grid, CV_THREADS, smem, st>>>(mdy, mx, p);
+  } else {
+    constexpr int ST = 3;
+    const size_t smem = ST * (16384 + 3 * 16384) + 1024 + 256;
+    rc = set_smem(umma_conv_wgrad_kernel<128, ST>, smem); if (rc) return rc;
+    umma_conv_wgrad_kernel<128, ST><<<grid, CV_THREADS, smem, st>>>(mdy, mx, p);
+  }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}

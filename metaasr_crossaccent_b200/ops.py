@@ -87,6 +87,27 @@ class CudaBackend:
             kind = ("fwd", "dgrad", "a_mn", "wgrad")[int(a_mn) * 2 + int(b_mn)]
             prof.setdefault((kind, M, N, K), []).append((e0, e1))
 
+    def _conv_umma_ok(self, *ts):
+        """implicit-GEMM tcgen05 convolution: bf16, contiguous, 16 B aligned, channels 64 / 128."""
+        if self.gemm_path != "umma":
+            return False
+        for t in ts:
+            if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.data_ptr() % 16:
+                return False
+            if t.dim() == 4 and t.shape[3] not in (64, 128):
+                return False
+        return True
+
+    def _timed_call(self, key, name, *args):
+        prof = self.prof
+        if prof is None:
+            return self._call(name, *args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._call(name, *args)
+        e1.record()
+        prof.setdefault(key, []).append((e0, e1))
+
     @staticmethod
     def _wgrad_splitk(rows_out, cols_out, k_red):
         """Split the reduction so that ~2 waves of 128x128 tiles cover the 148 SMs."""
@@ -152,6 +173,9 @@ class CudaBackend:
         """y = relu(conv3x3(x) + bias), NHWC; wp [Cout, 9*Cin]."""
         B, H, W, Cin = x.shape
         Cout = wp.shape[0]
+        if self._conv_umma_ok(x, wp, y):
+            return self._timed_call(("conv_fwd", B * H * W, Cout, 9 * Cin), "masr_umma_conv3x3_fwd", _p(x), _p(wp),
+                                    _p(bias), _p(y), B, H, W, Cin, Cout, 1, self.stream)
         col = self._im2col(x)
         y2 = y.view(B * H * W, Cout)
         if self._umma_ok(col, wp):
@@ -163,6 +187,9 @@ class CudaBackend:
         B, H, W, Cout = dy.shape
         Cin = dx.shape[3]
         P = B * H * W
+        if self._conv_umma_ok(dy, wp, dx) and (relu_src is None or relu_src.is_contiguous()):
+            return self._timed_call(("conv_dgrad", P, Cin, 9 * Cout), "masr_umma_conv3x3_dgrad", _p(dy), _p(wp), _p(dx),
+                                    _p(relu_src), B, H, W, Cin, Cout, self.stream)
         dcol = self.scratch("col", P * 9 * Cin, dy.dtype).view(P, 9 * Cin)
         dy2 = dy.view(P, Cout)
         if self._umma_ok(dy2, wp):
@@ -176,6 +203,10 @@ class CudaBackend:
         B, H, W, Cin = x.shape
         Cout = dy.shape[3]
         P = B * H * W
+        if self._conv_umma_ok(x, dy) and dwp.is_contiguous():
+            self._timed_call(("conv_wgrad", Cout, 9 * Cin, P), "masr_umma_conv3x3_wgrad", _p(x), _p(dy), _p(dwp),
+                             B, H, W, Cin, Cout, self.stream)
+            return self.colsum_add(dy.view(P, Cout), db)
         col = self._im2col(x)
         dy2 = dy.view(P, Cout)
         if self._umma_ok(dy2, col):
