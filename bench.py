@@ -177,6 +177,18 @@ def run_ours(args):
     ms_res, launches, prof, (t0, t1) = timed(step_resident, args.steps, args.warmup, profile=True)
     clocks = sampler.stop(t0, t1)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    if args.profile and rank == 0:
+        be.prof_ops = {}
+        step_resident()
+        torch.cuda.synchronize()
+        po, be.prof_ops = be.prof_ops, None
+        rows = sorted(((sum(a.elapsed_time(b) for a, b in v), len(v), k) for k, v in po.items()), reverse=True)
+        tot = sum(r[0] for r in rows)
+        with open(args.profile, "w") as f:
+            f.write(f"# per-entry-point CUDA-event times of ONE meta-step ({tot:.1f} ms summed; dtype {args.dtype})\n")
+            f.write("| ms | share | calls | entry point |\n|---|---|---|---|\n")
+            for ms, n, k in rows:
+                f.write(f"| {ms:.2f} | {100 * ms / tot:.1f}% | {n} | {k} |\n")
     loss_info = solver.flush_train_info()
 
     # ---- roofline of the dominant kernel, timed live with CUDA events inside the timed region
@@ -291,6 +303,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--profile", default=None, help="write a per-entry-point CUDA-event time table to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -41,6 +41,8 @@ class CudaBackend:
         self.gemm_path = gemm          # "simt" | "umma"
         self.launches = 0              # our kernels launched through this backend (bench: gpu_launches)
         self.prof = None               # dict -> per-launch CUDA events of the tensor-core GEMMs (bench.py)
+        self.prof_ops = None           # dict -> per-entry-point CUDA events (bench.py --profile)
+        self.prof_tag = ""
         self._scratch = {}
 
     # -------------------------------------------------------------- plumbing
@@ -49,10 +51,17 @@ class CudaBackend:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _call(self, name, *args, n_kernels=1):
+        po = self.prof_ops
+        if po is not None:          # bench.py --profile: CUDA events around every entry point
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = getattr(self.lib, name)(*args)
         if rc != 0:
             _lib.check(rc, name)
         self.launches += n_kernels
+        if po is not None:
+            e1.record()
+            po.setdefault(name + self.prof_tag, []).append((e0, e1))
 
     def scratch(self, key, numel, dtype):
         t = self._scratch.get(key)
