@@ -147,6 +147,18 @@ int masr_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
                   int B, int H, int Lq, int Lk, int hd, const int64_t* klens, int causal,
                   float p_drop, uint64_t seed, uint32_t site, void* stream);
 
+/* tcgen05 fast path of the two calls above: bf16, head dim 64, rows 16 B aligned (ld % 8 == 0).
+ * Forward handles any Lk (online soft-max over 128-key tiles); backward requires Lk <= 128 (one key
+ * tile per (batch, head); longer memories use masr_attn_bwd). */
+int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                       void* out, int64_t ldo, float* lse, int B, int H, int Lq, int Lk,
+                       const int64_t* klens, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
+int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                       const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                       float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                       int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
+                       float p_drop, uint64_t seed, uint32_t site, void* stream);
+
 /* ------------------------------------------------------------------ kernel 3: fused elementwise
  * residual + dropout + LayerNorm (post-norm TransformerEncoder/DecoderLayer, eps 1e-5):
  *   s = res + dropout(x)   (written back over x; res may be NULL)

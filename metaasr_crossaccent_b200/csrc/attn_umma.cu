@@ -1,0 +1,510 @@
+// Multi-head attention forward / backward on tcgen05 tensor cores (head dim 64, bf16, fp32 soft-max).
+//
+// Same contract as attention.cu (masks from lengths, dropout replayed from (seed, site, index)); this is
+// the fast path used for the hkust network (8 heads x 64).  One CTA = 128 query rows (fwd) or 128 key rows
+// (bwd) of one (batch, head); 192 threads:
+//   warp 0   TMA producer (Q / K / V / dO tiles as [128 rows x 64] boxes, 128B swizzle)
+//   warp 1   MMA issuer, TMEM owner
+//   warps 2-5 soft-max warps: thread r owns row r (TMEM lane r): tcgen05.ld of S / dP, exp, masks, dropout,
+//            P / dS written back to shared memory in the UMMA K-major swizzled layout for the second GEMMs
+// Forward, per 128-key tile:  S = Q K^T -> TMEM;  P = softmax-tile -> smem;  O_tile = P V -> TMEM;
+//            O (registers) = O * corr + O_tile  (online soft-max over key tiles).
+// Backward, per 128-query tile (keys fixed):  S = Q K^T, dP = dO V^T -> TMEM;  P, dS -> smem;
+//            dQ = dS K (fresh), dK += dS^T Q, dV += P^T dO (accumulated in TMEM over query tiles).
+// The transposed operands (K as [key, d] for dS K; dS^T, P^T, Q, dO reduced over queries) are the SAME
+// shared-memory tiles read through MN-major descriptors -- nothing is transposed in memory.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace masr {
+
+constexpr int AU_THREADS = 192;
+constexpr int AU_TILE = 128;
+constexpr uint32_t AU_T64 = 128 * 128;          // bytes of a [128 rows x 64 bf16] tile
+constexpr uint32_t AU_T128 = 2 * AU_T64;        // [128 rows x 128 bf16] = two 64-wide k-blocks
+
+// byte offset of the 16-byte chunk holding columns [8*c8, 8*c8+8) of row r in a [128 x 128] bf16 K-major SW128 tile
+__device__ __forceinline__ uint32_t sw_chunk_off(int r, int c8) {
+  return uint32_t(c8 >> 3) * AU_T64 + uint32_t(r) * 128 + (uint32_t((c8 & 7) ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct AttnFwdParams {
+  int B, H, Lq, Lk;
+  const int64_t* klens;
+  int causal;
+  float scale, p_drop, inv_keep;
+  uint64_t seed; uint32_t site;
+  __nv_bfloat16* out; int64_t ldo;
+  float* lse;
+};
+
+__global__ void __launch_bounds__(AU_THREADS, 1)
+attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, AttnFwdParams p) {
+  using namespace umma;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;                         // 16 KB
+  unsigned char* sKV = sQ + AU_T64;                 // 2 stages x (K 16 KB + V 16 KB)
+  unsigned char* sP = sKV + 4 * AU_T64;             // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AU_T128);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                     // [2]
+  uint64_t* kv_empty = bars + 3;                    // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int q0 = blockIdx.x * AU_TILE;
+  int kmax = p.Lk;
+  if (p.klens != nullptr) kmax = min(kmax, int(p.klens[b]));
+  if (p.causal) kmax = min(kmax, q0 + AU_TILE);
+  const int ntiles = (kmax + AU_TILE - 1) / AU_TILE;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, AU_T64);
+      tma_load_2d(sQ, &map_q, q_full, h * 64, b * p.Lq + q0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * AU_T64);
+        tma_load_2d(sKV + s * 2 * AU_T64, &map_k, &kv_full[s], h * 64, b * p.Lk + t * AU_TILE);
+        tma_load_2d(sKV + s * 2 * AU_T64 + AU_T64, &map_v, &kv_full[s], h * 64, b * p.Lk + t * AU_TILE);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);       // S = Q K^T
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);        // O = P V   (V read MN-major)
+      mbar_wait(q_full, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(&kv_full[s], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ), ak = smem_u32(sKV + s * 2 * AU_T64), av = ak + AU_T64, ap = smem_u32(sP);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tmem_S, desc_kmajor_sw128(aq + k * 32), desc_kmajor_sw128(ak + k * 32), idesc_s, k > 0 ? 1u : 0u);
+        mma_commit(s_full);
+        mbar_wait(p_full, t & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)      // 128 keys = 8 x K16: P k-block k/4, 32 B steps; V +16 key rows = 2048 B
+          mma_f16_ss(tmem_O, desc_kmajor_sw128(ap + (k >> 2) * AU_T64 + (k & 3) * 32),
+                     desc_mnmajor_sw128(av + k * 2048, AU_T64), idesc_o, k > 0 ? 1u : 0u);
+        mma_commit(o_full);
+        mma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_addr = uint32_t(qd * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) o[j] = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+      const int k0 = t * AU_TILE;
+      mbar_wait(s_full, t & 1);
+      tc_fence_after();
+      // pass 1: row maximum of the masked, scaled scores
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int kj = k0 + c * 32 + j;
+          const bool ok = (kj < kmax) && (!p.causal || kj <= qi);
+          if (ok) mx = fmaxf(mx, v[j] * p.scale);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = expf(m_run - m_use);           // exp(-inf) = 0 on the first tile
+      float lsum = 0.f;
+      // pass 2: probabilities -> shared memory (bf16, K-major swizzled), row sum
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int kj = k0 + c * 32 + j;
+          const bool ok = (kj < kmax) && (!p.causal || kj <= qi);
+          float pr = ok ? expf(v[j] * p.scale - m_use) : 0.f;
+          lsum += pr;
+          if (p.p_drop > 0.f && ok)
+            pr *= drop_scale(p.p_drop, p.inv_keep, p.seed, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
+          v[j] = pr;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+          pk.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(sP + sw_chunk_off(r, c * 4 + g)) = pk;
+        }
+      }
+      l_run = l_run * corr + lsum;
+      m_run = m_new;
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(p_full);
+      // O = O * corr + P V
+      mbar_wait(o_full, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[c * 32 + j] = o[c * 32 + j] * corr + v[j];
+      }
+      tc_fence_before();
+    }
+    if (qi < p.Lq) {
+      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* orow = p.out + (int64_t(b) * p.Lq + qi) * p.ldo + h * 64;
+#pragma unroll
+      for (int j = 0; j < 64; j += 8) {
+        float t8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t8[e] = o[j + e] * inv_l;
+        store8<__nv_bfloat16>(orow + j, t8);
+      }
+      p.lse[int64_t(bh) * p.Lq + qi] = l_run > 0.f ? m_run + logf(l_run) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// D[b,h,q] = dO_q . O_q  (one warp per (b, q, h) row of 64)
+__global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, int64_t ldo, const __nv_bfloat16* __restrict__ dout,
+                                 int64_t lddo, float* __restrict__ dsum, int B, int H, int Lq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = int64_t(B) * H * Lq;
+  for (int64_t idx = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5; idx < total;
+       idx += (int64_t(gridDim.x) * blockDim.x) >> 5) {
+    const int qi = int(idx % Lq);
+    const int h = int((idx / Lq) % H);
+    const int64_t b = idx / (int64_t(Lq) * H);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(out + (b * Lq + qi) * ldo + h * 64 + lane * 2);
+    const __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(dout + (b * Lq + qi) * lddo + h * 64 + lane * 2);
+    const float2 fa = __bfloat1622float2(a), fg = __bfloat1622float2(g);
+    const float s = warp_sum(fa.x * fg.x + fa.y * fg.y);
+    if (lane == 0) dsum[(b * H + h) * Lq + qi] = s;
+  }
+}
+
+struct AttnBwdParams {
+  int B, H, Lq, Lk;
+  const int64_t* klens;
+  int causal;
+  float scale, p_drop, inv_keep;
+  uint64_t seed; uint32_t site;
+  const float* lse; const float* dsum;
+  __nv_bfloat16* dq; int64_t lddq;
+  __nv_bfloat16* dk; int64_t lddk;
+  __nv_bfloat16* dv; int64_t lddv;
+};
+
+// Single key tile per (batch, head) CTA column: requires Lk <= 128 * gridDim.x with dQ written directly only
+// when gridDim.x == 1 (the host falls back to the CUDA-core kernels otherwise).
+__global__ void __launch_bounds__(AU_THREADS, 1)
+attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do, AttnBwdParams p) {
+  using namespace umma;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sK = smem;                         // 16 KB
+  unsigned char* sV = sK + AU_T64;                  // 16 KB
+  unsigned char* sQdO = sV + AU_T64;                // 2 stages x (Q 16 KB + dO 16 KB)
+  unsigned char* sP = sQdO + 4 * AU_T64;            // 32 KB  (dropped probabilities, bf16)
+  unsigned char* sdS = sP + AU_T128;                // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + AU_T128);
+  uint64_t* kv_full = bars;
+  uint64_t* qd_full = bars + 1;                     // [2]
+  uint64_t* qd_empty = bars + 3;                    // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dkv_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int k0 = blockIdx.x * AU_TILE;
+  int klen = p.Lk;
+  if (p.klens != nullptr) klen = min(klen, int(p.klens[b]));
+  const int nq_tiles = (p.Lq + AU_TILE - 1) / AU_TILE;
+  const int qt_begin = p.causal ? (k0 / AU_TILE) : 0;
+  const bool active = (k0 < klen) && (qt_begin < nq_tiles);
+  const int ntiles = active ? (nq_tiles - qt_begin) : 0;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_do);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(dq_full, 1); mbar_init(dkv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256, tm_dK = tmem_base + 320, tm_dV = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0 && active) {
+      mbar_arrive_expect_tx(kv_full, 2 * AU_T64);
+      tma_load_2d(sK, &map_k, kv_full, h * 64, b * p.Lk + k0);
+      tma_load_2d(sV, &map_v, kv_full, h * 64, b * p.Lk + k0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        const int q0 = (qt_begin + t) * AU_TILE;
+        mbar_wait(&qd_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qd_full[s], 2 * AU_T64);
+        tma_load_2d(sQdO + s * 2 * AU_T64, &map_q, &qd_full[s], h * 64, b * p.Lq + q0);
+        tma_load_2d(sQdO + s * 2 * AU_T64 + AU_T64, &map_do, &qd_full[s], h * 64, b * p.Lq + q0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && active) {
+      constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S = Q K^T ; dP = dO V^T
+      constexpr uint32_t id_dq = make_idesc_bf16(128, 64, 0, 1);     // dQ = dS K        (K read MN-major)
+      constexpr uint32_t id_dkv = make_idesc_bf16(128, 64, 1, 1);    // dK = dS^T Q ; dV = P^T dO
+      mbar_wait(kv_full, 0);
+      const uint32_t ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP), ads = smem_u32(sdS);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(&qd_full[s], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQdO + s * 2 * AU_T64), ado = aq + AU_T64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tm_S, desc_kmajor_sw128(aq + k * 32), desc_kmajor_sw128(ak + k * 32), id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tm_dP, desc_kmajor_sw128(ado + k * 32), desc_kmajor_sw128(av + k * 32), id_s, k > 0 ? 1u : 0u);
+        mma_commit(sdp_full);
+        mbar_wait(pds_full, t & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // dQ[q, d] = sum_key dS[q, key] K[key, d]
+          mma_f16_ss(tm_dQ, desc_kmajor_sw128(ads + (k >> 2) * AU_T64 + (k & 3) * 32),
+                     desc_mnmajor_sw128(ak + k * 2048, AU_T64), id_dq, k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // dK[key, d] += sum_q dS[q, key] Q[q, d];  dV[key, d] += sum_q P[q, key] dO[q, d]   (16 query rows / step)
+          const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
+          mma_f16_ss(tm_dK, desc_mnmajor_sw128(ads + k * 2048, AU_T64), desc_mnmajor_sw128(aq + k * 2048, AU_T64), id_dkv, acc);
+          mma_f16_ss(tm_dV, desc_mnmajor_sw128(ap + k * 2048, AU_T64), desc_mnmajor_sw128(ado + k * 2048, AU_T64), id_dkv, acc);
+        }
+        mma_commit(dq_full);
+        mma_commit(&qd_empty[s]);
+      }
+      mma_commit(dkv_full);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = uint32_t(qd * 32) << 16;
+    for (int t = 0; t < ntiles; ++t) {
+      const int q0 = (qt_begin + t) * AU_TILE;
+      const int qi = q0 + r;
+      const bool qok = qi < p.Lq;
+      const float lse_r = qok ? p.lse[int64_t(bh) * p.Lq + qi] : 0.f;
+      const float d_r = qok ? p.dsum[int64_t(bh) * p.Lq + qi] : 0.f;
+      mbar_wait(sdp_full, t & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float sv[32], dp[32];
+        tmem_ld_32x32(tm_S + lane_addr + c * 32, sv);
+        tmem_ld_32x32(tm_dP + lane_addr + c * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int kj = k0 + c * 32 + j;
+          const bool ok = qok && (kj < klen) && (!p.causal || kj <= qi);
+          float pr = 0.f, ds = 0.f;
+          if (ok) {
+            pr = expf(sv[j] * p.scale - lse_r);
+            const float dm = drop_scale(p.p_drop, p.inv_keep, p.seed, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
+            ds = pr * (dp[j] * dm - d_r) * p.scale;
+            pr *= dm;
+          }
+          sv[j] = pr; dp[j] = ds;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk, dk4;
+          pk.x = pack_bf16x2(sv[g * 8 + 0], sv[g * 8 + 1]); pk.y = pack_bf16x2(sv[g * 8 + 2], sv[g * 8 + 3]);
+          pk.z = pack_bf16x2(sv[g * 8 + 4], sv[g * 8 + 5]); pk.w = pack_bf16x2(sv[g * 8 + 6], sv[g * 8 + 7]);
+          dk4.x = pack_bf16x2(dp[g * 8 + 0], dp[g * 8 + 1]); dk4.y = pack_bf16x2(dp[g * 8 + 2], dp[g * 8 + 3]);
+          dk4.z = pack_bf16x2(dp[g * 8 + 4], dp[g * 8 + 5]); dk4.w = pack_bf16x2(dp[g * 8 + 6], dp[g * 8 + 7]);
+          const uint32_t off = sw_chunk_off(r, c * 4 + g);
+          *reinterpret_cast<uint4*>(sP + off) = pk;
+          *reinterpret_cast<uint4*>(sdS + off) = dk4;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(pds_full);
+      mbar_wait(dq_full, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld_32x32(tm_dQ + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (qok) {
+          __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) store8<__nv_bfloat16>(drow + j, v + j);
+        }
+      }
+      tc_fence_before();
+    }
+    // dK / dV of this key tile (row r = key k0 + r)
+    const int kj = k0 + r;
+    float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float vk[32], vv[32];
+      if (active) {
+        tmem_ld_32x32(tm_dK + lane_addr + c * 32, vk);
+        tmem_ld_32x32(tm_dV + lane_addr + c * 32, vv);
+        tmem_ld_wait();
+      }
+      if (kj < p.Lk) {
+        __nv_bfloat16* dkr = p.dk + (int64_t(b) * p.Lk + kj) * p.lddk + h * 64 + c * 32;
+        __nv_bfloat16* dvr = p.dv + (int64_t(b) * p.Lk + kj) * p.lddv + h * 64 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          store8<__nv_bfloat16>(dkr + j, active ? vk + j : zero8);
+          store8<__nv_bfloat16>(dvr + j, active ? vv + j : zero8);
+        }
+      }
+    }
+    // With a single key tile (gridDim.x == 1) every query tile is visited above, so dQ is fully written --
+    // except when the whole key tile is padding (klen == 0): then dQ is zero.
+    if (!active && gridDim.x == 1) {
+      for (int qi = r; qi < p.Lq; qi += AU_TILE) {
+        __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) store8<__nv_bfloat16>(drow + j, zero8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static int rows_map(CUtensorMap* out, const void* base, int64_t ld, int64_t nrows, int ncols) {
+  MASR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0, "umma attention: 16 B aligned rows required");
+  uint64_t dims[2] = {uint64_t(ncols), uint64_t(nrows)};
+  uint64_t strides[1] = {uint64_t(ld) * 2};
+  uint32_t box[2] = {64, 128};
+  return make_tmap_bf16(out, base, 2, dims, strides, box, true);
+}
+
+constexpr size_t AU_FWD_SMEM = AU_T64 + 4 * AU_T64 + AU_T128 + 256 + 1024;
+constexpr size_t AU_BWD_SMEM = 2 * AU_T64 + 4 * AU_T64 + 2 * AU_T128 + 256 + 1024;
+
+}  // namespace masr
+
+using namespace masr;
+
+extern "C" int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  void* out, int64_t ldo, float* lse, int B, int H, int Lq, int Lk,
+                                  const int64_t* klens, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  if (B == 0 || H == 0 || Lq == 0) return MASR_OK;
+  MASR_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "umma attention: out must be 16 B aligned");
+  CUtensorMap mq, mk, mv;
+  int rc = rows_map(&mq, q, ldq, int64_t(B) * Lq, H * 64); if (rc) return rc;
+  rc = rows_map(&mk, k, ldk, int64_t(B) * Lk, H * 64); if (rc) return rc;
+  rc = rows_map(&mv, v, ldv, int64_t(B) * Lk, H * 64); if (rc) return rc;
+  AttnFwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed, site,
+                  static_cast<__nv_bfloat16*>(out), ldo, lse};
+  static bool attr = false;
+  if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_FWD_SMEM))); attr = true; }
+  dim3 grid(unsigned(ceil_div64(Lq, AU_TILE)), unsigned(B * H));
+  attn_fwd_umma_kernel<<<grid, AU_THREADS, AU_FWD_SMEM, as_stream(stream)>>>(mq, mk, mv, p);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                  float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                  int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
+                                  float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  if (B == 0 || H == 0) return MASR_OK;
+  MASR_REQUIRE(Lk <= AU_TILE, "umma attention backward: Lk must be <= 128 (use masr_attn_bwd otherwise)");
+  MASR_REQUIRE(dsum_ws != nullptr, "attention backward needs a [B*H*Lq] fp32 workspace");
+  MASR_REQUIRE(lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && ldo % 2 == 0 && lddo % 2 == 0 &&
+               ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0,
+               "umma attention backward: gradients must be 16 B aligned");
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap mq, mk, mv, mdo;
+  int rc = rows_map(&mq, q, ldq, int64_t(B) * Lq, H * 64); if (rc) return rc;
+  rc = rows_map(&mk, k, ldk, int64_t(B) * Lk, H * 64); if (rc) return rc;
+  rc = rows_map(&mv, v, ldv, int64_t(B) * Lk, H * 64); if (rc) return rc;
+  rc = rows_map(&mdo, dout, lddo, int64_t(B) * Lq, H * 64); if (rc) return rc;
+  if (Lq > 0) {
+    const int64_t rows = int64_t(B) * H * Lq;
+    const int blocks = int(std::min<int64_t>(ceil_div64(rows, 8), int64_t(sm_count()) * 8));
+    attn_dsum_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out), ldo,
+                                             static_cast<const __nv_bfloat16*>(dout), lddo, dsum_ws, B, H, Lq);
+    MASR_LAUNCH_CHECK();
+  }
+  AttnBwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed, site,
+                  lse, dsum_ws, static_cast<__nv_bfloat16*>(dq), lddq, static_cast<__nv_bfloat16*>(dk), lddk,
+                  static_cast<__nv_bfloat16*>(dv), lddv};
+  static bool attr = false;
+  if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_BWD_SMEM))); attr = true; }
+  dim3 grid(1, unsigned(B * H));
+  attn_bwd_umma_kernel<<<grid, AU_THREADS, AU_BWD_SMEM, st>>>(mq, mk, mv, mdo, p);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}

@@ -34,15 +34,16 @@ __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __res
         tap[(dh + 1) * 3 + (dw + 1)] =
             (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(b * H + hh) * W + ww] : 0.f;
       }
-    T* dst = y + p * Cout + cg * 8;
+    float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float* wc = sw + (cg * 8 + c) * 9;
       float acc = sw[Cout * 9 + cg * 8 + c];
 #pragma unroll
       for (int t = 0; t < 9; ++t) acc = fmaf(tap[t], wc[t], acc);
-      dst[c] = from_f<T>(fmaxf(acc, 0.f));
+      o[c] = fmaxf(acc, 0.f);
     }
+    store8<T>(y + p * Cout + cg * 8, o);
   }
 }
 
@@ -212,6 +213,113 @@ __global__ void relu_bwd_kernel(const T* __restrict__ y, T* __restrict__ dx, int
     if (!(to_f<T>(y[i]) > 0.f)) dx[i] = from_f<T>(0.f);
 }
 
+// ------------------------------------------------------------------ vectorised pool kernels (C % 8 == 0)
+// One thread owns 8 consecutive channels of one 2x2 window: four 128-bit loads, one (fwd) or four (bwd)
+// 128-bit stores; a warp covers 256 contiguous channels-bytes per pixel -> fully coalesced NHWC traffic.
+template <typename T>
+__global__ void maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, ncg = C / 8;
+  const int64_t total = int64_t(B) * Ho * Wo * ncg;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int cg = int(idx % ncg);
+    const int wo = int((idx / ncg) % Wo);
+    const int ho = int((idx / (int64_t(ncg) * Wo)) % Ho);
+    const int64_t b = idx / (int64_t(ncg) * Wo * Ho);
+    const T* base = x + ((b * H + 2 * ho) * W + 2 * wo) * C + cg * 8;
+    float v0[8], v1[8], v2[8], v3[8];
+    load8<T>(base, v0); load8<T>(base + C, v1); load8<T>(base + int64_t(W) * C, v2); load8<T>(base + int64_t(W) * C + C, v3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v0[j] = fmaxf(fmaxf(v0[j], v1[j]), fmaxf(v2[j], v3[j]));
+    store8<T>(y + ((b * Ho + ho) * Wo + wo) * C + cg * 8, v0);
+  }
+}
+
+template <typename T>
+__global__ void maxpool_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                       int relu_mask, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, ncg = C / 8;
+  const int64_t total = int64_t(B) * Ho * Wo * ncg;
+  const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int cg = int(idx % ncg);
+    const int wo = int((idx / ncg) % Wo);
+    const int ho = int((idx / (int64_t(ncg) * Wo)) % Ho);
+    const int64_t b = idx / (int64_t(ncg) * Wo * Ho);
+    const int64_t o00 = ((b * H + 2 * ho) * W + 2 * wo) * C + cg * 8;
+    const int64_t rowstep = int64_t(W) * C;
+    float v0[8], v1[8], v2[8], v3[8], g[8];
+    load8<T>(x + o00, v0); load8<T>(x + o00 + C, v1); load8<T>(x + o00 + rowstep, v2); load8<T>(x + o00 + rowstep + C, v3);
+    load8<T>(dy + ((b * Ho + ho) * Wo + wo) * C + cg * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int arg = 0; float m = v0[j];
+      if (v1[j] > m) { m = v1[j]; arg = 1; }
+      if (v2[j] > m) { m = v2[j]; arg = 2; }
+      if (v3[j] > m) { m = v3[j]; arg = 3; }
+      const float gg = (!relu_mask || m > 0.f) ? g[j] : 0.f;
+      v0[j] = arg == 0 ? gg : 0.f; v1[j] = arg == 1 ? gg : 0.f; v2[j] = arg == 2 ? gg : 0.f; v3[j] = arg == 3 ? gg : 0.f;
+    }
+    store8<T>(dx + o00, v0); store8<T>(dx + o00 + C, v1); store8<T>(dx + o00 + rowstep, v2); store8<T>(dx + o00 + rowstep + C, v3);
+    // floor-mode pooling drops an odd last column / row: their gradient is zero
+    if ((W & 1) && wo == Wo - 1) { store8<T>(dx + o00 + 2 * C, zero8); store8<T>(dx + o00 + rowstep + 2 * C, zero8); }
+    if ((H & 1) && ho == Ho - 1) {
+      store8<T>(dx + o00 + 2 * rowstep, zero8); store8<T>(dx + o00 + 2 * rowstep + C, zero8);
+      if ((W & 1) && wo == Wo - 1) store8<T>(dx + o00 + 2 * rowstep + 2 * C, zero8);
+    }
+  }
+}
+
+// conv1 wgrad, latency-hiding variant: 4 pixel lanes x Cout threads per block, each thread walks its pixels
+// four at a time (independent loads in flight), many blocks, partials combined in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_wgrad_v2_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                             float* __restrict__ dw, float* __restrict__ db,
+                                                             int B, int H, int W, int Cout, int64_t pix_per_block) {
+  extern __shared__ float red[];           // [PL][Cout][10]
+  const int co = threadIdx.x % Cout;
+  const int lane = threadIdx.x / Cout;
+  const int PL = blockDim.x / Cout;
+  const int64_t P = int64_t(B) * H * W;
+  const int64_t p0 = blockIdx.x * pix_per_block;
+  const int64_t p1 = min(P, p0 + pix_per_block);
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  constexpr int U = 4;
+  for (int64_t pb = p0 + lane; pb < p1; pb += int64_t(PL) * U) {
+    float g[U], xv[U][9];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = pb + int64_t(u) * PL;
+      const bool ok = p < p1;
+      g[u] = ok ? to_f<T>(dy[p * Cout + co]) : 0.f;
+      const int wv = int(p % W);
+      const int hv = int((p / W) % H);
+      const int64_t b = p / (int64_t(W) * H);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = hv + t / 3 - 1, ww = wv + t % 3 - 1;
+        xv[u][t] = (ok && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(&x[(b * H + hh) * W + ww]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[t] = fmaf(g[u], xv[u][t], acc[t]);
+      acc[9] += g[u];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) red[(lane * Cout + co) * 10 + i] = acc[i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < Cout * 10; o += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += red[l * Cout * 10 + o];
+    const int c = o / 10, t = o % 10;
+    if (t < 9) atomicAdd(&dw[c * 9 + t], s); else atomicAdd(&db[c], s);
+  }
+}
+
 static inline int grid_for(int64_t total, int threads) {
   int64_t blocks = ceil_div64(total, threads);
   int64_t cap = int64_t(sm_count()) * 16;
@@ -241,12 +349,12 @@ extern "C" int masr_conv1_wgrad(const float* x, const void* dy, int dy_dtype, fl
   const int64_t P = int64_t(B) * H * W;
   if (P == 0) return MASR_OK;
   const int threads = 256, PL = threads / Cout;
-  int blocks = int(std::min<int64_t>(ceil_div64(P, 256), int64_t(sm_count()) * 4));
+  int blocks = int(std::min<int64_t>(ceil_div64(P, 64), int64_t(sm_count()) * 8));
   const int64_t ppb = ceil_div64(P, blocks);
   blocks = int(ceil_div64(P, ppb));
   const size_t smem = size_t(PL) * Cout * 10 * sizeof(float);
   MASR_DISPATCH_DTYPE(dy_dtype, T,
-      conv1_wgrad_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
+      conv1_wgrad_v2_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
           x, static_cast<const T*>(dy), dw, db, B, H, W, Cout, ppb));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -293,6 +401,13 @@ extern "C" int masr_conv_w_unprep_add(const float* dwp, float* dw, int Cout, int
 extern "C" int masr_maxpool2x2_fwd(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream) {
   const int64_t total = int64_t(B) * (H / 2) * (W / 2) * C;
   if (total == 0) return MASR_OK;
+  if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    MASR_DISPATCH_DTYPE(dtype, T,
+        maxpool_fwd_vec_kernel<T><<<grid_for(total / 8, 256), 256, 0, as_stream(stream)>>>(
+            static_cast<const T*>(x), static_cast<T*>(y), B, H, W, C));
+    MASR_LAUNCH_CHECK();
+    return MASR_OK;
+  }
   MASR_DISPATCH_DTYPE(dtype, T,
       maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
           static_cast<const T*>(x), static_cast<T*>(y), B, H, W, C));
@@ -304,6 +419,15 @@ extern "C" int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int 
                                    int B, int H, int W, int C, void* stream) {
   const int64_t total = int64_t(B) * H * W * C;
   if (total == 0) return MASR_OK;
+  const int64_t wins = int64_t(B) * (H / 2) * (W / 2) * (C / 8);
+  if (C % 8 == 0 && H >= 2 && W >= 2 && wins > 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+    MASR_DISPATCH_DTYPE(dtype, T,
+        maxpool_bwd_vec_kernel<T><<<grid_for(wins, 256), 256, 0, as_stream(stream)>>>(
+            static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), relu_mask, B, H, W, C));
+    MASR_LAUNCH_CHECK();
+    return MASR_OK;
+  }
   MASR_DISPATCH_DTYPE(dtype, T,
       maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
           static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), relu_mask, B, H, W, C));

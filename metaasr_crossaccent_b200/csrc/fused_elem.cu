@@ -122,6 +122,149 @@ __global__ void add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __re
   }
 }
 
+// Vectorised variants (d % 8 == 0, d <= 1024): a lane owns chunks of 8 consecutive elements
+// (chunk index = i * 32 + lane), i.e. 128-bit loads/stores and 1/8th of the instructions.
+template <typename T, int LN_MAX_CHUNKS>
+__global__ void __launch_bounds__(256)
+add_layernorm_fwd_vec_kernel(T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
+                             float* __restrict__ rstd_out, int rows, int d, float eps, float p, float inv_keep,
+                             uint64_t seed, uint32_t site) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nchunk = d / 8;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const int64_t base = int64_t(row) * d;
+    float v[LN_MAX_CHUNKS][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int ch = i * 32 + lane;
+      if (ch < nchunk) {
+        load8<T>(x + base + ch * 8, v[i]);
+        if (p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] *= drop_scale(p, inv_keep, seed, site, uint64_t(base + ch * 8 + j));
+        }
+        if (res != nullptr) {
+          float r[8];
+          load8<T>(res + base + ch * 8, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] = to_f<T>(from_f<T>(v[i][j])); sum += v[i][j]; }
+        store8<T>(x + base + ch * 8, v[i]);
+      }
+    }
+    const float mean = warp_sum(sum) / float(d);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i)
+      if (i * 32 + lane < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; var += t * t; }
+      }
+    const float rstd = rsqrtf(warp_sum(var) / float(d) + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int ch = i * 32 + lane;
+      if (ch < nchunk) {
+        float g[8], bt[8], o[8];
+        load8<float>(gamma + ch * 8, g);
+        load8<float>(beta + ch * 8, bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + bt[j];
+        store8<T>(y + base + ch * 8, o);
+      }
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
+template <typename T, int LN_MAX_CHUNKS>
+__global__ void __launch_bounds__(256)
+add_layernorm_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __restrict__ mean_in,
+                             const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ ds,
+                             int ds_accum, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                             int rows, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  extern __shared__ float red[];      // [warps][2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int nchunk = d / 8;
+  float dg[LN_MAX_CHUNKS][8], db[LN_MAX_CHUNKS][8], gm[LN_MAX_CHUNKS][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    const int ch = i * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gm[i][j] = 0.f; }
+    if (ch < nchunk) load8<float>(gamma + ch * 8, gm[i]);
+  }
+  for (int row = blockIdx.x * wpb + warp; row < rows; row += gridDim.x * wpb) {
+    const int64_t base = int64_t(row) * d;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float g[LN_MAX_CHUNKS][8], xh[LN_MAX_CHUNKS][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int ch = i * 32 + lane;
+      if (ch < nchunk) {
+        float dyv[8], sv[8];
+        load8<T>(dy + base + ch * 8, dyv);
+        load8<T>(s + base + ch * 8, sv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (sv[j] - mean) * rstd;
+          g[i][j] = dyv[j] * gm[i][j];
+          dg[i][j] += dyv[j] * xh[i][j];
+          db[i][j] += dyv[j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / float(d);
+    s2 = warp_sum(s2) / float(d);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int ch = i * 32 + lane;
+      if (ch < nchunk) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+        if (dx != nullptr) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = v[j] * drop_scale(p, inv_keep, seed, site, uint64_t(base + ch * 8 + j));
+          store8<T>(dx + base + ch * 8, o);
+        }
+        if (ds_accum) {
+          float o[8];
+          load8<T>(ds + base + ch * 8, o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += o[j];
+        }
+        store8<T>(ds + base + ch * 8, v);
+      }
+    }
+  }
+  float* rg = red + size_t(warp) * 2 * d;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    const int ch = i * 32 + lane;
+    if (ch < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { rg[ch * 8 + j] = dg[i][j]; rg[d + ch * 8 + j] = db[i][j]; }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < wpb; ++w) t += red[size_t(w) * 2 * d + c];
+    if (c < d) atomicAdd(&dgamma[c], t); else atomicAdd(&dbeta[c - d], t);
+  }
+}
+
 // ------------------------------------------------------------------ positional encoding / embedding / dropout
 template <typename T>
 __global__ void add_pe_dropout_kernel(T* __restrict__ x, const float* __restrict__ pe, int64_t n, int L, int d,
@@ -314,6 +457,17 @@ extern "C" int masr_add_layernorm_fwd(void* x_inout, const void* res, const floa
   const int threads = 256, wpb = threads / 32;
   const int blocks = int(std::min<int64_t>(ceil_div64(rows, wpb), int64_t(sm_count()) * 8));
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const bool vec = (d % 8 == 0) && ((reinterpret_cast<uintptr_t>(x_inout) | reinterpret_cast<uintptr_t>(res) |
+                                     reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                                     reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (vec) {
+#define LN_FWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (add_layernorm_fwd_vec_kernel<T, NCH><<<blocks, threads, 0, as_stream(stream)>>>( \
+          static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd, rows, d, eps, p_drop, inv_keep, seed, site)))
+    if (d <= 256) LN_FWD_VEC(1); else if (d <= 512) LN_FWD_VEC(2); else LN_FWD_VEC(4);
+#undef LN_FWD_VEC
+    MASR_LAUNCH_CHECK();
+    return MASR_OK;
+  }
   MASR_DISPATCH_DTYPE(dtype, T,
       add_layernorm_fwd_kernel<T><<<blocks, threads, 0, as_stream(stream)>>>(
           static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd,
@@ -335,6 +489,18 @@ extern "C" int masr_add_layernorm_bwd(const void* dy, const void* s, const float
   if (smem > 48 * 1024) {       // d > 768: opt in to more than the default 48 KB of dynamic shared memory
     MASR_CHECK_CUDA(cudaFuncSetAttribute(add_layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     MASR_CHECK_CUDA(cudaFuncSetAttribute(add_layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  }
+  const bool vec = (d % 8 == 0) && smem <= 48 * 1024 &&
+                   ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(ds) |
+                     reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(gamma)) & 15) == 0;
+  if (vec) {
+#define LN_BWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (add_layernorm_bwd_vec_kernel<T, NCH><<<blocks, threads, smem, as_stream(stream)>>>( \
+          static_cast<const T*>(dy), static_cast<const T*>(s), mean, rstd, gamma, static_cast<T*>(ds), ds_accum, static_cast<T*>(dx), \
+          dgamma, dbeta, rows, d, p_drop, inv_keep, seed, site)))
+    if (d <= 256) LN_BWD_VEC(1); else if (d <= 512) LN_BWD_VEC(2); else LN_BWD_VEC(4);
+#undef LN_BWD_VEC
+    MASR_LAUNCH_CHECK();
+    return MASR_OK;
   }
   MASR_DISPATCH_DTYPE(dtype, T,
       add_layernorm_bwd_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(

@@ -239,13 +239,29 @@ class CudaBackend:
         self._call("masr_relu_bwd", _p(y), _p(dx), _dt(y), y.numel(), self.stream)
 
     # -------------------------------------------------------------- attention
+    def _attn_umma_ok(self, hd, *ts):
+        """tcgen05 attention: bf16, head dim 64, 16 B aligned rows."""
+        if self.gemm_path != "umma" or hd != 64:
+            return False
+        return all(t.dtype == torch.bfloat16 and t.data_ptr() % 16 == 0 and t.stride(0) % 8 == 0 and t.stride(1) == 1
+                   for t in ts)
+
     def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
         hd = out.shape[1] // H
+        if self._attn_umma_ok(hd, q, k, v, out):
+            return self._call("masr_umma_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+                              out.stride(0), _p(lse), B, H, Lq, Lk, _p(klens), int(causal), float(p), seed, site,
+                              self.stream)
         self._call("masr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
                    _p(lse), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site, self.stream)
 
     def attn_bwd(self, q, k, v, out, dout, lse, dsum, dq, dk, dv, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
         hd = out.shape[1] // H
+        if Lk <= 128 and self._attn_umma_ok(hd, q, k, v, out, dout, dq, dk, dv):
+            return self._call("masr_umma_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+                              out.stride(0), _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0),
+                              _p(dk), dk.stride(0), _p(dv), dv.stride(0), B, H, Lq, Lk, _p(klens), int(causal),
+                              float(p), seed, site, self.stream, n_kernels=2)
         self._call("masr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
                    _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                    _p(dv), dv.stride(0), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site,

@@ -1,0 +1,91 @@
+"""GPU parity of the tcgen05 attention kernels (head dim 64, bf16) against the fp32 torch contract."""
+import pytest
+import torch
+
+from tests.torch_backend import TorchBackend
+from tests.test_kernels_gpu import close, rnd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,causal,use_klens,bwd", [
+    (2, 8, 128, 128, False, True, True),      # encoder self-attention at the BASELINE shape
+    (3, 8, 33, 33, True, False, True),        # decoder causal self-attention
+    (3, 8, 33, 128, False, True, True),       # decoder cross-attention with memory key padding
+    (2, 4, 200, 100, False, True, True),      # two query tiles
+    (2, 4, 70, 300, False, True, False),      # three key tiles (forward: online soft-max)
+    (1, 2, 150, 150, True, False, False),     # causal over two tiles (forward)
+])
+def test_umma_attention(dev, B, H, Lq, Lk, causal, use_klens, bwd):
+    from metaasr_crossaccent_b200.ops import CudaBackend
+    bf = torch.bfloat16
+    cb, tb = CudaBackend(dev, bf, gemm="umma"), TorchBackend(dev, bf)
+    d = H * 64
+    if Lq == Lk:
+        qkv = rnd((B * Lq, 3 * d), dev, bf, 1)
+        q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    else:
+        q = rnd((B * Lq, d), dev, bf, 1)
+        kv = rnd((B * Lk, 2 * d), dev, bf, 2)
+        k, v = kv[:, :d], kv[:, d:]
+    klens = None
+    if use_klens:
+        klens = torch.tensor([Lk] + [max(1, Lk - 17 * (i + 1)) for i in range(B - 1)], dtype=torch.int64, device=dev)
+    o1 = torch.full((B * Lq, d), 5.0, device=dev, dtype=bf)
+    o2 = torch.empty_like(o1)
+    l1 = torch.empty(B * H * Lq, device=dev)
+    l2 = torch.empty_like(l1)
+    before = cb.launches
+    cb.attn_fwd(q, k, v, o1, l1, B, H, Lq, Lk, klens, causal)
+    assert cb.launches == before + 1
+    tb.attn_fwd(q, k, v, o2, l2, B, H, Lq, Lk, klens, causal)
+    close(o1, o2, bf, what="umma attn out")
+    close(l1, l2, bf, what="umma attn lse")
+    if not bwd:
+        return
+    do = rnd((B * Lq, d), dev, bf, 3)
+    if Lq == Lk:
+        g1 = torch.full((B * Lq, 3 * d), 3.0, device=dev, dtype=bf)
+        g2 = g1.clone()
+        v1 = (g1[:, :d], g1[:, d:2 * d], g1[:, 2 * d:])
+        v2 = (g2[:, :d], g2[:, d:2 * d], g2[:, 2 * d:])
+    else:
+        v1 = (torch.full((B * Lq, d), 3.0, device=dev, dtype=bf), torch.full((B * Lk, d), 3.0, device=dev, dtype=bf),
+              torch.full((B * Lk, d), 3.0, device=dev, dtype=bf))
+        v2 = tuple(t.clone() for t in v1)
+    dsum = torch.empty(B * H * Lq, device=dev)
+    cb.attn_bwd(q, k, v, o2, do, l2, dsum, v1[0], v1[1], v1[2], B, H, Lq, Lk, klens, causal)
+    tb.attn_bwd(q, k, v, o2, do, l2, dsum, v2[0], v2[1], v2[2], B, H, Lq, Lk, klens, causal)
+    for a, b_, nm in zip(v1, v2, "qkv"):
+        close(a, b_, bf, what=f"umma attn d{nm}")
+
+
+def test_umma_attention_dropout(dev):
+    from metaasr_crossaccent_b200.ops import CudaBackend
+    bf = torch.bfloat16
+    cb = CudaBackend(dev, bf, gemm="umma")
+    B, H, L = 2, 4, 128
+    d = H * 64
+    q = torch.zeros(B * L, d, device=dev, dtype=bf)
+    k = torch.zeros(B * L, d, device=dev, dtype=bf)
+    v = torch.ones(B * L, d, device=dev, dtype=bf)
+    o = torch.empty(B * L, d, device=dev, dtype=bf)
+    lse = torch.empty(B * H * L, device=dev)
+    cb.attn_fwd(q, k, v, o, lse, B, H, L, L, None, False, 0.25, 99, 3)
+    assert abs(float(o.float().mean()) - 1.0) < 0.02          # E[kept / (1-p)] = 1
+    o2 = torch.empty_like(o)
+    cb.attn_fwd(q, k, v, o2, lse, B, H, L, L, None, False, 0.25, 99, 3)
+    assert torch.equal(o, o2)
+    # backward replays the same mask: dV_j = sum_i P_ij M_ij dO_i with uniform P -> mean 1 for dO = 1
+    do = torch.ones_like(o)
+    dq, dk, dv = torch.empty_like(o), torch.empty_like(o), torch.empty_like(o)
+    dsum = torch.empty(B * H * L, device=dev)
+    cb.attn_bwd(q, k, v, o, do, lse, dsum, dq, dk, dv, B, H, L, L, None, False, 0.25, 99, 3)
+    assert abs(float(dv.float().mean()) - 1.0) < 0.02
