@@ -198,9 +198,16 @@ int masr_permute_cf(const void* src, int src_dtype, void* dst, int dst_dtype, in
  *   stats  [4] double: {sum of row losses, n_correct, n_non_pad, 0} (accumulated; zero it first)
  *   argmax [N] int64 out (may be NULL); dlogits [N, C] fp32 out = d(mean loss)/d logits given
  *   inv_n = 1 / n_non_pad (may be NULL)
+ *   inv_n_dev (may be NULL): device-resident 1 / n_non_pad overriding inv_n (CUDA-graph replay)
  */
 int masr_ls_ce_fwd_bwd(const float* logits, const int64_t* gold, int N, int C, float eps, float inv_n,
-                       double* stats, int64_t* argmax, float* dlogits, void* stream);
+                       const float* inv_n_dev, double* stats, int64_t* argmax, float* dlogits, void* stream);
+
+/* Dropout seeds: every dropout site draws from (seed + *dev_ptr, site, element index).  dev_ptr (set once per
+ * process; NULL = offset 0) lives in device memory so a captured CUDA graph of the step replays with fresh
+ * masks; masr_seed_bump advances it on the stream. */
+int masr_set_seed_ptr(const uint64_t* dev_ptr);
+int masr_seed_bump(uint64_t* dev_ptr, uint64_t inc, void* stream);
 
 /* ------------------------------------------------------------------ kernel 4: flat multi-tensor ops
  * All operate on flat fp32 arenas of n elements (parameters laid out back to back).

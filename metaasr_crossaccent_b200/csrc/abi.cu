@@ -17,6 +17,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 int sm_count() { return g_sm_count; }
 
+const uint64_t* g_seed_dev_ptr = nullptr;
+
+__global__ void seed_bump_kernel(uint64_t* p, uint64_t inc) { *p += inc; }
+
 }  // namespace masr
 
 using namespace masr;
@@ -40,5 +44,17 @@ extern "C" int masr_init(int device) {
     return MASR_E_NOGPU;
   }
   g_sm_count = prop.multiProcessorCount;
+  return MASR_OK;
+}
+
+extern "C" int masr_set_seed_ptr(const uint64_t* dev_ptr) {
+  g_seed_dev_ptr = dev_ptr;
+  return MASR_OK;
+}
+
+extern "C" int masr_seed_bump(uint64_t* dev_ptr, uint64_t inc, void* stream) {
+  MASR_REQUIRE(dev_ptr != nullptr, "seed_bump: null pointer");
+  seed_bump_kernel<<<1, 1, 0, as_stream(stream)>>>(dev_ptr, inc);
+  MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -37,7 +37,8 @@ attn_fwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, i
                 const T* __restrict__ v, int64_t ldv, T* __restrict__ out, int64_t ldo,
                 float* __restrict__ lse, int B, int H, int Lq, int Lk, int hd,
                 const int64_t* __restrict__ klens, int causal, float scale,
-                float p, float inv_keep, uint64_t seed, uint32_t site) {
+                float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   __shared__ float Qs[AT_QT * AT_LD];
   __shared__ float Ks[AT_KT * AT_LD];
   __shared__ float Vs[AT_KT * AT_LD];
@@ -119,7 +120,8 @@ attn_bwd_dq_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k
                    const T* __restrict__ dout, int64_t lddo, const float* __restrict__ lse,
                    float* __restrict__ dsum, T* __restrict__ dq, int64_t lddq,
                    int B, int H, int Lq, int Lk, int hd, const int64_t* __restrict__ klens, int causal,
-                   float scale, float p, float inv_keep, uint64_t seed, uint32_t site) {
+                   float scale, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   __shared__ float Qs[AT_QT * AT_LD];
   __shared__ float dOs[AT_QT * AT_LD];
   __shared__ float Ks[AT_KT * AT_LD];
@@ -210,7 +212,8 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ 
                     const float* __restrict__ lse, const float* __restrict__ dsum,
                     T* __restrict__ dk, int64_t lddk, T* __restrict__ dv, int64_t lddv,
                     int B, int H, int Lq, int Lk, int hd, const int64_t* __restrict__ klens, int causal,
-                    float scale, float p, float inv_keep, uint64_t seed, uint32_t site) {
+                    float scale, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   __shared__ float Ks[AT_QT * AT_LD];
   __shared__ float Vs[AT_QT * AT_LD];
   __shared__ float Qs[AT_KT * AT_LD];
@@ -305,7 +308,7 @@ extern "C" int masr_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t 
   MASR_DISPATCH_DTYPE(dtype, T,
       attn_fwd_kernel<T><<<grid, AT_THREADS, 0, as_stream(stream)>>>(
           static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv,
-          static_cast<T*>(out), ldo, lse, B, H, Lq, Lk, hd, klens, causal, scale, p_drop, inv_keep, seed, site));
+          static_cast<T*>(out), ldo, lse, B, H, Lq, Lk, hd, klens, causal, scale, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -327,7 +330,7 @@ extern "C" int masr_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t 
         attn_bwd_dq_kernel<T><<<grid, AT_THREADS, 0, st>>>(
             static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv,
             static_cast<const T*>(out), ldo, static_cast<const T*>(dout), lddo, lse, dsum_ws,
-            static_cast<T*>(dq), lddq, B, H, Lq, Lk, hd, klens, causal, scale, p_drop, inv_keep, seed, site));
+            static_cast<T*>(dq), lddq, B, H, Lq, Lk, hd, klens, causal, scale, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
     MASR_LAUNCH_CHECK();
   }
   if (Lk > 0) {
@@ -336,7 +339,7 @@ extern "C" int masr_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t 
         attn_bwd_dkv_kernel<T><<<grid, AT_THREADS, 0, st>>>(
             static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv,
             static_cast<const T*>(dout), lddo, lse, dsum_ws, static_cast<T*>(dk), lddk, static_cast<T*>(dv), lddv,
-            B, H, Lq, Lk, hd, klens, causal, scale, p_drop, inv_keep, seed, site));
+            B, H, Lq, Lk, hd, klens, causal, scale, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
     MASR_LAUNCH_CHECK();
   }
   return MASR_OK;

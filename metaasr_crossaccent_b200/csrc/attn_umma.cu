@@ -40,6 +40,7 @@ struct AttnFwdParams {
   uint64_t seed; uint32_t site;
   __nv_bfloat16* out; int64_t ldo;
   float* lse;
+  const uint64_t* seed_ptr;      // device-resident per-step seed offset (CUDA-graph replay), may be NULL
 };
 
 __global__ void __launch_bounds__(AU_THREADS, 1)
@@ -61,6 +62,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t seed_eff = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int q0 = blockIdx.x * AU_TILE;
   int kmax = p.Lk;
@@ -162,7 +164,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           float pr = ok ? expf(v[j] * p.scale - m_use) : 0.f;
           lsum += pr;
           if (p.p_drop > 0.f && ok)
-            pr *= drop_scale(p.p_drop, p.inv_keep, p.seed, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
+            pr *= drop_scale(p.p_drop, p.inv_keep, seed_eff, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
           v[j] = pr;
         }
 #pragma unroll
@@ -237,6 +239,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dq; int64_t lddq;
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
+  const uint64_t* seed_ptr;
 };
 
 // Single key tile per (batch, head) CTA column: requires Lk <= 128 * gridDim.x with dQ written directly only
@@ -263,6 +266,7 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t seed_eff = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int k0 = blockIdx.x * AU_TILE;
   int klen = p.Lk;
@@ -364,7 +368,7 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           float pr = 0.f, ds = 0.f;
           if (ok) {
             pr = expf(sv[j] * p.scale - lse_r);
-            const float dm = drop_scale(p.p_drop, p.inv_keep, p.seed, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
+            const float dm = drop_scale(p.p_drop, p.inv_keep, seed_eff, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
             ds = pr * (dp[j] * dm - d_r) * p.scale;
             pr *= dm;
           }
@@ -465,7 +469,7 @@ extern "C" int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int
   rc = rows_map(&mk, k, ldk, int64_t(B) * Lk, H * 64); if (rc) return rc;
   rc = rows_map(&mv, v, ldv, int64_t(B) * Lk, H * 64); if (rc) return rc;
   AttnFwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed, site,
-                  static_cast<__nv_bfloat16*>(out), ldo, lse};
+                  static_cast<__nv_bfloat16*>(out), ldo, lse, g_seed_dev_ptr};
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_FWD_SMEM))); attr = true; }
   dim3 grid(unsigned(ceil_div64(Lq, AU_TILE)), unsigned(B * H));
@@ -500,7 +504,7 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
   }
   AttnBwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed, site,
                   lse, dsum_ws, static_cast<__nv_bfloat16*>(dq), lddq, static_cast<__nv_bfloat16*>(dk), lddk,
-                  static_cast<__nv_bfloat16*>(dv), lddv};
+                  static_cast<__nv_bfloat16*>(dv), lddv, g_seed_dev_ptr};
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_BWD_SMEM))); attr = true; }
   dim3 grid(1, unsigned(B * H));

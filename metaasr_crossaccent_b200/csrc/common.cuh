@@ -60,6 +60,12 @@ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t site, uint6
   z = z ^ (z >> 31);
   return uint32_t(z >> 40);   // 24 bits
 }
+// Seed of a dropout site = base (by value) + a device-resident per-step offset.  The offset lives in device
+// memory so that a captured CUDA graph of the step replays with fresh masks (masr_seed_bump advances it).
+struct SeedArg { uint64_t base; const uint64_t* bump; };
+__device__ __forceinline__ uint64_t resolve_seed(SeedArg s) { return s.base + (s.bump != nullptr ? *s.bump : 0ull); }
+extern const uint64_t* g_seed_dev_ptr;     // host-side global set by masr_set_seed_ptr (abi.cu)
+
 // returns the multiplier applied to a kept/dropped element: 1/(1-p) or 0
 __device__ __forceinline__ float drop_scale(float p, float inv_keep, uint64_t seed, uint32_t site, uint64_t idx) {
   if (p <= 0.f) return 1.f;

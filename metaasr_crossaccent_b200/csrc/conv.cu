@@ -320,6 +320,61 @@ __global__ void __launch_bounds__(256) conv1_wgrad_v2_kernel(const float* __rest
   }
 }
 
+// conv1 wgrad, row-segment variant: a thread (co, lane) handles SEG = 8 consecutive pixels of one image row
+// per iteration: the 3 x 10 input window is loaded once and slid over the 8 pixels (30 loads instead of
+// 72), index arithmetic is 32-bit and done once per segment.
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_wgrad_v3_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                             float* __restrict__ dw, float* __restrict__ db,
+                                                             int B, int H, int W, int Cout, int segs_per_row, int total_segs) {
+  extern __shared__ float red[];           // [PL][Cout][10]
+  constexpr int SEG = 8;
+  const int co = threadIdx.x % Cout;
+  const int lane = threadIdx.x / Cout;
+  const int PL = blockDim.x / Cout;
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  for (int sidx = blockIdx.x * PL + lane; sidx < total_segs; sidx += gridDim.x * PL) {
+    const unsigned us = unsigned(sidx);
+    const int sw = int(us % unsigned(segs_per_row));
+    const unsigned row = us / unsigned(segs_per_row);        // b * H + h
+    const int h = int(row % unsigned(H));
+    const int w0 = sw * SEG;
+    float win[3][SEG + 2];
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hh = h + dh - 1;
+      const bool hok = hh >= 0 && hh < H;
+      const float* xr = x + (int64_t(row) + (dh - 1)) * W;
+#pragma unroll
+      for (int j = 0; j < SEG + 2; ++j) {
+        const int ww = w0 + j - 1;
+        win[dh][j] = (hok && ww >= 0 && ww < W) ? __ldg(xr + ww) : 0.f;
+      }
+    }
+    const T* dyr = dy + (int64_t(row) * W + w0) * Cout + co;
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      const float g = (w0 + j < W) ? to_f<T>(dyr[int64_t(j) * Cout]) : 0.f;
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+        for (int dw_ = 0; dw_ < 3; ++dw_) acc[dh * 3 + dw_] = fmaf(g, win[dh][j + dw_], acc[dh * 3 + dw_]);
+      acc[9] += g;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) red[(lane * Cout + co) * 10 + i] = acc[i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < Cout * 10; o += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += red[l * Cout * 10 + o];
+    const int c = o / 10, t = o % 10;
+    if (t < 9) atomicAdd(&dw[c * 9 + t], s); else atomicAdd(&db[c], s);
+  }
+}
+
 static inline int grid_for(int64_t total, int threads) {
   int64_t blocks = ceil_div64(total, threads);
   int64_t cap = int64_t(sm_count()) * 16;
@@ -349,6 +404,17 @@ extern "C" int masr_conv1_wgrad(const float* x, const void* dy, int dy_dtype, fl
   const int64_t P = int64_t(B) * H * W;
   if (P == 0) return MASR_OK;
   const int threads = 256, PL = threads / Cout;
+  if (P * 2 < (int64_t(1) << 31)) {
+    const int segs_per_row = (W + 7) / 8;
+    const int total_segs = B * H * segs_per_row;
+    const int blocks3 = std::max(1, std::min((total_segs + PL - 1) / PL, sm_count() * 8));
+    const size_t smem3 = size_t(PL) * Cout * 10 * sizeof(float);
+    MASR_DISPATCH_DTYPE(dy_dtype, T,
+        conv1_wgrad_v3_kernel<T><<<blocks3, threads, smem3, as_stream(stream)>>>(
+            x, static_cast<const T*>(dy), dw, db, B, H, W, Cout, segs_per_row, total_segs));
+    MASR_LAUNCH_CHECK();
+    return MASR_OK;
+  }
   int blocks = int(std::min<int64_t>(ceil_div64(P, 64), int64_t(sm_count()) * 8));
   const int64_t ppb = ceil_div64(P, blocks);
   blocks = int(ceil_div64(P, ppb));

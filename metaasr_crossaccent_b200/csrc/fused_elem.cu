@@ -20,7 +20,8 @@ template <typename T>
 __global__ void add_layernorm_fwd_kernel(T* __restrict__ x, const T* __restrict__ res,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                         int rows, int d, float eps, float p, float inv_keep, uint64_t seed, uint32_t site) {
+                                         int rows, int d, float eps, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int per = (d + 31) / 32;
@@ -67,7 +68,8 @@ __global__ void add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __re
                                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                          const float* __restrict__ gamma, T* __restrict__ ds, int ds_accum,
                                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                         int rows, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+                                         int rows, int d, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   extern __shared__ float red[];      // [warps][2][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -129,7 +131,8 @@ __global__ void __launch_bounds__(256)
 add_layernorm_fwd_vec_kernel(T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                              const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
                              float* __restrict__ rstd_out, int rows, int d, float eps, float p, float inv_keep,
-                             uint64_t seed, uint32_t site) {
+                             SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nchunk = d / 8;
@@ -187,7 +190,8 @@ __global__ void __launch_bounds__(256)
 add_layernorm_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __restrict__ mean_in,
                              const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ ds,
                              int ds_accum, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                             int rows, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+                             int rows, int d, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   extern __shared__ float red[];      // [warps][2][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -268,7 +272,8 @@ add_layernorm_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ s, 
 // ------------------------------------------------------------------ positional encoding / embedding / dropout
 template <typename T>
 __global__ void add_pe_dropout_kernel(T* __restrict__ x, const float* __restrict__ pe, int64_t n, int L, int d,
-                                      float p, float inv_keep, uint64_t seed, uint32_t site) {
+                                      float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int c = int(i % d);
     const int l = int((i / d) % L);
@@ -280,7 +285,8 @@ __global__ void add_pe_dropout_kernel(T* __restrict__ x, const float* __restrict
 template <typename T>
 __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E,
                                     const float* __restrict__ pe, T* __restrict__ out, int64_t n, int L, int d,
-                                    float p, float inv_keep, uint64_t seed, uint32_t site) {
+                                    float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int c = int(i % d);
     const int64_t r = i / d;
@@ -292,7 +298,8 @@ __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float
 
 template <typename T>
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout, float* __restrict__ dE,
-                                 int64_t n, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+                                 int64_t n, int d, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int c = int(i % d);
     const int64_t r = i / d;
@@ -302,7 +309,8 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __res
 }
 
 template <typename T>
-__global__ void dropout_kernel(T* __restrict__ x, int64_t n, float p, float inv_keep, uint64_t seed, uint32_t site) {
+__global__ void dropout_kernel(T* __restrict__ x, int64_t n, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     x[i] = from_f<T>(to_f<T>(x[i]) * drop_scale(p, inv_keep, seed, site, uint64_t(i)));
 }
@@ -393,8 +401,9 @@ __global__ void permute_cf_kernel(const TS* __restrict__ src, TD* __restrict__ d
 //   q_c = (1-eps) for the gold class, eps/C otherwise (sums to 1 - eps/C)
 //   loss_row = -sum_c q_c (z_c - logZ);   d loss_row / d z_c = (sum q) softmax_c - q_c
 __global__ void ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ gold, int N, int C,
-                             float eps, float inv_n, double* __restrict__ stats, int64_t* __restrict__ argmax_out,
-                             float* __restrict__ dlogits) {
+                             float eps, float inv_n, const float* __restrict__ inv_n_dev, double* __restrict__ stats,
+                             int64_t* __restrict__ argmax_out, float* __restrict__ dlogits) {
+  if (inv_n_dev != nullptr) inv_n = *inv_n_dev;       // device-resident 1/n_non_pad (CUDA-graph replay)
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   double loss_acc = 0.0;
@@ -462,7 +471,7 @@ extern "C" int masr_add_layernorm_fwd(void* x_inout, const void* res, const floa
                                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
   if (vec) {
 #define LN_FWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (add_layernorm_fwd_vec_kernel<T, NCH><<<blocks, threads, 0, as_stream(stream)>>>( \
-          static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd, rows, d, eps, p_drop, inv_keep, seed, site)))
+          static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd, rows, d, eps, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site)))
     if (d <= 256) LN_FWD_VEC(1); else if (d <= 512) LN_FWD_VEC(2); else LN_FWD_VEC(4);
 #undef LN_FWD_VEC
     MASR_LAUNCH_CHECK();
@@ -471,7 +480,7 @@ extern "C" int masr_add_layernorm_fwd(void* x_inout, const void* res, const floa
   MASR_DISPATCH_DTYPE(dtype, T,
       add_layernorm_fwd_kernel<T><<<blocks, threads, 0, as_stream(stream)>>>(
           static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd,
-          rows, d, eps, p_drop, inv_keep, seed, site));
+          rows, d, eps, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -496,7 +505,7 @@ extern "C" int masr_add_layernorm_bwd(const void* dy, const void* s, const float
   if (vec) {
 #define LN_BWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (add_layernorm_bwd_vec_kernel<T, NCH><<<blocks, threads, smem, as_stream(stream)>>>( \
           static_cast<const T*>(dy), static_cast<const T*>(s), mean, rstd, gamma, static_cast<T*>(ds), ds_accum, static_cast<T*>(dx), \
-          dgamma, dbeta, rows, d, p_drop, inv_keep, seed, site)))
+          dgamma, dbeta, rows, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site)))
     if (d <= 256) LN_BWD_VEC(1); else if (d <= 512) LN_BWD_VEC(2); else LN_BWD_VEC(4);
 #undef LN_BWD_VEC
     MASR_LAUNCH_CHECK();
@@ -505,7 +514,7 @@ extern "C" int masr_add_layernorm_bwd(const void* dy, const void* s, const float
   MASR_DISPATCH_DTYPE(dtype, T,
       add_layernorm_bwd_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
           static_cast<const T*>(dy), static_cast<const T*>(s), mean, rstd, gamma, static_cast<T*>(ds), ds_accum,
-          static_cast<T*>(dx), dgamma, dbeta, rows, d, p_drop, inv_keep, seed, site));
+          static_cast<T*>(dx), dgamma, dbeta, rows, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -517,7 +526,7 @@ extern "C" int masr_add_pe_dropout(void* x, const float* pe, int dtype, int rows
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   MASR_DISPATCH_DTYPE(dtype, T,
       add_pe_dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-          static_cast<T*>(x), pe, n, L, d, p_drop, inv_keep, seed, site));
+          static_cast<T*>(x), pe, n, L, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -529,7 +538,7 @@ extern "C" int masr_embed_pe_fwd(const int64_t* ids, const float* E, const float
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   MASR_DISPATCH_DTYPE(dtype, T,
       embed_pe_fwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-          ids, E, pe, static_cast<T*>(out), n, L, d, p_drop, inv_keep, seed, site));
+          ids, E, pe, static_cast<T*>(out), n, L, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -542,7 +551,7 @@ extern "C" int masr_embed_bwd(const int64_t* ids, const void* dout, int dtype, f
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   MASR_DISPATCH_DTYPE(dtype, T,
       embed_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-          ids, static_cast<const T*>(dout), dE, n, d, p_drop, inv_keep, seed, site));
+          ids, static_cast<const T*>(dout), dE, n, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -551,7 +560,7 @@ extern "C" int masr_dropout(void* x, int dtype, int64_t n, float p_drop, uint64_
   if (n == 0 || p_drop <= 0.f) return MASR_OK;
   const float inv_keep = 1.f / (1.f - p_drop);
   MASR_DISPATCH_DTYPE(dtype, T,
-      dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(static_cast<T*>(x), n, p_drop, inv_keep, seed, site));
+      dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(static_cast<T*>(x), n, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -609,12 +618,12 @@ extern "C" int masr_permute_cf(const void* src, int src_dtype, void* dst, int ds
 }
 
 extern "C" int masr_ls_ce_fwd_bwd(const float* logits, const int64_t* gold, int N, int C, float eps, float inv_n,
-                                  double* stats, int64_t* argmax, float* dlogits, void* stream) {
+                                  const float* inv_n_dev, double* stats, int64_t* argmax, float* dlogits, void* stream) {
   MASR_REQUIRE(C > 0, "ls_ce: C must be positive");
   if (N == 0) return MASR_OK;
   const int threads = 128, wpb = threads / 32;
   const int blocks = int(std::min<int64_t>(ceil_div64(N, wpb), int64_t(sm_count()) * 8));
-  ls_ce_kernel<<<blocks, threads, 0, as_stream(stream)>>>(logits, gold, N, C, eps, inv_n, stats, argmax, dlogits);
+  ls_ce_kernel<<<blocks, threads, 0, as_stream(stream)>>>(logits, gold, N, C, eps, inv_n, inv_n_dev, stats, argmax, dlogits);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -279,10 +279,10 @@ extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* 
     case 1: return launch_umma<64, 4, false, true>(ma, mb, p, st);
     case 2: return launch_umma<64, 4, true, false>(ma, mb, p, st);
     case 3: return launch_umma<64, 4, true, true>(ma, mb, p, st);
-    case 4: return launch_umma<128, 4, false, false>(ma, mb, p, st);
-    case 5: return launch_umma<128, 4, false, true>(ma, mb, p, st);
-    case 6: return launch_umma<128, 4, true, false>(ma, mb, p, st);
-    default: return launch_umma<128, 4, true, true>(ma, mb, p, st);
+    case 4: return launch_umma<128, 3, false, false>(ma, mb, p, st);
+    case 5: return launch_umma<128, 3, false, true>(ma, mb, p, st);
+    case 6: return launch_umma<128, 3, true, false>(ma, mb, p, st);
+    default: return launch_umma<128, 3, true, true>(ma, mb, p, st);
   }
 }
 

@@ -162,6 +162,8 @@ class TransformerEngine:
         self._ws = {}
         self._sites = {}
         self.training = True
+        self.use_graphs = False           # CUDA-graph replay of forward+backward per (B, T, L1) shape
+        self._graphs = {}
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, sd):
@@ -367,7 +369,8 @@ class TransformerEngine:
         be.zero_(self.stats)
         argmax = buf("argmax", (Md,), torch.int64)
         dlogits = buf("dlogits", (Md, C), f32) if want_grad else None
-        be.ls_ce(logits, db["ys_out"].view(-1), self.eps_ls, 1.0 / max(db["n_total"], 1), self.stats, argmax, dlogits)
+        be.ls_ce(logits, db["ys_out"].view(-1), self.eps_ls, 1.0 / max(db["n_total"], 1), self.stats, argmax, dlogits,
+                 db.get("inv_n_dev"))
         return ws
 
     # ------------------------------------------------------------------ backward
@@ -518,11 +521,58 @@ class TransformerEngine:
     # ------------------------------------------------------------------ public step
     def forward_backward(self, db):
         """One run_batch(train=True) worth of device work.  Returns the workspace; the loss
-        statistics stay on the device in self.stats = [sum of row losses, n_correct, n_non_pad]."""
-        self.step_seed += 1
+        statistics stay on the device in self.stats = [sum of row losses, n_correct, n_non_pad].
+        With use_graphs the whole kernel schedule of a (B, T, L1) shape is captured once into a CUDA
+        graph and replayed: inputs are copied into static buffers, the dropout seed offset and 1/n live
+        in device memory, so a replay is one launch instead of ~270."""
+        if self.use_graphs and self.device.type == "cuda":
+            return self._forward_backward_graphed(db)
+        return self._forward_backward_eager(db)
+
+    def _forward_backward_eager(self, db):
+        self.weights_dirty = True             # training: the master weights may have moved since the last batch
+        if hasattr(self.be, "seed_bump"):
+            self.be.seed_bump(1)              # fresh dropout masks: device-resident seed offset += 1
+        else:
+            self.step_seed += 1
         ws = self.forward(db, want_grad=True)
         self.backward(db, ws)
         return ws
+
+    def _forward_backward_graphed(self, db):
+        B, T, L1 = db["B"], db["T"], db["L1"]
+        key = (B, T, L1, self.training)
+        ent = self._graphs.get(key)
+        if ent is None:
+            dev = self.device
+            sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev),
+                   "enc_lens": torch.empty(B, dtype=torch.int64, device=dev),
+                   "ys_in": torch.empty(B, L1, dtype=torch.int64, device=dev),
+                   "ys_out": torch.empty(B, L1, dtype=torch.int64, device=dev),
+                   "inv_n_dev": torch.empty(1, dtype=torch.float32, device=dev),
+                   "n_total": 1, "B": B, "T": T, "L1": L1}
+            self._load_static(sdb, db)
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):         # allocate workspaces / set kernel attributes eagerly first
+                self._forward_backward_eager(sdb)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ws = self._forward_backward_eager(sdb)
+            ent = (g, sdb, ws)
+            self._graphs[key] = ent
+        g, sdb, ws = ent
+        self._load_static(sdb, db)
+        g.replay()
+        return ws
+
+    def _load_static(self, sdb, db):
+        for k in ("x", "enc_lens", "ys_in", "ys_out"):
+            sdb[k].copy_(db[k], non_blocking=True)
+        sdb["inv_n_dev"].fill_(1.0 / max(db["n_total"], 1))
 
     def read_stats(self):
         """The single device->host read of a step: {'loss', 'acc'} like run_batch's info dict."""

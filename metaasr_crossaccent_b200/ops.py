@@ -11,6 +11,7 @@ from . import _lib
 
 F32, BF16 = 0, 1
 GEMM_RELU, GEMM_ACCUM, GEMM_SPLITK = 1, 2, 4
+_SEED_TENSORS = {}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -44,6 +45,12 @@ class CudaBackend:
         self.prof_ops = None           # dict -> per-entry-point CUDA events (bench.py --profile)
         self.prof_tag = ""
         self._scratch = {}
+        # one device-resident dropout seed offset per device, alive for the whole process (the library
+        # keeps its address; kernels add it to every dropout seed so CUDA-graph replays get fresh masks)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in _SEED_TENSORS:
+            _SEED_TENSORS[key] = torch.zeros(1, dtype=torch.int64, device=device)
+        self.set_seed_ptr(_SEED_TENSORS[key])
 
     # -------------------------------------------------------------- plumbing
     @property
@@ -306,10 +313,20 @@ class CudaBackend:
         rows = src.shape[0]
         self._call("masr_permute_cf", _p(src), _dt(src), _p(dst), _dt(dst), rows, Cc, Fq, int(inverse_add), self.stream)
 
-    def ls_ce(self, logits, gold, eps, inv_n, stats, argmax, dlogits):
+    def ls_ce(self, logits, gold, eps, inv_n, stats, argmax, dlogits, inv_n_dev=None):
         N, Cc = logits.shape
-        self._call("masr_ls_ce_fwd_bwd", _p(logits), _p(gold), N, Cc, float(eps), float(inv_n), _p(stats), _p(argmax),
-                   _p(dlogits), self.stream)
+        self._call("masr_ls_ce_fwd_bwd", _p(logits), _p(gold), N, Cc, float(eps), float(inv_n), _p(inv_n_dev), _p(stats),
+                   _p(argmax), _p(dlogits), self.stream)
+
+    def set_seed_ptr(self, t):
+        """Device-resident dropout seed offset (uint64 stored in an int64 tensor); see masr_set_seed_ptr."""
+        self._seed_t = t
+        rc = self.lib.masr_set_seed_ptr(_p(t))
+        if rc != 0:
+            _lib.check(rc, "masr_set_seed_ptr")
+
+    def seed_bump(self, inc=1):
+        self._call("masr_seed_bump", _p(self._seed_t), int(inc), self.stream)
 
     def zero_(self, t):
         """Device memset through the CUDA runtime (stream-ordered); counts as plumbing, not a kernel of ours."""

@@ -41,6 +41,7 @@ def get_trainer(cls, config, paras, id2accent):
             self.asr_model = B200Transformer(self.id2ch, self.config['asr_model'], backend, backend.device,
                                              self.label_smooth_rate, getattr(self.paras, 'seed', 531))
             am = self.config['asr_model']
+            self.asr_model.engine.use_graphs = bool(am.get('cuda_graphs', False))   # optional knob, default off
             if 'inner_optimizer_cls' not in am:                      # multi or mono
                 if am['optimizer_cls'] == 'noam':
                     self.asr_opt = FlatNoamAdam(self.asr_model.engine, am['optimizer_opt']['k'], am['d_model'],
@@ -69,7 +70,8 @@ def get_trainer(cls, config, paras, id2accent):
                 hb = db = x
             else:
                 hb = eng.prepare_batch(x, ilens, ys, olens)
-                db = eng.to_device(hb)
+                # graph replay copies the host batch straight into its static device buffers
+                db = hb if (train and eng.use_graphs) else eng.to_device(hb)
             if train:
                 eng.weights_dirty = True
                 ws = eng.forward_backward(db)

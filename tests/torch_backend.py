@@ -179,7 +179,9 @@ class TorchBackend:
         else:
             dst += src.view(rows, Fq, Cc).transpose(1, 2).reshape(rows, -1)
 
-    def ls_ce(self, logits, gold, eps, inv_n, stats, argmax, dlogits):
+    def ls_ce(self, logits, gold, eps, inv_n, stats, argmax, dlogits, inv_n_dev=None):
+        if inv_n_dev is not None:
+            inv_n = float(inv_n_dev[0])
         N, Cc = logits.shape
         keep = gold >= 0
         lz = logits.detach().clone().requires_grad_(True)
