@@ -13,6 +13,7 @@
 //          pixel tiles across CTAs, 3 taps (one kernel row) accumulate side by side in TMEM, fp32 atomics out
 #include "common.cuh"
 #include "umma.cuh"
+#include "epilogue.cuh"
 
 namespace masr {
 
@@ -70,6 +71,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_full_bar + 2);
+  static_assert(STAGES * STAGE_BYTES >= EpiLayout<BN, __nv_bfloat16>::BYTES, "staging tile must fit in the pipeline stages");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
@@ -139,52 +142,22 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    const bool use_bias = (MODE == 0) && p.bias != nullptr;
+    if (use_bias) {
+      for (int i = et; i < BN; i += 128) sbias[i] = p.bias[i];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int r = q * 32 + lane;
     const int h = h0 + r / p.tw, w = w0 + r % p.tw;
     const bool valid = (r < rows) && (h < p.H) && (w < p.W);
     const int64_t pix = (int64_t(b) * p.H + h) * p.W + w;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
-      tmem_ld_wait();
-      if (valid) {
-        __nv_bfloat16* orow = p.out + pix * p.Cn + c0;
-        if (MODE == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = v[j] + (p.bias != nullptr ? p.bias[c0 + j] : 0.f);
-            v[j] = p.relu ? fmaxf(t, 0.f) : t;
-          }
-        } else if (p.relu_src != nullptr) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.relu_src + pix * p.Cn + c0);
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 u = src[j / 8];
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h2[e]);
-              if (!(f.x > 0.f)) v[j + 2 * e] = 0.f;
-              if (!(f.y > 0.f)) v[j + 2 * e + 1] = 0.f;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 pk;
-          __nv_bfloat162 a0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-          __nv_bfloat162 a1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-          __nv_bfloat162 a2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-          __nv_bfloat162 a3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-          pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
-          pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
-          reinterpret_cast<uint4*>(orow)[j / 8] = pk;
-        }
-      }
-    }
+    __nv_bfloat16* orow = valid ? p.out + pix * p.Cn : nullptr;
+    const __nv_bfloat16* mrow = (valid && MODE == 1 && p.relu_src != nullptr) ? p.relu_src + pix * p.Cn : nullptr;
+    epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, orow, mrow, BN, true,
+                                     EPI_STORE, MODE == 0 && p.relu != 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -291,17 +264,10 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
         const int tap = (dh + 1) * 3 + j;
-#pragma unroll 1
-        for (int c0 = 0; c0 < CI; c0 += 32) {
-          float v[32];
-          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(j * CI + c0), v);
-          tmem_ld_wait();
-          if (co < p.Cout) {
-            float* dst = p.dwp + int64_t(co) * (9 * p.Cin) + tap * p.Cin + c0;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) atomicAdd(dst + e, v[e]);
-          }
-        }
+        // staged through shared memory: coalesced fp32 atomics (consecutive lanes -> consecutive addresses)
+        float* dst = (co < p.Cout) ? p.dwp + int64_t(co) * (9 * p.Cin) + tap * p.Cin : nullptr;
+        epilogue_tile<CI, float>(tmem_base + uint32_t(j * CI), q, lane, smem, nullptr, dst, nullptr, CI, true,
+                                 EPI_ATOMIC, false);
       }
     }
   }
@@ -339,11 +305,11 @@ extern "C" int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float*
   cudaStream_t st = as_stream(stream);
   constexpr int ST = 4;
   if (Cout == 64) {
-    const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256;
+    const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256 + 64 * 4;
     rc = set_smem(umma_conv_kernel<64, ST, 0>, smem); if (rc) return rc;
     umma_conv_kernel<64, ST, 0><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
   } else {
-    const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256;
+    const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256 + 128 * 4;
     rc = set_smem(umma_conv_kernel<128, ST, 0>, smem); if (rc) return rc;
     umma_conv_kernel<128, ST, 0><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
   }
@@ -371,11 +337,11 @@ extern "C" int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx,
   cudaStream_t st = as_stream(stream);
   constexpr int ST = 4;
   if (Cin == 64) {
-    const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256;
+    const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256 + 64 * 4;
     rc = set_smem(umma_conv_kernel<64, ST, 1>, smem); if (rc) return rc;
     umma_conv_kernel<64, ST, 1><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
   } else {
-    const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256;
+    const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256 + 128 * 4;
     rc = set_smem(umma_conv_kernel<128, ST, 1>, smem); if (rc) return rc;
     umma_conv_kernel<128, ST, 1><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
   }

@@ -12,6 +12,7 @@
 // descriptor (LBO/SBO) and two bits of the instruction descriptor, the data are never transposed in memory.
 #include "common.cuh"
 #include "umma.cuh"
+#include "epilogue.cuh"
 
 namespace masr {
 
@@ -80,6 +81,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_full_bar + 2);          // BN floats, 16 B aligned
+  static_assert(STAGES * STAGE_BYTES >= EpiLayout<BN, float>::BYTES, "staging tile must fit in the pipeline stages");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
@@ -150,70 +153,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mma_commit(tmem_full_bar);             // accumulator complete
     }
   } else {
-    // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+    // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4; staged through shared memory (epilogue.cuh) =====
     const int q = warp & 3;
+    const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
+    const bool relu = p.flags & MASR_GEMM_RELU, accum = p.flags & MASR_GEMM_ACCUM, splitk = p.flags & MASR_GEMM_SPLITK;
+    const bool use_bias = p.bias != nullptr && (!splitk || blockIdx.z == 0);
+    if (use_bias) {
+      for (int i = et; i < BN; i += 128) sbias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // bias tile visible to the 4 epilogue warps
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int m = m0 + q * 32 + lane;
-    const bool relu = p.flags & MASR_GEMM_RELU, accum = p.flags & MASR_GEMM_ACCUM, splitk = p.flags & MASR_GEMM_SPLITK;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
-      tmem_ld_wait();
-      if (m < p.M) {
-        const int nbase = n0 + c0;
-        if (p.c_is_f32) {
-          float* crow = static_cast<float*>(p.C) + int64_t(m) * p.ldc;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            if (n < p.N) {
-              float x = v[j];
-              if (p.bias != nullptr && (!splitk || blockIdx.z == 0)) x += p.bias[n];
-              if (splitk) { atomicAdd(crow + n, x); continue; }
-              if (accum) x += crow[n];
-              if (relu) x = fmaxf(x, 0.f);
-              crow[n] = x;
-            }
-          }
-        } else {
-          __nv_bfloat16* crow = static_cast<__nv_bfloat16*>(p.C) + int64_t(m) * p.ldc;
-          const bool vec_ok = (nbase + 32 <= p.N) && ((p.ldc & 7) == 0) && ((nbase & 7) == 0) &&
-                              ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            float t = v[j];
-            if (n < p.N) {
-              if (p.bias != nullptr) t += p.bias[n];
-              if (accum) t += __bfloat162float(crow[n]);
-              if (relu) t = fmaxf(t, 0.f);
-            }
-            x[j] = t;
-          }
-          if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(x[j], x[j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(x[j + 2], x[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j + 4], x[j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(x[j + 6], x[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(crow + nbase + j) = pk;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = nbase + j;
-              if (n < p.N) crow[n] = __float2bfloat16_rn(x[j]);
-            }
-          }
-        }
-      }
+    const int ncols = min(BN, p.N - n0);
+    const int mode = splitk ? EPI_ATOMIC : (accum ? EPI_ACCUM : EPI_STORE);
+    if (p.c_is_f32) {
+      float* row = (m < p.M) ? static_cast<float*>(p.C) + int64_t(m) * p.ldc + n0 : nullptr;
+      const bool vec_ok = ncols == BN && (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) + size_t(n0) * 4) & 15) == 0;
+      epilogue_tile<BN, float>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, row, nullptr, ncols, vec_ok, mode, relu);
+    } else {
+      __nv_bfloat16* row = (m < p.M) ? static_cast<__nv_bfloat16*>(p.C) + int64_t(m) * p.ldc + n0 : nullptr;
+      const bool vec_ok = ncols == BN && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) + size_t(n0) * 2) & 15) == 0;
+      epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, row, nullptr, ncols, vec_ok, mode, relu);
     }
   }
   tc_fence_before();
@@ -223,7 +184,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaGemmParams& p, cudaStream_t st) {
-  constexpr size_t smem = size_t(STAGES) * (UG_BM * UG_BK * 2 + BN * UG_BK * 2) + 1024 + 256;
+  constexpr size_t smem = size_t(STAGES) * (UG_BM * UG_BK * 2 + BN * UG_BK * 2) + 1024 + 256 + BN * 4;
   auto kern = umma_gemm_kernel<BN, STAGES, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
