@@ -125,6 +125,8 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int r = qd * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
+    // soft-max statistics are kept in the log2 domain: exp(x) = exp2(x * log2 e) is a single MUFU.EX2
+    const float sl2 = p.scale * 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f;
     float o[64];
 #pragma unroll
@@ -144,12 +146,12 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int j = 0; j < 32; ++j) {
           const int kj = k0 + c * 32 + j;
           const bool ok = (kj < kmax) && (!p.causal || kj <= qi);
-          if (ok) mx = fmaxf(mx, v[j] * p.scale);
+          if (ok) mx = fmaxf(mx, v[j] * sl2);
         }
       }
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = expf(m_run - m_use);           // exp(-inf) = 0 on the first tile
+      const float corr = exp2f(m_run - m_use);          // 2^(-inf) = 0 on the first tile
       float lsum = 0.f;
       // pass 2: probabilities -> shared memory (bf16, K-major swizzled), row sum
 #pragma unroll 1
@@ -161,7 +163,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int j = 0; j < 32; ++j) {
           const int kj = k0 + c * 32 + j;
           const bool ok = (kj < kmax) && (!p.causal || kj <= qi);
-          float pr = ok ? expf(v[j] * p.scale - m_use) : 0.f;
+          float pr = ok ? exp2f(v[j] * sl2 - m_use) : 0.f;
           lsum += pr;
           if (p.p_drop > 0.f && ok)
             pr *= drop_scale(p.p_drop, p.inv_keep, seed_eff, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
@@ -203,7 +205,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int e = 0; e < 8; ++e) t8[e] = o[j + e] * inv_l;
         store8<__nv_bfloat16>(orow + j, t8);
       }
-      p.lse[int64_t(bh) * p.Lq + qi] = l_run > 0.f ? m_run + logf(l_run) : -INFINITY;
+      p.lse[int64_t(bh) * p.Lq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
     }
   }
   tc_fence_before();
@@ -347,11 +349,12 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
     for (int t = 0; t < ntiles; ++t) {
       const int q0 = (qt_begin + t) * AU_TILE;
       const int qi = q0 + r;
       const bool qok = qi < p.Lq;
-      const float lse_r = qok ? p.lse[int64_t(bh) * p.Lq + qi] : 0.f;
+      const float lse_r = qok ? p.lse[int64_t(bh) * p.Lq + qi] * 1.4426950408889634f : 0.f;    // log2 domain
       const float d_r = qok ? p.dsum[int64_t(bh) * p.Lq + qi] : 0.f;
       mbar_wait(sdp_full, t & 1);
       tc_fence_after();
@@ -367,7 +370,7 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const bool ok = qok && (kj < klen) && (!p.causal || kj <= qi);
           float pr = 0.f, ds = 0.f;
           if (ok) {
-            pr = expf(sv[j] * p.scale - lse_r);
+            pr = exp2f(sv[j] * sl2 - lse_r);
             const float dm = drop_scale(p.p_drop, p.inv_keep, seed_eff, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
             ds = pr * (dp[j] * dm - d_r) * p.scale;
             pr *= dm;

@@ -52,13 +52,18 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 
 // ------------------------------------------------------------------ counter-based dropout RNG
 // keep(seed, site, idx) is a pure function, so the backward pass regenerates the forward mask.
-// 64-bit mix (splitmix64 finaliser) of (seed, site, element index) -> 24-bit uniform.
+// 32-bit integer hash ("lowbias32" multiply-xorshift finaliser, ~8 ALU instructions) of the element index
+// under a per-(seed, site) key -> 24-bit uniform.  The key is loop invariant (seed and site are kernel
+// arguments), so the per-element cost is one finaliser: the soft-max warps of the attention kernels and the
+// elementwise dropout kernels are ALU-bound on this function.
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
 __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t site, uint64_t idx) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t(site) + 1) + idx * 0xD1B54A32D192ED03ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return uint32_t(z >> 40);   // 24 bits
+  const uint32_t key = lowbias32(uint32_t(seed) ^ lowbias32(uint32_t(seed >> 32) + site * 0x9E3779B9u + 0x85EBCA6Bu));
+  const uint32_t x = uint32_t(idx) ^ (uint32_t(idx >> 32) * 0xC2B2AE35u);
+  return lowbias32(x ^ key) >> 8;   // 24 bits
 }
 // Seed of a dropout site = base (by value) + a device-resident per-step offset.  The offset lives in device
 // memory so that a captured CUDA graph of the step replays with fresh masks (masr_seed_bump advances it).

@@ -47,6 +47,64 @@ __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// conv1 forward, register-weight variant: the block stride is a multiple of Cout/8, so a thread keeps the same
+// 8-channel group for every pixel it visits and holds its 72 weights + 8 biases in registers; index
+// arithmetic is 32-bit.  HBM-bound on the NHWC bf16 output (8 channels = one 128-bit store per thread).
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, T* __restrict__ y,
+                                                           int B, int H, int W, int Cout) {
+  const int groups = Cout / 8;
+  const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = int(gtid % unsigned(groups));
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = bias[cg * 8 + c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[c][t] = w[(cg * 8 + c) * 9 + t];
+  }
+  const unsigned P = unsigned(B) * H * W;
+  const unsigned pstride = (gridDim.x * blockDim.x) / unsigned(groups);
+  constexpr int U = 3;                                      // pixels in flight per thread (latency hiding)
+  for (unsigned p0 = gtid / unsigned(groups); p0 < P; p0 += pstride * U) {
+    float tap[U][9];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = p0 + unsigned(u) * pstride;
+      const bool pok = p < P;
+      const int wv = int(p % unsigned(W));
+      const unsigned row = p / unsigned(W);                // b * H + h
+      const int hv = int(row % unsigned(H));
+#pragma unroll
+      for (int dh = -1; dh <= 1; ++dh) {
+        const int hh = hv + dh;
+        const bool hok = pok && hh >= 0 && hh < H;
+        const float* xr = x + (int64_t(row) + dh) * W;
+#pragma unroll
+        for (int dw = -1; dw <= 1; ++dw) {
+          const int ww = wv + dw;
+          tap[u][(dh + 1) * 3 + (dw + 1)] = (hok && ww >= 0 && ww < W) ? __ldg(xr + ww) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = p0 + unsigned(u) * pstride;
+      if (p >= P) break;
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float acc = br[c];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc = fmaf(tap[u][t], wr[c][t], acc);
+        o[c] = fmaxf(acc, 0.f);
+      }
+      store8<T>(y + int64_t(p) * Cout + cg * 8, o);
+    }
+  }
+}
+
 // dw[co][tap] += sum_p dy[p][co] x[p+tap], db[co] += sum_p dy[p][co].  Block = Cout x PL threads;
 // thread (co, lane) walks pixels lane, lane+PL, ... of the block's slice, so reads of dy are
 // contiguous over co.  Partials are combined in shared memory, then one atomicAdd per output.
@@ -391,6 +449,13 @@ extern "C" int masr_conv1_fwd(const float* x, const float* w, const float* bias,
   const int64_t total = int64_t(B) * H * W * (Cout / 8);
   if (total == 0) return MASR_OK;
   const size_t smem = size_t(Cout) * 10 * sizeof(float);
+  if (int64_t(B) * H * W < (int64_t(1) << 31) && 256 % (Cout / 8) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    const int blocks = int(std::min<int64_t>(ceil_div64(total, 256), int64_t(sm_count()) * 8));
+    MASR_DISPATCH_DTYPE(y_dtype, T,
+        conv1_fwd_v2_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(x, w, bias, static_cast<T*>(y), B, H, W, Cout));
+    MASR_LAUNCH_CHECK();
+    return MASR_OK;
+  }
   MASR_DISPATCH_DTYPE(y_dtype, T,
       conv1_fwd_kernel<T><<<grid_for(total, 256), 256, smem, as_stream(stream)>>>(
           x, w, bias, static_cast<T*>(y), B, H, W, Cout));

@@ -126,12 +126,24 @@ def main():
         pb = torch.empty(n, device=dev, dtype=bf)
         timeit("cast f32->bf16 24.9M", lambda: be.cast(p, pb), args.reps, tab, None, n * 6)
     if want("ctc"):
-        from metaasr_crossaccent_b200.ctc import ctc_fwd_bwd
-        for (T, B, C, L) in [(128, 32, 367, 34), (128, 512, 367, 34), (128, 2048, 367, 34)]:
+        # raw C-ABI call with device-resident arguments (the Python wrapper's host work would dominate)
+        for (T, B, C, L) in [(128, 32, 367, 34), (128, 148, 367, 34), (128, 512, 367, 34), (128, 2048, 367, 34),
+                             (375, 512, 367, 102), (750, 256, 367, 152)]:
             lg = torch.randn(T, B, C, device=dev)
-            tg = torch.randint(1, C, (B * L,))
-            il, tl = torch.full((B,), T, dtype=torch.int64), torch.full((B,), L, dtype=torch.int64)
-            timeit(f"ctc_fwd_bwd T{T} B{B} C{C} L{L}", lambda: ctc_fwd_bwd(lg, tg, il, tl), args.reps, tab, None, T * B * C * 8)
+            tg = torch.randint(1, C, (B * L,), device=dev)
+            offs = torch.arange(B, device=dev, dtype=torch.int64) * L
+            il = torch.full((B,), T, dtype=torch.int64, device=dev)
+            tl = torch.full((B,), L, dtype=torch.int64, device=dev)
+            nll, loss, grad = torch.empty(B, device=dev), torch.empty(1, device=dev), torch.empty_like(lg)
+            wsb = be.lib.masr_ctc_workspace_bytes(T, B, C, L)
+            ws = torch.empty(wsb // 4 + 1, device=dev) if wsb else None
+
+            def run():
+                rc = be.lib.masr_ctc_fwd_bwd(lg.data_ptr(), T, B, C, 0, tg.data_ptr(), offs.data_ptr(), il.data_ptr(),
+                                             tl.data_ptr(), L, 0, 1, 1.0, nll.data_ptr(), loss.data_ptr(), grad.data_ptr(),
+                                             ws.data_ptr() if ws is not None else None, wsb, be.stream)
+                assert rc == 0
+            timeit(f"ctc_fwd_bwd T{T} B{B} C{C} L{L}", run, args.reps, tab, None, T * B * C * 8)
     print("\n".join(tab))
 
 
