@@ -60,6 +60,10 @@ int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_is_logprob,
                      int blank, int zero_infinity, float grad_scale,
                      float* nll, float* loss, float* grad,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Profiling hook: record SM-clock timestamps of CTA 0 at the phase boundaries of the following CTC launches
+ * (start, setup done, emissions done, recursions done, -, end) and read them back (out6: 6 x int64). */
+int masr_ctc_debug_enable(int on);
+int masr_ctc_debug_read(long long* out6);
 /* Bytes of global workspace masr_ctc_fwd_bwd needs for this shape (0: tables fit in shared memory). */
 size_t masr_ctc_workspace_bytes(int T, int B, int C, int max_tgt_len);
 

@@ -253,6 +253,89 @@ __device__ __forceinline__ float lse3_2(float a, float b, float c) {      // log
   return m + lg2f(ex2f(a - m) + ex2f(b - m) + ex2f(c - m));
 }
 constexpr float CTC_LOG2E = 1.4426950408889634f, CTC_LN2 = 0.6931471805599453f;
+constexpr int CTC_F = 4;        // frames per warp iteration in the streaming phases
+constexpr int CTC_CPL = 12;     // classes per lane held in registers (fast path: C <= 384)
+
+
+// One warp runs one recursion (FWD: alpha, t = 0..Tb-1; !FWD: beta, t = Tb-1..0).  Lane l owns the SPL
+// consecutive states l*SPL .. l*SPL+SPL-1 in registers.  "Impossible" is a large negative finite number
+// instead of -inf so the log-sum-exp needs no special cases (2^(x - m) underflows to exactly 0).
+constexpr float CTC_NEG = -1.0e30f;
+template <int SPL, bool FWD>
+__device__ __forceinline__ void ctc_chain(float* __restrict__ tab, const float* __restrict__ E2, const int* __restrict__ tg,
+                                          int lane, int L, int S, int Tb, int Sstride, int L1stride, int blank) {
+  float a[SPL], e[SPL];
+  bool skip[SPL], valid[SPL];
+  int ecol[SPL];
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    const int j = s >> 1;
+    const bool odd = s & 1;
+    valid[i] = s < S;
+    ecol[i] = (odd && j < L) ? j : L;
+    if (FWD) skip[i] = odd && s > 1 && s < S && tg[j] != blank && tg[j] != tg[j - 1];
+    else     skip[i] = odd && s + 2 < S && tg[j] != blank && tg[j] != tg[j + 1];
+  }
+  const int tstep = FWD ? 1 : -1;
+  int t = FWD ? 0 : Tb - 1;
+  const float* Et = E2 + size_t(t) * L1stride;
+  float* dst = tab + size_t(t) * Sstride + lane * SPL;
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    float v = CTC_NEG;
+    if (FWD) { if (s == 0) v = Et[L]; else if (s == 1 && S > 1) v = Et[0]; }
+    else     { if (s == S - 1) v = Et[L]; else if (s == S - 2) v = Et[L - 1]; }
+    a[i] = v;
+    if (valid[i]) dst[i] = v;
+  }
+  Et += tstep * L1stride;
+  if (Tb > 1) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) e[i] = Et[ecol[i]];
+  }
+  for (int step = 1; step < Tb; ++step) {
+    dst += tstep * Sstride;
+    Et += tstep * L1stride;
+    float en[SPL];
+    const bool more = step + 1 < Tb;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) en[i] = more ? Et[ecol[i]] : 0.f;      // prefetch the next frame's emissions
+    float n1, n2;                                                          // neighbours across the lane boundary
+    if (FWD) {
+      if (SPL >= 2) { n1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1); n2 = __shfl_up_sync(0xffffffffu, a[SPL >= 2 ? SPL - 2 : 0], 1); }
+      else          { n1 = __shfl_up_sync(0xffffffffu, a[0], 1); n2 = __shfl_up_sync(0xffffffffu, a[0], 2); if (lane < 2) n2 = CTC_NEG; }
+      if (lane == 0) { n1 = CTC_NEG; n2 = CTC_NEG; }
+    } else {
+      if (SPL >= 2) { n1 = __shfl_down_sync(0xffffffffu, a[0], 1); n2 = __shfl_down_sync(0xffffffffu, a[SPL >= 2 ? 1 : 0], 1); }
+      else          { n1 = __shfl_down_sync(0xffffffffu, a[0], 1); n2 = __shfl_down_sync(0xffffffffu, a[0], 2); if (lane > 29) n2 = CTC_NEG; }
+      if (lane == 31) { n1 = CTC_NEG; n2 = CTC_NEG; }
+    }
+    float nw[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      float x1, x2;
+      if (FWD) {
+        x1 = (i >= 1) ? a[i >= 1 ? i - 1 : 0] : n1;
+        x2 = (i >= 2) ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? n1 : n2);
+      } else {
+        x1 = (i + 1 < SPL) ? a[i + 1 < SPL ? i + 1 : 0] : n1;
+        x2 = (i + 2 < SPL) ? a[i + 2 < SPL ? i + 2 : 0] : (i + 1 < SPL ? n1 : n2);
+      }
+      x2 = skip[i] ? x2 : CTC_NEG;
+      const float m = fmaxf(a[i], fmaxf(x1, x2));
+      const float v = m + lg2f(ex2f(a[i] - m) + ex2f(x1 - m) + ex2f(x2 - m)) + e[i];
+      nw[i] = valid[i] ? fmaxf(v, CTC_NEG) : CTC_NEG;
+    }
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      a[i] = nw[i];
+      e[i] = en[i];
+      if (valid[i]) dst[i] = nw[i];
+    }
+  }
+}
 
 template <int SPL>
 __global__ void __launch_bounds__(CTC_THREADS)
@@ -261,19 +344,22 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
                       const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                       int Lmax, int blank, int zero_infinity, float grad_scale,
                       float* __restrict__ nll_out, float* __restrict__ loss_out, float* __restrict__ grad,
-                      float* __restrict__ ws, int tables_in_smem) {
+                      float* __restrict__ ws, int tables_in_smem, long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = CTC_THREADS / 32;
+  // optional phase timestamps of CTA 0 (masr_ctc_debug_enable): [start, setup, phase0, chains, ll, end]
+#define CTC_STAMP(i) do { if (dbg != nullptr && b == 0 && tid == 0) dbg[i] = clock64(); } while (0)
+  CTC_STAMP(0);
   const int Sstride = 2 * Lmax + 1, L1stride = Lmax + 1;
 
   float* logZ2 = reinterpret_cast<float*>(smem_raw);                 // [T]
   int* tg = reinterpret_cast<int*>(logZ2 + T);                       // [Lmax]
   int* slot = tg + Lmax;                                             // [Lmax+1]
   int* cmap = slot + (Lmax + 1);                                     // [C]
-  float* Gw = reinterpret_cast<float*>(cmap + C);                    // [NW][L1stride] per-warp class posteriors
-  float* red = Gw + NW * L1stride;                                   // [4]
+  float* Gw = reinterpret_cast<float*>(cmap + C);                    // [NW][CTC_F][L1stride] per-warp class posteriors
+  float* red = Gw + NW * CTC_F * L1stride;                                   // [4]
   float* tbl = red + 4;
   const size_t table_floats = size_t(T) * (2 * Sstride + L1stride);
   if (!tables_in_smem) tbl = ws + size_t(b) * size_t(T) * (2 * Sstride + 2 * L1stride);
@@ -303,121 +389,92 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
   }
   __syncthreads();
 
-  // ---- phase 0: log2-domain normaliser and emission table, frame-parallel
-  for (int t = warp; t < Tb; t += NW) {
-    const float* row = acts + (int64_t(t) * B + b) * C;
-    float z2 = 0.f;
-    if (!is_logprob) {
-      float mx = CTC_NEG_INF;
-      for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
-      mx = warp_max(mx);
-      float se = 0.f;
-      for (int c = lane; c < C; c += 32) se += ex2f((row[c] - mx) * CTC_LOG2E);
-      se = warp_sum(se);
-      z2 = mx * CTC_LOG2E + lg2f(se);
+  CTC_STAMP(1);
+  // ---- phase 0: log2-domain normaliser and emission table.  A warp handles CTC_F frames at a time and
+  // issues all their row loads (CTC_F x ceil(C/32) independent 128 B requests per warp) before reducing:
+  // the phase is bounded by memory-level parallelism, not by per-frame round trips.
+  const bool fast_c = C <= 32 * CTC_CPL;
+  if (fast_c) {
+    for (int t0 = warp * CTC_F; t0 < Tb; t0 += NW * CTC_F) {
+      float x[CTC_F][CTC_CPL];
+#pragma unroll
+      for (int f = 0; f < CTC_F; ++f) {
+        const float* row = acts + (int64_t(min(t0 + f, Tb - 1)) * B + b) * C;
+#pragma unroll
+        for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; x[f][k] = c < C ? __ldg(row + c) : CTC_NEG; }
+      }
+      float z2[CTC_F];
+#pragma unroll
+      for (int f = 0; f < CTC_F; ++f) {
+        z2[f] = 0.f;
+        if (!is_logprob) {
+          float mx = CTC_NEG;
+#pragma unroll
+          for (int k = 0; k < CTC_CPL; ++k) mx = fmaxf(mx, x[f][k]);
+          mx = warp_max(mx);
+          float se = 0.f;
+#pragma unroll
+          for (int k = 0; k < CTC_CPL; ++k) se += ex2f((x[f][k] - mx) * CTC_LOG2E);
+          se = warp_sum(se);
+          z2[f] = mx * CTC_LOG2E + lg2f(se);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < CTC_F; ++f) {
+        const int t = t0 + f;
+        if (t < Tb) {
+          const float* row = acts + (int64_t(t) * B + b) * C;
+          if (lane == 0) logZ2[t] = z2[f];
+          float* Et = E2 + size_t(t) * L1stride;
+          for (int j = lane; j <= L; j += 32) Et[j] = __ldg(row + (j < L ? tg[j] : blank)) * CTC_LOG2E - z2[f];
+        }
+      }
     }
-    if (lane == 0) logZ2[t] = z2;
-    float* Et = E2 + size_t(t) * L1stride;
-    for (int j = lane; j <= L; j += 32) Et[j] = row[j < L ? tg[j] : blank] * CTC_LOG2E - z2;
+  } else {
+    for (int t = warp; t < Tb; t += NW) {
+      const float* row = acts + (int64_t(t) * B + b) * C;
+      float z2 = 0.f;
+      if (!is_logprob) {
+        float mx = CTC_NEG_INF;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += ex2f((row[c] - mx) * CTC_LOG2E);
+        se = warp_sum(se);
+        z2 = mx * CTC_LOG2E + lg2f(se);
+      }
+      if (lane == 0) logZ2[t] = z2;
+      float* Et = E2 + size_t(t) * L1stride;
+      for (int j = lane; j <= L; j += 32) Et[j] = row[j < L ? tg[j] : blank] * CTC_LOG2E - z2;
+    }
   }
   __syncthreads();
 
+  CTC_STAMP(2);
   // ---- phase 1: alpha in warp 0, beta in warp 1 (registers + shuffles, no block barrier)
   if (Tb > 0 && warp < 2) {
-    const bool fwd = (warp == 0);
-    float a[SPL];
-    bool skip[SPL];
-    int ecol[SPL];
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) {
-      const int s = lane * SPL + i;
-      const int j = s >> 1;
-      const bool odd = s & 1;
-      ecol[i] = (odd && j < L) ? j : L;
-      if (fwd) skip[i] = odd && s > 1 && s < S && tg[j] != blank && tg[j] != tg[j - 1];
-      else     skip[i] = odd && s + 2 < S && tg[j] != blank && tg[j] != tg[j + 1];
-    }
-    const int t0 = fwd ? 0 : Tb - 1;
-    {
-      const float* Et = E2 + size_t(t0) * L1stride;
-      float* dst = (fwd ? A : Bt) + size_t(t0) * Sstride;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        const int s = lane * SPL + i;
-        float v = CTC_NEG_INF;
-        if (fwd) { if (s == 0) v = Et[L]; else if (s == 1 && S > 1) v = Et[0]; }
-        else     { if (s == S - 1) v = Et[L]; else if (s == S - 2) v = Et[L - 1]; }
-        a[i] = v;
-        if (s < S) dst[s] = v;
-      }
-    }
-    float e[SPL];
-    if (Tb > 1) {
-      const float* En = E2 + size_t(fwd ? 1 : Tb - 2) * L1stride;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) e[i] = En[ecol[i]];
-    }
-    for (int step = 1; step < Tb; ++step) {
-      const int t = fwd ? step : Tb - 1 - step;
-      float en[SPL];
-      if (step + 1 < Tb) {                      // prefetch the next frame's emissions
-        const float* En = E2 + size_t(fwd ? t + 1 : t - 1) * L1stride;
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) en[i] = En[ecol[i]];
-      }
-      float n1, n2;                             // neighbours across the lane boundary
-      if (fwd) {
-        if (SPL >= 2) { n1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1); n2 = __shfl_up_sync(0xffffffffu, a[SPL >= 2 ? SPL - 2 : 0], 1); }
-        else          { n1 = __shfl_up_sync(0xffffffffu, a[0], 1); n2 = __shfl_up_sync(0xffffffffu, a[0], 2); if (lane < 2) n2 = CTC_NEG_INF; }
-        if (lane == 0) { n1 = CTC_NEG_INF; n2 = CTC_NEG_INF; }
-      } else {
-        if (SPL >= 2) { n1 = __shfl_down_sync(0xffffffffu, a[0], 1); n2 = __shfl_down_sync(0xffffffffu, a[SPL >= 2 ? 1 : 0], 1); }
-        else          { n1 = __shfl_down_sync(0xffffffffu, a[0], 1); n2 = __shfl_down_sync(0xffffffffu, a[0], 2); if (lane > 29) n2 = CTC_NEG_INF; }
-        if (lane == 31) { n1 = CTC_NEG_INF; n2 = CTC_NEG_INF; }
-      }
-      float nw[SPL];
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        float x1, x2;
-        if (fwd) {
-          x1 = (i >= 1) ? a[i >= 1 ? i - 1 : 0] : n1;
-          x2 = (i >= 2) ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? n1 : n2);
-        } else {
-          x1 = (i + 1 < SPL) ? a[i + 1 < SPL ? i + 1 : 0] : n1;
-          x2 = (i + 2 < SPL) ? a[i + 2 < SPL ? i + 2 : 0] : (i + 1 < SPL ? n1 : n2);
-        }
-        if (!skip[i]) x2 = CTC_NEG_INF;
-        const int s = lane * SPL + i;
-        nw[i] = (s < S) ? lse3_2(a[i], x1, x2) + e[i] : CTC_NEG_INF;
-      }
-      float* dst = (fwd ? A : Bt) + size_t(t) * Sstride;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        a[i] = nw[i];
-        e[i] = en[i];
-        const int s = lane * SPL + i;
-        if (s < S) dst[s] = nw[i];
-      }
-    }
+    if (warp == 0) ctc_chain<SPL, true>(A, E2, tg, lane, L, S, Tb, Sstride, L1stride, blank);
+    else           ctc_chain<SPL, false>(Bt, E2, tg, lane, L, S, Tb, Sstride, L1stride, blank);
   }
   __syncthreads();
   if (!tables_in_smem) __threadfence_block();
+  CTC_STAMP(3);
 
   if (tid == 0) {
     float ll2;
     if (Tb > 0) {
       const float* last = A + size_t(Tb - 1) * Sstride;
-      ll2 = lse3_2(last[S - 1], S > 1 ? last[S - 2] : CTC_NEG_INF, CTC_NEG_INF);
+      ll2 = lse3_2(last[S - 1], S > 1 ? last[S - 2] : CTC_NEG, CTC_NEG);
     } else {
-      ll2 = (S == 1) ? 0.f : CTC_NEG_INF;
+      ll2 = (S == 1) ? 0.f : CTC_NEG;
     }
     red[0] = ll2;
   }
   __syncthreads();
   const float ll2 = red[0];
-  const bool feasible = (ll2 != CTC_NEG_INF);
+  const bool feasible = (ll2 > 0.5f * CTC_NEG);
   if (tid == 0) {
-    float nll = -ll2 * CTC_LN2;
+    float nll = feasible ? -ll2 * CTC_LN2 : INFINITY;
     if (!feasible && zero_infinity) nll = 0.f;
     nll_out[b] = nll;
     if (loss_out != nullptr) atomicAdd(loss_out, nll / float(max(L, 1)) / float(B));
@@ -425,46 +482,111 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
   if (grad == nullptr) return;
   const float scale = grad_scale / (float(B) * float(max(L, 1)));
 
-  // ---- phase 3: posteriors + gradient rows, frame-parallel
-  float* G = Gw + warp * L1stride;
-  for (int t = warp; t < T; t += NW) {
-    float* grow = grad + (int64_t(t) * B + b) * C;
-    if (t >= Tb || !feasible) {
-      const float fill = (!feasible && !zero_infinity && t < Tb) ? NAN : 0.f;
-      for (int c = lane; c < C; c += 32) grow[c] = fill;
-      continue;
+  // ---- phase 3: posteriors + gradient rows.  Again CTC_F frames per warp iteration: the activation rows are
+  // requested first, the class posteriors of the frames are formed while those loads are in flight
+  // (shuffle sum for the blank, shared-memory atomics only where a label repeats), then each gradient row
+  // is written once, coalesced.
+  float* Gbase = Gw + warp * CTC_F * L1stride;
+  int ucls[CTC_CPL];
+#pragma unroll
+  for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; ucls[k] = (fast_c && c < C) ? cmap[c] : -1; }
+  int pcol[SPL], pslot[SPL];          // per strided state: emission column, posterior slot (-1 = blank: shuffle sum)
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s2 = lane + 32 * i;
+    const bool odd = s2 & 1;
+    pcol[i] = (odd && s2 < S) ? (s2 >> 1) : L;
+    pslot[i] = (odd && s2 < S) ? slot[s2 >> 1] : -1;
+    if (pslot[i] == L) pslot[i] = -1;  // a label equal to the blank class joins the blank sum
+  }
+  for (int t0 = warp * CTC_F; t0 < T; t0 += NW * CTC_F) {
+    float x[CTC_F][CTC_CPL];
+    if (fast_c) {
+#pragma unroll
+      for (int f = 0; f < CTC_F; ++f) {
+        const int t = t0 + f;
+        const bool live = feasible && t < Tb;
+        const float* row = acts + (int64_t(live ? t : 0) * B + b) * C;
+#pragma unroll
+        for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; x[f][k] = (live && c < C) ? __ldg(row + c) : 0.f; }
+      }
     }
-    for (int j = lane; j <= L; j += 32) G[j] = 0.f;
+    // class posteriors of the CTC_F frames: states in the outer loop (strided over lanes), frames unrolled
+    // inside -> CTC_F independent load/exp chains per state (ILP) instead of one frame at a time
+    for (int j = lane; j < CTC_F * L1stride; j += 32) Gbase[j] = 0.f;
     __syncwarp();
-    const float* At = A + size_t(t) * Sstride;
-    const float* Btt = Bt + size_t(t) * Sstride;
-    const float* Et = E2 + size_t(t) * L1stride;
-    float blank_sum = 0.f;
-    for (int s = lane; s < S; s += 32) {
-      const int j = (s & 1) ? (s >> 1) : L;
-      const float ab = At[s] + Btt[s];
-      const float g = (ab == CTC_NEG_INF) ? 0.f : ex2f(ab - Et[j] - ll2);
-      if (s & 1) { if (g != 0.f) atomicAdd(&G[slot[j]], g); }
-      else blank_sum += g;
+    float blank_sum[CTC_F];
+#pragma unroll
+    for (int f = 0; f < CTC_F; ++f) blank_sum[f] = 0.f;
+    if (feasible && Tb > 0) {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        const int s2 = lane + 32 * i;
+        if (s2 < S) {
+#pragma unroll
+          for (int f = 0; f < CTC_F; ++f) {
+            const int t = min(t0 + f, Tb - 1);
+            const float g = ex2f(A[size_t(t) * Sstride + s2] + Bt[size_t(t) * Sstride + s2] - E2[size_t(t) * L1stride + pcol[i]] - ll2);
+            if (t0 + f < Tb) {
+              if (pslot[i] >= 0) { if (g != 0.f) atomicAdd(&Gbase[f * L1stride + pslot[i]], g); }
+              else blank_sum[f] += g;
+            }
+          }
+        }
+      }
     }
-    blank_sum = warp_sum(blank_sum);
+#pragma unroll
+    for (int f = 0; f < CTC_F; ++f) blank_sum[f] = warp_sum(blank_sum[f]);
     __syncwarp();
-    if (lane == 0) G[L] += blank_sum;
+    if (lane < CTC_F) {
+      float bs = blank_sum[0];
+#pragma unroll
+      for (int f = 1; f < CTC_F; ++f) if (lane == f) bs = blank_sum[f];
+      Gbase[lane * L1stride + L] += bs;
+    }
     __syncwarp();
-    const float* row = acts + (int64_t(t) * B + b) * C;
-    const float z2 = logZ2[t];
-    for (int c = lane; c < C; c += 32) {
-      const float pr = ex2f(row[c] * CTC_LOG2E - z2);
-      const int u = cmap[c];
-      grow[c] = (pr - (u >= 0 ? G[u] : 0.f)) * scale;
+#pragma unroll
+    for (int f = 0; f < CTC_F; ++f) {
+      const int t = t0 + f;
+      if (t >= T) continue;
+      float* grow = grad + (int64_t(t) * B + b) * C;
+      if (t >= Tb || !feasible) {
+        const float fill = (!feasible && !zero_infinity && t < Tb) ? NAN : 0.f;
+        for (int c = lane; c < C; c += 32) grow[c] = fill;
+        continue;
+      }
+      const float* G = Gbase + f * L1stride;
+      const float z2 = logZ2[t];
+      if (fast_c) {
+#pragma unroll
+        for (int k = 0; k < CTC_CPL; ++k) {
+          const int c = lane + 32 * k;
+          if (c < C) {
+            const float pr = ex2f(x[f][k] * CTC_LOG2E - z2);
+            grow[c] = (pr - (ucls[k] >= 0 ? G[ucls[k]] : 0.f)) * scale;
+          }
+        }
+      } else {
+        const float* row = acts + (int64_t(t) * B + b) * C;
+        for (int c = lane; c < C; c += 32) {
+          const float pr = ex2f(row[c] * CTC_LOG2E - z2);
+          const int u = cmap[c];
+          grow[c] = (pr - (u >= 0 ? G[u] : 0.f)) * scale;
+        }
+      }
     }
     __syncwarp();
   }
+  __syncthreads();
+  CTC_STAMP(5);
+#undef CTC_STAMP
 }
+
+static long long* g_ctc_dbg = nullptr;
 
 static size_t ctc2_small_bytes(int T, int Lmax, int C) {
   return sizeof(float) * size_t(T) + sizeof(int) * (size_t(Lmax) + (Lmax + 1) + C) +
-         sizeof(float) * (size_t(CTC_THREADS / 32) * (Lmax + 1) + 4);
+         sizeof(float) * (size_t(CTC_THREADS / 32) * CTC_F * (Lmax + 1) + 4);
 }
 static size_t ctc2_table_bytes(int T, int Lmax) {
   return sizeof(float) * size_t(T) * (2 * (2 * size_t(Lmax) + 1) + (size_t(Lmax) + 1));
@@ -478,7 +600,7 @@ static int launch_ctc2(const float* acts, int T, int B, int C, int is_logprob, c
   MASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_fwd_bwd_v2_kernel<SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   ctc_fwd_bwd_v2_kernel<SPL><<<B, CTC_THREADS, smem, st>>>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens,
                                                            Lmax, blank, zero_infinity, grad_scale, nll, loss, grad, ws,
-                                                           in_smem ? 1 : 0);
+                                                           in_smem ? 1 : 0, g_ctc_dbg);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -549,5 +671,18 @@ extern "C" int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_
                                                    tgt_lens, max_tgt_len, blank, zero_infinity, grad_scale,
                                                    nll, loss, grad, static_cast<float*>(workspace), in_smem ? 1 : 0);
   MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+// Profiling hook: phase timestamps (SM clock) of CTA 0 of the next CTC launches; out[6] on the host.
+extern "C" int masr_ctc_debug_enable(int on) {
+  if (on && g_ctc_dbg == nullptr) { MASR_CHECK_CUDA(cudaMalloc(&g_ctc_dbg, 8 * sizeof(long long))); }
+  if (!on && g_ctc_dbg != nullptr) { cudaFree(g_ctc_dbg); g_ctc_dbg = nullptr; }
+  return MASR_OK;
+}
+extern "C" int masr_ctc_debug_read(long long* out6) {
+  MASR_REQUIRE(g_ctc_dbg != nullptr, "ctc debug not enabled");
+  MASR_CHECK_CUDA(cudaDeviceSynchronize());
+  MASR_CHECK_CUDA(cudaMemcpy(out6, g_ctc_dbg, 6 * sizeof(long long), cudaMemcpyDeviceToHost));
   return MASR_OK;
 }

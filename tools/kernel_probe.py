@@ -144,6 +144,14 @@ def main():
                                              ws.data_ptr() if ws is not None else None, wsb, be.stream)
                 assert rc == 0
             timeit(f"ctc_fwd_bwd T{T} B{B} C{C} L{L}", run, args.reps, tab, None, T * B * C * 8)
+            import ctypes
+            be.lib.masr_ctc_debug_enable(1)
+            run()
+            buf = (ctypes.c_longlong * 6)()
+            be.lib.masr_ctc_debug_read(buf)
+            be.lib.masr_ctc_debug_enable(0)
+            st = list(buf)
+            tab.append(f"    CTA0 cycles: setup {st[1]-st[0]}, emissions {st[2]-st[1]}, recursions {st[3]-st[2]}, posteriors+grad {st[5]-st[3]}")
     print("\n".join(tab))
 
 
