@@ -1,5 +1,6 @@
 // Library-level entry points of the C ABI: version, error reporting, device initialisation.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace masr {
 
@@ -16,6 +17,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 int sm_count() { return g_sm_count; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MASR_PDL"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 
 const uint64_t* g_seed_dev_ptr = nullptr;
 

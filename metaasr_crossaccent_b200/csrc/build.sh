@@ -10,7 +10,9 @@ mkdir -p "$HERE/build"
 pids=()
 for f in "$HERE"/*.cu; do
   o="$HERE/build/$(basename "${f%.cu}").o"
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$HERE/../../include/metaasr_b200.h" -nt "$o" ]]; then
+  stale=0
+  for h in "$HERE"/*.cuh "$HERE/../../include/metaasr_b200.h"; do [[ "$h" -nt "$o" ]] && stale=1; done
+  if [[ ! -f "$o" || "$f" -nt "$o" || $stale == 1 ]]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
     pids+=($!)
   fi

@@ -97,6 +97,28 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 int sm_count();
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Kernels of the step form one long dependent chain of small launches.  With the programmatic-stream-
+// serialization attribute the NEXT kernel's CTAs may become resident while this one still runs, so its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, index math) overlaps our tail; it must call
+// pdl_wait() before touching global memory -- that returns once every prerequisite grid has completed and
+// flushed.  Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();            // MASR_PDL=0 in the environment disables the attribute (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace masr
 
 namespace masr {

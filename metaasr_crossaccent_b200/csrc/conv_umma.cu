@@ -60,18 +60,22 @@ struct ConvParams {
 // MODE 0 = forward, 1 = dgrad
 template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(CV_THREADS, 1)
-umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_m, ConvParams p) {
   using namespace umma;
   constexpr uint32_t A_BYTES = 128 * 128;                 // up to 128 pixel rows of 128 B
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t MASK_BYTES = (MODE == 1) ? 128 * BN * 2 : 0;      // dgrad: ReLU mask tile, fetched up front
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  unsigned char* smask = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smask + MASK_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* sbias = reinterpret_cast<float*>(tmem_full_bar + 2);
+  uint64_t* mask_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_full_bar + 4);
   static_assert(STAGES * STAGE_BYTES >= EpiLayout<BN, __nv_bfloat16>::BYTES, "staging tile must fit in the pipeline stages");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,11 +88,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int cpb = p.Cred / 64;
   const int num_kb = 9 * cpb;
 
+  const bool has_mask = (MODE == 1) && p.relu_src != nullptr;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_w);
+    if (has_mask) prefetch_tmap(&map_m);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(mask_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
@@ -96,11 +104,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx_bytes = uint32_t(rows) * 128 + B_BYTES;
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (MODE == 1 && kb == STAGES && has_mask) {
+          // the ReLU mask tile of the output pixels (same box as an A tile, no shift): needed only by the
+          // epilogue, so it is queued behind the first ring fill and lands long before the main loop ends
+          mbar_arrive_expect_tx(mask_bar, uint32_t(rows) * 128 * (BN / 64));
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_4d(smask + c * 16384, &map_m, mask_bar, c * 64, w0, h0, b);
+        }
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
@@ -155,9 +171,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool valid = (r < rows) && (h < p.H) && (w < p.W);
     const int64_t pix = (int64_t(b) * p.H + h) * p.W + w;
     __nv_bfloat16* orow = valid ? p.out + pix * p.Cn : nullptr;
-    const __nv_bfloat16* mrow = (valid && MODE == 1 && p.relu_src != nullptr) ? p.relu_src + pix * p.Cn : nullptr;
-    epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, orow, mrow, BN, true,
-                                     EPI_STORE, MODE == 0 && p.relu != 0);
+    if (has_mask) mbar_wait(mask_bar, 0);
+    epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, orow, nullptr, BN, true,
+                                     EPI_STORE, MODE == 0 && p.relu != 0, has_mask ? smask : nullptr);
   }
   tc_fence_before();
   __syncthreads();
@@ -307,13 +323,12 @@ extern "C" int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float*
   if (Cout == 64) {
     const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256 + 64 * 4;
     rc = set_smem(umma_conv_kernel<64, ST, 0>, smem); if (rc) return rc;
-    umma_conv_kernel<64, ST, 0><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
+    MASR_CHECK_CUDA(launch_pdl(umma_conv_kernel<64, ST, 0>, dim3(grid), dim3(CV_THREADS), smem, st, ma, mw, ma, p));
   } else {
     const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256 + 128 * 4;
     rc = set_smem(umma_conv_kernel<128, ST, 0>, smem); if (rc) return rc;
-    umma_conv_kernel<128, ST, 0><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
+    MASR_CHECK_CUDA(launch_pdl(umma_conv_kernel<128, ST, 0>, dim3(grid), dim3(CV_THREADS), smem, st, ma, mw, ma, p));
   }
-  MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
 
@@ -335,17 +350,22 @@ extern "C" int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx,
                static_cast<const __nv_bfloat16*>(relu_src), nullptr, 0};
   const unsigned grid = unsigned(B * t.nh * t.nw);
   cudaStream_t st = as_stream(stream);
-  constexpr int ST = 4;
-  if (Cin == 64) {
-    const size_t smem = ST * (16384 + 64 * 128) + 1024 + 256 + 64 * 4;
-    rc = set_smem(umma_conv_kernel<64, ST, 1>, smem); if (rc) return rc;
-    umma_conv_kernel<64, ST, 1><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
-  } else {
-    const size_t smem = ST * (16384 + 128 * 128) + 1024 + 256 + 128 * 4;
-    rc = set_smem(umma_conv_kernel<128, ST, 1>, smem); if (rc) return rc;
-    umma_conv_kernel<128, ST, 1><<<grid, CV_THREADS, smem, st>>>(ma, mw, p);
+  CUtensorMap mm = ma;                       // ReLU mask tile of the OUTPUT pixels (Cin channels), same box
+  if (relu_src != nullptr) {
+    rc = act_map(&mm, relu_src, B, H, W, Cin, t.tw, t.th);
+    if (rc != MASR_OK) return rc;
   }
-  MASR_LAUNCH_CHECK();
+  if (Cin == 64) {
+    constexpr int ST = 3;                    // 3 x 24 KB ring + 16 KB mask tile: two CTAs per SM
+    const size_t smem = ST * (16384 + 64 * 128) + 128 * 64 * 2 + 1024 + 256 + 64 * 4;
+    rc = set_smem(umma_conv_kernel<64, ST, 1>, smem); if (rc) return rc;
+    MASR_CHECK_CUDA(launch_pdl(umma_conv_kernel<64, ST, 1>, dim3(grid), dim3(CV_THREADS), smem, st, ma, mw, mm, p));
+  } else {
+    constexpr int ST = 4;
+    const size_t smem = ST * (16384 + 128 * 128) + 128 * 128 * 2 + 1024 + 256 + 128 * 4;
+    rc = set_smem(umma_conv_kernel<128, ST, 1>, smem); if (rc) return rc;
+    MASR_CHECK_CUDA(launch_pdl(umma_conv_kernel<128, ST, 1>, dim3(grid), dim3(CV_THREADS), smem, st, ma, mw, mm, p));
+  }
   return MASR_OK;
 }
 

@@ -27,10 +27,13 @@ struct EpiLayout {
 // dst_row    : global pointer of this thread's output row (BN contiguous OutT), nullptr = row not stored
 // mask_row   : optional bf16 row (same shape); output is zeroed where mask <= 0 (ReLU backward)
 // ncols      : number of valid columns (<= BN); vec_ok: rows are 16 B aligned and ncols == BN
+// smask      : optional mask tile already resident in shared memory (bf16 output, vec_ok only): [128 rows x
+//              64 ch] halves of 16 KB in the TMA 128B-swizzled layout, row = TMEM lane; replaces mask_row
 template <int BN, typename OutT>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane, unsigned char* stage,
                                               const float* sbias, OutT* dst_row, const __nv_bfloat16* mask_row,
-                                              int ncols, bool vec_ok, int mode, bool relu) {
+                                              int ncols, bool vec_ok, int mode, bool relu,
+                                              const unsigned char* smask = nullptr) {
   using L = EpiLayout<BN, OutT>;
   const int r = q * 32 + lane;
   unsigned char* my = stage + r * L::ROWB;
@@ -83,10 +86,16 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
         const int ch = ch0 + it * 32;
         uint4 val = *reinterpret_cast<const uint4*>(stage + row * L::ROWB + ch * 16);
         if constexpr (sizeof(OutT) == 2) {
-          if (msk != nullptr || mode == EPI_ACCUM) {
+          if (msk != nullptr || smask != nullptr || mode == EPI_ACCUM) {
             float f[8];
             load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(&val), f);
-            if (msk != nullptr) {
+            if (smask != nullptr) {
+              float mk[8];
+              load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(
+                                       smask + (ch >> 3) * 16384 + row * 128 + (((ch & 7) ^ (row & 7)) << 4)), mk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (!(mk[e] > 0.f)) f[e] = 0.f;
+            } else if (msk != nullptr) {
               float mk[8];
               load8<__nv_bfloat16>(msk + ch * 8, mk);
 #pragma unroll

@@ -65,9 +65,10 @@ struct UmmaGemmParams {
   const float* bias;
   int flags;
   int kb_per_split;                // k-blocks per blockIdx.z slice (split-K: fp32 atomics into C)
+  int stages;                      // depth of the TMA->MMA ring (host: deep when one CTA owns an SM)
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaGemmParams p) {
   using namespace umma;
@@ -77,12 +78,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ unsigned char smem_dyn[];
   // 1024 B alignment is required by the 128 B swizzle atom
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;                                          // >= MIN_STAGES
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* sbias = reinterpret_cast<float*>(tmem_full_bar + 2);          // BN floats, 16 B aligned
-  static_assert(STAGES * STAGE_BYTES >= EpiLayout<BN, float>::BYTES, "staging tile must fit in the pipeline stages");
+  static_assert(MIN_STAGES * STAGE_BYTES >= EpiLayout<BN, float>::BYTES, "staging tile must fit in the pipeline stages");
+  pdl_launch_dependents();          // the next kernel's prologue may overlap this kernel (see common.cuh)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
@@ -102,13 +105,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                       // everything above touched no global memory
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + A_BYTES;
@@ -128,15 +131,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int c = 0; c < BN / 64; ++c)
             tma_load_2d(sb + c * (64 * UG_BK * 2), &map_b, &full_bar[s], n0 + c * 64, k0);
         }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
@@ -149,6 +152,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs have read it
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       mma_commit(tmem_full_bar);             // accumulator complete
     }
@@ -182,20 +186,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaGemmParams& p, cudaStream_t st) {
-  constexpr size_t smem = size_t(STAGES) * (UG_BM * UG_BK * 2 + BN * UG_BK * 2) + 1024 + 256 + BN * 4;
-  auto kern = umma_gemm_kernel<BN, STAGES, A_MN, B_MN>;
+template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
+static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmParams p, cudaStream_t st) {
+  constexpr size_t STAGE = size_t(UG_BM * UG_BK * 2 + BN * UG_BK * 2);
+  constexpr int MAX_STAGES = int((200 * 1024) / STAGE);
+  auto kern = umma_gemm_kernel<BN, MIN_STAGES, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
-    MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(MAX_STAGES * STAGE + 1024 + 512 + BN * 4)));
     attr_set = true;
   }
   const int total_kb = int(ceil_div64(p.K, UG_BK));
   const int nsplit = int(ceil_div64(total_kb, p.kb_per_split));
   dim3 grid(unsigned(ceil_div64(p.N, BN)), unsigned(ceil_div64(p.M, UG_BM)), unsigned(nsplit));
-  kern<<<grid, UG_THREADS, smem, st>>>(ma, mb, p);
-  MASR_LAUNCH_CHECK();
+  // one CTA per SM (grid fits in a wave): use the whole shared memory as a deep ring -- a lone CTA has to
+  // cover the full L2/HBM latency by itself; otherwise keep two CTAs per SM resident (epilogue of one
+  // overlaps the main loop of the other)
+  const int64_t ctas = int64_t(grid.x) * grid.y * grid.z;
+  int stages = (ctas <= sm_count()) ? MAX_STAGES : MIN_STAGES;
+  stages = std::max(MIN_STAGES, std::min(stages, std::min(p.kb_per_split, total_kb)));
+  p.stages = stages;
+  const size_t smem = size_t(stages) * STAGE + 1024 + 512 + BN * 4;
+  MASR_CHECK_CUDA(launch_pdl(kern, grid, dim3(UG_THREADS), smem, st, ma, mb, p));
   return MASR_OK;
 }
 
@@ -223,16 +236,18 @@ extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* 
   MASR_REQUIRE(M > 0 && N > 0 && K > 0, "umma gemm: empty problem");
   MASR_REQUIRE(!(flags & MASR_GEMM_SPLITK) || c_dtype == MASR_F32, "umma gemm: split-K needs an fp32 C");
   MASR_REQUIRE(!((flags & MASR_GEMM_SPLITK) && (flags & MASR_GEMM_RELU)), "umma gemm: split-K cannot fuse ReLU");
-  const int BN = (N <= 64) ? 64 : 128;
   const int total_kb = (K + UG_BK - 1) / UG_BK;
   int kb_per_split = total_kb;
   if ((flags & MASR_GEMM_SPLITK) && splitk > 1) kb_per_split = (total_kb + splitk - 1) / splitk;
+  // narrow tiles when 128-wide ones would leave most of the 148 SMs idle (decoder-sized problems)
+  const int64_t tiles128 = ceil_div64(M, UG_BM) * ceil_div64(N, 128) * ceil_div64(total_kb, kb_per_split);
+  const int BN = (N <= 64 || tiles128 * 3 < sm_count() * 2) ? 64 : 128;
   CUtensorMap ma, mb;
   int rc = operand_map(&ma, A, lda, M, K, a_mn != 0, UG_BM);
   if (rc != MASR_OK) return rc;
   rc = operand_map(&mb, B, ldb, N, K, b_mn != 0, BN);
   if (rc != MASR_OK) return rc;
-  UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, kb_per_split};
+  UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, kb_per_split, 0};
   cudaStream_t st = as_stream(stream);
   const int key = (BN == 64 ? 0 : 4) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
   switch (key) {

@@ -164,6 +164,11 @@ class TransformerEngine:
         self.training = True
         self.use_graphs = False           # CUDA-graph replay of forward+backward per (B, T, L1) shape
         self._graphs = {}
+        # weight-gradient GEMMs (and bias sums) never feed the back-propagation chain: they run on a
+        # second stream, concurrently with the dgrad chain (small launches fill only part of the 148 SMs)
+        self.multi_stream = self.device.type == "cuda"
+        self._side = None
+        self._side_busy = False
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, sd):
@@ -251,6 +256,25 @@ class TransformerEngine:
             dev[k] = t.to(self.device, non_blocking=True)
         dev.update({k: hb[k] for k in ("n_total", "B", "T", "L1")})
         return dev
+
+    # ------------------------------------------------------------------ side stream (fork / join)
+    def _fork(self, fn):
+        """Run fn() on the side stream, ordered after everything queued so far on the current stream."""
+        if not self.multi_stream:
+            return fn()
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        self._side.wait_stream(torch.cuda.current_stream(self.device))
+        self.be.scratch_tag = "side"
+        with torch.cuda.stream(self._side):
+            fn()
+        self.be.scratch_tag = ""
+        self._side_busy = True
+
+    def _join(self):
+        if self._side_busy:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side_busy = False
 
     # ------------------------------------------------------------------ forward
     def forward(self, db, want_grad=True):
@@ -389,34 +413,40 @@ class TransformerEngine:
         P, W, G = self.P, self.W, self.G
         be.zero_(self.grads)
 
+        fork = self._fork
+
+        def wgrad(x, dy, dw, db):
+            fork(lambda: be.linear_wgrad(x, dy, dw, db))
+
         def ffn_bwd(pre, g_s, f1, h_in, g_res, Mrows, tag):
             """g_s: grad wrt linear2 output; accumulates the FFN input gradient into g_res."""
-            be.linear_wgrad(f1, g_s, G[pre + ".linear2.weight"], G[pre + ".linear2.bias"])
+            wgrad(f1, g_s, G[pre + ".linear2.weight"], G[pre + ".linear2.bias"])
             g_f1 = buf(tag + ".g_f1", (Mrows, ff))
             be.linear_dgrad(g_s, W[pre + ".linear2.weight"], g_f1)
             be.dropout(g_f1, pd, seed, self.site(pre + ".df"))
             be.relu_bwd(f1, g_f1)
-            be.linear_wgrad(h_in, g_f1, G[pre + ".linear1.weight"], G[pre + ".linear1.bias"])
+            wgrad(h_in, g_f1, G[pre + ".linear1.weight"], G[pre + ".linear1.bias"])
             be.linear_dgrad(g_f1, W[pre + ".linear1.weight"], g_res, accumulate=True)
 
         def self_attn_bwd(pre, g_o, qkv, ctx, lse, x_in, g_res, Mrows, L, klens, causal, tag, site):
-            be.linear_wgrad(ctx, g_o, G[pre + ".self_attn.out_proj.weight"], G[pre + ".self_attn.out_proj.bias"])
-            g_ctx = buf(tag + ".g_ctx", (Mrows, d))
+            wgrad(ctx, g_o, G[pre + ".self_attn.out_proj.weight"], G[pre + ".self_attn.out_proj.bias"])
+            g_ctx = buf(tag[:2] + ".g_ctx", (Mrows, d))
             be.linear_dgrad(g_o, W[pre + ".self_attn.out_proj.weight"], g_ctx)
             g_qkv = buf(tag + ".g_qkv", (Mrows, 3 * d))
-            dsum = buf(tag + ".dsum", (B * H * L,), f32)
+            dsum = buf(tag[:2] + ".dsum", (B * H * L,), f32)
             be.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, g_ctx, lse, dsum,
                         g_qkv[:, :d], g_qkv[:, d:2 * d], g_qkv[:, 2 * d:], B, H, L, L, klens, causal, pd, seed, site)
-            be.linear_wgrad(x_in, g_qkv, G[pre + ".self_attn.in_proj_weight"], G[pre + ".self_attn.in_proj_bias"])
+            wgrad(x_in, g_qkv, G[pre + ".self_attn.in_proj_weight"], G[pre + ".self_attn.in_proj_bias"])
             be.linear_dgrad(g_qkv, W[pre + ".self_attn.in_proj_weight"], g_res, accumulate=True)
 
+        # Buffers read by a forked weight-gradient GEMM are private to their (layer, sub-layer): the dgrad
+        # chain on the main stream must not overwrite them while the side stream still reads them.
         # ---- output projection + final decoder norm
         dlogits = ws["dlogits"]
-        be.linear_wgrad(ws["d.out"], dlogits, G["char_trans.weight"], G["char_trans.bias"])
+        wgrad(ws["d.out"], dlogits, G["char_trans.weight"], G["char_trans.bias"])
         g_out = buf("g.out", (Md, d))
         be.linear_dgrad(dlogits, W["char_trans.weight"], g_out)
         gd = [buf("g.dA", (Md, d)), buf("g.dB", (Md, d))]
-        g_br = buf("g.dBr", (Md, d))                       # gradient of the sub-layer (branch) output
         cur = 0
         be.add_layernorm_bwd(g_out, ws["dec_last"], ws["dec.m"], ws["dec.r"], P["decoder.norm.weight"], gd[cur], False,
                              None, G["decoder.norm.weight"], G["decoder.norm.bias"])
@@ -424,24 +454,27 @@ class TransformerEngine:
         first_mem = True
         for l in reversed(range(cfg.dec_layers)):
             pre = f"decoder.layers.{l}"
+            tag = f"gd{l}"
             # norm3 / FFN
             nxt = 1 - cur
+            g_br = buf(tag + ".br3", (Md, d))                  # gradient of the sub-layer (branch) output
             be.add_layernorm_bwd(gd[cur], ws[f"d{l}.s3"], ws[f"d{l}.m3"], ws[f"d{l}.r3"], P[pre + ".norm3.weight"],
                                  gd[nxt], False, g_br, G[pre + ".norm3.weight"], G[pre + ".norm3.bias"],
                                  pd, seed, self.site(pre + ".d3"))
-            ffn_bwd(pre, g_br, ws[f"d{l}.f1"], ws[f"d{l}.h2"], gd[nxt], Md, "gd")
+            ffn_bwd(pre, g_br, ws[f"d{l}.f1"], ws[f"d{l}.h2"], gd[nxt], Md, tag)
             cur = nxt
             # norm2 / cross attention
             nxt = 1 - cur
+            g_br = buf(tag + ".br2", (Md, d))
             be.add_layernorm_bwd(gd[cur], ws[f"d{l}.s2"], ws[f"d{l}.m2"], ws[f"d{l}.r2"], P[pre + ".norm2.weight"],
                                  gd[nxt], False, g_br, G[pre + ".norm2.weight"], G[pre + ".norm2.bias"],
                                  pd, seed, self.site(pre + ".d2"))
-            be.linear_wgrad(ws[f"d{l}.ctx2"], g_br, G[pre + ".multihead_attn.out_proj.weight"],
-                            G[pre + ".multihead_attn.out_proj.bias"])
+            wgrad(ws[f"d{l}.ctx2"], g_br, G[pre + ".multihead_attn.out_proj.weight"],
+                  G[pre + ".multihead_attn.out_proj.bias"])
             g_ctx = buf("gd.g_ctx", (Md, d))
             be.linear_dgrad(g_br, W[pre + ".multihead_attn.out_proj.weight"], g_ctx)
-            g_q2 = buf("gd.g_q2", (Md, d))
-            g_kv2 = buf("gd.g_kv2", (Me, 2 * d))
+            g_q2 = buf(tag + ".g_q2", (Md, d))
+            g_kv2 = buf(tag + ".g_kv2", (Me, 2 * d))
             dsum = buf("gd.dsum", (B * H * L1,), f32)
             kv2 = ws[f"d{l}.kv2"]
             be.attn_bwd(ws[f"d{l}.q2"], kv2[:, :d], kv2[:, d:], ws[f"d{l}.ctx2"], g_ctx, ws[f"d{l}.lse2"], dsum,
@@ -449,25 +482,28 @@ class TransformerEngine:
                         pd, seed, self.site(pre + ".ca"))
             Wc = W[pre + ".multihead_attn.in_proj_weight"]
             Gw, Gb = G[pre + ".multihead_attn.in_proj_weight"], G[pre + ".multihead_attn.in_proj_bias"]
-            be.linear_wgrad(ws[f"d{l}.h1"], g_q2, Gw[:d], Gb[:d])
+            wgrad(ws[f"d{l}.h1"], g_q2, Gw[:d], Gb[:d])
             be.linear_dgrad(g_q2, Wc[:d], gd[nxt], accumulate=True)
-            be.linear_wgrad(ws["mem"], g_kv2, Gw[d:], Gb[d:])
+            wgrad(ws["mem"], g_kv2, Gw[d:], Gb[d:])
             be.linear_dgrad(g_kv2, Wc[d:], g_mem, accumulate=not first_mem)
             first_mem = False
             cur = nxt
             # norm1 / causal self attention
             nxt = 1 - cur
+            g_br = buf(tag + ".br1", (Md, d))
             be.add_layernorm_bwd(gd[cur], ws[f"d{l}.s1"], ws[f"d{l}.m1"], ws[f"d{l}.r1"], P[pre + ".norm1.weight"],
                                  gd[nxt], False, g_br, G[pre + ".norm1.weight"], G[pre + ".norm1.bias"],
                                  pd, seed, self.site(pre + ".d1"))
             self_attn_bwd(pre, g_br, ws[f"d{l}.qkv"], ws[f"d{l}.ctx1"], ws[f"d{l}.lse1"], ws[f"d{l}.in"], gd[nxt],
-                          Md, L1, None, True, "gd", self.site(pre + ".sa"))
+                          Md, L1, None, True, tag, self.site(pre + ".sa"))
             cur = nxt
-        be.embed_bwd(db["ys_in"].view(-1), gd[cur], G["pre_embed.weight"], L1, ppd, seed, self.site("dec.pe"))
+        # the scatter-add into the tied embedding matrix shares its target with the char_trans wgrad: keep
+        # both on the side stream (ordered); nothing on the main stream touches gd[] after this point
+        g_emb = gd[cur]
+        fork(lambda: be.embed_bwd(db["ys_in"].view(-1), g_emb, G["pre_embed.weight"], L1, ppd, seed, self.site("dec.pe")))
 
         # ---- encoder
         ge = [buf("g.eA", (Me, d)), buf("g.eB", (Me, d))]
-        g_ebr = buf("g.eBr", (Me, d))
         cur = 0
         if cfg.dec_layers == 0:
             be.zero_(g_mem)
@@ -475,48 +511,59 @@ class TransformerEngine:
                              None, G["encoder.norm.weight"], G["encoder.norm.bias"])
         for l in reversed(range(cfg.enc_layers)):
             pre = f"encoder.layers.{l}"
+            tag = f"ge{l}"
             nxt = 1 - cur
+            g_ebr = buf(tag + ".br2", (Me, d))
             be.add_layernorm_bwd(ge[cur], ws[f"e{l}.s2"], ws[f"e{l}.m2"], ws[f"e{l}.r2"], P[pre + ".norm2.weight"],
                                  ge[nxt], False, g_ebr, G[pre + ".norm2.weight"], G[pre + ".norm2.bias"],
                                  pd, seed, self.site(pre + ".d2"))
-            ffn_bwd(pre, g_ebr, ws[f"e{l}.f1"], ws[f"e{l}.h1"], ge[nxt], Me, "ge")
+            ffn_bwd(pre, g_ebr, ws[f"e{l}.f1"], ws[f"e{l}.h1"], ge[nxt], Me, tag)
             cur = nxt
             nxt = 1 - cur
+            g_ebr = buf(tag + ".br1", (Me, d))
             be.add_layernorm_bwd(ge[cur], ws[f"e{l}.s1"], ws[f"e{l}.m1"], ws[f"e{l}.r1"], P[pre + ".norm1.weight"],
                                  ge[nxt], False, g_ebr, G[pre + ".norm1.weight"], G[pre + ".norm1.bias"],
                                  pd, seed, self.site(pre + ".d1"))
             x_in = ws["h0"] if l == 0 else ws[f"e{l - 1}.h2"]
             self_attn_bwd(pre, g_ebr, ws[f"e{l}.qkv"], ws[f"e{l}.ctx"], ws[f"e{l}.lse"], x_in, ge[nxt],
-                          Me, T4, db["enc_lens"], False, "ge", self.site(pre + ".sa"))
+                          Me, T4, db["enc_lens"], False, tag, self.site(pre + ".sa"))
             cur = nxt
         g_h0 = ge[cur]
         be.dropout(g_h0, ppd, seed, self.site("enc.pe"))
 
         # ---- vgg2enc + VGG front end
         p2f = ws["p2"].view(Me, F4 * 128)
-        be.zero_(self.d_vgg2enc_p)
-        be.linear_wgrad(p2f, g_h0, self.d_vgg2enc_p, G["vgg2enc.bias"])
-        be.permute_cf(self.d_vgg2enc_p, G["vgg2enc.weight"], cfg.vgg_ch, cfg.f4, True)
+
+        def vgg2enc_wgrad():
+            be.zero_(self.d_vgg2enc_p)
+            be.linear_wgrad(p2f, g_h0, self.d_vgg2enc_p, G["vgg2enc.bias"])
+            be.permute_cf(self.d_vgg2enc_p, G["vgg2enc.weight"], cfg.vgg_ch, cfg.f4, True)
+        fork(vgg2enc_wgrad)
         g_p2 = buf("g.p2", (B, T4, F4, 128))
         be.linear_dgrad(g_h0, self.vgg2enc_p, g_p2.view(Me, F4 * 128))
         g_a4 = buf("g.a4", (B, T2, F2, 128))
         be.maxpool_bwd(ws["a4"], g_p2, g_a4, True)
-        for i in (2, 5, 7):
-            be.zero_(self.dwp[i])
-        be.conv3x3_wgrad(ws["a3"], g_a4, self.dwp[7], G["feat_extractor.7.bias"])
+
+        def conv_wgrad(i, x, dy):
+            def run():
+                be.zero_(self.dwp[i])
+                be.conv3x3_wgrad(x, dy, self.dwp[i], G[f"feat_extractor.{i}.bias"])
+                be.conv_w_unprep_add(self.dwp[i], G[f"feat_extractor.{i}.weight"])
+            fork(run)
+
+        conv_wgrad(7, ws["a3"], g_a4)
         g_a3 = buf("g.a3", (B, T2, F2, 128))
         be.conv3x3_dgrad(g_a4, self.wp[7], g_a3, ws["a3"])
-        be.conv3x3_wgrad(ws["p1"], g_a3, self.dwp[5], G["feat_extractor.5.bias"])
+        conv_wgrad(5, ws["p1"], g_a3)
         g_p1 = buf("g.p1", (B, T2, F2, 64))
         be.conv3x3_dgrad(g_a3, self.wp[5], g_p1, None)
         g_a2 = buf("g.a2", (B, T, F0, 64))
         be.maxpool_bwd(ws["a2"], g_p1, g_a2, True)
-        be.conv3x3_wgrad(ws["a1"], g_a2, self.dwp[2], G["feat_extractor.2.bias"])
+        conv_wgrad(2, ws["a1"], g_a2)
         g_a1 = buf("g.a1", (B, T, F0, 64))
         be.conv3x3_dgrad(g_a2, self.wp[2], g_a1, ws["a1"])
         be.conv1_wgrad(db["x"], g_a1, G["feat_extractor.0.weight"], G["feat_extractor.0.bias"])
-        for i in (2, 5, 7):
-            be.conv_w_unprep_add(self.dwp[i], G[f"feat_extractor.{i}.weight"])
+        self._join()
 
     # ------------------------------------------------------------------ public step
     def forward_backward(self, db):

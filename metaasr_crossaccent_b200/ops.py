@@ -45,6 +45,7 @@ class CudaBackend:
         self.prof_ops = None           # dict -> per-entry-point CUDA events (bench.py --profile)
         self.prof_tag = ""
         self._scratch = {}
+        self.scratch_tag = ""         # set by the engine while it launches on its side stream
         # one device-resident dropout seed offset per device, alive for the whole process (the library
         # keeps its address; kernels add it to every dropout seed so CUDA-graph replays get fresh masks)
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -181,7 +182,8 @@ class CudaBackend:
 
     def _im2col(self, x):
         B, H, W, Cin = x.shape
-        col = self.scratch("col", B * H * W * 9 * Cin, x.dtype).view(B * H * W, 9 * Cin)
+        # scratch is private to the launching lane (the engine forks weight-gradient work to a side stream)
+        col = self.scratch(("col", self.scratch_tag), B * H * W * 9 * Cin, x.dtype).view(B * H * W, 9 * Cin)
         self._call("masr_im2col3x3", _p(x), _p(col), _dt(x), B, H, W, Cin, self.stream)
         return col
 
@@ -206,7 +208,7 @@ class CudaBackend:
         if self._conv_umma_ok(dy, wp, dx) and (relu_src is None or relu_src.is_contiguous()):
             return self._timed_call(("conv_dgrad", P, Cin, 9 * Cout), "masr_umma_conv3x3_dgrad", _p(dy), _p(wp), _p(dx),
                                     _p(relu_src), B, H, W, Cin, Cout, self.stream)
-        dcol = self.scratch("col", P * 9 * Cin, dy.dtype).view(P, 9 * Cin)
+        dcol = self.scratch(("col", self.scratch_tag), P * 9 * Cin, dy.dtype).view(P, 9 * Cin)
         dy2 = dy.view(P, Cout)
         if self._umma_ok(dy2, wp):
             self.umma_gemm(dy2, 0, wp, 1, dcol, None, P, 9 * Cin, Cout, 0)
