@@ -200,12 +200,14 @@ int masr_permute_cf(const void* src, int src_dtype, void* dst, int dst_dtype, in
 /* label-smoothed cross entropy + accuracy + gradient, src/transformer_torch_trainer.py:64-92.
  *   logits [N, C] fp32, gold [N] int64 (IGNORE_ID = -1 rows are skipped)
  *   stats  [4] double: {sum of row losses, n_correct, n_non_pad, 0} (accumulated; zero it first)
- *   argmax [N] int64 out (may be NULL); dlogits [N, C] fp32 out = d(mean loss)/d logits given
- *   inv_n = 1 / n_non_pad (may be NULL)
+ *   argmax [N] int64 out (may be NULL); dlogits [N, C] out (fp32 or bf16 per dl_dtype, row stride ld_dl >= C
+ *   elements; a bf16 gradient with ld_dl % 8 == 0 feeds the tcgen05 GEMMs directly) = d(mean loss)/d logits
+ *   given inv_n = 1 / n_non_pad (may be NULL)
  *   inv_n_dev (may be NULL): device-resident 1 / n_non_pad overriding inv_n (CUDA-graph replay)
  */
 int masr_ls_ce_fwd_bwd(const float* logits, const int64_t* gold, int N, int C, float eps, float inv_n,
-                       const float* inv_n_dev, double* stats, int64_t* argmax, float* dlogits, void* stream);
+                       const float* inv_n_dev, double* stats, int64_t* argmax, void* dlogits, int dl_dtype,
+                       int64_t ld_dl, void* stream);
 
 /* Dropout seeds: every dropout site draws from (seed + *dev_ptr, site, element index).  dev_ptr (set once per
  * process; NULL = offset 0) lives in device memory so a captured CUDA graph of the step replays with fresh

@@ -67,7 +67,7 @@ SIGNATURES = {
     "masr_colsum_add": [c_p, c_i, c_i64, c_p, c_i, c_i, c_p],
     "masr_cast": [c_p, c_i, c_p, c_i, c_i64, c_p],
     "masr_permute_cf": [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
-    "masr_ls_ce_fwd_bwd": [c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p],
+    "masr_ls_ce_fwd_bwd": [c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_i, c_i64, c_p],
     "masr_set_seed_ptr": [c_p],
     "masr_seed_bump": [c_p, c_u64, c_p],
     "masr_mt_sumsq": [c_p, c_i64, c_p, c_i, c_p],

@@ -62,13 +62,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t seed_eff = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
-  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
-  const int q0 = blockIdx.x * AU_TILE;
-  int kmax = p.Lk;
-  if (p.klens != nullptr) kmax = min(kmax, int(p.klens[b]));
-  if (p.causal) kmax = min(kmax, q0 + AU_TILE);
-  const int ntiles = (kmax + AU_TILE - 1) / AU_TILE;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
@@ -82,6 +76,14 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();           // global memory (lengths, seed offset, tiles) is only touched below
+  const uint64_t seed_eff = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int q0 = blockIdx.x * AU_TILE;
+  int kmax = p.Lk;
+  if (p.klens != nullptr) kmax = min(kmax, int(p.klens[b]));
+  if (p.causal) kmax = min(kmax, q0 + AU_TILE);
+  const int ntiles = (kmax + AU_TILE - 1) / AU_TILE;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
   if (warp == 0) {
@@ -216,6 +218,8 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // D[b,h,q] = dO_q . O_q  (one warp per (b, q, h) row of 64)
 __global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, int64_t ldo, const __nv_bfloat16* __restrict__ dout,
                                  int64_t lddo, float* __restrict__ dsum, int B, int H, int Lq) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t total = int64_t(B) * H * Lq;
   for (int64_t idx = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5; idx < total;
@@ -268,15 +272,7 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t seed_eff = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
-  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
-  const int k0 = blockIdx.x * AU_TILE;
-  int klen = p.Lk;
-  if (p.klens != nullptr) klen = min(klen, int(p.klens[b]));
-  const int nq_tiles = (p.Lq + AU_TILE - 1) / AU_TILE;
-  const int qt_begin = p.causal ? (k0 / AU_TILE) : 0;
-  const bool active = (k0 < klen) && (qt_begin < nq_tiles);
-  const int ntiles = active ? (nq_tiles - qt_begin) : 0;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_do);
@@ -290,6 +286,16 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const uint64_t seed_eff = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
+  const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+  const int k0 = blockIdx.x * AU_TILE;
+  int klen = p.Lk;
+  if (p.klens != nullptr) klen = min(klen, int(p.klens[b]));
+  const int nq_tiles = (p.Lq + AU_TILE - 1) / AU_TILE;
+  const int qt_begin = p.causal ? (k0 / AU_TILE) : 0;
+  const bool active = (k0 < klen) && (qt_begin < nq_tiles);
+  const int ntiles = active ? (nq_tiles - qt_begin) : 0;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256, tm_dK = tmem_base + 320, tm_dV = tmem_base + 384;
 
   if (warp == 0) {
@@ -476,7 +482,7 @@ extern "C" int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_FWD_SMEM))); attr = true; }
   dim3 grid(unsigned(ceil_div64(Lq, AU_TILE)), unsigned(B * H));
-  attn_fwd_umma_kernel<<<grid, AU_THREADS, AU_FWD_SMEM, as_stream(stream)>>>(mq, mk, mv, p);
+  MASR_CHECK_CUDA(launch_pdl(attn_fwd_umma_kernel, grid, dim3(AU_THREADS), AU_FWD_SMEM, as_stream(stream), mq, mk, mv, p));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -501,9 +507,8 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
   if (Lq > 0) {
     const int64_t rows = int64_t(B) * H * Lq;
     const int blocks = int(std::min<int64_t>(ceil_div64(rows, 8), int64_t(sm_count()) * 8));
-    attn_dsum_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out), ldo,
-                                             static_cast<const __nv_bfloat16*>(dout), lddo, dsum_ws, B, H, Lq);
-    MASR_LAUNCH_CHECK();
+    MASR_CHECK_CUDA(launch_pdl(attn_dsum_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(out), ldo,
+                               static_cast<const __nv_bfloat16*>(dout), lddo, dsum_ws, B, H, Lq));
   }
   AttnBwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed, site,
                   lse, dsum_ws, static_cast<__nv_bfloat16*>(dq), lddq, static_cast<__nv_bfloat16*>(dk), lddk,
@@ -511,7 +516,7 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_BWD_SMEM))); attr = true; }
   dim3 grid(1, unsigned(B * H));
-  attn_bwd_umma_kernel<<<grid, AU_THREADS, AU_BWD_SMEM, st>>>(mq, mk, mv, mdo, p);
+  MASR_CHECK_CUDA(launch_pdl(attn_bwd_umma_kernel, grid, dim3(AU_THREADS), AU_BWD_SMEM, st, mq, mk, mv, mdo, p));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -12,6 +12,8 @@ template <typename T>
 __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ bias, T* __restrict__ y,
                                  int B, int H, int W, int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sw[];            // [Cout][9] weights then [Cout] bias
   for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * 9 + i] = bias[i];
@@ -54,6 +56,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv1_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, T* __restrict__ y,
                                                            int B, int H, int W, int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = Cout / 8;
   const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = int(gtid % unsigned(groups));
@@ -112,6 +116,8 @@ template <typename T>
 __global__ void conv1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                    float* __restrict__ dw, float* __restrict__ db,
                                    int B, int H, int W, int Cout, int64_t pix_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];           // [PL][Cout][10]
   const int co = threadIdx.x % Cout;
   const int lane = threadIdx.x / Cout;
@@ -153,6 +159,8 @@ __global__ void conv1_wgrad_kernel(const float* __restrict__ x, const T* __restr
 template <typename T>
 __global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col,
                                  int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(B) * H * W * 9 * C;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -172,6 +180,8 @@ __global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col,
 template <typename T>
 __global__ void col2im3x3_kernel(const T* __restrict__ dcol, T* __restrict__ dx,
                                  const T* __restrict__ relu_src, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = int64_t(B) * H * W * C;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -196,6 +206,8 @@ __global__ void col2im3x3_kernel(const T* __restrict__ dcol, T* __restrict__ dx,
 // w [Cout][Cin][3][3] fp32 -> wp [Cout][tap][Cin]
 template <typename T>
 __global__ void conv_w_prep_kernel(const float* __restrict__ w, T* __restrict__ wp, int Cout, int Cin) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int total = Cout * Cin * 9;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int ci = idx % Cin;
@@ -205,6 +217,8 @@ __global__ void conv_w_prep_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 __global__ void conv_w_unprep_add_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int total = Cout * Cin * 9;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int ci = idx % Cin;
@@ -217,6 +231,8 @@ __global__ void conv_w_unprep_add_kernel(const float* __restrict__ dwp, float* _
 // ------------------------------------------------------------------ max pool 2x2 / 2, floor mode
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = int64_t(B) * Ho * Wo * C;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -239,6 +255,8 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, i
 template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                    int relu_mask, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = int64_t(B) * H * W * C;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -267,6 +285,8 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
 
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ y, T* __restrict__ dx, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     if (!(to_f<T>(y[i]) > 0.f)) dx[i] = from_f<T>(0.f);
 }
@@ -276,6 +296,8 @@ __global__ void relu_bwd_kernel(const T* __restrict__ y, T* __restrict__ dx, int
 // 128-bit stores; a warp covers 256 contiguous channels-bytes per pixel -> fully coalesced NHWC traffic.
 template <typename T>
 __global__ void maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, ncg = C / 8;
   const int64_t total = int64_t(B) * Ho * Wo * ncg;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
@@ -295,6 +317,8 @@ __global__ void maxpool_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ 
 template <typename T>
 __global__ void maxpool_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                        int relu_mask, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, ncg = C / 8;
   const int64_t total = int64_t(B) * Ho * Wo * ncg;
   const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -333,6 +357,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv1_wgrad_v2_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                              float* __restrict__ dw, float* __restrict__ db,
                                                              int B, int H, int W, int Cout, int64_t pix_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];           // [PL][Cout][10]
   const int co = threadIdx.x % Cout;
   const int lane = threadIdx.x / Cout;
@@ -385,6 +411,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv1_wgrad_v3_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                              float* __restrict__ dw, float* __restrict__ db,
                                                              int B, int H, int W, int Cout, int segs_per_row, int total_segs) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];           // [PL][Cout][10]
   constexpr int SEG = 8;
   const int co = threadIdx.x % Cout;
@@ -452,12 +480,12 @@ extern "C" int masr_conv1_fwd(const float* x, const float* w, const float* bias,
   if (int64_t(B) * H * W < (int64_t(1) << 31) && 256 % (Cout / 8) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     const int blocks = int(std::min<int64_t>(ceil_div64(total, 256), int64_t(sm_count()) * 8));
     MASR_DISPATCH_DTYPE(y_dtype, T,
-        conv1_fwd_v2_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(x, w, bias, static_cast<T*>(y), B, H, W, Cout));
+        launch_pdl(conv1_fwd_v2_kernel<T>, dim3(blocks), dim3(256), 0, as_stream(stream), x, w, bias, static_cast<T*>(y), B, H, W, Cout));
     MASR_LAUNCH_CHECK();
     return MASR_OK;
   }
   MASR_DISPATCH_DTYPE(y_dtype, T,
-      conv1_fwd_kernel<T><<<grid_for(total, 256), 256, smem, as_stream(stream)>>>(
+      launch_pdl(conv1_fwd_kernel<T>, dim3(grid_for(total, 256)), dim3(256), smem, as_stream(stream), 
           x, w, bias, static_cast<T*>(y), B, H, W, Cout));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -475,7 +503,7 @@ extern "C" int masr_conv1_wgrad(const float* x, const void* dy, int dy_dtype, fl
     const int blocks3 = std::max(1, std::min((total_segs + PL - 1) / PL, sm_count() * 8));
     const size_t smem3 = size_t(PL) * Cout * 10 * sizeof(float);
     MASR_DISPATCH_DTYPE(dy_dtype, T,
-        conv1_wgrad_v3_kernel<T><<<blocks3, threads, smem3, as_stream(stream)>>>(
+        launch_pdl(conv1_wgrad_v3_kernel<T>, dim3(blocks3), dim3(threads), smem3, as_stream(stream), 
             x, static_cast<const T*>(dy), dw, db, B, H, W, Cout, segs_per_row, total_segs));
     MASR_LAUNCH_CHECK();
     return MASR_OK;
@@ -485,7 +513,7 @@ extern "C" int masr_conv1_wgrad(const float* x, const void* dy, int dy_dtype, fl
   blocks = int(ceil_div64(P, ppb));
   const size_t smem = size_t(PL) * Cout * 10 * sizeof(float);
   MASR_DISPATCH_DTYPE(dy_dtype, T,
-      conv1_wgrad_v2_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
+      launch_pdl(conv1_wgrad_v2_kernel<T>, dim3(blocks), dim3(threads), smem, as_stream(stream), 
           x, static_cast<const T*>(dy), dw, db, B, H, W, Cout, ppb));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -495,7 +523,7 @@ extern "C" int masr_im2col3x3(const void* x, void* col, int dtype, int B, int H,
   const int64_t total = int64_t(B) * H * W * 9 * Cin;
   if (total == 0) return MASR_OK;
   MASR_DISPATCH_DTYPE(dtype, T,
-      im2col3x3_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      launch_pdl(im2col3x3_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), 
           static_cast<const T*>(x), static_cast<T*>(col), B, H, W, Cin));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -506,7 +534,7 @@ extern "C" int masr_col2im3x3(const void* dcol, void* dx, int dtype, const void*
   const int64_t total = int64_t(B) * H * W * Cin;
   if (total == 0) return MASR_OK;
   MASR_DISPATCH_DTYPE(dtype, T,
-      col2im3x3_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      launch_pdl(col2im3x3_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), 
           static_cast<const T*>(dcol), static_cast<T*>(dx), static_cast<const T*>(relu_src), B, H, W, Cin));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -516,7 +544,7 @@ extern "C" int masr_conv_w_prep(const float* w, void* wp, int dtype, int Cout, i
   const int total = Cout * Cin * 9;
   if (total == 0) return MASR_OK;
   MASR_DISPATCH_DTYPE(dtype, T,
-      conv_w_prep_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, static_cast<T*>(wp), Cout, Cin));
+      launch_pdl(conv_w_prep_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), w, static_cast<T*>(wp), Cout, Cin));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -524,7 +552,7 @@ extern "C" int masr_conv_w_prep(const float* w, void* wp, int dtype, int Cout, i
 extern "C" int masr_conv_w_unprep_add(const float* dwp, float* dw, int Cout, int Cin, void* stream) {
   const int total = Cout * Cin * 9;
   if (total == 0) return MASR_OK;
-  conv_w_unprep_add_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dwp, dw, Cout, Cin);
+  launch_pdl(conv_w_unprep_add_kernel, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), dwp, dw, Cout, Cin);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -534,13 +562,13 @@ extern "C" int masr_maxpool2x2_fwd(const void* x, void* y, int dtype, int B, int
   if (total == 0) return MASR_OK;
   if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     MASR_DISPATCH_DTYPE(dtype, T,
-        maxpool_fwd_vec_kernel<T><<<grid_for(total / 8, 256), 256, 0, as_stream(stream)>>>(
+        launch_pdl(maxpool_fwd_vec_kernel<T>, dim3(grid_for(total / 8, 256)), dim3(256), 0, as_stream(stream), 
             static_cast<const T*>(x), static_cast<T*>(y), B, H, W, C));
     MASR_LAUNCH_CHECK();
     return MASR_OK;
   }
   MASR_DISPATCH_DTYPE(dtype, T,
-      maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      launch_pdl(maxpool_fwd_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), 
           static_cast<const T*>(x), static_cast<T*>(y), B, H, W, C));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -554,13 +582,13 @@ extern "C" int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int 
   if (C % 8 == 0 && H >= 2 && W >= 2 && wins > 0 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
     MASR_DISPATCH_DTYPE(dtype, T,
-        maxpool_bwd_vec_kernel<T><<<grid_for(wins, 256), 256, 0, as_stream(stream)>>>(
+        launch_pdl(maxpool_bwd_vec_kernel<T>, dim3(grid_for(wins, 256)), dim3(256), 0, as_stream(stream), 
             static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), relu_mask, B, H, W, C));
     MASR_LAUNCH_CHECK();
     return MASR_OK;
   }
   MASR_DISPATCH_DTYPE(dtype, T,
-      maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+      launch_pdl(maxpool_bwd_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), 
           static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), relu_mask, B, H, W, C));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -569,7 +597,7 @@ extern "C" int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int 
 extern "C" int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, void* stream) {
   if (n == 0) return MASR_OK;
   MASR_DISPATCH_DTYPE(dtype, T,
-      relu_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(static_cast<const T*>(y), static_cast<T*>(dx), n));
+      launch_pdl(relu_bwd_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), static_cast<const T*>(y), static_cast<T*>(dx), n));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -211,6 +211,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   const int my_tiles = (ntiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
   const int co_chunks = p.Cout / 64;
 
+  pdl_launch_dependents();
   // rows [th*tw, 64) of every chunk are never written by TMA: zero the ring once so they contribute 0
   for (uint32_t i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += CV_THREADS)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -227,6 +228,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -389,12 +391,12 @@ extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp
     constexpr int ST = 4;
     const size_t smem = ST * (16384 + 3 * 8192) + 1024 + 256;
     rc = set_smem(umma_conv_wgrad_kernel<64, ST>, smem); if (rc) return rc;
-    umma_conv_wgrad_kernel<64, ST><<<grid, CV_THREADS, smem, st>>>(mdy, mx, p);
+    MASR_CHECK_CUDA(launch_pdl(umma_conv_wgrad_kernel<64, ST>, grid, dim3(CV_THREADS), smem, st, mdy, mx, p));
   } else {
     constexpr int ST = 3;
     const size_t smem = ST * (16384 + 3 * 16384) + 1024 + 256;
     rc = set_smem(umma_conv_wgrad_kernel<128, ST>, smem); if (rc) return rc;
-    umma_conv_wgrad_kernel<128, ST><<<grid, CV_THREADS, smem, st>>>(mdy, mx, p);
+    MASR_CHECK_CUDA(launch_pdl(umma_conv_wgrad_kernel<128, ST>, grid, dim3(CV_THREADS), smem, st, mdy, mx, p));
   }
   MASR_LAUNCH_CHECK();
   return MASR_OK;

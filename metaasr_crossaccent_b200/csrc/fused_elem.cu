@@ -21,6 +21,8 @@ __global__ void add_layernorm_fwd_kernel(T* __restrict__ x, const T* __restrict_
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                          int rows, int d, float eps, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -69,6 +71,8 @@ __global__ void add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __re
                                          const float* __restrict__ gamma, T* __restrict__ ds, int ds_accum,
                                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                          int rows, int d, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   extern __shared__ float red[];      // [warps][2][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -132,6 +136,8 @@ add_layernorm_fwd_vec_kernel(T* __restrict__ x, const T* __restrict__ res, const
                              const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
                              float* __restrict__ rstd_out, int rows, int d, float eps, float p, float inv_keep,
                              SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -191,6 +197,8 @@ add_layernorm_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ s, 
                              const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ ds,
                              int ds_accum, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                              int rows, int d, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   extern __shared__ float red[];      // [warps][2][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -273,6 +281,8 @@ add_layernorm_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ s, 
 template <typename T>
 __global__ void add_pe_dropout_kernel(T* __restrict__ x, const float* __restrict__ pe, int64_t n, int L, int d,
                                       float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int c = int(i % d);
@@ -286,6 +296,8 @@ template <typename T>
 __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E,
                                     const float* __restrict__ pe, T* __restrict__ out, int64_t n, int L, int d,
                                     float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int c = int(i % d);
@@ -299,6 +311,8 @@ __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float
 template <typename T>
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout, float* __restrict__ dE,
                                  int64_t n, int d, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int c = int(i % d);
@@ -310,6 +324,8 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __res
 
 template <typename T>
 __global__ void dropout_kernel(T* __restrict__ x, int64_t n, float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t seed = resolve_seed(seed_arg);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     x[i] = from_f<T>(to_f<T>(x[i]) * drop_scale(p, inv_keep, seed, site, uint64_t(i)));
@@ -319,6 +335,8 @@ __global__ void dropout_kernel(T* __restrict__ x, int64_t n, float p, float inv_
 // (8 * gridDim.y); partials reduced over ty in shared memory; one atomicAdd per column per block.
 template <typename T>
 __global__ void colsum_add_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out, int M, int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int n = blockIdx.x * 32 + tx;
@@ -340,6 +358,8 @@ __global__ void colsum_add_kernel(const T* __restrict__ x, int64_t ldx, float* _
 // 512 contiguous bytes; row partials are combined in shared memory, one atomicAdd per column per block.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out, int M, int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[256 * 8];
   const int ncg = N / 8;
   const int rl_count = 256 / ncg;
@@ -375,6 +395,8 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     dst[i] = from_f<TD>(to_f<TS>(src[i]));
 }
@@ -382,6 +404,8 @@ __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, in
 // forward: dst[r, f*C + c] = src[r, c*F + f]; inverse_add: dst[r, c*F + f] += src[r, f*C + c]
 template <typename TS, typename TD>
 __global__ void permute_cf_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t rows, int C, int F, int inverse_add) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n = rows * C * F;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = i / (int64_t(C) * F);
@@ -400,9 +424,12 @@ __global__ void permute_cf_kernel(const TS* __restrict__ src, TD* __restrict__ d
 // src/transformer_torch_trainer.py:64-84.  One warp per row of C logits.
 //   q_c = (1-eps) for the gold class, eps/C otherwise (sums to 1 - eps/C)
 //   loss_row = -sum_c q_c (z_c - logZ);   d loss_row / d z_c = (sum q) softmax_c - q_c
+template <typename DT>
 __global__ void ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ gold, int N, int C,
                              float eps, float inv_n, const float* __restrict__ inv_n_dev, double* __restrict__ stats,
-                             int64_t* __restrict__ argmax_out, float* __restrict__ dlogits) {
+                             int64_t* __restrict__ argmax_out, DT* __restrict__ dlogits, int64_t ld_dl) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (inv_n_dev != nullptr) inv_n = *inv_n_dev;       // device-resident 1/n_non_pad (CUDA-graph replay)
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -434,16 +461,16 @@ __global__ void ls_ce_kernel(const float* __restrict__ logits, const int64_t* __
       if (lane == 0) { loss_acc += double(row_loss); nonpad += 1; correct += (am == int(g)); }
     }
     if (dlogits != nullptr) {
-      float* dz = dlogits + int64_t(row) * C;
+      DT* dz = dlogits + int64_t(row) * ld_dl;
       if (valid) {
         const float q_on = 1.f - eps, q_off = eps / float(C);
         const float qsum = q_on + float(C - 1) * q_off;
         for (int c = lane; c < C; c += 32) {
           const float sm = expf(z[c] - logZ);
-          dz[c] = (qsum * sm - (c == int(g) ? q_on : q_off)) * inv_n;
+          dz[c] = from_f<DT>((qsum * sm - (c == int(g) ? q_on : q_off)) * inv_n);
         }
       } else {
-        for (int c = lane; c < C; c += 32) dz[c] = 0.f;
+        for (int c = lane; c < C; c += 32) dz[c] = from_f<DT>(0.f);
       }
     }
   }
@@ -470,7 +497,7 @@ extern "C" int masr_add_layernorm_fwd(void* x_inout, const void* res, const floa
                                      reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
                                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
   if (vec) {
-#define LN_FWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (add_layernorm_fwd_vec_kernel<T, NCH><<<blocks, threads, 0, as_stream(stream)>>>( \
+#define LN_FWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (launch_pdl(add_layernorm_fwd_vec_kernel<T, NCH>, dim3(blocks), dim3(threads), 0, as_stream(stream),  \
           static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd, rows, d, eps, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site)))
     if (d <= 256) LN_FWD_VEC(1); else if (d <= 512) LN_FWD_VEC(2); else LN_FWD_VEC(4);
 #undef LN_FWD_VEC
@@ -478,7 +505,7 @@ extern "C" int masr_add_layernorm_fwd(void* x_inout, const void* res, const floa
     return MASR_OK;
   }
   MASR_DISPATCH_DTYPE(dtype, T,
-      add_layernorm_fwd_kernel<T><<<blocks, threads, 0, as_stream(stream)>>>(
+      launch_pdl(add_layernorm_fwd_kernel<T>, dim3(blocks), dim3(threads), 0, as_stream(stream), 
           static_cast<T*>(x_inout), static_cast<const T*>(res), gamma, beta, static_cast<T*>(y), mean, rstd,
           rows, d, eps, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
@@ -503,7 +530,7 @@ extern "C" int masr_add_layernorm_bwd(const void* dy, const void* s, const float
                    ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(ds) |
                      reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(gamma)) & 15) == 0;
   if (vec) {
-#define LN_BWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (add_layernorm_bwd_vec_kernel<T, NCH><<<blocks, threads, smem, as_stream(stream)>>>( \
+#define LN_BWD_VEC(NCH) MASR_DISPATCH_DTYPE(dtype, T, (launch_pdl(add_layernorm_bwd_vec_kernel<T, NCH>, dim3(blocks), dim3(threads), smem, as_stream(stream),  \
           static_cast<const T*>(dy), static_cast<const T*>(s), mean, rstd, gamma, static_cast<T*>(ds), ds_accum, static_cast<T*>(dx), \
           dgamma, dbeta, rows, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site)))
     if (d <= 256) LN_BWD_VEC(1); else if (d <= 512) LN_BWD_VEC(2); else LN_BWD_VEC(4);
@@ -512,7 +539,7 @@ extern "C" int masr_add_layernorm_bwd(const void* dy, const void* s, const float
     return MASR_OK;
   }
   MASR_DISPATCH_DTYPE(dtype, T,
-      add_layernorm_bwd_kernel<T><<<blocks, threads, smem, as_stream(stream)>>>(
+      launch_pdl(add_layernorm_bwd_kernel<T>, dim3(blocks), dim3(threads), smem, as_stream(stream), 
           static_cast<const T*>(dy), static_cast<const T*>(s), mean, rstd, gamma, static_cast<T*>(ds), ds_accum,
           static_cast<T*>(dx), dgamma, dbeta, rows, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
@@ -525,7 +552,7 @@ extern "C" int masr_add_pe_dropout(void* x, const float* pe, int dtype, int rows
   if (n == 0) return MASR_OK;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   MASR_DISPATCH_DTYPE(dtype, T,
-      add_pe_dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      launch_pdl(add_pe_dropout_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), 
           static_cast<T*>(x), pe, n, L, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -537,7 +564,7 @@ extern "C" int masr_embed_pe_fwd(const int64_t* ids, const float* E, const float
   if (n == 0) return MASR_OK;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   MASR_DISPATCH_DTYPE(dtype, T,
-      embed_pe_fwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      launch_pdl(embed_pe_fwd_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), 
           ids, E, pe, static_cast<T*>(out), n, L, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -550,7 +577,7 @@ extern "C" int masr_embed_bwd(const int64_t* ids, const void* dout, int dtype, f
   if (n == 0) return MASR_OK;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   MASR_DISPATCH_DTYPE(dtype, T,
-      embed_bwd_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      launch_pdl(embed_bwd_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), 
           ids, static_cast<const T*>(dout), dE, n, d, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -560,7 +587,7 @@ extern "C" int masr_dropout(void* x, int dtype, int64_t n, float p_drop, uint64_
   if (n == 0 || p_drop <= 0.f) return MASR_OK;
   const float inv_keep = 1.f / (1.f - p_drop);
   MASR_DISPATCH_DTYPE(dtype, T,
-      dropout_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(static_cast<T*>(x), n, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
+      launch_pdl(dropout_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), static_cast<T*>(x), n, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -572,7 +599,7 @@ extern "C" int masr_colsum_add(const void* x, int dtype, int64_t ldx, float* out
     const int rl_count = 256 / (N / 8);
     const int blocks = int(std::min<int64_t>(ceil_div64(M, int64_t(rl_count) * 4), int64_t(sm_count()) * 4));
     MASR_DISPATCH_DTYPE(dtype, T,
-        colsum_vec_kernel<T><<<std::max(blocks, 1), 256, 0, as_stream(stream)>>>(static_cast<const T*>(x), ldx, out, M, N));
+        launch_pdl(colsum_vec_kernel<T>, dim3(std::max(blocks, 1)), dim3(256), 0, as_stream(stream), static_cast<const T*>(x), ldx, out, M, N));
     MASR_LAUNCH_CHECK();
     return MASR_OK;
   }
@@ -580,7 +607,7 @@ extern "C" int masr_colsum_add(const void* x, int dtype, int64_t ldx, float* out
   const int gy = int(std::min<int64_t>(ceil_div64(M, 8 * 8), 64));
   dim3 grid(unsigned(ceil_div64(N, 32)), unsigned(gy));
   MASR_DISPATCH_DTYPE(dtype, T,
-      colsum_add_kernel<T><<<grid, block, 0, as_stream(stream)>>>(static_cast<const T*>(x), ldx, out, M, N));
+      launch_pdl(colsum_add_kernel<T>, dim3(grid), dim3(block), 0, as_stream(stream), static_cast<const T*>(x), ldx, out, M, N));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -590,13 +617,13 @@ extern "C" int masr_cast(const void* src, int src_dtype, void* dst, int dst_dtyp
   cudaStream_t st = as_stream(stream);
   const int g = grid_for(n, 256);
   if (src_dtype == MASR_F32 && dst_dtype == MASR_BF16)
-    cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
+    launch_pdl(cast_kernel<float, __nv_bfloat16>, dim3(g), dim3(256), 0, st, static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
   else if (src_dtype == MASR_BF16 && dst_dtype == MASR_F32)
-    cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
+    launch_pdl(cast_kernel<__nv_bfloat16, float>, dim3(g), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
   else if (src_dtype == MASR_F32 && dst_dtype == MASR_F32)
-    cast_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), n);
+    launch_pdl(cast_kernel<float, float>, dim3(g), dim3(256), 0, st, static_cast<const float*>(src), static_cast<float*>(dst), n);
   else if (src_dtype == MASR_BF16 && dst_dtype == MASR_BF16)
-    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n);
+    launch_pdl(cast_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n);
   else { set_error("masr_cast: bad dtype"); return MASR_E_INVALID; }
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -609,21 +636,28 @@ extern "C" int masr_permute_cf(const void* src, int src_dtype, void* dst, int ds
   cudaStream_t st = as_stream(stream);
   const int g = grid_for(n, 256);
   if (src_dtype == MASR_F32 && dst_dtype == MASR_F32)
-    permute_cf_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), rows, C, F, inverse_add);
+    launch_pdl(permute_cf_kernel<float, float>, dim3(g), dim3(256), 0, st, static_cast<const float*>(src), static_cast<float*>(dst), rows, C, F, inverse_add);
   else if (src_dtype == MASR_F32 && dst_dtype == MASR_BF16 && !inverse_add)
-    permute_cf_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), rows, C, F, 0);
+    launch_pdl(permute_cf_kernel<float, __nv_bfloat16>, dim3(g), dim3(256), 0, st, static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), rows, C, F, 0);
   else { set_error("masr_permute_cf: unsupported dtype combination"); return MASR_E_INVALID; }
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
 
 extern "C" int masr_ls_ce_fwd_bwd(const float* logits, const int64_t* gold, int N, int C, float eps, float inv_n,
-                                  const float* inv_n_dev, double* stats, int64_t* argmax, float* dlogits, void* stream) {
+                                  const float* inv_n_dev, double* stats, int64_t* argmax, void* dlogits, int dl_dtype,
+                                  int64_t ld_dl, void* stream) {
   MASR_REQUIRE(C > 0, "ls_ce: C must be positive");
+  MASR_REQUIRE(dlogits == nullptr || ld_dl >= C, "ls_ce: dlogits leading dimension must be >= C");
   if (N == 0) return MASR_OK;
   const int threads = 128, wpb = threads / 32;
   const int blocks = int(std::min<int64_t>(ceil_div64(N, wpb), int64_t(sm_count()) * 8));
-  ls_ce_kernel<<<blocks, threads, 0, as_stream(stream)>>>(logits, gold, N, C, eps, inv_n, inv_n_dev, stats, argmax, dlogits);
-  MASR_LAUNCH_CHECK();
+  if (dl_dtype == MASR_BF16) {
+    MASR_CHECK_CUDA(launch_pdl(ls_ce_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), 0, as_stream(stream), logits, gold, N, C,
+                               eps, inv_n, inv_n_dev, stats, argmax, static_cast<__nv_bfloat16*>(dlogits), ld_dl));
+  } else {
+    MASR_CHECK_CUDA(launch_pdl(ls_ce_kernel<float>, dim3(blocks), dim3(threads), 0, as_stream(stream), logits, gold, N, C,
+                               eps, inv_n, inv_n_dev, stats, argmax, static_cast<float*>(dlogits), ld_dl));
+  }
   return MASR_OK;
 }

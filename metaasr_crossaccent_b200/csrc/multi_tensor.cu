@@ -26,6 +26,8 @@ __device__ __forceinline__ float clip_coef(const double* sumsq, float max_norm) 
 }
 
 __global__ void __launch_bounds__(MT_THREADS) mt_sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[MT_THREADS / 32];
   const int64_t n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -45,11 +47,15 @@ __global__ void __launch_bounds__(MT_THREADS) mt_sumsq_kernel(const float* __res
   }
 }
 
-__global__ void mt_zero_double_kernel(double* p) { *p = 0.0; }
+__global__ void mt_zero_double_kernel(double* p) {
+  pdl_launch_dependents();
+  pdl_wait(); *p = 0.0; }
 
 __global__ void __launch_bounds__(MT_THREADS)
 mt_clip_sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, int64_t n,
                    const double* __restrict__ sumsq, float max_norm, float lr, float mu, int nesterov, int first) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double ss = *sumsq;
   if (ss != ss) return;                            // NaN gradient norm: skip the step (:245-248)
   const float coef = clip_coef(sumsq, max_norm);
@@ -81,6 +87,8 @@ mt_clip_sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restri
 
 __global__ void __launch_bounds__(MT_THREADS)
 mt_clip_kernel(float* __restrict__ g, int64_t n, const double* __restrict__ sumsq, float max_norm) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float coef = clip_coef(sumsq, max_norm);
   const int64_t n4 = n / 4;
   float4* g4 = reinterpret_cast<float4*>(g);
@@ -93,6 +101,8 @@ mt_clip_kernel(float* __restrict__ g, int64_t n, const double* __restrict__ sums
 __global__ void __launch_bounds__(MT_THREADS)
 mt_accumulate_kernel(float* __restrict__ upd, const float* __restrict__ g, int64_t n,
                      const double* __restrict__ sumsq, float max_norm) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float coef = sumsq != nullptr ? clip_coef(sumsq, max_norm) : 1.f;
   const int64_t n4 = n / 4;
   float4* u4 = reinterpret_cast<float4*>(upd);
@@ -107,6 +117,8 @@ mt_accumulate_kernel(float* __restrict__ upd, const float* __restrict__ g, int64
 
 __global__ void __launch_bounds__(MT_THREADS)
 mt_reptile_delta_kernel(float* __restrict__ upd, const float* __restrict__ theta, const float* __restrict__ phi, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n4 = n / 4;
   float4* u4 = reinterpret_cast<float4*>(upd);
   const float4* t4 = reinterpret_cast<const float4*>(theta);
@@ -125,6 +137,8 @@ __global__ void __launch_bounds__(MT_THREADS)
 mt_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ upd,
                int64_t n, float count, float step_size, float b1, float b2, float eps, float bc2_sqrt,
                const double* __restrict__ skip_if_nan, const double* __restrict__ clip_sumsq, float max_norm) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (skip_if_nan != nullptr) { const double ss = *skip_if_nan; if (ss != ss) return; }
   const float coef = (clip_sumsq != nullptr ? clip_coef(clip_sumsq, max_norm) : 1.f);
   const int64_t n4 = n / 4;
@@ -155,6 +169,8 @@ mt_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__
 
 __global__ void __launch_bounds__(MT_THREADS)
 mt_axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n4 = n / 4;
   float4* y4 = reinterpret_cast<float4*>(y);
   const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -181,9 +197,9 @@ using namespace masr;
 extern "C" int masr_mt_sumsq(const float* g, int64_t n, double* out, int zero_first, void* stream) {
   MT_ALIGN_CHECK(g);
   cudaStream_t st = as_stream(stream);
-  if (zero_first) { mt_zero_double_kernel<<<1, 1, 0, st>>>(out); MASR_LAUNCH_CHECK(); }
+  if (zero_first) { launch_pdl(mt_zero_double_kernel, dim3(1), dim3(1), 0, st, out); MASR_LAUNCH_CHECK(); }
   if (n == 0) return MASR_OK;
-  mt_sumsq_kernel<<<mt_grid(n / 4), MT_THREADS, 0, st>>>(g, n, out);
+  launch_pdl(mt_sumsq_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, st, g, n, out);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -192,7 +208,7 @@ extern "C" int masr_mt_clip_sgd(float* p, float* g, float* buf, int64_t n, const
                                 float lr, float momentum, int nesterov, int first_step, void* stream) {
   MT_ALIGN_CHECK(p, g, buf);
   if (n == 0) return MASR_OK;
-  mt_clip_sgd_kernel<<<mt_grid(n / 4), MT_THREADS, 0, as_stream(stream)>>>(p, g, buf, n, sumsq, max_norm, lr, momentum, nesterov, first_step);
+  launch_pdl(mt_clip_sgd_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), p, g, buf, n, sumsq, max_norm, lr, momentum, nesterov, first_step);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -200,7 +216,7 @@ extern "C" int masr_mt_clip_sgd(float* p, float* g, float* buf, int64_t n, const
 extern "C" int masr_mt_clip(float* g, int64_t n, const double* sumsq, float max_norm, void* stream) {
   MT_ALIGN_CHECK(g);
   if (n == 0) return MASR_OK;
-  mt_clip_kernel<<<mt_grid(n / 4), MT_THREADS, 0, as_stream(stream)>>>(g, n, sumsq, max_norm);
+  launch_pdl(mt_clip_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), g, n, sumsq, max_norm);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -208,7 +224,7 @@ extern "C" int masr_mt_clip(float* g, int64_t n, const double* sumsq, float max_
 extern "C" int masr_mt_accumulate(float* upd, const float* g, int64_t n, const double* sumsq, float max_norm, void* stream) {
   MT_ALIGN_CHECK(upd, g);
   if (n == 0) return MASR_OK;
-  mt_accumulate_kernel<<<mt_grid(n / 4), MT_THREADS, 0, as_stream(stream)>>>(upd, g, n, sumsq, max_norm);
+  launch_pdl(mt_accumulate_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), upd, g, n, sumsq, max_norm);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -216,7 +232,7 @@ extern "C" int masr_mt_accumulate(float* upd, const float* g, int64_t n, const d
 extern "C" int masr_mt_reptile_delta(float* upd, const float* theta, const float* phi, int64_t n, void* stream) {
   MT_ALIGN_CHECK(upd, theta, phi);
   if (n == 0) return MASR_OK;
-  mt_reptile_delta_kernel<<<mt_grid(n / 4), MT_THREADS, 0, as_stream(stream)>>>(upd, theta, phi, n);
+  launch_pdl(mt_reptile_delta_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), upd, theta, phi, n);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -228,7 +244,7 @@ extern "C" int masr_mt_adam(float* p, float* m, float* v, const float* upd, int6
   if (n == 0) return MASR_OK;
   const float step_size = float(double(lr) / bc1);
   const float bc2_sqrt = float(sqrt(bc2));
-  mt_adam_kernel<<<mt_grid(n / 4), MT_THREADS, 0, as_stream(stream)>>>(
+  launch_pdl(mt_adam_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), 
       p, m, v, upd, n, count, step_size, beta1, beta2, eps, bc2_sqrt, skip_if_nan, clip_sumsq, max_norm);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
@@ -237,7 +253,7 @@ extern "C" int masr_mt_adam(float* p, float* m, float* v, const float* upd, int6
 extern "C" int masr_mt_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
   MT_ALIGN_CHECK(y, x);
   if (n == 0) return MASR_OK;
-  mt_axpy_kernel<<<mt_grid(n / 4), MT_THREADS, 0, as_stream(stream)>>>(y, x, a, n);
+  launch_pdl(mt_axpy_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), y, x, a, n);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

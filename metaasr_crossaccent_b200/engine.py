@@ -392,7 +392,12 @@ class TransformerEngine:
         # ---- label-smoothed CE, accuracy, d logits
         be.zero_(self.stats)
         argmax = buf("argmax", (Md,), torch.int64)
-        dlogits = buf("dlogits", (Md, C), f32) if want_grad else None
+        # d logits in the compute dtype, rows padded to a multiple of 8 elements so that (in bf16 mode) the
+        # output-projection dgrad / wgrad run on the tcgen05 path (TMA needs 16-byte row strides)
+        dlogits = None
+        if want_grad:
+            dlogits = buf("dlogits", (Md, (C + 7) // 8 * 8))[:, :C]
+            ws["dlogits_v"] = dlogits
         be.ls_ce(logits, db["ys_out"].view(-1), self.eps_ls, 1.0 / max(db["n_total"], 1), self.stats, argmax, dlogits,
                  db.get("inv_n_dev"))
         return ws
@@ -442,7 +447,7 @@ class TransformerEngine:
         # Buffers read by a forked weight-gradient GEMM are private to their (layer, sub-layer): the dgrad
         # chain on the main stream must not overwrite them while the side stream still reads them.
         # ---- output projection + final decoder norm
-        dlogits = ws["dlogits"]
+        dlogits = ws["dlogits_v"]
         wgrad(ws["d.out"], dlogits, G["char_trans.weight"], G["char_trans.bias"])
         g_out = buf("g.out", (Md, d))
         be.linear_dgrad(dlogits, W["char_trans.weight"], g_out)

@@ -318,7 +318,8 @@ class CudaBackend:
     def ls_ce(self, logits, gold, eps, inv_n, stats, argmax, dlogits, inv_n_dev=None):
         N, Cc = logits.shape
         self._call("masr_ls_ce_fwd_bwd", _p(logits), _p(gold), N, Cc, float(eps), float(inv_n), _p(inv_n_dev), _p(stats),
-                   _p(argmax), _p(dlogits), self.stream)
+                   _p(argmax), _p(dlogits), _dt(dlogits) if dlogits is not None else F32,
+                   dlogits.stride(0) if dlogits is not None else Cc, self.stream)
 
     def set_seed_ptr(self, t):
         """Device-resident dropout seed offset (uint64 stored in an int64 tensor); see masr_set_seed_ptr."""

@@ -296,6 +296,13 @@ def test_ls_ce(dev):
     assert abs(float(s1[0]) - float(s2[0])) <= 1e-5 * abs(float(s2[0]))
     close(g1, g2, torch.float32, 1e-5, "dlogits")
     assert float(g1[::7].abs().max()) == 0.0
+    # bf16 gradient written into rows padded to a multiple of 8 elements (feeds the tcgen05 GEMMs directly)
+    pad = torch.full((N, 368), 7.0, device=dev, dtype=torch.bfloat16)
+    s3 = torch.zeros(4, dtype=torch.float64, device=dev)
+    cb.ls_ce(logits, gold, 0.2, 1.0 / n_tot, s3, a1, pad[:, :C])
+    assert torch.equal(s3, s1)
+    assert float((pad[:, :C].float() - g2).abs().max()) <= 8e-3 * float(g2.abs().max())
+    assert float(pad[:, C:].min()) == 7.0                        # padding column untouched
 
 
 def test_flat_multi_tensor_ops(dev):
