@@ -87,7 +87,7 @@ attn_fwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, i
         l[r] = l[r] * corr + warp_sum(pj);
         float pd = pj;
         if (p > 0.f && valid)
-          pd = pj * drop_scale(p, inv_keep, seed, site, (uint64_t(bh) * Lq + qi) * uint64_t(Lk) + kj);
+          pd = pj * attn_drop_scale(p, seed, site, uint32_t(bh) * uint32_t(Lq) + uint32_t(qi), kj);
         float a0 = acc0[r] * corr, a1 = acc1[r] * corr;
         const int jn = min(32, nk - c0);
         for (int jj = 0; jj < jn; ++jj) {
@@ -178,7 +178,7 @@ attn_bwd_dq_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k
           float d = 0.f, dp = 0.f;
           for (int c = 0; c < hd; ++c) { d = fmaf(qrow[c], krow[c], d); dp = fmaf(dorow[c], vrow[c], dp); }
           const float pj = expf(d * scale - L[r]);
-          const float dm = drop_scale(p, inv_keep, seed, site, (uint64_t(bh) * Lq + qi) * uint64_t(Lk) + kj);
+          const float dm = attn_drop_scale(p, seed, site, uint32_t(bh) * uint32_t(Lq) + uint32_t(qi), kj);
           ds = pj * (dp * dm - D[r]) * scale;
         }
         const int jn = min(32, nk - c0);
@@ -262,7 +262,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ 
             float d = 0.f, dp = 0.f;
             for (int c = 0; c < hd; ++c) { d = fmaf(qrow[c], krow[c], d); dp = fmaf(dorow[c], vrow[c], dp); }
             const float pj = expf(d * scale - Ls[i]);
-            const float dm = drop_scale(p, inv_keep, seed, site, (uint64_t(bh) * Lq + qi) * uint64_t(Lk) + kj);
+            const float dm = attn_drop_scale(p, seed, site, uint32_t(bh) * uint32_t(Lq) + uint32_t(qi), kj);
             pm = pj * dm;
             ds = pj * (dp * dm - Ds[i]) * scale;
           }

@@ -2,11 +2,16 @@
 //
 // Same contract as attention.cu (masks from lengths, dropout replayed from (seed, site, index)); this is
 // the fast path used for the hkust network (8 heads x 64).  One CTA = 128 query rows (fwd) or 128 key rows
-// (bwd) of one (batch, head); 192 threads:
+// (bwd) of one (batch, head); 320 threads:
 //   warp 0   TMA producer (Q / K / V / dO tiles as [128 rows x 64] boxes, 128B swizzle)
 //   warp 1   MMA issuer, TMEM owner
-//   warps 2-5 soft-max warps: thread r owns row r (TMEM lane r): tcgen05.ld of S / dP, exp, masks, dropout,
-//            P / dS written back to shared memory in the UMMA K-major swizzled layout for the second GEMMs
+//   warps 2-9 soft-max warps: TWO threads per row (TMEM lane r = 32 * (warp % 4) + lane; warps 2-5 own key
+//            columns 0-63 of the tile, warps 6-9 columns 64-127): tcgen05.ld of S / dP, exp2, masks, dropout,
+//            P / dS written back to shared memory in the UMMA K-major swizzled layout for the second GEMMs.
+//            The soft-max is the critical path of these small problems (the GEMMs take < 1 us): one warp per
+//            scheduler with 128 keys per thread was latency-bound at ~19 us per tile; two warps per scheduler,
+//            a single MUFU.EX2 per element, tile-uniform masking and a dropout hash shared by two keys cut it
+//            to ~2 us.  Row maxima / sums are exchanged between the two threads of a row through shared memory.
 // Forward, per 128-key tile:  S = Q K^T -> TMEM;  P = softmax-tile -> smem;  O_tile = P V -> TMEM;
 //            O (registers) = O * corr + O_tile  (online soft-max over key tiles).
 // Backward, per 128-query tile (keys fixed):  S = Q K^T, dP = dO V^T -> TMEM;  P, dS -> smem;
@@ -18,7 +23,8 @@
 
 namespace masr {
 
-constexpr int AU_THREADS = 192;
+constexpr int AU_THREADS = 320;
+constexpr int AU_SM_THREADS = 256;     // soft-max threads (warps 2..9)
 constexpr int AU_TILE = 128;
 constexpr uint32_t AU_T64 = 128 * 128;          // bytes of a [128 rows x 64 bf16] tile
 constexpr uint32_t AU_T128 = 2 * AU_T64;        // [128 rows x 128 bf16] = two 64-wide k-blocks
@@ -32,18 +38,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {      // single MUFU.EX2 (flush-to-zero; 2^-inf = 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 struct AttnFwdParams {
   int B, H, Lq, Lk;
   const int64_t* klens;
   int causal;
   float scale, p_drop, inv_keep;
+  uint32_t thr16;                // dropout threshold on 16-bit uniforms (common.cuh attn_drop_*)
   uint64_t seed; uint32_t site;
   __nv_bfloat16* out; int64_t ldo;
   float* lse;
   const uint64_t* seed_ptr;      // device-resident per-step seed offset (CUDA-graph replay), may be NULL
 };
 
-__global__ void __launch_bounds__(AU_THREADS, 1)
+__global__ void __launch_bounds__(AU_THREADS, 2)
 attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, AttnFwdParams p) {
   using namespace umma;
@@ -60,6 +74,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* p_full = bars + 6;
   uint64_t* o_full = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch = reinterpret_cast<float*>(bars + 10);        // [2][128] row maxima, then [2][128] row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -68,7 +83,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, AU_SM_THREADS); mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -124,62 +139,69 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;                   // which 64 key columns of the tile this thread owns
     const int r = qd * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     // soft-max statistics are kept in the log2 domain: exp(x) = exp2(x * log2 e) is a single MUFU.EX2
     const float sl2 = p.scale * 1.4426950408889634f;
+    const bool drop = p.p_drop > 0.f;
+    const uint32_t rowkey = attn_drop_rowkey(seed_eff, p.site, uint32_t(bh) * uint32_t(p.Lq) + uint32_t(qi));
     float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
+    float o[32];                                         // O columns [32*half, 32*half+32) of this row
 #pragma unroll
-    for (int j = 0; j < 64; ++j) o[j] = 0.f;
+    for (int j = 0; j < 32; ++j) o[j] = 0.f;
     for (int t = 0; t < ntiles; ++t) {
-      const int k0 = t * AU_TILE;
+      const int c0 = t * AU_TILE + half * 64;            // first key of this thread's 64 columns
+      // keys [c0, c0 + lim) are visible to this row: key padding / causal mask as ONE bound
+      const int lim = max(0, min(64, min(kmax, p.causal ? qi + 1 : kmax) - c0));
       mbar_wait(s_full, t & 1);
       tc_fence_after();
-      // pass 1: row maximum of the masked, scaled scores
+      float sv[64];
+      tmem_ld_32x32(tmem_S + lane_addr + half * 64, sv);
+      tmem_ld_32x32(tmem_S + lane_addr + half * 64 + 32, sv + 32);
+      tmem_ld_wait();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
+      if (lim == 64) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int kj = k0 + c * 32 + j;
-          const bool ok = (kj < kmax) && (!p.causal || kj <= qi);
-          if (ok) mx = fmaxf(mx, v[j] * sl2);
-        }
+        for (int j = 0; j < 64; ++j) mx = fmaxf(mx, sv[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) mx = fmaxf(mx, j < lim ? sv[j] : -INFINITY);
       }
+      mx *= sl2;                                         // sl2 > 0: scaling commutes with the maximum
+      xch[half * 128 + r] = mx;
+      softmax_bar();
+      mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f(m_run - m_use);          // 2^(-inf) = 0 on the first tile
+      const float corr = fast_exp2(m_run - m_use);       // 2^(-inf) = 0 on the first tile
       float lsum = 0.f;
-      // pass 2: probabilities -> shared memory (bf16, K-major swizzled), row sum
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
+      // probabilities -> shared memory (bf16, K-major swizzled), row sum; 8 keys = one 16-byte chunk
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int kj = k0 + c * 32 + j;
-          const bool ok = (kj < kmax) && (!p.causal || kj <= qi);
-          float pr = ok ? exp2f(v[j] * sl2 - m_use) : 0.f;
-          lsum += pr;
-          if (p.p_drop > 0.f && ok)
-            pr *= drop_scale(p.p_drop, p.inv_keep, seed_eff, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
-          v[j] = pr;
-        }
+      for (int g = 0; g < 8; ++g) {
+        float pr[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-          pk.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(sP + sw_chunk_off(r, c * 4 + g)) = pk;
+        for (int e = 0; e < 8; ++e) {
+          const int j = g * 8 + e;
+          const float ex = fast_exp2(fmaf(sv[j], sl2, -m_use));
+          pr[e] = (lim == 64 || j < lim) ? ex : 0.f;
+          lsum += pr[e];
         }
+        if (drop) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const uint32_t bits = attn_drop_pair(rowkey, uint32_t(c0 + g * 8 + e) >> 1);
+            pr[e] = ((bits & 0xffffu) >= p.thr16) ? pr[e] * p.inv_keep : 0.f;
+            pr[e + 1] = ((bits >> 16) >= p.thr16) ? pr[e + 1] * p.inv_keep : 0.f;
+          }
+        }
+        uint4 pk;
+        pk.x = pack_bf16x2(pr[0], pr[1]); pk.y = pack_bf16x2(pr[2], pr[3]);
+        pk.z = pack_bf16x2(pr[4], pr[5]); pk.w = pack_bf16x2(pr[6], pr[7]);
+        *reinterpret_cast<uint4*>(sP + sw_chunk_off(r, half * 8 + g)) = pk;
       }
-      l_run = l_run * corr + lsum;
+      l_run = l_run * corr + lsum;                       // partial over this thread's columns (same m in both halves)
       m_run = m_new;
       tc_fence_before();
       fence_proxy_async();
@@ -187,27 +209,28 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       // O = O * corr + P V
       mbar_wait(o_full, t & 1);
       tc_fence_after();
+      float v[32];
+      tmem_ld_32x32(tmem_O + lane_addr + half * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[c * 32 + j] = o[c * 32 + j] * corr + v[j];
-      }
+      for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], corr, v[j]);
       tc_fence_before();
     }
+    xch[256 + half * 128 + r] = l_run;
+    softmax_bar();
+    l_run += xch[256 + (half ^ 1) * 128 + r];
     if (qi < p.Lq) {
       const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* orow = p.out + (int64_t(b) * p.Lq + qi) * p.ldo + h * 64;
+      __nv_bfloat16* orow = p.out + (int64_t(b) * p.Lq + qi) * p.ldo + h * 64 + half * 32;
 #pragma unroll
-      for (int j = 0; j < 64; j += 8) {
+      for (int j = 0; j < 32; j += 8) {
         float t8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) t8[e] = o[j + e] * inv_l;
         store8<__nv_bfloat16>(orow + j, t8);
       }
-      p.lse[int64_t(bh) * p.Lq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+      if (half == 0)
+        p.lse[int64_t(bh) * p.Lq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
     }
   }
   tc_fence_before();
@@ -240,6 +263,7 @@ struct AttnBwdParams {
   const int64_t* klens;
   int causal;
   float scale, p_drop, inv_keep;
+  uint32_t thr16;
   uint64_t seed; uint32_t site;
   const float* lse; const float* dsum;
   __nv_bfloat16* dq; int64_t lddq;
@@ -278,7 +302,7 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); prefetch_tmap(&map_do);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(dq_full, 1); mbar_init(dkv_full, 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, AU_SM_THREADS); mbar_init(dq_full, 1); mbar_init(dkv_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -353,35 +377,44 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;                   // key columns [64*half, 64*half+64) of S / dP; 32 of the 64 output columns
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
+    const bool drop = p.p_drop > 0.f;
     for (int t = 0; t < ntiles; ++t) {
       const int q0 = (qt_begin + t) * AU_TILE;
       const int qi = q0 + r;
       const bool qok = qi < p.Lq;
       const float lse_r = qok ? p.lse[int64_t(bh) * p.Lq + qi] * 1.4426950408889634f : 0.f;    // log2 domain
       const float d_r = qok ? p.dsum[int64_t(bh) * p.Lq + qi] : 0.f;
+      const uint32_t rowkey = attn_drop_rowkey(seed_eff, p.site, uint32_t(bh) * uint32_t(p.Lq) + uint32_t(qi));
       mbar_wait(sdp_full, t & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;                     // 32-column chunk of the key tile
+        const int c0 = k0 + c * 32;
+        const int lim = qok ? max(0, min(32, min(klen, p.causal ? qi + 1 : klen) - c0)) : 0;
         float sv[32], dp[32];
         tmem_ld_32x32(tm_S + lane_addr + c * 32, sv);
         tmem_ld_32x32(tm_dP + lane_addr + c * 32, dp);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int kj = k0 + c * 32 + j;
-          const bool ok = qok && (kj < klen) && (!p.causal || kj <= qi);
-          float pr = 0.f, ds = 0.f;
-          if (ok) {
-            pr = exp2f(sv[j] * sl2 - lse_r);
-            const float dm = drop_scale(p.p_drop, p.inv_keep, seed_eff, p.site, (uint64_t(bh) * p.Lq + qi) * uint64_t(p.Lk) + kj);
-            ds = pr * (dp[j] * dm - d_r) * p.scale;
-            pr *= dm;
+        for (int j = 0; j < 32; j += 2) {
+          float dm0 = 1.f, dm1 = 1.f;
+          if (drop) {
+            const uint32_t bits = attn_drop_pair(rowkey, uint32_t(c0 + j) >> 1);
+            dm0 = ((bits & 0xffffu) >= p.thr16) ? p.inv_keep : 0.f;
+            dm1 = ((bits >> 16) >= p.thr16) ? p.inv_keep : 0.f;
           }
-          sv[j] = pr; dp[j] = ds;
+          const float e0 = fast_exp2(fmaf(sv[j], sl2, -lse_r)), e1 = fast_exp2(fmaf(sv[j + 1], sl2, -lse_r));
+          const float p0 = (j < lim) ? e0 : 0.f, p1 = (j + 1 < lim) ? e1 : 0.f;
+          const float g0 = (j < lim) ? dp[j] : 0.f, g1 = (j + 1 < lim) ? dp[j + 1] : 0.f;   // dP may hold garbage there
+          dp[j] = p0 * (g0 * dm0 - d_r) * p.scale;
+          dp[j + 1] = p1 * (g1 * dm1 - d_r) * p.scale;
+          sv[j] = p0 * dm0;
+          sv[j + 1] = p1 * dm1;
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -400,37 +433,35 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_arrive(pds_full);
       mbar_wait(dq_full, t & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         float v[32];
-        tmem_ld_32x32(tm_dQ + lane_addr + c * 32, v);
+        tmem_ld_32x32(tm_dQ + lane_addr + half * 32, v);
         tmem_ld_wait();
         if (qok) {
-          __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64 + c * 32;
+          __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64 + half * 32;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) store8<__nv_bfloat16>(drow + j, v + j);
         }
       }
       tc_fence_before();
     }
-    // dK / dV of this key tile (row r = key k0 + r)
+    // dK / dV of this key tile (row r = key k0 + r), output columns [32*half, 32*half+32)
     const int kj = k0 + r;
     float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (active) {
       mbar_wait(dkv_full, 0);
       tc_fence_after();
     }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       float vk[32], vv[32];
       if (active) {
-        tmem_ld_32x32(tm_dK + lane_addr + c * 32, vk);
-        tmem_ld_32x32(tm_dV + lane_addr + c * 32, vv);
+        tmem_ld_32x32(tm_dK + lane_addr + half * 32, vk);
+        tmem_ld_32x32(tm_dV + lane_addr + half * 32, vv);
         tmem_ld_wait();
       }
       if (kj < p.Lk) {
-        __nv_bfloat16* dkr = p.dk + (int64_t(b) * p.Lk + kj) * p.lddk + h * 64 + c * 32;
-        __nv_bfloat16* dvr = p.dv + (int64_t(b) * p.Lk + kj) * p.lddv + h * 64 + c * 32;
+        __nv_bfloat16* dkr = p.dk + (int64_t(b) * p.Lk + kj) * p.lddk + h * 64 + half * 32;
+        __nv_bfloat16* dvr = p.dv + (int64_t(b) * p.Lk + kj) * p.lddv + h * 64 + half * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           store8<__nv_bfloat16>(dkr + j, active ? vk + j : zero8);
@@ -442,9 +473,9 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     // except when the whole key tile is padding (klen == 0): then dQ is zero.
     if (!active && gridDim.x == 1) {
       for (int qi = r; qi < p.Lq; qi += AU_TILE) {
-        __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64;
+        __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64 + half * 32;
 #pragma unroll
-        for (int j = 0; j < 64; j += 8) store8<__nv_bfloat16>(drow + j, zero8);
+        for (int j = 0; j < 32; j += 8) store8<__nv_bfloat16>(drow + j, zero8);
       }
     }
   }
@@ -461,7 +492,7 @@ static int rows_map(CUtensorMap* out, const void* base, int64_t ld, int64_t nrow
   return make_tmap_bf16(out, base, 2, dims, strides, box, true);
 }
 
-constexpr size_t AU_FWD_SMEM = AU_T64 + 4 * AU_T64 + AU_T128 + 256 + 1024;
+constexpr size_t AU_FWD_SMEM = AU_T64 + 4 * AU_T64 + AU_T128 + 256 + 2048 + 1024;
 constexpr size_t AU_BWD_SMEM = 2 * AU_T64 + 4 * AU_T64 + 2 * AU_T128 + 256 + 1024;
 
 }  // namespace masr
@@ -477,7 +508,8 @@ extern "C" int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int
   int rc = rows_map(&mq, q, ldq, int64_t(B) * Lq, H * 64); if (rc) return rc;
   rc = rows_map(&mk, k, ldk, int64_t(B) * Lk, H * 64); if (rc) return rc;
   rc = rows_map(&mv, v, ldv, int64_t(B) * Lk, H * 64); if (rc) return rc;
-  AttnFwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed, site,
+  const uint32_t thr16 = attn_drop_thr16(p_drop);
+  AttnFwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? attn_drop_inv_keep(thr16) : 1.f, thr16, seed, site,
                   static_cast<__nv_bfloat16*>(out), ldo, lse, g_seed_dev_ptr};
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_FWD_SMEM))); attr = true; }
@@ -510,7 +542,8 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
     MASR_CHECK_CUDA(launch_pdl(attn_dsum_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(out), ldo,
                                static_cast<const __nv_bfloat16*>(dout), lddo, dsum_ws, B, H, Lq));
   }
-  AttnBwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed, site,
+  const uint32_t thr16 = attn_drop_thr16(p_drop);
+  AttnBwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? attn_drop_inv_keep(thr16) : 1.f, thr16, seed, site,
                   lse, dsum_ws, static_cast<__nv_bfloat16*>(dq), lddq, static_cast<__nv_bfloat16*>(dk), lddk,
                   static_cast<__nv_bfloat16*>(dv), lddv, g_seed_dev_ptr};
   static bool attr = false;

@@ -78,6 +78,29 @@ __device__ __forceinline__ float drop_scale(float p, float inv_keep, uint64_t se
   return u >= p ? inv_keep : 0.f;
 }
 
+// Attention-probability dropout.  All attention kernels (CUDA-core and tcgen05, forward and backward) share this
+// function, so the backward of a site replays the forward's mask whichever kernel ran it.  One 32-bit hash per
+// PAIR of keys, 16 bits each (the soft-max warps are ALU-bound on this); keep-probability = 1 - thr16 / 65536.
+__host__ __device__ __forceinline__ uint32_t attn_drop_thr16(float p) {
+  const float t = p * 65536.f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : uint32_t(t));
+}
+__host__ __device__ __forceinline__ float attn_drop_inv_keep(uint32_t thr16) { return 65536.f / float(65536u - thr16); }
+// row = (batch * heads + head) * Lq + query index
+__device__ __forceinline__ uint32_t attn_drop_rowkey(uint64_t seed, uint32_t site, uint32_t row) {
+  const uint32_t key = lowbias32(uint32_t(seed) ^ lowbias32(uint32_t(seed >> 32) + site * 0x9E3779B9u + 0x85EBCA6Bu));
+  return lowbias32((row * 0x9E3779B9u) ^ key);
+}
+__device__ __forceinline__ uint32_t attn_drop_pair(uint32_t rowkey, uint32_t kpair) { return lowbias32(rowkey + kpair * 0x85EBCA77u); }
+__device__ __forceinline__ bool attn_drop_keep(uint32_t bits, int kj, uint32_t thr16) {
+  return ((bits >> ((kj & 1) << 4)) & 0xffffu) >= thr16;
+}
+__device__ __forceinline__ float attn_drop_scale(float p, uint64_t seed, uint32_t site, uint32_t row, int kj) {
+  if (p <= 0.f) return 1.f;
+  const uint32_t thr = attn_drop_thr16(p);
+  return attn_drop_keep(attn_drop_pair(attn_drop_rowkey(seed, site, row), uint32_t(kj) >> 1), kj, thr) ? attn_drop_inv_keep(thr) : 0.f;
+}
+
 // ------------------------------------------------------------------ warp / block reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -89,3 +89,29 @@ def test_umma_attention_dropout(dev):
     dsum = torch.empty(B * H * L, device=dev)
     cb.attn_bwd(q, k, v, o, do, lse, dsum, dq, dk, dv, B, H, L, L, None, False, 0.25, 99, 3)
     assert abs(float(dv.float().mean()) - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,causal", [(2, 8, 128, 128, False), (3, 8, 33, 33, True), (3, 8, 33, 128, False)])
+def test_umma_attention_dropout_matches_cuda_core_kernels(dev, B, H, Lq, Lk, causal):
+    """The tcgen05 and the CUDA-core attention kernels share ONE dropout function (common.cuh attn_drop_*), so with
+    the same (seed, site) they drop the same probabilities: forward and backward agree to bf16 rounding."""
+    from metaasr_crossaccent_b200.ops import CudaBackend
+    bf = torch.bfloat16
+    cu, cs = CudaBackend(dev, bf, gemm="umma"), CudaBackend(dev, bf, gemm="simt")
+    d = H * 64
+    q = rnd((B * Lq, d), dev, bf, 1)
+    kv = rnd((B * Lk, 2 * d), dev, bf, 2)
+    k, v = kv[:, :d], kv[:, d:]
+    klens = None if causal else torch.tensor([Lk] + [max(1, Lk - 9 * (i + 1)) for i in range(B - 1)], dtype=torch.int64, device=dev)
+    outs = []
+    for be in (cu, cs):
+        o = torch.empty(B * Lq, d, device=dev, dtype=bf)
+        lse = torch.empty(B * H * Lq, device=dev)
+        be.attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, klens, causal, 0.3, 1234, 7)
+        do = rnd((B * Lq, d), dev, bf, 3)
+        dq, dk, dv = torch.empty_like(q), torch.empty(B * Lk, d, device=dev, dtype=bf), torch.empty(B * Lk, d, device=dev, dtype=bf)
+        dsum = torch.empty(B * H * Lq, device=dev)
+        be.attn_bwd(q, k, v, o, do, lse, dsum, dq, dk, dv, B, H, Lq, Lk, klens, causal, 0.3, 1234, 7)
+        outs.append((o, lse, dq, dk, dv))
+    for a, b_, nm in zip(outs[0], outs[1], ("out", "lse", "dq", "dk", "dv")):
+        close(a, b_, bf, what=f"dropout parity {nm}")
