@@ -35,7 +35,7 @@ extern "C" {
 #define MASR_F32 0
 #define MASR_BF16 1
 
-#define MASR_ABI_VERSION 1
+#define MASR_ABI_VERSION 2
 
 int masr_abi_version(void);
 const char* masr_last_error(void);
@@ -91,6 +91,25 @@ int masr_gemm(const void* A, int a_dtype, int64_t sam, int64_t sak,
 int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
                    void* C, int c_dtype, int64_t ldc, const float* bias,
                    int M, int N, int K, int flags, int splitk, void* stream);
+/* Fused epilogue / side outputs of masr_umma_gemm_ex (zero-initialise; NULL = none):
+ *   rowsum     : rowsum[M] (fp32) += sum_k A(m,k).  For a wgrad GEMM (A = dy^T) this is the bias gradient
+ *                (torch: dy.sum(0)); computed on the tensor cores by a second accumulator fed with an all-ones
+ *                B tile, so no separate column-sum pass over dy is needed
+ *   mask       : bf16 [M,N] (row stride ldmask): C = mask > 0 ? C * mask_scale : 0.  With mask = the stored
+ *                output of ReLU(+dropout) and mask_scale = 1/(1-p): the backward of both, fused in a dgrad GEMM
+ *   p_drop     : dropout on C after bias / ReLU with masr_dropout's element index m*N+n under (seed, site)  */
+typedef struct masr_gemm_epilogue {
+  float* rowsum;
+  const void* mask;
+  int64_t ldmask;
+  float mask_scale;
+  float p_drop;
+  uint64_t seed;
+  uint32_t site;
+} masr_gemm_epilogue;
+int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                      void* C, int c_dtype, int64_t ldc, const float* bias,
+                      int M, int N, int K, int flags, int splitk, const masr_gemm_epilogue* epi, void* stream);
 /* Convenience form of the above: A [M,K] and B [N,K] both K-major ("TN"). */
 int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
                       void* C, int c_dtype, int64_t ldc, const float* bias,
@@ -106,7 +125,8 @@ int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float* bias, void
                           int B, int H, int W, int Cin, int Cout, int relu, void* stream);
 int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx, const void* relu_src,
                             int B, int H, int W, int Cin, int Cout, void* stream);
-int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp,
+/* db (may be NULL): [Cout] fp32 bias gradient += sum over pixels of dy, fused (tensor-core row sums). */
+int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp, float* db,
                             int B, int H, int W, int Cin, int Cout, void* stream);
 /* conv1: Cin = 1.  x [B,H,W] fp32 -> y [B,H,W,Cout] act, bias+ReLU fused.  w [Cout,9] fp32. */
 int masr_conv1_fwd(const float* x, const float* w, const float* bias, void* y, int y_dtype,

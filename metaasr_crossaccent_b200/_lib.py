@@ -35,10 +35,11 @@ SIGNATURES = {
     "masr_ctc_debug_read": [c_p],
     "masr_gemm": [c_p, c_i, c_i64, c_i64, c_p, c_i, c_i64, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_gemm": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_umma_gemm_ex": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "masr_umma_gemm_tn": [c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_dgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
-    "masr_umma_conv3x3_wgrad": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_umma_conv3x3_wgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_conv1_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_conv1_wgrad": [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_im2col3x3": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -80,6 +81,12 @@ SIGNATURES = {
 }
 SPECIAL_RESTYPE = {"masr_last_error": C.c_char_p, "masr_ctc_workspace_bytes": c_sz}
 EXTRA = {"masr_last_error": [], "masr_ctc_workspace_bytes": [c_i, c_i, c_i, c_i]}
+
+
+class GemmEpilogue(C.Structure):
+    """masr_gemm_epilogue of include/metaasr_b200.h."""
+    _fields_ = [("rowsum", c_p), ("mask", c_p), ("ldmask", c_i64), ("mask_scale", c_f), ("p_drop", c_f),
+                ("seed", c_u64), ("site", c_u32)]
 
 
 class MetaASRLibraryError(RuntimeError):

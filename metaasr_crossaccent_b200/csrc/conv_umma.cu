@@ -11,6 +11,7 @@
 //   dgrad: D[pix, ci] = sum_{tap,co} dY[pix-tap, co] * Wp[co, tap*Cin+ci]     A K-major (4-D), B MN-major
 //   wgrad: D_tap[co, ci] = sum_pix dY[pix, co] * X[pix+tap, ci]               A, B MN-major (4-D), split over
 //          pixel tiles across CTAs, 3 taps (one kernel row) accumulate side by side in TMEM, fp32 atomics out
+#include <type_traits>
 #include "common.cuh"
 #include "umma.cuh"
 #include "epilogue.cuh"
@@ -172,8 +173,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int64_t pix = (int64_t(b) * p.H + h) * p.W + w;
     __nv_bfloat16* orow = valid ? p.out + pix * p.Cn : nullptr;
     if (has_mask) mbar_wait(mask_bar, 0);
-    epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, orow, nullptr, BN, true,
-                                     EPI_STORE, MODE == 0 && p.relu != 0, has_mask ? smask : nullptr);
+    EpiOpts o;
+    o.sbias = use_bias ? sbias : nullptr;
+    o.relu = MODE == 0 && p.relu != 0;
+    o.smask = has_mask ? smask : nullptr;
+    epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, orow, BN, true, EPI_STORE, o);
   }
   tc_fence_before();
   __syncthreads();
@@ -185,6 +189,7 @@ struct WgradParams {
   int B, H, W, Cout, Cin;
   int tw, th, nw, nh;
   float* dwp;          // [Cout, 9*Cin] fp32, accumulated with atomics
+  float* db;           // [Cout] fp32 bias gradient (+= sum over pixels of dy), may be NULL
 };
 
 // One CTA: kernel row dh = blockIdx.y - 1, pixel tiles blockIdx.x, +gridDim.x, ...  (split-K over pixels).
@@ -199,13 +204,16 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   constexpr uint32_t TMEM_COLS = (3 * CI <= 256) ? 256 : 512;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  unsigned char* sones = smem + STAGES * STAGE_BYTES;     // 2 KB of bf16 1.0: B operand of the bias-gradient MMA
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sones + 2048);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  static_assert(3 * CI + 16 <= TMEM_COLS, "bias-gradient accumulator must fit");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dh = int(blockIdx.y) - 1;
+  const bool rowsum = p.db != nullptr && blockIdx.y == 0;  // the dh = -1 CTAs also sum dy over their pixels
   const int rows = p.th * p.tw;                            // <= 64 pixel rows per stage
   const int ntiles = p.B * p.nh * p.nw;
   const int my_tiles = (ntiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
@@ -215,6 +223,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   // rows [th*tw, 64) of every chunk are never written by TMA: zero the ring once so they contribute 0
   for (uint32_t i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += CV_THREADS)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 128) reinterpret_cast<uint4*>(sones)[threadIdx.x] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   fence_proxy_async();
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_dy);
@@ -253,24 +262,37 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, CI, 1, 1);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+      constexpr uint32_t idesc_ones = make_idesc_bf16(128, 16, 1, 0);
+      const uint64_t dones = desc_kmajor_sw128(smem_u32(sones));
+      // two copies of the loop (with / without the bias-gradient accumulator): no conditionally issued tcgen05.mma
+      auto tloop = [&](auto with_rowsum) {
+        constexpr bool RS = decltype(with_rowsum)::value;
+        for (int it = 0; it < my_tiles; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const uint32_t sb = sa + A_BYTES + j * B_BYTES;
+          for (int j = 0; j < 3; ++j) {
+            const uint32_t sb = sa + A_BYTES + j * B_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = desc_mnmajor_sw128(sa + k * 2048, 8192);
-            const uint64_t db = desc_mnmajor_sw128(sb + k * 2048, 8192);
-            mma_f16_ss(tmem_base + uint32_t(j * CI), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = desc_mnmajor_sw128(sa + k * 2048, 8192);
+              const uint64_t db = desc_mnmajor_sw128(sb + k * 2048, 8192);
+              mma_f16_ss(tmem_base + uint32_t(j * CI), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
           }
+          if constexpr (RS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss(tmem_base + uint32_t(3 * CI), desc_mnmajor_sw128(sa + k * 2048, 8192), dones, idesc_ones,
+                         (it > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(&empty_bar[s]);
         }
-        mma_commit(&empty_bar[s]);
-      }
+      };
+      if (rowsum) tloop(std::true_type{}); else tloop(std::false_type{});
       mma_commit(tmem_full_bar);
     }
   } else {
@@ -284,8 +306,13 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         const int tap = (dh + 1) * 3 + j;
         // staged through shared memory: coalesced fp32 atomics (consecutive lanes -> consecutive addresses)
         float* dst = (co < p.Cout) ? p.dwp + int64_t(co) * (9 * p.Cin) + tap * p.Cin : nullptr;
-        epilogue_tile<CI, float>(tmem_base + uint32_t(j * CI), q, lane, smem, nullptr, dst, nullptr, CI, true,
-                                 EPI_ATOMIC, false);
+        epilogue_tile<CI, float>(tmem_base + uint32_t(j * CI), q, lane, smem, dst, CI, true, EPI_ATOMIC, EpiOpts());
+      }
+      if (rowsum) {                 // column 0 of the ones-accumulator = sum over this CTA's pixels of dy[:, co]
+        float v[32];
+        tmem_ld_32x32(tmem_base + uint32_t(3 * CI) + (uint32_t(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (co < p.Cout) atomicAdd(p.db + co, v[0]);
       }
     }
   }
@@ -372,7 +399,7 @@ extern "C" int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx,
 }
 
 // dwp[Cout, 9*Cin] (fp32) += sum_pix dy[pix, co] * x[pix+tap, ci]
-extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp,
+extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp, float* db,
                                        int B, int H, int W, int Cin, int Cout, void* stream) {
   MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
   if (B * H * W == 0) return MASR_OK;
@@ -382,19 +409,19 @@ extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp
   if (rc != MASR_OK) return rc;
   rc = act_map(&mx, x, B, H, W, Cin, t.tw, t.th);
   if (rc != MASR_OK) return rc;
-  WgradParams p{B, H, W, Cout, Cin, t.tw, t.th, t.nw, t.nh, dwp};
+  WgradParams p{B, H, W, Cout, Cin, t.tw, t.th, t.nw, t.nh, dwp, db};
   const int ntiles = B * t.nh * t.nw;
   const int gx = std::max(1, std::min(ntiles, sm_count() / 3));
   dim3 grid(unsigned(gx), 3, 1);
   cudaStream_t st = as_stream(stream);
   if (Cin == 64) {
     constexpr int ST = 4;
-    const size_t smem = ST * (16384 + 3 * 8192) + 1024 + 256;
+    const size_t smem = ST * (16384 + 3 * 8192) + 2048 + 1024 + 256;
     rc = set_smem(umma_conv_wgrad_kernel<64, ST>, smem); if (rc) return rc;
     MASR_CHECK_CUDA(launch_pdl(umma_conv_wgrad_kernel<64, ST>, grid, dim3(CV_THREADS), smem, st, mdy, mx, p));
   } else {
     constexpr int ST = 3;
-    const size_t smem = ST * (16384 + 3 * 16384) + 1024 + 256;
+    const size_t smem = ST * (16384 + 3 * 16384) + 2048 + 1024 + 256;
     rc = set_smem(umma_conv_wgrad_kernel<128, ST>, smem); if (rc) return rc;
     MASR_CHECK_CUDA(launch_pdl(umma_conv_wgrad_kernel<128, ST>, grid, dim3(CV_THREADS), smem, st, mdy, mx, p));
   }

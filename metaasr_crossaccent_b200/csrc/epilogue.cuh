@@ -1,5 +1,6 @@
 // Shared epilogue of the tcgen05 kernels: TMEM accumulator tile [128 rows x BN fp32] -> registers ->
-// (bias, ReLU) -> shared-memory staging tile -> COALESCED global stores / accumulates / fp32 atomics.
+// (bias, ReLU, dropout) -> shared-memory staging tile -> (ReLU/dropout-backward mask) -> COALESCED global
+// stores / accumulates / fp32 vector reductions.
 //
 // Phase 1: thread r (= TMEM lane r) converts its row and parks it in the staging tile (rows padded by 16 B:
 //          conflict-free 128-bit shared stores) together with the row's global destination pointer.
@@ -22,18 +23,37 @@ struct EpiLayout {
   static constexpr int BYTES = PTR_OFF + 128 * 16;
 };
 
+// Optional fused element-wise work of one tile
+struct EpiOpts {
+  const float* sbias = nullptr;          // BN floats in shared memory
+  bool relu = false;                     // max(x, 0) after the bias
+  // forward dropout applied after bias / ReLU: element (row, col) of the tile has the linear index
+  // drop_row_base + col  (same index as masr_dropout on the contiguous [M, N] tensor)
+  float p_drop = 0.f, inv_keep = 1.f;
+  uint64_t seed = 0; uint32_t site = 0;
+  int64_t drop_row_base = 0;
+  // backward mask: output is zeroed where mask <= 0 and multiplied by mask_scale elsewhere.  With
+  // mask = the forward output of ReLU(+dropout) and mask_scale = 1/(1-p) this IS the backward of both
+  // (an element is positive iff it passed the ReLU and was kept)
+  const __nv_bfloat16* mask_row = nullptr;     // global, this thread's row (bf16 outputs only)
+  const unsigned char* smask = nullptr;        // or: mask tile resident in shared memory ([128 x 64] halves of
+                                               // 16 KB in the TMA 128B-swizzled layout, row = TMEM lane)
+  float mask_scale = 1.f;
+};
+
+__device__ __forceinline__ void apply_mask8(float* f, const uint4& mraw, float scale) {
+  float mk[8];
+  load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(&mraw), mk);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = (mk[e] > 0.f) ? f[e] * scale : 0.f;
+}
+
 // stage      : >= EpiLayout::BYTES bytes of shared memory, 16 B aligned, private to the 4 epilogue warps
-// sbias      : BN floats in shared memory or nullptr
 // dst_row    : global pointer of this thread's output row (BN contiguous OutT), nullptr = row not stored
-// mask_row   : optional bf16 row (same shape); output is zeroed where mask <= 0 (ReLU backward)
 // ncols      : number of valid columns (<= BN); vec_ok: rows are 16 B aligned and ncols == BN
-// smask      : optional mask tile already resident in shared memory (bf16 output, vec_ok only): [128 rows x
-//              64 ch] halves of 16 KB in the TMA 128B-swizzled layout, row = TMEM lane; replaces mask_row
 template <int BN, typename OutT>
-__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane, unsigned char* stage,
-                                              const float* sbias, OutT* dst_row, const __nv_bfloat16* mask_row,
-                                              int ncols, bool vec_ok, int mode, bool relu,
-                                              const unsigned char* smask = nullptr) {
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane, unsigned char* stage, OutT* dst_row,
+                                              int ncols, bool vec_ok, int mode, const EpiOpts& o) {
   using L = EpiLayout<BN, OutT>;
   const int r = q * 32 + lane;
   unsigned char* my = stage + r * L::ROWB;
@@ -44,16 +64,21 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
     float v[32];
     umma::tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
     umma::tmem_ld_wait();
-    if (sbias != nullptr) {
+    if (o.sbias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);
+        const float4 b4 = *reinterpret_cast<const float4*>(o.sbias + c0 + j);
         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
       }
     }
-    if (relu) {
+    if (o.relu) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (o.p_drop > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] *= drop_scale(o.p_drop, o.inv_keep, o.seed, o.site, uint64_t(o.drop_row_base + c0 + j));
     }
     if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
@@ -66,7 +91,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
   }
   void** ptrs = reinterpret_cast<void**>(stage + L::PTR_OFF);
   ptrs[2 * r] = dst_row;
-  ptrs[2 * r + 1] = const_cast<__nv_bfloat16*>(mask_row);
+  ptrs[2 * r + 1] = const_cast<__nv_bfloat16*>(o.mask_row);
   __syncwarp();
   // ---- phase 2: this warp's rows q*32 .. q*32+31
   if (vec_ok) {
@@ -75,50 +100,70 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
     constexpr int IPR = CPR > 32 ? CPR / 32 : 1;                   // iterations per row (BN*size > 512 B)
     const int sub = lane / (CPR < 32 ? CPR : 32);
     const int ch0 = lane % (CPR < 32 ? CPR : 32);
+    if constexpr (sizeof(OutT) == 2) {
+      constexpr int UNR = 4;                                       // mask loads of 4 iterations in flight
+      static_assert((32 / RPI) % UNR == 0, "row batches");
 #pragma unroll 1
-    for (int rr = 0; rr < 32; rr += RPI) {
-      const int row = q * 32 + rr + sub;
-      OutT* dst = static_cast<OutT*>(ptrs[2 * row]);
-      const __nv_bfloat16* msk = static_cast<const __nv_bfloat16*>(ptrs[2 * row + 1]);
-      if (dst == nullptr) continue;
+      for (int rr = 0; rr < 32; rr += RPI * UNR) {
+        uint4 mraw[UNR];
+        OutT* dsts[UNR];
+        bool mk[UNR];                      // per ROW (this lane's own mask_row says nothing about the rows it drains)
 #pragma unroll
-      for (int it = 0; it < IPR; ++it) {
-        const int ch = ch0 + it * 32;
-        uint4 val = *reinterpret_cast<const uint4*>(stage + row * L::ROWB + ch * 16);
-        if constexpr (sizeof(OutT) == 2) {
-          if (msk != nullptr || smask != nullptr || mode == EPI_ACCUM) {
+        for (int u = 0; u < UNR; ++u) {
+          const int row = q * 32 + rr + u * RPI + sub;
+          dsts[u] = static_cast<OutT*>(ptrs[2 * row]);
+          mraw[u] = make_uint4(0, 0, 0, 0);
+          mk[u] = false;
+          if (dsts[u] == nullptr) continue;
+          const __nv_bfloat16* gm = static_cast<const __nv_bfloat16*>(ptrs[2 * row + 1]);
+          if (o.smask != nullptr) {
+            mraw[u] = *reinterpret_cast<const uint4*>(o.smask + (ch0 >> 3) * 16384 + row * 128 + (((ch0 & 7) ^ (row & 7)) << 4));
+            mk[u] = true;
+          } else if (gm != nullptr) {
+            mraw[u] = *reinterpret_cast<const uint4*>(gm + ch0 * 8);
+            mk[u] = true;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int row = q * 32 + rr + u * RPI + sub;
+          OutT* dst = dsts[u];
+          if (dst == nullptr) continue;
+          uint4 val = *reinterpret_cast<const uint4*>(stage + row * L::ROWB + ch0 * 16);
+          if (mk[u] || mode == EPI_ACCUM) {
             float f[8];
             load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(&val), f);
-            if (smask != nullptr) {
-              float mk[8];
-              load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(
-                                       smask + (ch >> 3) * 16384 + row * 128 + (((ch & 7) ^ (row & 7)) << 4)), mk);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) if (!(mk[e] > 0.f)) f[e] = 0.f;
-            } else if (msk != nullptr) {
-              float mk[8];
-              load8<__nv_bfloat16>(msk + ch * 8, mk);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) if (!(mk[e] > 0.f)) f[e] = 0.f;
-            }
+            if (mk[u]) apply_mask8(f, mraw[u], o.mask_scale);
             if (mode == EPI_ACCUM) {
               float old[8];
-              load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(dst) + ch * 8, old);
+              load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(dst) + ch0 * 8, old);
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += old[e];
             }
-            store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dst) + ch * 8, f);
+            store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dst) + ch0 * 8, f);
           } else {
-            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + ch * 16) = val;
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + ch0 * 16) = val;
           }
-        } else {
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int rr = 0; rr < 32; rr += RPI) {
+        const int row = q * 32 + rr + sub;
+        OutT* dst = static_cast<OutT*>(ptrs[2 * row]);
+        if (dst == nullptr) continue;
+#pragma unroll
+        for (int it = 0; it < IPR; ++it) {
+          const int ch = ch0 + it * 32;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + row * L::ROWB + ch * 16);
           float* d4 = reinterpret_cast<float*>(dst) + ch * 4;
           const float4 f = *reinterpret_cast<const float4*>(&val);
           if (mode == EPI_ATOMIC) {
-            atomicAdd(d4, f.x); atomicAdd(d4 + 1, f.y); atomicAdd(d4 + 2, f.z); atomicAdd(d4 + 3, f.w);
+            // one 128-bit reduction (REDG.E.ADD.F32x4) instead of four scalar atomics
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
           } else if (mode == EPI_ACCUM) {
-            const float4 o = *reinterpret_cast<const float4*>(d4);
-            *reinterpret_cast<float4*>(d4) = make_float4(f.x + o.x, f.y + o.y, f.z + o.z, f.w + o.w);
+            const float4 old = *reinterpret_cast<const float4*>(d4);
+            *reinterpret_cast<float4*>(d4) = make_float4(f.x + old.x, f.y + old.y, f.z + old.z, f.w + old.w);
           } else {
             *reinterpret_cast<float4*>(d4) = f;
           }
@@ -136,7 +181,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
       const OutT* src = reinterpret_cast<const OutT*>(stage + row * L::ROWB);
       for (int c = lane; c < ncols; c += 32) {
         float f = to_f<OutT>(src[c]);
-        if (msk != nullptr && !(__bfloat162float(msk[c]) > 0.f)) f = 0.f;
+        if (msk != nullptr) f = (__bfloat162float(msk[c]) > 0.f) ? f * o.mask_scale : 0.f;
         if constexpr (sizeof(OutT) == 4) {
           if (mode == EPI_ATOMIC) { atomicAdd(reinterpret_cast<float*>(dst) + c, f); continue; }
         }

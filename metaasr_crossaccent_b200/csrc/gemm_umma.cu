@@ -10,6 +10,7 @@
 // Operand forms (template): K-major ("TN" forward GEMM: x[M,K] w[N,K]) or MN-major (dgrad: w[N,K] read as
 // B[K_out, N_red]; wgrad: dy[M,N], x[M,K] reduced over M) -- the latter only changes the TMA box, the smem
 // descriptor (LBO/SBO) and two bits of the instruction descriptor, the data are never transposed in memory.
+#include <type_traits>
 #include "common.cuh"
 #include "umma.cuh"
 #include "epilogue.cuh"
@@ -66,6 +67,10 @@ struct UmmaGemmParams {
   int flags;
   int kb_per_split;                // k-blocks per blockIdx.z slice (split-K: fp32 atomics into C)
   int stages;                      // depth of the TMA->MMA ring (host: deep when one CTA owns an SM)
+  // fused extras (masr_gemm_epilogue)
+  float* rowsum;                   // rowsum[m] += sum_k A(m,k): a second, 16-column accumulator fed by an all-ones B tile
+  const __nv_bfloat16* mask; int64_t ldmask; float mask_scale;
+  float p_drop, inv_keep; uint64_t seed; const uint64_t* seed_ptr; uint32_t site;
 };
 
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
@@ -79,7 +84,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // 1024 B alignment is required by the 128 B swizzle atom
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;                                          // >= MIN_STAGES
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  unsigned char* sones = smem + STAGES * STAGE_BYTES;                   // 2 KB: [16 x 64] bf16 tile of 1.0 (row sums)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sones + 2048);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -100,7 +106,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  const bool rowsum = p.rowsum != nullptr && blockIdx.x == 0;          // the n-tile-0 CTAs also sum A's rows
+  const uint32_t tmem_cols = p.rowsum != nullptr ? 2 * BN : BN;
+  if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  if (rowsum && threadIdx.x >= 64) {
+    reinterpret_cast<uint4*>(sones)[threadIdx.x - 64] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async();            // generic-proxy writes -> visible to the tensor core's async-proxy reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -138,22 +150,32 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+      constexpr uint32_t idesc_ones = make_idesc_bf16(UG_BM, 16, A_MN ? 1 : 0, 0);
+      const uint64_t dones = desc_kmajor_sw128(smem_u32(sones));
+      // Two copies of the k-loop (with / without the row-sum accumulator) so that neither contains a
+      // conditionally issued tcgen05.mma: the loop body is straight-line code for the single issuing thread.
+      auto kloop = [&](auto with_rowsum) {
+        constexpr bool RS = decltype(with_rowsum)::value;
+        int s = 0; uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < UG_BK / 16; ++k) {
-          // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 k-rows = +2048 B
-          const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sa + k * 32);
-          const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sb + k * 32);
-          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < UG_BK / 16; ++k) {
+            // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 k-rows = +2048 B
+            const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sa + k * 32);
+            const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sb + k * 32);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            mma_f16_ss(tmem_base, da, db, idesc, acc);
+            if constexpr (RS) mma_f16_ss(tmem_base + BN, da, dones, idesc_ones, acc);
+          }
+          mma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        mma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs have read it
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
+      };
+      if (rowsum) kloop(std::true_type{}); else kloop(std::false_type{});
       mma_commit(tmem_full_bar);             // accumulator complete
     }
   } else {
@@ -171,30 +193,47 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int m = m0 + q * 32 + lane;
     const int ncols = min(BN, p.N - n0);
     const int mode = splitk ? EPI_ATOMIC : (accum ? EPI_ACCUM : EPI_STORE);
+    EpiOpts o;
+    o.sbias = use_bias ? sbias : nullptr;
+    o.relu = relu;
+    if (p.p_drop > 0.f) {
+      o.p_drop = p.p_drop; o.inv_keep = p.inv_keep; o.site = p.site;
+      o.seed = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
+      o.drop_row_base = int64_t(m) * p.N + n0;
+    }
+    o.mask_scale = p.mask_scale;      // warp-uniform: a lane drains OTHER rows' chunks in phase 2
+    if (p.mask != nullptr && m < p.M) o.mask_row = p.mask + int64_t(m) * p.ldmask + n0;
     if (p.c_is_f32) {
       float* row = (m < p.M) ? static_cast<float*>(p.C) + int64_t(m) * p.ldc + n0 : nullptr;
       const bool vec_ok = ncols == BN && (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) + size_t(n0) * 4) & 15) == 0;
-      epilogue_tile<BN, float>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, row, nullptr, ncols, vec_ok, mode, relu);
+      epilogue_tile<BN, float>(tmem_base, q, lane, smem, row, ncols, vec_ok, mode, o);
     } else {
       __nv_bfloat16* row = (m < p.M) ? static_cast<__nv_bfloat16*>(p.C) + int64_t(m) * p.ldc + n0 : nullptr;
-      const bool vec_ok = ncols == BN && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) + size_t(n0) * 2) & 15) == 0;
-      epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, use_bias ? sbias : nullptr, row, nullptr, ncols, vec_ok, mode, relu);
+      const bool vec_ok = ncols == BN && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) + size_t(n0) * 2) & 15) == 0 &&
+                          (p.mask == nullptr || ((p.ldmask & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.mask) + size_t(n0) * 2) & 15) == 0));
+      epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, row, ncols, vec_ok, mode, o);
+    }
+    if (rowsum) {                   // column 0 of the ones-accumulator = sum_k A(m, k)
+      float v[32];
+      tmem_ld_32x32(tmem_base + BN + (uint32_t(q * 32) << 16), v);
+      tmem_ld_wait();
+      if (m < p.M) atomicAdd(p.rowsum + m, v[0]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
 static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmParams p, cudaStream_t st) {
   constexpr size_t STAGE = size_t(UG_BM * UG_BK * 2 + BN * UG_BK * 2);
-  constexpr int MAX_STAGES = int((200 * 1024) / STAGE);
+  constexpr int MAX_STAGES = int((198 * 1024) / STAGE);
   auto kern = umma_gemm_kernel<BN, MIN_STAGES, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
     MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(MAX_STAGES * STAGE + 1024 + 512 + BN * 4)));
+                                         int(MAX_STAGES * STAGE + 2048 + 1024 + 512 + BN * 4)));
     attr_set = true;
   }
   const int total_kb = int(ceil_div64(p.K, UG_BK));
@@ -207,7 +246,7 @@ static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmPar
   int stages = (ctas <= sm_count()) ? MAX_STAGES : MIN_STAGES;
   stages = std::max(MIN_STAGES, std::min(stages, std::min(p.kb_per_split, total_kb)));
   p.stages = stages;
-  const size_t smem = size_t(stages) * STAGE + 1024 + 512 + BN * 4;
+  const size_t smem = size_t(stages) * STAGE + 2048 + 1024 + 512 + BN * 4;
   MASR_CHECK_CUDA(launch_pdl(kern, grid, dim3(UG_THREADS), smem, st, ma, mb, p));
   return MASR_OK;
 }
@@ -230,9 +269,9 @@ using namespace masr;
 // C[M,N] = A[M,K] B[N,K]^T  (a_mn / b_mn = 0) or with MN-major operands:
 //   a_mn: A is stored as At[K, M] (M contiguous, leading dimension lda)
 //   b_mn: B is stored as Bt[K, N] (N contiguous, leading dimension ldb)
-extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
-                              void* C, int c_dtype, int64_t ldc, const float* bias,
-                              int M, int N, int K, int flags, int splitk, void* stream) {
+extern "C" int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                                 void* C, int c_dtype, int64_t ldc, const float* bias,
+                                 int M, int N, int K, int flags, int splitk, const masr_gemm_epilogue* epi, void* stream) {
   MASR_REQUIRE(M > 0 && N > 0 && K > 0, "umma gemm: empty problem");
   MASR_REQUIRE(!(flags & MASR_GEMM_SPLITK) || c_dtype == MASR_F32, "umma gemm: split-K needs an fp32 C");
   MASR_REQUIRE(!((flags & MASR_GEMM_SPLITK) && (flags & MASR_GEMM_RELU)), "umma gemm: split-K cannot fuse ReLU");
@@ -247,7 +286,18 @@ extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* 
   if (rc != MASR_OK) return rc;
   rc = operand_map(&mb, B, ldb, N, K, b_mn != 0, BN);
   if (rc != MASR_OK) return rc;
-  UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, kb_per_split, 0};
+  UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, kb_per_split, 0,
+                   nullptr, nullptr, 0, 1.f, 0.f, 1.f, 0, nullptr, 0};
+  if (epi != nullptr) {
+    MASR_REQUIRE(epi->mask == nullptr || c_dtype == MASR_BF16, "umma gemm: the output mask needs a bf16 C");
+    MASR_REQUIRE(!(epi->p_drop > 0.f && (flags & MASR_GEMM_SPLITK)), "umma gemm: split-K cannot fuse dropout");
+    p.rowsum = epi->rowsum;
+    p.mask = static_cast<const __nv_bfloat16*>(epi->mask); p.ldmask = epi->ldmask; p.mask_scale = epi->mask_scale;
+    if (epi->p_drop > 0.f) {
+      p.p_drop = epi->p_drop; p.inv_keep = 1.f / (1.f - epi->p_drop);
+      p.seed = epi->seed; p.seed_ptr = g_seed_dev_ptr; p.site = epi->site;
+    }
+  }
   cudaStream_t st = as_stream(stream);
   const int key = (BN == 64 ? 0 : 4) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
   switch (key) {
@@ -260,6 +310,12 @@ extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* 
     case 6: return launch_umma<128, 3, true, false>(ma, mb, p, st);
     default: return launch_umma<128, 3, true, true>(ma, mb, p, st);
   }
+}
+
+extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                              void* C, int c_dtype, int64_t ldc, const float* bias,
+                              int M, int N, int K, int flags, int splitk, void* stream) {
+  return masr_umma_gemm_ex(A, lda, a_mn, B, ldb, b_mn, C, c_dtype, ldc, bias, M, N, K, flags, splitk, nullptr, stream);
 }
 
 extern "C" int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,

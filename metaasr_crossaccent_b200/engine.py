@@ -329,8 +329,8 @@ class TransformerEngine:
             be.add_layernorm_fwd(s1, h, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1,
                                  buf(f"e{l}.m1", (Me,), f32), buf(f"e{l}.r1", (Me,), f32), pd, seed, self.site(pre + ".d1"))
             f1 = buf(f"e{l}.f1", (Me, ff))
-            be.linear_fwd(h1, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True)
-            be.dropout(f1, pd, seed, self.site(pre + ".df"))
+            be.linear_fwd(h1, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True,
+                          dropout=(pd, seed, self.site(pre + ".df")))
             s2 = buf(f"e{l}.s2", (Me, d))
             be.linear_fwd(f1, W[pre + ".linear2.weight"], P[pre + ".linear2.bias"], s2)
             h2 = buf(f"e{l}.h2", (Me, d))
@@ -374,8 +374,8 @@ class TransformerEngine:
             be.add_layernorm_fwd(s2, h1, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], h2,
                                  buf(f"d{l}.m2", (Md,), f32), buf(f"d{l}.r2", (Md,), f32), pd, seed, self.site(pre + ".d2"))
             f1 = buf(f"d{l}.f1", (Md, ff))
-            be.linear_fwd(h2, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True)
-            be.dropout(f1, pd, seed, self.site(pre + ".df"))
+            be.linear_fwd(h2, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True,
+                          dropout=(pd, seed, self.site(pre + ".df")))
             s3 = buf(f"d{l}.s3", (Md, d))
             be.linear_fwd(f1, W[pre + ".linear2.weight"], P[pre + ".linear2.bias"], s3)
             h3 = buf(f"d{l}.h3", (Md, d))
@@ -427,9 +427,8 @@ class TransformerEngine:
             """g_s: grad wrt linear2 output; accumulates the FFN input gradient into g_res."""
             wgrad(f1, g_s, G[pre + ".linear2.weight"], G[pre + ".linear2.bias"])
             g_f1 = buf(tag + ".g_f1", (Mrows, ff))
-            be.linear_dgrad(g_s, W[pre + ".linear2.weight"], g_f1)
-            be.dropout(g_f1, pd, seed, self.site(pre + ".df"))
-            be.relu_bwd(f1, g_f1)
+            # f1 = dropout(relu(.)): its backward (mask f1 > 0, scale 1/(1-p)) is fused into the dgrad epilogue
+            be.linear_dgrad(g_s, W[pre + ".linear2.weight"], g_f1, relu_drop_mask=f1, p=pd)
             wgrad(h_in, g_f1, G[pre + ".linear1.weight"], G[pre + ".linear1.bias"])
             be.linear_dgrad(g_f1, W[pre + ".linear1.weight"], g_res, accumulate=True)
 

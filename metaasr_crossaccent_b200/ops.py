@@ -92,13 +92,19 @@ class CudaBackend:
                 return False
         return True
 
-    def umma_gemm(self, A, a_mn, B, b_mn, C, bias, M, N, K, flags=0, splitk=1):
+    def umma_gemm(self, A, a_mn, B, b_mn, C, bias, M, N, K, flags=0, splitk=1, rowsum=None, mask=None, mask_scale=1.0,
+                  p_drop=0.0, seed=0, site=0):
         prof = self.prof
         if prof is not None:        # bench.py: CUDA events around every launch, on the launching stream
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self._call("masr_umma_gemm", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), _dt(C),
-                   C.stride(0), _p(bias), M, N, K, flags, int(splitk), self.stream)
+        epi = None
+        if rowsum is not None or mask is not None or p_drop > 0.0:
+            epi = _lib.GemmEpilogue(_p(rowsum), _p(mask), mask.stride(0) if mask is not None else 0, float(mask_scale),
+                                    float(p_drop), int(seed), int(site))
+            epi = _lib.C.byref(epi)
+        self._call("masr_umma_gemm_ex", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), _dt(C),
+                   C.stride(0), _p(bias), M, N, K, flags, int(splitk), epi, self.stream)
         if prof is not None:
             e1.record()
             kind = ("fwd", "dgrad", "a_mn", "wgrad")[int(a_mn) * 2 + int(b_mn)]
@@ -127,28 +133,52 @@ class CudaBackend:
 
     @staticmethod
     def _wgrad_splitk(rows_out, cols_out, k_red):
-        """Split the reduction so that ~2 waves of 128x128 tiles cover the 148 SMs."""
+        """Weight-gradient GEMMs run on the engine's side stream, next to the dgrad chain: keep them on FEW SMs
+        with long k-loops (no fp32 atomics, deterministic) and split the reduction only when a CTA's k-loop
+        would exceed ~64 k-blocks or the output has too few tiles to matter."""
         tiles = ((rows_out + 127) // 128) * ((cols_out + 127) // 128)
-        return max(1, min((k_red + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+        kb = (k_red + 63) // 64
+        sk = (kb + 63) // 64
+        while tiles * sk < 16 and kb // (sk * 2) >= 8:
+            sk *= 2
+        return max(1, sk)
 
-    def linear_fwd(self, x, w, bias, y, relu=False):
-        """y[M,N] = x[M,K] @ w[N,K]^T + bias (nn.Linear forward)."""
+    def linear_fwd(self, x, w, bias, y, relu=False, dropout=None):
+        """y[M,N] = x[M,K] @ w[N,K]^T + bias (nn.Linear forward); optional fused ReLU and dropout
+        (dropout = (p, seed, site), identical to a following self.dropout(y, p, seed, site))."""
         M, K = x.shape
         N = w.shape[0]
         assert w.shape[1] == K and y.shape == (M, N) and x.stride(1) == 1 and w.stride(1) == 1 and y.stride(1) == 1
+        p, seed, site = dropout if dropout is not None else (0.0, 0, 0)
         if self._umma_ok(x, w):
-            return self.umma_gemm(x, 0, w, 0, y, bias, M, N, K, GEMM_RELU if relu else 0)
-        self.gemm(x, x.stride(0), 1, w, w.stride(0), 1, y, y.stride(0), bias, M, N, K, GEMM_RELU if relu else 0)
+            if p > 0.0 and y.is_contiguous() and y.dtype == torch.bfloat16:
+                return self.umma_gemm(x, 0, w, 0, y, bias, M, N, K, GEMM_RELU if relu else 0, p_drop=p, seed=seed, site=site)
+            self.umma_gemm(x, 0, w, 0, y, bias, M, N, K, GEMM_RELU if relu else 0)
+        else:
+            self.gemm(x, x.stride(0), 1, w, w.stride(0), 1, y, y.stride(0), bias, M, N, K, GEMM_RELU if relu else 0)
+        if p > 0.0:
+            self.dropout(y, p, seed, site)
 
-    def linear_dgrad(self, dy, w, dx, accumulate=False):
-        """dx[M,K] (+)= dy[M,N] @ w[N,K]."""
+    def linear_dgrad(self, dy, w, dx, accumulate=False, relu_drop_mask=None, p=0.0):
+        """dx[M,K] (+)= dy[M,N] @ w[N,K].  relu_drop_mask = the stored forward output f of ReLU followed by
+        dropout(p) whose gradient dx is: the backward of both is fused as dx = f > 0 ? dx / (1-p) : 0
+        (an element of f is positive iff it passed the ReLU and was kept)."""
         M, N = dy.shape
         K = w.shape[1]
         assert dx.shape == (M, K) and dy.stride(1) == 1 and w.stride(1) == 1 and dx.stride(1) == 1
+        assert relu_drop_mask is None or not accumulate
+        scale = 1.0 / (1.0 - p) if p > 0.0 else 1.0
         if self._umma_ok(dy, w):
-            return self.umma_gemm(dy, 0, w, 1, dx, None, M, K, N, GEMM_ACCUM if accumulate else 0)
-        self.gemm(dy, dy.stride(0), 1, w, 1, w.stride(0), dx, dx.stride(0), None, M, K, N,
-                  GEMM_ACCUM if accumulate else 0)
+            if relu_drop_mask is not None and dx.dtype == torch.bfloat16 and relu_drop_mask.dtype == torch.bfloat16:
+                return self.umma_gemm(dy, 0, w, 1, dx, None, M, K, N, 0, mask=relu_drop_mask, mask_scale=scale)
+            self.umma_gemm(dy, 0, w, 1, dx, None, M, K, N, GEMM_ACCUM if accumulate else 0)
+        else:
+            self.gemm(dy, dy.stride(0), 1, w, 1, w.stride(0), dx, dx.stride(0), None, M, K, N,
+                      GEMM_ACCUM if accumulate else 0)
+        if relu_drop_mask is not None:
+            self.relu_bwd(relu_drop_mask, dx)
+            if scale != 1.0:
+                self.scale_(dx, scale)
 
     def linear_wgrad(self, x, dy, dw, db):
         """dw[N,K] += dy[M,N]^T @ x[M,K] (fp32); db[N] += column sums of dy."""
@@ -157,7 +187,8 @@ class CudaBackend:
         assert dw.shape == (N, K) and dw.dtype == torch.float32 and dw.stride(1) == 1
         if self._umma_ok(dy, x):
             sk = self._wgrad_splitk(N, K, M)
-            self.umma_gemm(dy, 1, x, 1, dw, None, N, K, M, GEMM_SPLITK if sk > 1 else GEMM_ACCUM, sk)
+            # bias gradient = row sums of dy^T: a second tensor-core accumulator of the same kernel
+            return self.umma_gemm(dy, 1, x, 1, dw, None, N, K, M, GEMM_SPLITK if sk > 1 else GEMM_ACCUM, sk, rowsum=db)
         else:
             tiles = ((N + 127) // 128) * ((K + 127) // 128)
             splitk = max(1, min((M + 255) // 256, (4 * 148 + tiles - 1) // tiles))
@@ -222,9 +253,8 @@ class CudaBackend:
         Cout = dy.shape[3]
         P = B * H * W
         if self._conv_umma_ok(x, dy) and dwp.is_contiguous():
-            self._timed_call(("conv_wgrad", Cout, 9 * Cin, P), "masr_umma_conv3x3_wgrad", _p(x), _p(dy), _p(dwp),
-                             B, H, W, Cin, Cout, self.stream)
-            return self.colsum_add(dy.view(P, Cout), db)
+            return self._timed_call(("conv_wgrad", Cout, 9 * Cin, P), "masr_umma_conv3x3_wgrad", _p(x), _p(dy), _p(dwp),
+                                    _p(db), B, H, W, Cin, Cout, self.stream)
         col = self._im2col(x)
         dy2 = dy.view(P, Cout)
         if self._umma_ok(dy2, col):
@@ -243,6 +273,10 @@ class CudaBackend:
     def maxpool_bwd(self, x, dy, dx, relu_mask=True):
         B, H, W, Cc = x.shape
         self._call("masr_maxpool2x2_bwd", _p(x), _p(dy), _p(dx), _dt(x), int(relu_mask), B, H, W, Cc, self.stream)
+
+    def scale_(self, x, a):
+        """x *= a (only used by the non-tensor-core fallback of the fused ReLU/dropout backward)."""
+        x.mul_(a)
 
     def relu_bwd(self, y, dx):
         self._call("masr_relu_bwd", _p(y), _p(dx), _dt(y), y.numel(), self.stream)

@@ -379,3 +379,37 @@ def test_umma_gemm(dev, M, N, K, a_mn, b_mn):
     C2 = torch.zeros(M, Np, device=dev)
     cb.umma_gemm(Av, a_mn, Bv, b_mn, C2[:, :N], None, M, N, K, GEMM_SPLITK, 3)
     close(C2[:, :N], ref, torch.float32, 2e-3, "umma split-K")
+
+
+@pytest.mark.parametrize("M,N,K", [(1056, 2048, 512), (4096, 512, 2048), (200, 96, 72), (130, 64, 264)])
+def test_umma_gemm_fused_epilogues(dev, M, N, K):
+    """masr_umma_gemm_ex extras: tensor-core row sums (bias gradient of a wgrad GEMM), ReLU+dropout fused into a
+    forward GEMM (bit-identical to GEMM followed by masr_dropout), and the fused ReLU/dropout backward mask."""
+    from metaasr_crossaccent_b200.ops import CudaBackend, GEMM_ACCUM, GEMM_RELU, GEMM_SPLITK
+    cb = CudaBackend(dev, torch.bfloat16, gemm="umma")
+    bf = torch.bfloat16
+    x, w, bias = rnd((M, K), dev, bf, 1), rnd((N, K), dev, bf, 2, 0.1), rnd((N,), dev, torch.float32, 3)
+    # forward: relu + dropout in the epilogue == separate dropout kernel on the same (seed, site)
+    y1, y2 = torch.empty(M, N, device=dev, dtype=bf), torch.empty(M, N, device=dev, dtype=bf)
+    cb.linear_fwd(x, w, bias, y1, relu=True, dropout=(0.1, 77, 5))
+    cb.linear_fwd(x, w, bias, y2, relu=True)
+    cb.dropout(y2, 0.1, 77, 5)
+    assert torch.equal(y1 == 0, y2 == 0)         # same mask; values differ only by the rounding order
+    close(y1, y2, bf, what="fused relu+dropout forward")
+    keep = float((y1 != 0).float().mean()) / max(float((torch.relu(x.float() @ w.float().t() + bias) > 0).float().mean()), 1e-9)
+    assert abs(keep - 0.9) < 0.02
+    # backward of relu + dropout fused into the dgrad epilogue: dx = (f > 0) ? dgrad / (1 - p) : 0
+    dy = rnd((M, K), dev, bf, 4)        # gradient wrt a [M, K]-shaped output of a second linear with weight w2 [K, N]
+    w2 = rnd((K, N), dev, bf, 5, 0.1)
+    g1 = torch.full((M, N), 3.0, device=dev, dtype=bf)
+    cb.linear_dgrad(dy, w2, g1, relu_drop_mask=y1, p=0.1)
+    ref = (dy.float() @ w2.float()) * (y1.float() > 0) / 0.9
+    close(g1, ref, bf, what="fused relu/dropout backward")
+    # wgrad with fused bias gradient (row sums of dy^T), with and without split-K
+    dyo = rnd((M, N), dev, bf, 6)
+    for sk in (1, 3):
+        dw, db = torch.zeros(N, K, device=dev), rnd((N,), dev, torch.float32, 7)
+        db0 = db.clone()
+        cb.umma_gemm(dyo, 1, x, 1, dw, None, N, K, M, GEMM_SPLITK if sk > 1 else GEMM_ACCUM, sk, rowsum=db)
+        close(dw, dyo.float().t() @ x.float(), torch.float32, 2e-3, "wgrad")
+        close(db - db0, dyo.float().sum(0), torch.float32, 2e-3, "fused bias gradient")

@@ -20,14 +20,18 @@ class TorchBackend:
         self.launches = 0
 
     # ---- GEMM family
-    def linear_fwd(self, x, w, bias, y, relu=False):
+    def linear_fwd(self, x, w, bias, y, relu=False, dropout=None):
+        assert dropout is None or dropout[0] == 0.0
         o = x.float() @ w.float().t()
         if bias is not None:
             o = o + bias
         y.copy_(F.relu(o) if relu else o)
 
-    def linear_dgrad(self, dy, w, dx, accumulate=False):
+    def linear_dgrad(self, dy, w, dx, accumulate=False, relu_drop_mask=None, p=0.0):
         o = dy.float() @ w.float()
+        if relu_drop_mask is not None:
+            assert not accumulate
+            o = o * (relu_drop_mask.float() > 0) / (1.0 - p)
         dx.copy_(dx.float() + o if accumulate else o)
 
     def linear_wgrad(self, x, dy, dw, db):
