@@ -278,9 +278,11 @@ extern "C" int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const voi
   const int total_kb = (K + UG_BK - 1) / UG_BK;
   int kb_per_split = total_kb;
   if ((flags & MASR_GEMM_SPLITK) && splitk > 1) kb_per_split = (total_kb + splitk - 1) / splitk;
-  // narrow tiles when 128-wide ones would leave most of the 148 SMs idle (decoder-sized problems)
+  // narrow tiles when 128-wide ones would leave most of the 148 SMs idle AND the k-loop is short (decoder-sized,
+  // latency-bound problems).  Long k-loops are bound by the L2->shared-memory operand traffic (measured ~6 TB/s
+  // chip-wide for these access patterns), where a 128x64 tile moves 1.5x the bytes per flop of a 128x128 one.
   const int64_t tiles128 = ceil_div64(M, UG_BM) * ceil_div64(N, 128) * ceil_div64(total_kb, kb_per_split);
-  const int BN = (N <= 64 || tiles128 * 3 < sm_count() * 2) ? 64 : 128;
+  const int BN = (N <= 64 || (tiles128 * 3 < sm_count() * 2 && kb_per_split <= 16)) ? 64 : 128;
   CUtensorMap ma, mb;
   int rc = operand_map(&ma, A, lda, M, K, a_mn != 0, UG_BM);
   if (rc != MASR_OK) return rc;

@@ -133,15 +133,13 @@ class CudaBackend:
 
     @staticmethod
     def _wgrad_splitk(rows_out, cols_out, k_red):
-        """Weight-gradient GEMMs run on the engine's side stream, next to the dgrad chain: keep them on FEW SMs
-        with long k-loops (no fp32 atomics, deterministic) and split the reduction only when a CTA's k-loop
-        would exceed ~64 k-blocks or the output has too few tiles to matter."""
+        """Weight-gradient GEMMs run on the engine's side stream, next to the dgrad chain.  They are bound by
+        the L2->shared-memory operand traffic: one CTA sustains only ~50-60 GB/s, the chip ~6 TB/s, so split
+        the reduction until 128-192 CTAs pull operands (fp32 vector reductions combine the slices), but keep
+        at least 8 k-blocks per slice."""
         tiles = ((rows_out + 127) // 128) * ((cols_out + 127) // 128)
         kb = (k_red + 63) // 64
-        sk = (kb + 63) // 64
-        while tiles * sk < 16 and kb // (sk * 2) >= 8:
-            sk *= 2
-        return max(1, sk)
+        return max(1, min(kb // 8, 192 // max(tiles, 1)))
 
     def linear_fwd(self, x, w, bias, y, relu=False, dropout=None):
         """y[M,N] = x[M,K] @ w[N,K]^T + bias (nn.Linear forward); optional fused ReLU and dropout
