@@ -60,7 +60,7 @@ struct ConvParams {
 
 // MODE 0 = forward, 1 = dgrad
 template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(CV_THREADS, 1)
+__global__ void __launch_bounds__(CV_THREADS, 2)
 umma_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_m, ConvParams p) {
   using namespace umma;
@@ -321,6 +321,10 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// conv_band.cu: halo-reuse variant; returns 1 when it does not apply (geometry / disabled)
+int conv_band_try(int mode, const void* act, const void* wp, void* out, const void* relu_src, const float* bias, int relu,
+                  int B, int H, int W, int Cin, int Cout, cudaStream_t st);
+
 template <typename K>
 static int set_smem(K kern, size_t smem) {
   MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -336,6 +340,10 @@ extern "C" int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float*
                                      int B, int H, int W, int Cin, int Cout, int relu, void* stream) {
   MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
   if (B * H * W == 0) return MASR_OK;
+  {
+    const int brc = conv_band_try(0, x, wp, y, nullptr, bias, relu, B, H, W, Cin, Cout, as_stream(stream));
+    if (brc != 1) return brc;
+  }
   const ConvTile t = pick_tile(H, W, 128);
   CUtensorMap ma, mw;
   int rc = act_map(&ma, x, B, H, W, Cin, t.tw, t.th);
@@ -366,6 +374,10 @@ extern "C" int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx,
                                        int B, int H, int W, int Cin, int Cout, void* stream) {
   MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
   if (B * H * W == 0) return MASR_OK;
+  {
+    const int brc = conv_band_try(1, dy, wp, dx, relu_src, nullptr, 0, B, H, W, Cin, Cout, as_stream(stream));
+    if (brc != 1) return brc;
+  }
   const ConvTile t = pick_tile(H, W, 128);
   CUtensorMap ma, mw;
   int rc = act_map(&ma, dy, B, H, W, Cout, t.tw, t.th);

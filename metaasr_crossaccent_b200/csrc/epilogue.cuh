@@ -58,40 +58,46 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
   const int r = q * 32 + lane;
   unsigned char* my = stage + r * L::ROWB;
   __syncwarp();                       // a previous call's phase 2 (same warp, same rows) has finished reading
-  // ---- phase 1
+  // ---- phase 1 (two 32-column TMEM loads in flight; the bias chunk is fetched while they complete)
+  constexpr int CB = BN >= 64 ? 64 : 32;                // columns per batch
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    float v[32];
-    umma::tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+  for (int c0 = 0; c0 < BN; c0 += CB) {
+    float v[CB];
+#pragma unroll
+    for (int h = 0; h < CB; h += 32) umma::tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0 + h), v + h);
+    float4 b4[CB / 4];
+    if (o.sbias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < CB / 4; ++j) b4[j] = *reinterpret_cast<const float4*>(o.sbias + c0 + 4 * j);
+    }
     umma::tmem_ld_wait();
     if (o.sbias != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(o.sbias + c0 + j);
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-      }
+      for (int j = 0; j < CB / 4; ++j) { v[4 * j] += b4[j].x; v[4 * j + 1] += b4[j].y; v[4 * j + 2] += b4[j].z; v[4 * j + 3] += b4[j].w; }
     }
     if (o.relu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      for (int j = 0; j < CB; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (o.p_drop > 0.f) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < CB; ++j)
         v[j] *= drop_scale(o.p_drop, o.inv_keep, o.seed, o.site, uint64_t(o.drop_row_base + c0 + j));
     }
     if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(my) + c0 + j, v + j);
+      for (int j = 0; j < CB; j += 8) store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(my) + c0 + j, v + j);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
+      for (int j = 0; j < CB; j += 4)
         *reinterpret_cast<float4*>(my + (c0 + j) * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
   void** ptrs = reinterpret_cast<void**>(stage + L::PTR_OFF);
-  ptrs[2 * r] = dst_row;
-  ptrs[2 * r + 1] = const_cast<__nv_bfloat16*>(o.mask_row);
+  if (!(sizeof(OutT) == 2 && vec_ok)) {            // the bf16 vector path passes row pointers by shuffle
+    ptrs[2 * r] = dst_row;
+    ptrs[2 * r + 1] = const_cast<__nv_bfloat16*>(o.mask_row);
+  }
   __syncwarp();
   // ---- phase 2: this warp's rows q*32 .. q*32+31
   if (vec_ok) {
@@ -101,48 +107,60 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
     const int sub = lane / (CPR < 32 ? CPR : 32);
     const int ch0 = lane % (CPR < 32 ? CPR : 32);
     if constexpr (sizeof(OutT) == 2) {
-      constexpr int UNR = 4;                                       // mask loads of 4 iterations in flight
-      static_assert((32 / RPI) % UNR == 0, "row batches");
-#pragma unroll 1
-      for (int rr = 0; rr < 32; rr += RPI * UNR) {
-        uint4 mraw[UNR];
-        OutT* dsts[UNR];
-        bool mk[UNR];                      // per ROW (this lane's own mask_row says nothing about the rows it drains)
+      // Row pointers travel by warp shuffle (the row's owner is lane `row % 32` of this warp), all shared-memory
+      // and mask loads of the warp's 32 rows are issued before the first store: no dependent round trips.
+      constexpr int NIT = 32 / RPI;                                // 8 (BN = 64) or 16 (BN = 128)
+      const unsigned long long my_dst = reinterpret_cast<unsigned long long>(dst_row);
+      const unsigned long long my_msk = reinterpret_cast<unsigned long long>(o.mask_row);
+      const bool any_gmask = __any_sync(0xffffffffu, o.mask_row != nullptr);
+      uint4 val[NIT];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int row = q * 32 + rr + u * RPI + sub;
-          dsts[u] = static_cast<OutT*>(ptrs[2 * row]);
-          mraw[u] = make_uint4(0, 0, 0, 0);
-          mk[u] = false;
-          if (dsts[u] == nullptr) continue;
-          const __nv_bfloat16* gm = static_cast<const __nv_bfloat16*>(ptrs[2 * row + 1]);
-          if (o.smask != nullptr) {
-            mraw[u] = *reinterpret_cast<const uint4*>(o.smask + (ch0 >> 3) * 16384 + row * 128 + (((ch0 & 7) ^ (row & 7)) << 4));
-            mk[u] = true;
-          } else if (gm != nullptr) {
-            mraw[u] = *reinterpret_cast<const uint4*>(gm + ch0 * 8);
-            mk[u] = true;
-          }
+      for (int i = 0; i < NIT; ++i)
+        val[i] = *reinterpret_cast<const uint4*>(stage + (q * 32 + i * RPI + sub) * L::ROWB + ch0 * 16);
+      if (o.smask == nullptr && !any_gmask && mode == EPI_STORE) {
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          const unsigned long long d = __shfl_sync(0xffffffffu, my_dst, i * RPI + sub);
+          if (d != 0ull) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(d) + ch0 * 16) = val[i];
         }
+      } else {
+        constexpr int UNR = NIT >= 8 ? 8 : NIT;                    // mask loads in flight per batch
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int row = q * 32 + rr + u * RPI + sub;
-          OutT* dst = dsts[u];
-          if (dst == nullptr) continue;
-          uint4 val = *reinterpret_cast<const uint4*>(stage + row * L::ROWB + ch0 * 16);
-          if (mk[u] || mode == EPI_ACCUM) {
+        for (int i0 = 0; i0 < NIT; i0 += UNR) {
+          uint4 mraw[UNR];
+          unsigned long long dd[UNR];
+          bool mk[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int lrow = (i0 + u) * RPI + sub;                 // row within this warp's 32
+            const int row = q * 32 + lrow;
+            dd[u] = __shfl_sync(0xffffffffu, my_dst, lrow);
+            const unsigned long long gm = any_gmask ? __shfl_sync(0xffffffffu, my_msk, lrow) : 0ull;
+            mraw[u] = make_uint4(0, 0, 0, 0);
+            mk[u] = false;
+            if (dd[u] == 0ull) continue;
+            if (o.smask != nullptr) {
+              mraw[u] = *reinterpret_cast<const uint4*>(o.smask + (ch0 >> 3) * 16384 + row * 128 + (((ch0 & 7) ^ (row & 7)) << 4));
+              mk[u] = true;
+            } else if (gm != 0ull) {
+              mraw[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(gm) + ch0 * 8);
+              mk[u] = true;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (dd[u] == 0ull) continue;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(dd[u]);
             float f[8];
-            load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(&val), f);
+            load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(&val[i0 + u]), f);
             if (mk[u]) apply_mask8(f, mraw[u], o.mask_scale);
             if (mode == EPI_ACCUM) {
               float old[8];
-              load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(dst) + ch0 * 8, old);
+              load8<__nv_bfloat16>(dst + ch0 * 8, old);
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += old[e];
             }
-            store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dst) + ch0 * 8, f);
-          } else {
-            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + ch0 * 16) = val;
+            store8<__nv_bfloat16>(dst + ch0 * 8, f);
           }
         }
       }

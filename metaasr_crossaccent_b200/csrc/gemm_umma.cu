@@ -74,7 +74,7 @@ struct UmmaGemmParams {
 };
 
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(UG_THREADS, 1)
+__global__ void __launch_bounds__(UG_THREADS, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaGemmParams p) {
   using namespace umma;
   constexpr uint32_t A_BYTES = UG_BM * UG_BK * 2;          // 16 KB
@@ -120,15 +120,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   pdl_wait();                       // everything above touched no global memory
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer: the whole warp runs the loop, one elected lane issues (see umma::elect_one_sync) =====
+    {
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         const int k0 = (kb_begin + kb) * UG_BK;
+        if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         if (!A_MN) {
           tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);               // box {64 k, 128 m}
         } else {
@@ -143,12 +144,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int c = 0; c < BN / 64; ++c)
             tma_load_2d(sb + c * (64 * UG_BK * 2), &map_b, &full_bar[s], n0 + c * 64, k0);
         }
+        }
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (converged warp, elected lane issues) =====
+    {
       constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t idesc_ones = make_idesc_bf16(UG_BM, 16, A_MN ? 1 : 0, 0);
       const uint64_t dones = desc_kmajor_sw128(smem_u32(sones));
@@ -162,21 +165,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < UG_BK / 16; ++k) {
-            // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 k-rows = +2048 B
-            const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sa + k * 32);
-            const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sb + k * 32);
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            mma_f16_ss(tmem_base, da, db, idesc, acc);
-            if constexpr (RS) mma_f16_ss(tmem_base + BN, da, dones, idesc_ones, acc);
+            for (int k = 0; k < UG_BK / 16; ++k) {
+              // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 k-rows = +2048 B
+              const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sa + k * 32);
+              const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sb + k * 32);
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              mma_f16_ss(tmem_base, da, db, idesc, acc);
+              if constexpr (RS) mma_f16_ss(tmem_base + BN, da, dones, idesc_ones, acc);
+            }
+            mma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs have read it
           }
-          mma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       };
       if (rowsum) kloop(std::true_type{}); else kloop(std::false_type{});
-      mma_commit(tmem_full_bar);             // accumulator complete
+      if (elect_one_sync()) mma_commit(tmem_full_bar);             // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4; staged through shared memory (epilogue.cuh) =====

@@ -35,6 +35,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// One lane of a CONVERGED warp (warp-uniform predicate).  The single-thread tcgen05 / TMA instructions take their
+// descriptors from uniform registers: issued under `if (lane == 0)` the compiler has to wrap every one of them in
+// a vote / elect / R2UR "waterfall" loop (~100+ cycles per tcgen05.mma, measured: the tensor pipe idles at 50 %);
+// issued by a converged warp under elect.sync they compile to a plainly predicated UTCHMMA.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
