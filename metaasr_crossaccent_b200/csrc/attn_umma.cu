@@ -101,34 +101,42 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int ntiles = (kmax + AU_TILE - 1) / AU_TILE;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
+  // producer / issuer warps run converged; one elected lane issues (umma::elect_one_sync)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, AU_T64);
       tma_load_2d(sQ, &map_q, q_full, h * 64, b * p.Lq + q0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t & 1;
+      mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&kv_full[s], 2 * AU_T64);
         tma_load_2d(sKV + s * 2 * AU_T64, &map_k, &kv_full[s], h * 64, b * p.Lk + t * AU_TILE);
         tma_load_2d(sKV + s * 2 * AU_T64 + AU_T64, &map_v, &kv_full[s], h * 64, b * p.Lk + t * AU_TILE);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);       // S = Q K^T
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);        // O = P V   (V read MN-major)
-      mbar_wait(q_full, 0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        mbar_wait(&kv_full[s], (t >> 1) & 1);
-        tc_fence_after();
-        const uint32_t aq = smem_u32(sQ), ak = smem_u32(sKV + s * 2 * AU_T64), av = ak + AU_T64, ap = smem_u32(sP);
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);       // S = Q K^T
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);        // O = P V   (V read MN-major)
+    mbar_wait(q_full, 0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t & 1;
+      mbar_wait(&kv_full[s], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sKV + s * 2 * AU_T64), av = ak + AU_T64, ap = smem_u32(sP);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_f16_ss(tmem_S, desc_kmajor_sw128(aq + k * 32), desc_kmajor_sw128(ak + k * 32), idesc_s, k > 0 ? 1u : 0u);
         mma_commit(s_full);
-        mbar_wait(p_full, t & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(p_full, t & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)      // 128 keys = 8 x K16: P k-block k/4, 32 B steps; V +16 key rows = 2048 B
           mma_f16_ss(tmem_O, desc_kmajor_sw128(ap + (k >> 2) * AU_T64 + (k & 3) * 32),
@@ -136,6 +144,7 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mma_commit(o_full);
         mma_commit(&kv_empty[s]);
       }
+      __syncwarp();
     }
   } else {
     const int qd = warp & 3;
@@ -322,22 +331,29 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int ntiles = active ? (nq_tiles - qt_begin) : 0;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256, tm_dK = tmem_base + 320, tm_dV = tmem_base + 384;
 
+  // producer / issuer warps run converged (`active` is CTA-uniform); one elected lane issues
   if (warp == 0) {
-    if (lane == 0 && active) {
-      mbar_arrive_expect_tx(kv_full, 2 * AU_T64);
-      tma_load_2d(sK, &map_k, kv_full, h * 64, b * p.Lk + k0);
-      tma_load_2d(sV, &map_v, kv_full, h * 64, b * p.Lk + k0);
+    if (active) {
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(kv_full, 2 * AU_T64);
+        tma_load_2d(sK, &map_k, kv_full, h * 64, b * p.Lk + k0);
+        tma_load_2d(sV, &map_v, kv_full, h * 64, b * p.Lk + k0);
+      }
+      __syncwarp();
       for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
         const int q0 = (qt_begin + t) * AU_TILE;
         mbar_wait(&qd_empty[s], ((t >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&qd_full[s], 2 * AU_T64);
-        tma_load_2d(sQdO + s * 2 * AU_T64, &map_q, &qd_full[s], h * 64, b * p.Lq + q0);
-        tma_load_2d(sQdO + s * 2 * AU_T64 + AU_T64, &map_do, &qd_full[s], h * 64, b * p.Lq + q0);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&qd_full[s], 2 * AU_T64);
+          tma_load_2d(sQdO + s * 2 * AU_T64, &map_q, &qd_full[s], h * 64, b * p.Lq + q0);
+          tma_load_2d(sQdO + s * 2 * AU_T64 + AU_T64, &map_do, &qd_full[s], h * 64, b * p.Lq + q0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && active) {
+    if (active) {
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S = Q K^T ; dP = dO V^T
       constexpr uint32_t id_dq = make_idesc_bf16(128, 64, 0, 1);     // dQ = dS K        (K read MN-major)
       constexpr uint32_t id_dkv = make_idesc_bf16(128, 64, 1, 1);    // dK = dS^T Q ; dV = P^T dO
@@ -348,32 +364,39 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_wait(&qd_full[s], (t >> 1) & 1);
         tc_fence_after();
         const uint32_t aq = smem_u32(sQdO + s * 2 * AU_T64), ado = aq + AU_T64;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_f16_ss(tm_S, desc_kmajor_sw128(aq + k * 32), desc_kmajor_sw128(ak + k * 32), id_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            mma_f16_ss(tm_S, desc_kmajor_sw128(aq + k * 32), desc_kmajor_sw128(ak + k * 32), id_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_f16_ss(tm_dP, desc_kmajor_sw128(ado + k * 32), desc_kmajor_sw128(av + k * 32), id_s, k > 0 ? 1u : 0u);
-        mma_commit(sdp_full);
+          for (int k = 0; k < 4; ++k)
+            mma_f16_ss(tm_dP, desc_kmajor_sw128(ado + k * 32), desc_kmajor_sw128(av + k * 32), id_s, k > 0 ? 1u : 0u);
+          mma_commit(sdp_full);
+        }
+        __syncwarp();
         mbar_wait(pds_full, t & 1);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // dQ[q, d] = sum_key dS[q, key] K[key, d]
-          mma_f16_ss(tm_dQ, desc_kmajor_sw128(ads + (k >> 2) * AU_T64 + (k & 3) * 32),
-                     desc_mnmajor_sw128(ak + k * 2048, AU_T64), id_dq, k > 0 ? 1u : 0u);
-        }
+          for (int k = 0; k < 8; ++k) {
+            // dQ[q, d] = sum_key dS[q, key] K[key, d]
+            mma_f16_ss(tm_dQ, desc_kmajor_sw128(ads + (k >> 2) * AU_T64 + (k & 3) * 32),
+                       desc_mnmajor_sw128(ak + k * 2048, AU_T64), id_dq, k > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // dK[key, d] += sum_q dS[q, key] Q[q, d];  dV[key, d] += sum_q P[q, key] dO[q, d]   (16 query rows / step)
-          const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
-          mma_f16_ss(tm_dK, desc_mnmajor_sw128(ads + k * 2048, AU_T64), desc_mnmajor_sw128(aq + k * 2048, AU_T64), id_dkv, acc);
-          mma_f16_ss(tm_dV, desc_mnmajor_sw128(ap + k * 2048, AU_T64), desc_mnmajor_sw128(ado + k * 2048, AU_T64), id_dkv, acc);
+          for (int k = 0; k < 8; ++k) {
+            // dK[key, d] += sum_q dS[q, key] Q[q, d];  dV[key, d] += sum_q P[q, key] dO[q, d]   (16 query rows / step)
+            const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
+            mma_f16_ss(tm_dK, desc_mnmajor_sw128(ads + k * 2048, AU_T64), desc_mnmajor_sw128(aq + k * 2048, AU_T64), id_dkv, acc);
+            mma_f16_ss(tm_dV, desc_mnmajor_sw128(ap + k * 2048, AU_T64), desc_mnmajor_sw128(ado + k * 2048, AU_T64), id_dkv, acc);
+          }
+          mma_commit(dq_full);
+          mma_commit(&qd_empty[s]);
         }
-        mma_commit(dq_full);
-        mma_commit(&qd_empty[s]);
+        __syncwarp();
       }
-      mma_commit(dkv_full);
+      if (elect_one_sync()) mma_commit(dkv_full);
+      __syncwarp();
     }
   } else {
     const int qd = warp & 3;

@@ -101,8 +101,8 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const int first = int(blockIdx.x), step = int(gridDim.x);
 
   if (warp == 6) {
-    // ===== input (A) producer =====
-    if (lane == 0) {
+    // ===== input (A) producer (converged warp, elected lane issues) =====
+    {
       const uint32_t tx = uint32_t(p.nr) * uint32_t(W2) * 128u;
       int slot = 0; uint32_t ph = 0;
       for (int tile = first; tile < p.ntiles; tile += step) {
@@ -112,6 +112,7 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll 1
         for (int cc = 0; cc < CH; ++cc) {
           mbar_wait(&a_empty[slot], ph ^ 1);
+          if (elect_one_sync()) {
           mbar_arrive_expect_tx(&a_full[slot], tx);
           // one box per padded row (W2 pixels): a single large box is served serially by the TMA unit (measured
           // ~16 B/cycle), several boxes stream concurrently.  Row r lands at a 128-byte aligned (not 1024-byte
@@ -120,6 +121,8 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           for (int r = 0; r < p.nr; r += p.rows_per_box)
             tma_load_4d(sA + slot * p.slot_bytes + uint32_t(r) * uint32_t(W2) * 128u, &map_a, &a_full[slot], cc * 64, -1,
                         hp_lo - 1 + r, b);
+          }
+          __syncwarp();
           slot ^= 1; if (slot == 0) ph ^= 1;
         }
       }

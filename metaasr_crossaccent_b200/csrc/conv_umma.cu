@@ -240,7 +240,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // converged warp, one elected lane issues (umma::elect_one_sync)
       const uint32_t tx_bytes = uint32_t(rows) * 128 * uint32_t(co_chunks + 3 * (CI / 64));
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = int(blockIdx.x) + it * int(gridDim.x);
@@ -250,17 +250,20 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* sa = smem + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-        for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * 8192, &map_dy, &full_bar[s], c * 64, w0, h0, b);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * 8192, &map_dy, &full_bar[s], c * 64, w0, h0, b);
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+          for (int j = 0; j < 3; ++j)
 #pragma unroll
-          for (int c = 0; c < CI / 64; ++c)
-            tma_load_4d(sa + A_BYTES + j * B_BYTES + c * 8192, &map_x, &full_bar[s], c * 64, w0 + (j - 1), h0 + dh, b);
+            for (int c = 0; c < CI / 64; ++c)
+              tma_load_4d(sa + A_BYTES + j * B_BYTES + c * 8192, &map_x, &full_bar[s], c * 64, w0 + (j - 1), h0 + dh, b);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, CI, 1, 1);
       constexpr uint32_t idesc_ones = make_idesc_bf16(128, 16, 1, 0);
       const uint64_t dones = desc_kmajor_sw128(smem_u32(sones));
@@ -273,27 +276,31 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const uint32_t sb = sa + A_BYTES + j * B_BYTES;
+            for (int j = 0; j < 3; ++j) {
+              const uint32_t sb = sa + A_BYTES + j * B_BYTES;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = desc_mnmajor_sw128(sa + k * 2048, 8192);
-              const uint64_t db = desc_mnmajor_sw128(sb + k * 2048, 8192);
-              mma_f16_ss(tmem_base + uint32_t(j * CI), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = desc_mnmajor_sw128(sa + k * 2048, 8192);
+                const uint64_t db = desc_mnmajor_sw128(sb + k * 2048, 8192);
+                mma_f16_ss(tmem_base + uint32_t(j * CI), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              }
             }
-          }
-          if constexpr (RS) {
+            if constexpr (RS) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16_ss(tmem_base + uint32_t(3 * CI), desc_mnmajor_sw128(sa + k * 2048, 8192), dones, idesc_ones,
-                         (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tmem_base + uint32_t(3 * CI), desc_mnmajor_sw128(sa + k * 2048, 8192), dones, idesc_ones,
+                           (it > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(&empty_bar[s]);
           }
-          mma_commit(&empty_bar[s]);
+          __syncwarp();
         }
       };
       if (rowsum) tloop(std::true_type{}); else tloop(std::false_type{});
-      mma_commit(tmem_full_bar);
+      if (elect_one_sync()) mma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
