@@ -125,6 +125,13 @@ int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float* bias, void
                           int B, int H, int W, int Cin, int Cout, int relu, void* stream);
 int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx, const void* relu_src,
                             int B, int H, int W, int Cin, int Cout, void* stream);
+/* First convolution (Cin = 1 -> 64) on the tensor cores: 3x3 patches (K = 9 padded to 16) are built in shared memory
+ * as a UMMA operand; y / dy are bf16 NHWC, x / w / bias / dw / db fp32.  Same results as masr_conv1_fwd /
+ * masr_conv1_wgrad up to the bf16 rounding of x (and w in the forward). */
+int masr_umma_conv1_fwd(const float* x, const float* w, const float* bias, void* y,
+                        int B, int H, int W, int Cout, void* stream);
+int masr_umma_conv1_wgrad(const float* x, const void* dy, float* dw, float* db,
+                          int B, int H, int W, int Cout, void* stream);
 /* db (may be NULL): [Cout] fp32 bias gradient += sum over pixels of dy, fused (tensor-core row sums). */
 int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp, float* db,
                             int B, int H, int W, int Cin, int Cout, void* stream);

@@ -39,6 +39,8 @@ SIGNATURES = {
     "masr_umma_gemm_tn": [c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_dgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_umma_conv1_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "masr_umma_conv1_wgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_wgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_conv1_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_conv1_wgrad": [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p],

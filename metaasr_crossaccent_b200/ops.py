@@ -195,12 +195,20 @@ class CudaBackend:
             self.colsum_add(dy, db)
 
     # -------------------------------------------------------------- conv front end
+    def _conv1_umma_ok(self, x, act, Cout):
+        return (self.gemm_path == "umma" and Cout == 64 and act.dtype == torch.bfloat16 and act.is_contiguous()
+                and x.dtype == torch.float32 and x.is_contiguous() and act.data_ptr() % 16 == 0)
+
     def conv1_fwd(self, x, w, bias, y):
         B, H, W = x.shape
+        if self._conv1_umma_ok(x, y, w.shape[0]):
+            return self._call("masr_umma_conv1_fwd", _p(x), _p(w), _p(bias), _p(y), B, H, W, w.shape[0], self.stream)
         self._call("masr_conv1_fwd", _p(x), _p(w), _p(bias), _p(y), _dt(y), B, H, W, w.shape[0], self.stream)
 
     def conv1_wgrad(self, x, dy, dw, db):
         B, H, W = x.shape
+        if self._conv1_umma_ok(x, dy, dw.shape[0]):
+            return self._call("masr_umma_conv1_wgrad", _p(x), _p(dy), _p(dw), _p(db), B, H, W, dw.shape[0], self.stream)
         self._call("masr_conv1_wgrad", _p(x), _p(dy), _dt(dy), _p(dw), _p(db), B, H, W, dw.shape[0], self.stream)
 
     def conv_w_prep(self, w, wp):

@@ -48,3 +48,27 @@ def test_umma_conv3x3(dev, B, H, W, Cin, Cout):
     tb.conv3x3_wgrad(x, dy, dwp2, db2)
     close(dwp1, dwp2, torch.float32, 2e-3, "umma conv wgrad")
     close(db1, db2, torch.float32, 1e-4, "conv bias grad")
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 13, 83), (3, 64, 83), (1, 1, 1), (2, 100, 37)])
+def test_umma_conv1(dev, B, H, W):
+    """First convolution (Cin = 1) on the tensor cores: patches built in shared memory as a UMMA operand (forward),
+    dY streamed by TMA with K = pixels and an all-ones tap row for the bias gradient (wgrad)."""
+    from metaasr_crossaccent_b200.ops import CudaBackend
+    bf = torch.bfloat16
+    cb, tb = CudaBackend(dev, bf, gemm="umma"), TorchBackend(dev, bf)
+    x = rnd((B, H, W), dev, torch.float32, 1)
+    w = rnd((64, 1, 3, 3), dev, torch.float32, 2, 0.3)
+    bias = rnd((64,), dev, torch.float32, 3, 0.1)
+    y1 = torch.full((B, H, W, 64), 9.0, device=dev, dtype=bf)
+    y2 = torch.empty_like(y1)
+    cb.conv1_fwd(x, w, bias, y1)
+    tb.conv1_fwd(x, w, bias, y2)
+    close(y1, y2, bf, what="umma conv1 fwd")
+    dy = rnd((B, H, W, 64), dev, bf, 4) * (y2 > 0)
+    dw1, db1 = rnd((64, 1, 3, 3), dev, torch.float32, 5), rnd((64,), dev, torch.float32, 6)
+    dw2, db2 = dw1.clone(), db1.clone()
+    cb.conv1_wgrad(x, dy, dw1, db1)
+    tb.conv1_wgrad(x, dy, dw2, db2)
+    close(dw1, dw2, torch.float32, 1e-2, "umma conv1 wgrad")      # x enters the tensor core as bf16
+    close(db1, db2, torch.float32, 1e-4, "umma conv1 bias grad")  # exact products (dy * 1.0), fp32 accumulation
