@@ -11,6 +11,7 @@ import sys
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__m_xbar2l1tex_read_bytes.sum",
         "sm__inst_executed_pipe_tensor_subpipe_umma.sum", "sm__pipe_tensor_subpipe_umma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
         "lts__t_sector_hit_rate.pct", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
