@@ -12,6 +12,7 @@
 //   wgrad: D_tap[co, ci] = sum_pix dY[pix, co] * X[pix+tap, ci]               A, B MN-major (4-D), split over
 //          pixel tiles across CTAs, 3 taps (one kernel row) accumulate side by side in TMEM, fp32 atomics out
 #include <type_traits>
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 #include "epilogue.cuh"
@@ -328,6 +329,155 @@ umma_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ------------------------------------------------------------------ wgrad, row-group variant
+// K-block = r whole image rows in a padded pitch Wp = W + 4 (w = -2 .. W + 1, out-of-bounds zero fill), rounded up
+// to a multiple of 16 rows (<= 128).  dY and X use the SAME flattening, so the three dw taps of a kernel row are
+// the X region read from row offsets -1 / 0 / +1: ONE X box per k-block instead of three shifted ones, and
+// 85-90 % of the MMA rows carry pixels (the tile variant above filled 42 of 64).  Cout = 64 uses M = 64 MMAs
+// (its accumulator occupies 16 lanes of each TMEM quadrant) instead of padding co to 128.
+struct Wgrad2Params {
+  int B, H, W, Cin, Cout;
+  int wp, r, kr;        // pitch, image rows per k-block, MMA rows per k-block (multiple of 16)
+  int ntiles, tiles_per_img;
+  float* dwp; float* db;
+};
+
+template <int CO, int CI, int STAGES>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+umma_conv_wgrad2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, Wgrad2Params p) {
+  using namespace umma;
+  constexpr uint32_t DY_CHUNK = 128 * 128;                 // up to 128 k-rows of 128 B per 64-co chunk
+  constexpr uint32_t X_CHUNK = 17 * 1024;                  // 1 margin row + 128 + 1 margin row (130 x 128 B), padded to 17 KB
+  static_assert(X_CHUNK % 1024 == 0, "X chunk must keep 1024 B alignment");
+  constexpr uint32_t A_BYTES = (CO / 64) * DY_CHUNK;
+  constexpr uint32_t B_BYTES = (CI / 64) * X_CHUNK;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (3 * CI + 16 <= 256) ? 256 : 512;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sones = smem + STAGES * STAGE_BYTES;
+  unsigned char* sStage = smem;                            // fp32 epilogue staging aliases the (by then idle) ring
+  static_assert(STAGES * STAGE_BYTES >= EpiLayout<CI, float>::BYTES, "staging tile must fit in the ring");
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sones + 2048);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dh = int(blockIdx.y) - 1;
+  const bool rowsum = p.db != nullptr && blockIdx.y == 0;
+  const int my_tiles = (p.ntiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int ksteps = p.kr / 16;
+
+  pdl_launch_dependents();
+  // rows never written by TMA (k-rows beyond wp * r, the X margin rows) must read as zeros: clear the ring once
+  for (uint32_t i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += CV_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 128) reinterpret_cast<uint4*>(sones)[threadIdx.x] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_dy);
+    prefetch_tmap(&map_x);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    const uint32_t tx_bytes = uint32_t(p.wp * p.r) * 128u * uint32_t(CO / 64 + CI / 64);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = int(blockIdx.x) + it * int(gridDim.x);
+      const int b = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.r;
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      unsigned char* sa = smem + s * STAGE_BYTES;
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+#pragma unroll
+        for (int c = 0; c < CO / 64; ++c) tma_load_4d(sa + c * DY_CHUNK, &map_dy, &full_bar[s], c * 64, -2, h0, b);
+#pragma unroll
+        for (int c = 0; c < CI / 64; ++c)               // lands one row (128 B) into the chunk: row -1 is the margin
+          tma_load_4d(sa + A_BYTES + c * X_CHUNK + 128, &map_x, &full_bar[s], c * 64, -2, h0 + dh, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(CO, CI, 1, 1);
+    constexpr uint32_t idesc_ones = make_idesc_bf16(CO, 16, 1, 0);
+    const uint64_t dones = desc_kmajor_sw128(smem_u32(sones));
+    auto tloop = [&](auto with_rowsum) {
+      constexpr bool RS = decltype(with_rowsum)::value;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sx = sa + A_BYTES + 128;           // X row 0 of the box
+        if (elect_one_sync()) {
+#pragma unroll 1
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = desc_mnmajor_sw128(sa + k * 2048, DY_CHUNK);
+            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)                   // tap dw = j - 1: the same X bytes, one row earlier / later
+              mma_f16_ss(tmem_base + uint32_t(j * CI), da, desc_mnmajor_sw128(sx + (j - 1) * 128 + k * 2048, X_CHUNK), idesc, acc);
+            if constexpr (RS) mma_f16_ss(tmem_base + uint32_t(3 * CI), da, dones, idesc_ones, acc);
+          }
+          mma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+      }
+    };
+    if (rowsum) tloop(std::true_type{}); else tloop(std::false_type{});
+    if (elect_one_sync()) mma_commit(tmem_full_bar);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    if (my_tiles > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      // M = 128: TMEM lane = co.  M = 64: rows 16 q .. 16 q + 15 sit in lanes 0..15 of quadrant q.
+      const int co = (CO == 128) ? q * 32 + lane : q * 16 + lane;
+      const bool row_ok = (CO == 128) ? true : lane < 16;
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const int tap = (dh + 1) * 3 + j;
+        float* dst = row_ok ? p.dwp + int64_t(co) * (9 * p.Cin) + tap * p.Cin : nullptr;
+        epilogue_tile<CI, float>(tmem_base + uint32_t(j * CI), q, lane, sStage, dst, CI, true, EPI_ATOMIC, EpiOpts());
+      }
+      if (rowsum) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + uint32_t(3 * CI) + (uint32_t(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (row_ok) atomicAdd(p.db + co, v[0]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+template <int CO, int CI, int STAGES>
+static int launch_wgrad2(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgrad2Params& p, cudaStream_t st) {
+  constexpr size_t STAGE = size_t(CO / 64) * 128 * 128 + size_t(CI / 64) * 17 * 1024;
+  const size_t smem = STAGES * STAGE + 2048 + 256 + 1024;
+  auto kern = umma_conv_wgrad2_kernel<CO, CI, STAGES>;
+  static bool attr = false;
+  if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  const int gx = std::max(1, std::min(p.ntiles, sm_count() / 3));
+  MASR_CHECK_CUDA(launch_pdl(kern, dim3(unsigned(gx), 3, 1), dim3(CV_THREADS), smem, st, mdy, mx, p));
+  return MASR_OK;
+}
+
 // conv_band.cu: halo-reuse variant; returns 1 when it does not apply (geometry / disabled)
 int conv_band_try(int mode, const void* act, const void* wp, void* out, const void* relu_src, const float* bias, int relu,
                   int B, int H, int W, int Cin, int Cout, cudaStream_t st);
@@ -422,6 +572,33 @@ extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp
                                        int B, int H, int W, int Cin, int Cout, void* stream) {
   MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
   if (B * H * W == 0) return MASR_OK;
+  {
+    // row-group variant: whole image rows in a (W + 4) pitch; needs the k-block to fit 128 MMA rows
+    const int wp = W + 4;
+    const int r = std::max(1, std::min(H, 96 / wp));
+    const int kr = (wp * r + 15) / 16 * 16;
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("MASR_CONV_WGRAD2"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    if (enabled && kr <= 128 && wp <= 256) {
+      CUtensorMap mdy2, mx2;
+      uint32_t box[4] = {64, uint32_t(wp), uint32_t(r), 1};
+      uint64_t dd[4] = {uint64_t(Cout), uint64_t(W), uint64_t(H), uint64_t(B)};
+      uint64_t ds[3] = {uint64_t(Cout) * 2, uint64_t(W) * Cout * 2, uint64_t(H) * W * Cout * 2};
+      int rc2 = make_tmap_bf16(&mdy2, dy, 4, dd, ds, box, true);
+      if (rc2 != MASR_OK) return rc2;
+      uint64_t xd[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
+      uint64_t xs[3] = {uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
+      rc2 = make_tmap_bf16(&mx2, x, 4, xd, xs, box, true);
+      if (rc2 != MASR_OK) return rc2;
+      const int tpi = (H + r - 1) / r;
+      Wgrad2Params p2{B, H, W, Cin, Cout, wp, r, kr, B * tpi, tpi, dwp, db};
+      cudaStream_t st2 = as_stream(stream);
+      if (Cout == 64 && Cin == 64) return launch_wgrad2<64, 64, 6>(mdy2, mx2, p2, st2);
+      if (Cout == 128 && Cin == 64) return launch_wgrad2<128, 64, 4>(mdy2, mx2, p2, st2);
+      if (Cout == 128 && Cin == 128) return launch_wgrad2<128, 128, 3>(mdy2, mx2, p2, st2);
+      if (Cout == 64 && Cin == 128) return launch_wgrad2<64, 128, 4>(mdy2, mx2, p2, st2);
+    }
+  }
   const ConvTile t = pick_tile(H, W, 64);
   CUtensorMap mdy, mx;
   int rc = act_map(&mdy, dy, B, H, W, Cout, t.tw, t.th);
