@@ -39,10 +39,10 @@ WORKLOAD = ("FOMAML meta-step, fometa-hkust transformer (d512 h8 ff2048 2enc 4de
             "meta_k 1, inner batch 32 x T512 x 83-dim fbank, L=32 unigram150 ids")
 
 
-def hkust_config(dtype, gemm, dropout=0.1, graphs=True):
+def hkust_config(dtype, gemm, dropout=0.1, graphs=True, lanes=1):
     am = {"idim": IDIM, "nheads": 8, "d_model": 512, "d_inner": 2048, "dropout": dropout, "tgt_share_weight": 1,
           "encoder": {"nlayers": 2}, "decoder": {"nlayers": 4}, "pos_dropout": dropout, "dtype": dtype, "gemm": gemm,
-          "cuda_graphs": graphs,
+          "cuda_graphs": graphs, "task_lanes": lanes,
           "inner_optimizer_cls": "SGD", "inner_optimizer_opt": {"momentum": 0.9, "nesterov": True},
           "meta_opt_cls": "noam", "meta": {"optimizer_opt": {"k": 1.0, "warmup_steps": 25000}}}
     solver = {"setting": "fometa-transformer-hkust", "total_steps": 1000000, "label_smoothing": 0.2,
@@ -124,7 +124,8 @@ def run_ours(args):
                                pretrain_suffix="bench", log_root=None)
     import random
     random.seed(531); torch.manual_seed(531)
-    solver = get_trainer(I.FOMetaASRInterface, hkust_config(args.dtype, gemm, graphs=not args.no_graphs), paras, id2accent)
+    solver = get_trainer(I.FOMetaASRInterface, hkust_config(args.dtype, gemm, graphs=not args.no_graphs, lanes=args.lanes),
+                         paras, id2accent)
     solver.set_model()
     eng, be = solver.asr_model.engine, solver.backend
 
@@ -242,7 +243,8 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "parallelism": f"task-dp{world}",
-                   "accents_per_rank": len(mine), "gemm_path": gemm, "cuda_graphs": bool(graphs),
+                   "accents_per_rank": len(mine), "task_lanes": min(args.lanes, len(mine)), "gemm_path": gemm,
+                   "cuda_graphs": bool(graphs),
                    "l2": "activations streamed per batch (several GB) >> 126 MB L2; no explicit flush"},
         "e2e": {"value": round(FRAMES_PER_STEP / (ms_e2e * 1e-3), 1), "unit": "frames/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(len(mine) * 4 * 8),
@@ -326,6 +328,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-graphs", dest="no_graphs", action="store_true", help="launch every kernel from the host")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="accents of a rank's share that run concurrently on one GPU (asr_model.task_lanes)")
     ap.add_argument("--profile", default=None, help="write a per-entry-point CUDA-event time table to this file")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -158,6 +158,10 @@ class TransformerEngine:
         self.d_vgg2enc_p = torch.zeros(cfg.d_model, cfg.vgg_o_dim, dtype=torch.float32, device=self.device)
         self.weights_dirty = True
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        # device-resident dropout seed offset of THIS engine (kernels add it to every dropout seed; a captured
+        # CUDA graph bumps it at replay).  Per engine, so that engines running concurrently on different
+        # streams cannot change each other's masks between a forward and its backward.
+        self.seed_t = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.step_seed = int(seed) * 1000003
         self._ws = {}
         self._sites = {}
@@ -265,10 +269,10 @@ class TransformerEngine:
         if self._side is None:
             self._side = torch.cuda.Stream(self.device)
         self._side.wait_stream(torch.cuda.current_stream(self.device))
-        self.be.scratch_tag = "side"
+        self.be.scratch_tag = (id(self), "side")
         with torch.cuda.stream(self._side):
             fn()
-        self.be.scratch_tag = ""
+        self.be.scratch_tag = (id(self), "main")
         self._side_busy = True
 
     def _join(self):
@@ -281,6 +285,7 @@ class TransformerEngine:
         """Runs the network on a device batch; fills ws['logits'] [B*L1, C] fp32 and the loss
         statistics; with want_grad also d(mean loss)/d logits."""
         cfg, be = self.cfg, self.be
+        self._bind_seed()
         self.prep_weights()
         B, T, L1 = db["B"], db["T"], db["L1"]
         F0 = cfg.idim
@@ -580,8 +585,14 @@ class TransformerEngine:
             return self._forward_backward_graphed(db)
         return self._forward_backward_eager(db)
 
+    def _bind_seed(self):
+        self.be.scratch_tag = (id(self), "main")   # backend scratch buffers are private to this engine
+        if hasattr(self.be, "set_seed_ptr"):
+            self.be.set_seed_ptr(self.seed_t)  # kernels launched from here on read this engine's offset
+
     def _forward_backward_eager(self, db):
         self.weights_dirty = True             # training: the master weights may have moved since the last batch
+        self._bind_seed()
         if hasattr(self.be, "seed_bump"):
             self.be.seed_bump(1)              # fresh dropout masks: device-resident seed offset += 1
         else:

@@ -188,44 +188,85 @@ class FOMetaMixin:
         self._stats_ring = torch.zeros(max(self.num_pretrain, 1), 4, dtype=torch.float64, device=eng.device)
         self._ring_sizes = []
 
+    # -- lanes: independent accents of a meta-batch may run CONCURRENTLY on one GPU (asr_model.task_lanes > 1)
+    def _lane(self, i):
+        """Lane 0 is the solver's own engine / optimizer / accumulators; further lanes own a private engine
+        (fast weights, gradients, workspaces, CUDA graphs, dropout seed), inner optimizer, norm and update
+        arena, and a CUDA stream.  Tasks only share the read-only meta weights `_original_flat`."""
+        lanes = self.__dict__.setdefault('_lanes', [])
+        while len(lanes) <= i:
+            k = len(lanes)
+            eng0 = self.asr_model.engine
+            if k == 0:
+                lanes.append(_Lane(eng0, self.asr_opt, self._gnorm, self._upd_flat, None))
+                continue
+            from .engine import TransformerEngine
+            eng = TransformerEngine(eng0.cfg, eng0.be, eng0.device, eng0.eps_ls, seed=531 + 7919 * k)
+            eng.use_graphs, eng.multi_stream = eng0.use_graphs, eng0.multi_stream
+            eng.seed_t.fill_(k << 40)
+            io = self.config['asr_model'].get('inner_optimizer_opt', {})
+            sgd = FlatInnerSGD(eng, self.inner_lr, io.get('momentum', 0.0), io.get('nesterov', False))
+            lanes.append(_Lane(eng, sgd, torch.zeros_like(self._gnorm), torch.zeros_like(self._upd_flat),
+                               torch.cuda.Stream(eng0.device)))
+        return lanes[i]
+
+    def _train_batch(self, lane, idx, x, ilens, ys, olens, accent_idx=None):
+        """run_batch(train=True, sync=False) on a lane's engine."""
+        if lane.stream is None:
+            return self.run_batch(idx, x, ilens, ys, olens, train=True, accent_idx=accent_idx, sync=False)
+        eng = lane.eng
+        if isinstance(x, dict):
+            db = x
+        else:
+            hb = eng.prepare_batch(x, ilens, ys, olens)
+            db = hb if eng.use_graphs else eng.to_device(hb)
+        eng.weights_dirty = True
+        eng.forward_backward(db)
+
     # -- fo_meta_interface.py:223-250
-    def run_task(self, batches):
-        eng = self.asr_model.engine
+    def run_task(self, batches, lane=None):
+        lane = lane or self._lane(0)
+        eng = lane.eng
         be = eng.be
         self._counter += 1
         be.copy_(eng.params, self._original_flat)              # load_state_dict(_original): one flat copy
         eng.weights_dirty = True
-        self.asr_model.train()
-        self.asr_opt.reset()                                   # fresh SGD per task
+        if lane.stream is None:
+            self.asr_model.train()
+        eng.training = True
+        lane.sgd.reset()                                       # fresh SGD per task
         for (idx, (x, ilens, ys, olens)) in batches:
-            self.run_batch(idx, x, ilens, ys, olens, train=True, sync=False)
-            be.mt_sumsq(eng.grads[:eng.layout.total], self._gnorm)          # clip_grad_norm_ (device-side norm)
-            self.asr_opt.step(self._gnorm, GRAD_CLIP)                        # NaN norm -> kernel skips the step
+            self._train_batch(lane, idx, x, ilens, ys, olens)
+            be.mt_sumsq(eng.grads[:eng.layout.total], lane.gnorm)           # clip_grad_norm_ (device-side norm)
+            lane.sgd.step(lane.gnorm, GRAD_CLIP)                             # NaN norm -> kernel skips the step
 
     # -- fo_meta_interface.py:145-154 (inner-loop test) + :180-198
-    def inner_test(self, val_batch):
-        eng = self.asr_model.engine
+    def inner_test(self, val_batch, lane=None, slot=None):
+        lane = lane or self._lane(0)
+        eng = lane.eng
         be = eng.be
         idx, (x, ilens, ys, olens) = val_batch
         if self.paras.algo == 'fomaml':
-            self.run_batch(idx, x, ilens, ys, olens, train=True, accent_idx=idx, sync=False)
-            be.mt_sumsq(eng.grads[:eng.layout.total], self._gnorm)
+            self._train_batch(lane, idx, x, ilens, ys, olens, accent_idx=idx)
+            be.mt_sumsq(eng.grads[:eng.layout.total], lane.gnorm)
         else:   # reptile: the held-out batch only produces logging statistics (no gradient needed)
             hb = eng.prepare_batch(x, ilens, ys, olens)
             eng.forward(eng.to_device(hb), want_grad=False)
-        slot = len(self._ring_sizes)
+        if slot is None:
+            slot = len(self._ring_sizes)
+            self._ring_sizes.append(len(ys))
         self._stats_ring[slot].copy_(eng.stats)
-        self._ring_sizes.append(len(ys))
-        self._partial_meta_update()
+        self._partial_meta_update(lane)
 
-    def _partial_meta_update(self):
-        eng = self.asr_model.engine
+    def _partial_meta_update(self, lane=None):
+        lane = lane or self._lane(0)
+        eng = lane.eng
         n = eng.layout.total
         self._updates = self._upd_flat
         if self.paras.algo == 'fomaml':       # _updates[n] += clip(p.grad)
-            eng.be.mt_accumulate(self._upd_flat[:n], eng.grads[:n], self._gnorm, GRAD_CLIP)
+            eng.be.mt_accumulate(lane.upd[:n], eng.grads[:n], lane.gnorm, GRAD_CLIP)
         elif self.paras.algo == 'reptile':    # _updates[n] += theta - phi
-            eng.be.mt_reptile_delta(self._upd_flat[:n], self._original_flat[:n], eng.params[:n])
+            eng.be.mt_reptile_delta(lane.upd[:n], self._original_flat[:n], eng.params[:n])
         else:
             raise ValueError(f"Not support meta algo {self.paras.algo}")
 
@@ -255,9 +296,36 @@ class FOMetaMixin:
         if global_task_count is not None:
             self._global_task_count = global_task_count
         self._ring_sizes = []
-        for tr_batches, val_batch in tasks:
-            self.run_task(tr_batches)
-            self.inner_test(val_batch)
+        n_lanes = min(int(self.config['asr_model'].get('task_lanes', 1)), len(tasks))
+        if n_lanes <= 1 or self.asr_model.engine.device.type != 'cuda':
+            for tr_batches, val_batch in tasks:
+                self.run_task(tr_batches)
+                self.inner_test(val_batch)
+        else:
+            # Accents are independent given the meta weights: run them on n_lanes CUDA streams so that the
+            # small-kernel phases of one accent (decoder, LayerNorm, attention: a fraction of the 148 SMs)
+            # overlap another accent's work.  The LAST task runs on lane 0, so asr_model still ends the
+            # meta-step holding the last task's fast weights (fo_meta_interface.py:70-88, App. C #14).
+            eng0 = self.asr_model.engine
+            main = torch.cuda.current_stream(eng0.device)
+            lanes = [self._lane(i) for i in range(n_lanes)]
+            lane0_stream = torch.cuda.Stream(eng0.device) if not hasattr(self, '_lane0_stream') else self._lane0_stream
+            self._lane0_stream = lane0_stream
+            streams = [lane0_stream] + [l.stream for l in lanes[1:]]
+            for st in streams:
+                st.wait_stream(main)
+            self._ring_sizes = [len(t[1][1][2]) for t in tasks]
+            for i, (tr_batches, val_batch) in enumerate(tasks):
+                li = (len(tasks) - 1 - i) % n_lanes
+                with torch.cuda.stream(streams[li]):
+                    self.run_task(tr_batches, lanes[li])
+                    self.inner_test(val_batch, lanes[li], slot=i)
+            for st in streams:
+                main.wait_stream(st)
+            n = eng0.layout.total
+            for l in lanes[1:]:                      # combine the lanes' accumulators (then clear them)
+                eng0.be.mt_axpy(self._upd_flat[:n], l.upd[:n], 1.0)
+                eng0.be.zero_(l.upd)
         self._final_meta_update()
 
     def flush_train_info(self):
@@ -304,6 +372,13 @@ class FOMetaMixin:
             self.dashboard.set_status('pretrained(SIGINT)')
         else:
             self.dashboard.set_status('pretrained')
+
+
+class _Lane:
+    """One concurrent task slot of a meta-step (see FOMetaMixin._lane)."""
+
+    def __init__(self, eng, sgd, gnorm, upd, stream):
+        self.eng, self.sgd, self.gnorm, self.upd, self.stream = eng, sgd, gnorm, upd, stream
 
 
 class _MetaNoamAdam:

@@ -72,11 +72,14 @@ class CudaBackend:
             po.setdefault(name + self.prof_tag, []).append((e0, e1))
 
     def scratch(self, key, numel, dtype):
+        """Scratch buffers are keyed by (owner lane, size, dtype) and never re-allocated: a captured CUDA graph
+        keeps their addresses, and engines that run concurrently (task lanes) must not share them."""
+        key = (key, int(numel), dtype)
         t = self._scratch.get(key)
-        if t is None or t.numel() < numel or t.dtype != dtype:
+        if t is None:
             t = torch.empty(int(numel), dtype=dtype, device=self.device)
             self._scratch[key] = t
-        return t[:numel]
+        return t
 
     # -------------------------------------------------------------- GEMM family
     def gemm(self, A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, flags=0, splitk=1):

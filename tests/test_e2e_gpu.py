@@ -113,6 +113,48 @@ def test_fomaml_meta_step_vs_reference_golden(dev):
         check_adam_weights(z, "s0.w.", ["s0.mg."], n, s._original[n], s.meta_opt.lr)
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_task_lanes_match_sequential_meta_step(dev, graphs):
+    """asr_model.task_lanes = 2 runs the two accents of the golden meta-step concurrently on two CUDA streams
+    (private engines, one shared read-only copy of the meta weights): same inner-test losses, same
+    meta-gradient and same updated meta weights as the sequential schedule, up to fp32 summation order."""
+    z = np.load(GOLD / "fomaml_tiny.npz")
+    results = []
+    for lanes in (1, 2):
+        s = make_solver("fomaml")
+        s.config["asr_model"]["task_lanes"] = lanes
+        s.asr_model.engine.use_graphs = graphs
+        load_tiny(s)
+        captured = {}
+        orig = s.meta_opt.step
+
+        def spy(upd, count, orig=orig, captured=captured):
+            captured["mg"] = (upd / count).clone()
+            return orig(upd, count)
+        s.meta_opt.step = spy
+        for step in range(2):                                     # second step replays graphs / reuses lanes
+            tasks = []
+            for acc in range(2):
+                tr = [(acc, load_batch(z, f"s0.a{acc}.tr{j}.")) for j in range(2)]
+                tasks.append((tr, (acc, load_batch(z, f"s0.a{acc}.te."))))
+            s.meta_step_on_tasks(tasks)
+            infos = s.flush_train_info()
+        torch.cuda.synchronize()
+        results.append(([i["loss"] for i in infos], captured["mg"].clone(), s._original_flat.clone(),
+                        s.asr_model.engine.params.clone()))
+    (l1, g1, w1, f1), (l2, g2, w2, f2) = results
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l1, l2)), (l1, l2)
+    assert float((g1 - g2).norm()) <= 1e-5 * float(g1.norm())
+    # Adam (eps 1e-9) turns a ~0 gradient into a +-lr move of arbitrary sign (SURVEY 7.3 #7): compare the updated
+    # weights where the meta-gradient is above the fp32 re-ordering noise
+    sig = g1.abs() > 1e-4 * g1.abs().max()
+    n = g1.numel()
+    assert float((w1[:n] - w2[:n])[sig].abs().max()) <= 1e-4        # << the Adam step (lr ~ 4e-4) of those entries
+    assert float(sig.float().mean()) > 0.5
+    # asr_model holds the LAST task's fast weights (started from meta weights that differ only in the noise entries)
+    assert float((f1[:n] - f2[:n])[sig].abs().max()) <= 5e-3
+
+
 def test_multi_step_vs_reference_golden(dev):
     z = np.load(GOLD / "multi_tiny.npz")
     s = make_solver("multi", meta=False)
