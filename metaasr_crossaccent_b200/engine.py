@@ -236,8 +236,15 @@ class TransformerEngine:
         assert B == ilens.shape[0] == len(ys), "Batch size mismatch"
         enc_lens = torch.floor(ilens.to(dtype=torch.float32) / 4).to(dtype=torch.int64)
         L1 = max(int(y.numel()) for y in ys) + 1
-        ys_in = torch.full((B, L1), cfg.eos_id, dtype=torch.int64)
-        ys_out = torch.full((B, L1), IGNORE_ID, dtype=torch.int64)
+        # enc_lens | ys_in | ys_out live back to back in ONE int64 host buffer (pinned on a GPU box, taken from a
+        # small ring): a single asynchronous H2D copy per batch.  Pageable sources would make every copy block
+        # the host until the stream drains, which serialises the lanes / the run-ahead of the launch thread.
+        meta = self._host_meta(B * (1 + 2 * L1))
+        meta[:B] = enc_lens
+        ys_in = meta[B:B + B * L1].view(B, L1)
+        ys_out = meta[B + B * L1:].view(B, L1)
+        ys_in.fill_(cfg.eos_id)
+        ys_out.fill_(IGNORE_ID)
         for b, y in enumerate(ys):
             n = int(y.numel())
             ys_in[b, 0] = cfg.sos_id
@@ -247,17 +254,44 @@ class TransformerEngine:
         if olens is not None:
             olens += 1
         n_total = int(ys_out.ne(IGNORE_ID).sum())
-        return {"x": xs_pad, "enc_lens": enc_lens, "ys_in": ys_in, "ys_out": ys_out, "n_total": n_total,
+        return {"x": xs_pad, "enc_lens": meta[:B], "ys_in": ys_in, "ys_out": ys_out, "meta": meta, "n_total": n_total,
                 "B": B, "T": xs_pad.shape[1], "L1": L1}
 
+    def _host_meta(self, numel):
+        """int64 host staging buffer from a ring of 64 (pinned when CUDA is present); an entry is reused only
+        after the copy that last read it has completed (event per entry)."""
+        ring = self.__dict__.setdefault("_meta_ring", {"i": 0, "bufs": [None] * 64, "evs": [None] * 64})
+        i = ring["i"] = (ring["i"] + 1) % 64
+        if ring["evs"][i] is not None:
+            ring["evs"][i].synchronize()
+        t = ring["bufs"][i]
+        if t is None or t.numel() < numel:
+            t = torch.empty(max(numel, 4096), dtype=torch.int64, pin_memory=self.device.type == "cuda")
+            ring["bufs"][i] = t
+        self._meta_last = i
+        return t[:numel]
+
+    def _meta_copied(self, hb):
+        """Record that the H2D copy of hb['meta'] has been enqueued on the current stream."""
+        if self.device.type == "cuda" and "_meta_ring" in self.__dict__:
+            ring = self._meta_ring
+            for i, t in enumerate(ring["bufs"]):
+                if t is not None and t.data_ptr() == hb["meta"].data_ptr():
+                    ev = ring["evs"][i] or torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(self.device))
+                    ring["evs"][i] = ev
+                    break
+
     def to_device(self, hb):
-        """H2D of one prepared batch (pinned host memory when available, non-blocking)."""
-        dev = {}
-        for k in ("x", "enc_lens", "ys_in", "ys_out"):
-            t = hb[k]
-            if self.device.type == "cuda" and not t.is_pinned():
-                t = t.pin_memory()
-            dev[k] = t.to(self.device, non_blocking=True)
+        """H2D of one prepared batch: x and the packed int64 block (two asynchronous copies)."""
+        x = hb["x"]
+        if self.device.type == "cuda" and not x.is_pinned():
+            x = x.pin_memory()
+        B, L1 = hb["B"], hb["L1"]
+        meta = hb["meta"].to(self.device, non_blocking=True)
+        self._meta_copied(hb)
+        dev = {"x": x.to(self.device, non_blocking=True), "meta": meta, "enc_lens": meta[:B],
+               "ys_in": meta[B:B + B * L1].view(B, L1), "ys_out": meta[B + B * L1:].view(B, L1)}
         dev.update({k: hb[k] for k in ("n_total", "B", "T", "L1")})
         return dev
 
@@ -607,10 +641,10 @@ class TransformerEngine:
         ent = self._graphs.get(key)
         if ent is None:
             dev = self.device
+            smeta = torch.empty(B * (1 + 2 * L1), dtype=torch.int64, device=dev)
             sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev),
-                   "enc_lens": torch.empty(B, dtype=torch.int64, device=dev),
-                   "ys_in": torch.empty(B, L1, dtype=torch.int64, device=dev),
-                   "ys_out": torch.empty(B, L1, dtype=torch.int64, device=dev),
+                   "meta": smeta, "enc_lens": smeta[:B],
+                   "ys_in": smeta[B:B + B * L1].view(B, L1), "ys_out": smeta[B + B * L1:].view(B, L1),
                    "inv_n_dev": torch.empty(1, dtype=torch.float32, device=dev),
                    "n_total": 1, "B": B, "T": T, "L1": L1}
             self._load_static(sdb, db)
@@ -632,8 +666,14 @@ class TransformerEngine:
         return ws
 
     def _load_static(self, sdb, db):
-        for k in ("x", "enc_lens", "ys_in", "ys_out"):
-            sdb[k].copy_(db[k], non_blocking=True)
+        sdb["x"].copy_(db["x"], non_blocking=True)
+        if "meta" in db:
+            sdb["meta"].copy_(db["meta"], non_blocking=True)
+            if db["meta"].device.type == "cpu":
+                self._meta_copied(db)
+        else:
+            for k in ("enc_lens", "ys_in", "ys_out"):
+                sdb[k].copy_(db[k], non_blocking=True)
         sdb["inv_n_dev"].fill_(1.0 / max(db["n_total"], 1))
 
     def read_stats(self):
