@@ -42,6 +42,7 @@ struct BandParams {
   uint32_t slot_bytes;     // bytes of one A slot (multiple of 1024)
   int sb;                  // weight ring depth (RES: 9 * CH resident k-blocks)
   int rows_per_box;        // padded rows per TMA box of the input region (nr is a multiple of it)
+  int pf_dist;             // L2 prefetch distance in tiles (0 = off)
   __nv_bfloat16* out;
   const __nv_bfloat16* relu_src;   // dgrad: multiply by (relu_src > 0)
   const float* bias;               // fwd
@@ -109,6 +110,17 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int b = tile / p.tiles_per_img, ti = tile % p.tiles_per_img;
         const int f0 = W2 + 1 + ti * CB_MT;
         const int hp_lo = (f0 - W2 - 1) / W2;
+        // L2 prefetch of the region this CTA will load `pf` tiles from now (only two slots = one load in flight:
+        // without it every load pays the full HBM latency and the tile period is latency-bound)
+        const int ptile = tile + p.pf_dist * step;
+        if (p.pf_dist > 0 && ptile < p.ntiles && elect_one_sync()) {
+          const int pb = ptile / p.tiles_per_img, pti = ptile % p.tiles_per_img;
+          const int pf0 = W2 + 1 + pti * CB_MT;
+          const int php = (pf0 - W2 - 1) / W2;
+          for (int cc = 0; cc < CH; ++cc)
+            for (int r = 0; r < p.nr; r += p.rows_per_box) tma_prefetch_4d(&map_a, cc * 64, -1, php - 1 + r, pb);
+        }
+        __syncwarp();
 #pragma unroll 1
         for (int cc = 0; cc < CH; ++cc) {
           mbar_wait(&a_empty[slot], ph ^ 1);
@@ -159,12 +171,23 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp runs the loop (uniform control flow and addresses), one elected lane issues =====
+    // ===== MMA issuer: the whole warp runs the loop (uniform control flow and addresses), one elected lane issues.
+    // The single issuing thread is the critical resource of the N = 64 layers (a 128x64x16 MMA occupies the tensor
+    // pipe for only 32 cycles): descriptors are built ONCE per (tile, chunk) and advanced by adding encoded byte
+    // offsets (start address field = bytes >> 4: +2 per K16 step, +8 per pixel row, +1024 per 128-row group).
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, MODE == 1 ? 1 : 0);
       int aslot = 0; uint32_t aph = 0;
       int bs = 0; uint32_t bph = 0;
       int it = 0;
+      // encoded row offset of tap t relative to the region's first needed row
+      int tap_rows[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dh = t / 3 - 1, dw = t % 3 - 1;
+        tap_rows[t] = (MODE == 0) ? (dh + 1) * W2 + (dw + 1) : (1 - dh) * W2 + (1 - dw);
+      }
+      const uint64_t db_res0 = (MODE == 1) ? desc_mnmajor_sw128(smem_u32(sB), 8192) : desc_kmajor_sw128(smem_u32(sB));
       for (int tile = first; tile < p.ntiles; tile += step, ++it) {
         const int ti = tile % p.tiles_per_img;
         const int f0 = W2 + 1 + ti * CB_MT;
@@ -179,22 +202,27 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int cc = 0; cc < CH; ++cc) {
           mbar_wait(&a_full[aslot], aph);
           tc_fence_after();
-          const uint32_t abase = smem_u32(sA + aslot * p.slot_bytes);
-#pragma unroll 1
+          const uint64_t da0 = make_smem_desc(smem_u32(sA + aslot * p.slot_bytes) + uint32_t(off) * 128u, 16, 1024);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
-            // forward reads the input at centre + tap, dgrad reads dY at centre - tap
-            const int shift = (MODE == 0) ? (dh + 1) * W2 + (dw + 1) : (1 - dh) * W2 + (1 - dw);
-            if (!RES) { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
-            const uint32_t sb = smem_u32(sB + (RES ? cc * 9 + tap : bs) * B_BYTES);
+            uint64_t db0;
+            if (RES) {
+              db0 = db_res0 + uint64_t((cc * 9 + tap) * (B_BYTES >> 4));
+            } else {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(sB + bs * B_BYTES);
+              db0 = (MODE == 1) ? desc_mnmajor_sw128(sb, 8192) : desc_kmajor_sw128(sb);
+            }
+            const uint64_t da_tap = da0 + uint64_t(tap_rows[tap]) * 8u;
             if (elect_one_sync()) {
 #pragma unroll
               for (int m = 0; m < NM; ++m) {
-                const uint32_t arow = abase + uint32_t(off + m * 128 + shift) * 128u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t da = band_a_desc(arow + k * 32, p.desc_mode);
-                  const uint64_t db = (MODE == 1) ? desc_mnmajor_sw128(sb + k * 2048, 8192) : desc_kmajor_sw128(sb + k * 32);
+                  // K16 step: A +32 B; B K-major +32 B, MN-major (dgrad) +16 co-rows = +2048 B
+                  const uint64_t da = da_tap + uint64_t(m * 1024 + k * 2);
+                  const uint64_t db = db0 + uint64_t(MODE == 1 ? k * 128 : k * 2);
                   mma_f16_ss(acc0 + uint32_t(m * BN), da, db, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
                 }
               }
@@ -346,7 +374,9 @@ int conv_band_try(int mode, const void* act, const void* wp, void* out, const vo
   uint32_t wb[2] = {64, mode == 0 ? uint32_t(Cout) : 64u};
   rc = make_tmap_bf16(&mw, wp, 2, wd, ws, wb, true);
   if (rc != MASR_OK) return rc;
-  BandParams p{B, H, W, g.W2, Cin, g.tiles_per_img, B * g.tiles_per_img, g.nr, g.slot_bytes, g.sb, rpb,
+  static int pf = -1;
+  if (pf < 0) { const char* e = getenv("MASR_CONV_BAND_PF"); pf = e != nullptr ? atoi(e) : 2; }
+  BandParams p{B, H, W, g.W2, Cin, g.tiles_per_img, B * g.tiles_per_img, g.nr, g.slot_bytes, g.sb, rpb, pf,
                static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(relu_src), bias, relu, band_desc_mode()};
   const int key = (mode << 2) | ((Cred == 128 ? 1 : 0) << 1) | (Cn == 128 ? 1 : 0);
   switch (key) {
