@@ -123,7 +123,9 @@ int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
  * wp is the [Cout, 9*Cin] bf16 layout of masr_conv_w_prep; dwp the same layout in fp32 (accumulated). */
 int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float* bias, void* y,
                           int B, int H, int W, int Cin, int Cout, int relu, void* stream);
-int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx, const void* relu_src,
+/* wpt (may be NULL): the transposed weight layout [Cin][tap][Cout] of masr_conv_w_prep_t; when given, dgrad reads
+ * its B operand K-major like the forward pass (faster than reading wp MN-major). */
+int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, const void* wpt, void* dx, const void* relu_src,
                             int B, int H, int W, int Cin, int Cout, void* stream);
 /* First convolution (Cin = 1 -> 64) on the tensor cores: 3x3 patches (K = 9 padded to 16) are built in shared memory
  * as a UMMA operand; y / dy are bf16 NHWC, x / w / bias / dw / db fp32.  Same results as masr_conv1_fwd /
@@ -148,6 +150,8 @@ int masr_col2im3x3(const void* dcol, void* dx, int dtype, const void* relu_src,
                    int B, int H, int W, int Cin, void* stream);
 /* weight layout prep: w [Cout,Cin,3,3] fp32 -> wp [Cout, 9*Cin] (k = tap*Cin+ci) of dtype */
 int masr_conv_w_prep(const float* w, void* wp, int dtype, int Cout, int Cin, void* stream);
+/* w [Cout,Cin,3,3] fp32 -> wpt [Cin, 9*Cout] (tap-major inside a row): the dgrad operand layout */
+int masr_conv_w_prep_t(const float* w, void* wpt, int dtype, int Cout, int Cin, void* stream);
 /* dw [Cout,Cin,3,3] += dwp [Cout, 9*Cin] (fp32) */
 int masr_conv_w_unprep_add(const float* dwp, float* dw, int Cout, int Cin, void* stream);
 /* 2x2/2 floor-mode max pool, NHWC */

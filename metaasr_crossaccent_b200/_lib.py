@@ -38,7 +38,7 @@ SIGNATURES = {
     "masr_umma_gemm_ex": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "masr_umma_gemm_tn": [c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
-    "masr_umma_conv3x3_dgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_umma_conv3x3_dgrad": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv1_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv1_wgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_wgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -47,6 +47,7 @@ SIGNATURES = {
     "masr_im2col3x3": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_col2im3x3": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_conv_w_prep": [c_p, c_p, c_i, c_i, c_i, c_p],
+    "masr_conv_w_prep_t": [c_p, c_p, c_i, c_i, c_i, c_p],
     "masr_conv_w_unprep_add": [c_p, c_p, c_i, c_i, c_p],
     "masr_maxpool2x2_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_maxpool2x2_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

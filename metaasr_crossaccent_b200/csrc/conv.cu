@@ -216,6 +216,19 @@ __global__ void conv_w_prep_kernel(const float* __restrict__ w, T* __restrict__ 
     wp[idx] = from_f<T>(w[(co * Cin + ci) * 9 + tap]);
   }
 }
+// w [Cout][Cin][3][3] fp32 -> wpt [Cin][tap][Cout]: the K-major B operand of the dgrad implicit GEMM
+template <typename T>
+__global__ void conv_w_prep_t_kernel(const float* __restrict__ w, T* __restrict__ wpt, int Cout, int Cin) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int total = Cout * Cin * 9;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int co = idx % Cout;
+    const int tap = (idx / Cout) % 9;
+    const int ci = idx / (9 * Cout);
+    wpt[idx] = from_f<T>(w[(co * Cin + ci) * 9 + tap]);
+  }
+}
 __global__ void conv_w_unprep_add_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin) {
   pdl_launch_dependents();
   pdl_wait();
@@ -545,6 +558,15 @@ extern "C" int masr_conv_w_prep(const float* w, void* wp, int dtype, int Cout, i
   if (total == 0) return MASR_OK;
   MASR_DISPATCH_DTYPE(dtype, T,
       launch_pdl(conv_w_prep_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), w, static_cast<T*>(wp), Cout, Cin));
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_conv_w_prep_t(const float* w, void* wpt, int dtype, int Cout, int Cin, void* stream) {
+  const int total = Cout * Cin * 9;
+  if (total == 0) return MASR_OK;
+  MASR_DISPATCH_DTYPE(dtype, T,
+      launch_pdl(conv_w_prep_t_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), w, static_cast<T*>(wpt), Cout, Cin));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

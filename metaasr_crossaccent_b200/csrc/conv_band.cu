@@ -56,7 +56,9 @@ __device__ __forceinline__ uint64_t band_a_desc(uint32_t addr, int mode) {
   return d;
 }
 
-// CH = reduction channels / 64, BN = output channels, MODE 0 = forward, 1 = dgrad, NM = 128-centre groups per tile,
+// CH = reduction channels / 64, BN = output channels, MODE 0 = forward, 1 = dgrad (weights read MN-major from the
+// forward layout), 2 = dgrad with the transposed weight layout wpt [Cin][tap][Cout] (K-major B like the forward:
+// measurably faster than MN-major B), NM = 128-centre groups per tile,
 // RES = the whole weight tensor (9 * CH k-blocks) stays resident in shared memory (loaded once per CTA)
 template <int CH, int BN, int MODE, int NM, bool RES>
 __global__ void __launch_bounds__(CB_THREADS, 1)
@@ -144,8 +146,8 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (lane == 0) {
       auto load_kb = [&](int kb, unsigned char* sb, uint64_t* bar) {
         const int cc = kb / 9, tap = kb % 9;
-        if (MODE == 0) {
-          tma_load_2d(sb, &map_w, bar, tap * p.Cin + cc * 64, 0);                          // box {64 k, BN rows(co)}
+        if (MODE != 1) {
+          tma_load_2d(sb, &map_w, bar, tap * p.Cin + cc * 64, 0);                          // box {64 k, BN rows}
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 64; ++c)                                                 // box {64 ci, 64 rows(co)}
@@ -176,7 +178,7 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // pipe for only 32 cycles): descriptors are built ONCE per (tile, chunk) and advanced by adding encoded byte
     // offsets (start address field = bytes >> 4: +2 per K16 step, +8 per pixel row, +1024 per 128-row group).
     {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, MODE == 1 ? 1 : 0);
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, MODE == 1 ? 1 : 0);   // B major
       int aslot = 0; uint32_t aph = 0;
       int bs = 0; uint32_t bph = 0;
       int it = 0;
@@ -243,7 +245,7 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ===== epilogue =====
     const int q = warp & 3;
     const int et = threadIdx.x - 64;
-    const bool use_bias = (MODE == 0) && p.bias != nullptr;
+    const bool use_bias = (MODE == 0) && p.bias != nullptr;   // MODE 1 / 2: dgrad
     if (use_bias) {
       for (int i = et; i < BN; i += 128) sbias[i] = p.bias[i];
     }
@@ -254,6 +256,25 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int b = tile / p.tiles_per_img, ti = tile % p.tiles_per_img;
       const int f0 = W2 + 1 + ti * CB_MT;
       const int ab = it & 1;
+      if (MODE != 0 && p.relu_src != nullptr) {
+        // dgrad: pull the ReLU mask rows of the tile two iterations ahead into L2 (one 128 B line per lane and
+        // 64 channels): the mask streams from HBM, and the epilogue's own loads would otherwise expose that
+        // latency once per 128-centre group, making the epilogue (not the MMAs) the pace setter
+        const int ptile = tile + 2 * step;
+        if (ptile < p.ntiles) {
+          const int pb = ptile / p.tiles_per_img, pti = ptile % p.tiles_per_img;
+#pragma unroll 1
+          for (int m = 0; m < NM; ++m) {
+            const int pf = W2 + 1 + pti * CB_MT + m * 128 + q * 32 + lane;
+            const int php = pf / W2, pwp = pf - php * W2;
+            if (pf <= last_centre && pwp >= 1 && pwp <= p.W && php >= 1 && php <= p.H) {
+              const __nv_bfloat16* mp = p.relu_src + ((int64_t(pb) * p.H + (php - 1)) * p.W + (pwp - 1)) * BN;
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + c * 64));
+            }
+          }
+        }
+      }
       mbar_wait(&t_full[ab], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -266,7 +287,10 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         EpiOpts o;
         o.sbias = use_bias ? sbias : nullptr;
         o.relu = MODE == 0 && p.relu != 0;
-        if (MODE == 1 && p.relu_src != nullptr && valid) o.mask_row = p.relu_src + pix * BN;
+        if (MODE != 0 && p.relu_src != nullptr) {          // mask row = destination row + a constant offset
+          o.mask_at_dst_delta = true;
+          o.mask_delta = reinterpret_cast<const unsigned char*>(p.relu_src) - reinterpret_cast<const unsigned char*>(p.out);
+        }
         epilogue_tile<BN, __nv_bfloat16>(tmem_base + uint32_t((ab * NM + m) * BN), q, lane, sStage, orow, BN, true, EPI_STORE, o);
       }
       tc_fence_before();
@@ -355,6 +379,7 @@ static int launch_band(const CUtensorMap& ma, const CUtensorMap& mw, const BandP
 }
 
 // returns MASR_OK when the band kernel ran, 1 when the caller should use the tile kernel of conv_umma.cu
+// mode 0: forward (wp [Cout][tap][Cin]); 1: dgrad reading wp MN-major; 2: dgrad with wpt [Cin][tap][Cout]
 int conv_band_try(int mode, const void* act, const void* wp, void* out, const void* relu_src, const float* bias, int relu,
                   int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
   if (!band_enabled()) return 1;
@@ -369,14 +394,16 @@ int conv_band_try(int mode, const void* act, const void* wp, void* out, const vo
   uint32_t box[4] = {64, uint32_t(g.W2), uint32_t(rpb), 1};
   int rc = make_tmap_bf16(&ma, act, 4, dims, strides, box, true);
   if (rc != MASR_OK) return rc;
-  uint64_t wd[2] = {uint64_t(9 * Cin), uint64_t(Cout)};
-  uint64_t ws[1] = {uint64_t(9 * Cin) * 2};
-  uint32_t wb[2] = {64, mode == 0 ? uint32_t(Cout) : 64u};
+  // weight tensor as a 2-D map: rows = output channels of the GEMM for K-major B (modes 0, 2)
+  uint64_t wd[2] = {uint64_t(9 * (mode == 2 ? Cout : Cin)), uint64_t(mode == 2 ? Cin : Cout)};
+  uint64_t ws[1] = {wd[0] * 2};
+  uint32_t wb[2] = {64, mode == 1 ? 64u : uint32_t(Cn)};
   rc = make_tmap_bf16(&mw, wp, 2, wd, ws, wb, true);
   if (rc != MASR_OK) return rc;
+  const int kstride = mode == 2 ? Cout : Cin;              // columns per tap inside the weight rows
   static int pf = -1;
   if (pf < 0) { const char* e = getenv("MASR_CONV_BAND_PF"); pf = e != nullptr ? atoi(e) : 2; }
-  BandParams p{B, H, W, g.W2, Cin, g.tiles_per_img, B * g.tiles_per_img, g.nr, g.slot_bytes, g.sb, rpb, pf,
+  BandParams p{B, H, W, g.W2, kstride, g.tiles_per_img, B * g.tiles_per_img, g.nr, g.slot_bytes, g.sb, rpb, pf,
                static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(relu_src), bias, relu, band_desc_mode()};
   const int key = (mode << 2) | ((Cred == 128 ? 1 : 0) << 1) | (Cn == 128 ? 1 : 0);
   switch (key) {
@@ -387,7 +414,11 @@ int conv_band_try(int mode, const void* act, const void* wp, void* out, const vo
     case 4: return launch_band<1, 64, 1>(ma, mw, p, g, st);
     case 5: return launch_band<1, 128, 1>(ma, mw, p, g, st);
     case 6: return launch_band<2, 64, 1>(ma, mw, p, g, st);
-    default: return launch_band<2, 128, 1>(ma, mw, p, g, st);
+    case 7: return launch_band<2, 128, 1>(ma, mw, p, g, st);
+    case 8: return launch_band<1, 64, 2>(ma, mw, p, g, st);
+    case 9: return launch_band<1, 128, 2>(ma, mw, p, g, st);
+    case 10: return launch_band<2, 64, 2>(ma, mw, p, g, st);
+    default: return launch_band<2, 128, 2>(ma, mw, p, g, st);
   }
 }
 

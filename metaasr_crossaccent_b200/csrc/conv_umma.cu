@@ -421,14 +421,19 @@ umma_conv_wgrad2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sx = sa + A_BYTES + 128;           // X row 0 of the box
+        // descriptors once per k-block; a K16 step advances both operands by 16 rows = 2048 B (+128 encoded),
+        // the dw taps are one pixel row (128 B, +8 encoded) apart
+        const uint64_t da0 = desc_mnmajor_sw128(sa, DY_CHUNK);
+        const uint64_t dx0 = desc_mnmajor_sw128(sx - 128, X_CHUNK);
         if (elect_one_sync()) {
 #pragma unroll 1
           for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = desc_mnmajor_sw128(sa + k * 2048, DY_CHUNK);
+            const uint64_t da = da0 + uint64_t(k * 128);
+            const uint64_t dx = dx0 + uint64_t(k * 128);
             const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
 #pragma unroll
             for (int j = 0; j < 3; ++j)                   // tap dw = j - 1: the same X bytes, one row earlier / later
-              mma_f16_ss(tmem_base + uint32_t(j * CI), da, desc_mnmajor_sw128(sx + (j - 1) * 128 + k * 2048, X_CHUNK), idesc, acc);
+              mma_f16_ss(tmem_base + uint32_t(j * CI), da, dx + uint64_t(j * 8), idesc, acc);
             if constexpr (RS) mma_f16_ss(tmem_base + uint32_t(3 * CI), da, dones, idesc_ones, acc);
           }
           mma_commit(&empty_bar[s]);
@@ -527,12 +532,13 @@ extern "C" int masr_umma_conv3x3_fwd(const void* x, const void* wp, const float*
 }
 
 // dx[B,H,W,Cin] = conv3x3^T(dy[B,H,W,Cout]) (times (relu_src > 0) when relu_src != NULL)
-extern "C" int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, void* dx, const void* relu_src,
+extern "C" int masr_umma_conv3x3_dgrad(const void* dy, const void* wp, const void* wpt, void* dx, const void* relu_src,
                                        int B, int H, int W, int Cin, int Cout, void* stream) {
   MASR_REQUIRE((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "umma conv: channels must be 64 or 128");
   if (B * H * W == 0) return MASR_OK;
   {
-    const int brc = conv_band_try(1, dy, wp, dx, relu_src, nullptr, 0, B, H, W, Cin, Cout, as_stream(stream));
+    const int brc = wpt != nullptr ? conv_band_try(2, dy, wpt, dx, relu_src, nullptr, 0, B, H, W, Cin, Cout, as_stream(stream))
+                                   : conv_band_try(1, dy, wp, dx, relu_src, nullptr, 0, B, H, W, Cin, Cout, as_stream(stream));
     if (brc != 1) return brc;
   }
   const ConvTile t = pick_tile(H, W, 128);

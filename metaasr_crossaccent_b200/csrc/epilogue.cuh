@@ -39,8 +39,23 @@ struct EpiOpts {
   const unsigned char* smask = nullptr;        // or: mask tile resident in shared memory ([128 x 64] halves of
                                                // 16 KB in the TMA 128B-swizzled layout, row = TMEM lane)
   float mask_scale = 1.f;
+  // or: the mask row lives at a constant byte offset from the destination row (same [pixels, channels] layout):
+  // no second pointer per row has to travel through the warp
+  bool mask_at_dst_delta = false;
+  long long mask_delta = 0;
 };
 
+// packed variant for scale == 1: v * (mask > 0 ? 1 : 0) on bf16x2 words (no fp32 round trip)
+__device__ __forceinline__ uint4 apply_mask8_packed(const uint4& val, const uint4& mraw) {
+  uint4 out;
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+  const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+  const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mraw);
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o2[e] = __hmul2(v2[e], __hgt2(m2[e], zero));
+  return out;
+}
 __device__ __forceinline__ void apply_mask8(float* f, const uint4& mraw, float scale) {
   float mk[8];
   load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(&mraw), mk);
@@ -117,7 +132,28 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
 #pragma unroll
       for (int i = 0; i < NIT; ++i)
         val[i] = *reinterpret_cast<const uint4*>(stage + (q * 32 + i * RPI + sub) * L::ROWB + ch0 * 16);
-      if (o.smask == nullptr && !any_gmask && mode == EPI_STORE) {
+      if (o.mask_at_dst_delta && mode == EPI_STORE) {
+        unsigned long long dd[NIT];
+        uint4 mraw[NIT];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          dd[i] = __shfl_sync(0xffffffffu, my_dst, i * RPI + sub);
+          mraw[i] = make_uint4(0, 0, 0, 0);
+          if (dd[i] != 0ull) mraw[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(dd[i]) + o.mask_delta + ch0 * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          if (dd[i] == 0ull) continue;
+          if (o.mask_scale == 1.f) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dd[i]) + ch0 * 16) = apply_mask8_packed(val[i], mraw[i]);
+          } else {
+            float f[8];
+            load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(&val[i]), f);
+            apply_mask8(f, mraw[i], o.mask_scale);
+            store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dd[i]) + ch0 * 8, f);
+          }
+        }
+      } else if (o.smask == nullptr && !any_gmask && mode == EPI_STORE) {
 #pragma unroll
         for (int i = 0; i < NIT; ++i) {
           const unsigned long long d = __shfl_sync(0xffffffffu, my_dst, i * RPI + sub);

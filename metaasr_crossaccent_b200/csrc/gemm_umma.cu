@@ -165,12 +165,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
+          // descriptors once per k-block, advanced by encoded offsets (start-address field = bytes >> 4):
+          // K-major +16 elements = +32 B -> +2; MN-major +16 k-rows = +2048 B -> +128
+          const uint64_t da0 = A_MN ? desc_mnmajor_sw128(sa, 64 * UG_BK * 2) : desc_kmajor_sw128(sa);
+          const uint64_t db0 = B_MN ? desc_mnmajor_sw128(sb, 64 * UG_BK * 2) : desc_kmajor_sw128(sb);
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < UG_BK / 16; ++k) {
-              // K-major: +16 elements = +32 B inside the swizzle row; MN-major: +16 k-rows = +2048 B
-              const uint64_t da = A_MN ? desc_mnmajor_sw128(sa + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sa + k * 32);
-              const uint64_t db = B_MN ? desc_mnmajor_sw128(sb + k * 2048, 64 * UG_BK * 2) : desc_kmajor_sw128(sb + k * 32);
+              const uint64_t da = da0 + uint64_t(A_MN ? k * 128 : k * 2);
+              const uint64_t db = db0 + uint64_t(B_MN ? k * 128 : k * 2);
               const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
               mma_f16_ss(tmem_base, da, db, idesc, acc);
               if constexpr (RS) mma_f16_ss(tmem_base + BN, da, dones, idesc_ones, acc);

@@ -149,11 +149,14 @@ class TransformerEngine:
         if self.act_dtype != torch.float32:
             self.shadow = torch.zeros(n, dtype=self.act_dtype, device=self.device)
         self.W = OrderedDict()      # name -> compute-dtype weight used by GEMMs
+        self.wpt = {}               # conv idx -> [Cin, 9*Cout] compute dtype (dgrad operand), tensor-core path only
         self.wp = {}                # conv idx -> [Cout, 9*Cin] compute dtype
         self.dwp = {}               # conv idx -> fp32 gradient in the same layout
         for i, (co, ci) in zip((2, 5, 7), ((64, 64), (128, 64), (128, 128))):
             self.wp[i] = torch.zeros(co, 9 * ci, dtype=self.act_dtype, device=self.device)
             self.dwp[i] = torch.zeros(co, 9 * ci, dtype=torch.float32, device=self.device)
+            if hasattr(backend, "conv_w_prep_t") and getattr(backend, "gemm_path", "") == "umma":
+                self.wpt[i] = torch.zeros(ci, 9 * co, dtype=self.act_dtype, device=self.device)
         self.vgg2enc_p = torch.zeros(cfg.d_model, cfg.vgg_o_dim, dtype=self.act_dtype, device=self.device)
         self.d_vgg2enc_p = torch.zeros(cfg.d_model, cfg.vgg_o_dim, dtype=torch.float32, device=self.device)
         self.weights_dirty = True
@@ -203,6 +206,8 @@ class TransformerEngine:
         self.W = src
         for i in (2, 5, 7):
             be.conv_w_prep(self.P[f"feat_extractor.{i}.weight"], self.wp[i])
+            if i in self.wpt:
+                be.conv_w_prep_t(self.P[f"feat_extractor.{i}.weight"], self.wpt[i])
         be.permute_cf(self.P["vgg2enc.weight"], self.vgg2enc_p, self.cfg.vgg_ch, self.cfg.f4, False)
         self.weights_dirty = False
 
@@ -596,15 +601,15 @@ class TransformerEngine:
 
         conv_wgrad(7, ws["a3"], g_a4)
         g_a3 = buf("g.a3", (B, T2, F2, 128))
-        be.conv3x3_dgrad(g_a4, self.wp[7], g_a3, ws["a3"])
+        be.conv3x3_dgrad(g_a4, self.wp[7], g_a3, ws["a3"], **({"wpt": self.wpt[7]} if 7 in self.wpt else {}))
         conv_wgrad(5, ws["p1"], g_a3)
         g_p1 = buf("g.p1", (B, T2, F2, 64))
-        be.conv3x3_dgrad(g_a3, self.wp[5], g_p1, None)
+        be.conv3x3_dgrad(g_a3, self.wp[5], g_p1, None, **({"wpt": self.wpt[5]} if 5 in self.wpt else {}))
         g_a2 = buf("g.a2", (B, T, F0, 64))
         be.maxpool_bwd(ws["a2"], g_p1, g_a2, True)
         conv_wgrad(2, ws["a1"], g_a2)
         g_a1 = buf("g.a1", (B, T, F0, 64))
-        be.conv3x3_dgrad(g_a2, self.wp[2], g_a1, ws["a1"])
+        be.conv3x3_dgrad(g_a2, self.wp[2], g_a1, ws["a1"], **({"wpt": self.wpt[2]} if 2 in self.wpt else {}))
         be.conv1_wgrad(db["x"], g_a1, G["feat_extractor.0.weight"], G["feat_extractor.0.bias"])
         self._join()
 

@@ -217,6 +217,10 @@ class CudaBackend:
     def conv_w_prep(self, w, wp):
         self._call("masr_conv_w_prep", _p(w), _p(wp), _dt(wp), w.shape[0], w.shape[1], self.stream)
 
+    def conv_w_prep_t(self, w, wpt):
+        """wpt [Cin, 9*Cout]: transposed operand layout for the dgrad implicit GEMM."""
+        self._call("masr_conv_w_prep_t", _p(w), _p(wpt), _dt(wpt), w.shape[0], w.shape[1], self.stream)
+
     def conv_w_unprep_add(self, dwp, dw):
         self._call("masr_conv_w_unprep_add", _p(dwp), _p(dw), dw.shape[0], dw.shape[1], self.stream)
 
@@ -240,14 +244,14 @@ class CudaBackend:
             return self.umma_gemm(col, 0, wp, 0, y2, bias, B * H * W, Cout, 9 * Cin, GEMM_RELU)
         self.gemm(col, 9 * Cin, 1, wp, 9 * Cin, 1, y, Cout, bias, B * H * W, Cout, 9 * Cin, GEMM_RELU)
 
-    def conv3x3_dgrad(self, dy, wp, dx, relu_src=None):
-        """dx = conv3x3^T(dy) (times (relu_src > 0) when given)."""
+    def conv3x3_dgrad(self, dy, wp, dx, relu_src=None, wpt=None):
+        """dx = conv3x3^T(dy) (times (relu_src > 0) when given); wpt: optional conv_w_prep_t layout."""
         B, H, W, Cout = dy.shape
         Cin = dx.shape[3]
         P = B * H * W
         if self._conv_umma_ok(dy, wp, dx) and (relu_src is None or relu_src.is_contiguous()):
-            return self._timed_call(("conv_dgrad", P, Cin, 9 * Cout), "masr_umma_conv3x3_dgrad", _p(dy), _p(wp), _p(dx),
-                                    _p(relu_src), B, H, W, Cin, Cout, self.stream)
+            return self._timed_call(("conv_dgrad", P, Cin, 9 * Cout), "masr_umma_conv3x3_dgrad", _p(dy), _p(wp), _p(wpt),
+                                    _p(dx), _p(relu_src), B, H, W, Cin, Cout, self.stream)
         dcol = self.scratch(("col", self.scratch_tag), P * 9 * Cin, dy.dtype).view(P, 9 * Cin)
         dy2 = dy.view(P, Cout)
         if self._umma_ok(dy2, wp):

@@ -35,12 +35,16 @@ def test_umma_conv3x3(dev, B, H, W, Cin, Cout):
     tb.conv3x3_fwd(x, wp, bias, y2)
     close(y1, y2, bf, what="umma conv fwd")
     dy = rnd((B, H, W, Cout), dev, bf, 4)
+    wpt = torch.empty(Cin, 9 * Cout, device=dev, dtype=bf)
+    cb.conv_w_prep_t(w, wpt)
+    assert torch.equal(wpt.view(Cin, 9, Cout), wp.view(Cout, 9, Cin).permute(2, 1, 0))
     for mask in (None, x):
-        dx1 = torch.full((B, H, W, Cin), 9.0, device=dev, dtype=bf)
-        dx2 = torch.empty_like(dx1)
-        cb.conv3x3_dgrad(dy, wp, dx1, mask)
-        tb.conv3x3_dgrad(dy, wp, dx2, mask)
-        close(dx1, dx2, bf, what="umma conv dgrad")
+        for t in (None, wpt):              # weights read MN-major from wp, or K-major from the transposed layout
+            dx1 = torch.full((B, H, W, Cin), 9.0, device=dev, dtype=bf)
+            dx2 = torch.empty_like(dx1)
+            cb.conv3x3_dgrad(dy, wp, dx1, mask, wpt=t)
+            tb.conv3x3_dgrad(dy, wp, dx2, mask)
+            close(dx1, dx2, bf, what="umma conv dgrad")
     dwp1 = rnd((Cout, 9 * Cin), dev, torch.float32, 5)
     db1 = torch.zeros(Cout, device=dev)
     dwp2, db2 = dwp1.clone(), db1.clone()

@@ -71,7 +71,9 @@ def main():
             fl = 2.0 * B * H * W * Co * 9 * Ci
             timeit(f"conv3x3_fwd   {B}x{H}x{W} {Ci}->{Co}", lambda: be.conv3x3_fwd(x, wp, bias, y), args.reps, tab, fl)
             dx = torch.empty_like(x)
-            timeit(f"conv3x3_dgrad {B}x{H}x{W} {Ci}->{Co}", lambda: be.conv3x3_dgrad(dy, wp, dx, x), args.reps, tab, fl)
+            wpt = torch.empty(Ci, 9 * Co, device=dev, dtype=bf)
+            be.conv_w_prep_t(w, wpt)
+            timeit(f"conv3x3_dgrad {B}x{H}x{W} {Ci}->{Co}", lambda: be.conv3x3_dgrad(dy, wp, dx, x, wpt=wpt), args.reps, tab, fl)
             dwp, db = torch.zeros(Co, 9 * Ci, device=dev), torch.zeros(Co, device=dev)
             timeit(f"conv3x3_wgrad {B}x{H}x{W} {Ci}->{Co} (+colsum)", lambda: be.conv3x3_wgrad(x, dy, dwp, db), args.reps, tab, fl)
         x1 = torch.randn(32, 512, 83, device=dev)
