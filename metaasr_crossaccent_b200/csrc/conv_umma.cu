@@ -483,6 +483,163 @@ static int launch_wgrad2(const CUtensorMap& mdy, const CUtensorMap& mx, const Wg
   return MASR_OK;
 }
 
+// ------------------------------------------------------------------ wgrad for Cin = Cout = 64: tap pairs as M = 128
+// With 64 output channels the [co x ci] accumulators above are M = 64 MMAs, which occupy the tensor pipe exactly
+// as long as M = 128 ones.  Here the product is transposed and TWO TAPS share one MMA:
+//     D[(tap, ci), co] = sum_pix X[pix + tap, ci] . dY[pix, co]
+// A = the X region (MN-major, K rows = pixels).  The second 64-row half of M is the SAME bytes shifted by one tap:
+// the descriptor's leading-dimension byte offset (distance between 64-element M chunks) is set to 128 B (next dw)
+// or Wp * 128 B (next dh).  Nine taps = four M = 128 groups + one M = 64 group: 5 MMAs per K16 step instead of 9,
+// all nine taps in ONE CTA (X region = three image rows), so X and dY cross the L2->smem path once instead of three
+// times.  The bias gradient is an all-ones A tile against the same dY operand.
+struct Wgrad3Params {
+  int B, H, W;
+  int wp, kr;           // pitch W + 4, MMA rows per k-block (multiple of 16)
+  int ntiles;           // B * H image rows
+  float* dwp; float* db;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+umma_conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, Wgrad3Params p) {
+  using namespace umma;
+  constexpr uint32_t DY_BYTES = 128 * 128;                 // 16 KB: up to 128 k-rows
+  constexpr uint32_t X_BYTES = 48 * 1024;                  // margin row + 3 image rows (<= 3 * 124) + tail
+  constexpr uint32_t STAGE_BYTES = DY_BYTES + X_BYTES;
+  constexpr uint32_t TMEM_COLS = 512;                      // 4 x 64 (tap pairs) + 64 (last tap | bias) = 320
+  constexpr int PITCH = 65;                                // staging row pitch (floats): conflict-free transposition
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sones = smem + STAGES * STAGE_BYTES;
+  float* sStage = reinterpret_cast<float*>(smem);          // epilogue staging aliases the (by then idle) ring
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sones + 2048);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  static_assert(STAGES * STAGE_BYTES >= 128 * PITCH * 4, "staging must fit in the ring");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (p.ntiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int ksteps = p.kr / 16;
+  const int wp = p.wp;
+
+  pdl_launch_dependents();
+  for (uint32_t i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += CV_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 128) reinterpret_cast<uint4*>(sones)[threadIdx.x] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_dy);
+    prefetch_tmap(&map_x);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    const uint32_t tx_bytes = uint32_t(wp) * 128u * 4u;   // 1 row of dY + 3 rows of X
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = int(blockIdx.x) + it * int(gridDim.x);
+      const int b = tile / p.H, h = tile % p.H;
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      unsigned char* sa = smem + s * STAGE_BYTES;
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        tma_load_4d(sa, &map_dy, &full_bar[s], 0, -2, h, b);                       // box {64, wp, 1, 1}
+        tma_load_4d(sa + DY_BYTES + 128, &map_x, &full_bar[s], 0, -2, h - 1, b);   // box {64, wp, 3, 1}, after the margin row
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 64, 1, 1);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t sdy = smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t sx = sdy + DY_BYTES;                 // smem row 0 = margin, box row r at smem row r + 1
+      // A descriptors: start row (dh + 1) * wp + dw + 1, second M chunk one tap further (LBO)
+      const uint64_t db0 = make_smem_desc(sdy, 0, 1024);
+      const uint64_t a_g0 = make_smem_desc(sx + uint32_t(0 * wp + 0) * 128u, 128, 1024);            // (-1,-1) & (-1, 0)
+      const uint64_t a_g1 = make_smem_desc(sx + uint32_t(1 * wp + 0) * 128u, 128, 1024);            // ( 0,-1) & ( 0, 0)
+      const uint64_t a_g2 = make_smem_desc(sx + uint32_t(2 * wp + 0) * 128u, 128, 1024);            // ( 1,-1) & ( 1, 0)
+      const uint64_t a_g3 = make_smem_desc(sx + uint32_t(0 * wp + 2) * 128u, uint32_t(wp) * 128u, 1024);   // (-1, 1) & ( 0, 1)
+      // ( 1, 1) | all-ones rows: the second M chunk is the 2 KB tile of 1.0 (its distance shrinks as the start
+      // address advances), so rows 64..127 of this accumulator are sum_pix dY[pix, co] = the bias gradient
+      const uint32_t g4_start = sx + uint32_t(2 * wp + 2) * 128u;
+      const uint64_t a_g4 = make_smem_desc(g4_start, smem_u32(sones) - g4_start, 1024);
+      if (elect_one_sync()) {
+#pragma unroll 1
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ko = uint64_t(k * 128);           // 16 rows = 2048 B
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          const uint64_t db = db0 + ko;
+          mma_f16_ss(tmem_base + 0, a_g0 + ko, db, idesc128, acc);
+          mma_f16_ss(tmem_base + 64, a_g1 + ko, db, idesc128, acc);
+          mma_f16_ss(tmem_base + 128, a_g2 + ko, db, idesc128, acc);
+          mma_f16_ss(tmem_base + 192, a_g3 + ko, db, idesc128, acc);
+          mma_f16_ss(tmem_base + 256, a_g4 + ko - (ko << 16), db, idesc128, acc);   // start += 2048 B, LBO -= 2048 B
+        }
+        mma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) mma_commit(tmem_full_bar);
+    __syncwarp();
+  } else if (my_tiles > 0) {
+    // ===== epilogue: transpose [(tap, ci), co] -> dwp[co][tap * 64 + ci] through shared memory, fp32 reductions =====
+    const int q = warp & 3;
+    const int et = (warp - 2) * 32 + lane;                // 0..127
+    const int r = q * 32 + lane;                          // TMEM lane
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    // taps of group g: first half, second half (-1 = none)
+    const int tapA[5] = {0, 3, 6, 2, 8};
+    const int tapB[5] = {1, 4, 7, 5, -1};
+#pragma unroll 1
+    for (int g = 0; g < 5; ++g) {
+      float v[64];
+      tmem_ld_32x32(tmem_base + uint32_t(g * 64) + (uint32_t(q * 32) << 16), v);
+      tmem_ld_32x32(tmem_base + uint32_t(g * 64 + 32) + (uint32_t(q * 32) << 16), v + 32);
+      tmem_ld_wait();
+      // lane r = row r = (tap half, ci); the last group's second half is the bias gradient (all rows equal)
+      if (g == 4 && r == 64 && p.db != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) atomicAdd(p.db + c, v[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 64; ++c) sStage[r * PITCH + c] = v[c];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // 128 threads: thread -> (half, 4 consecutive ci), loop over co
+      const int half = et >> 6, l4 = (et & 63) >> 2, cosub = et & 3;
+      const int tap = half == 0 ? tapA[g] : tapB[g];
+      if (tap >= 0) {
+#pragma unroll 1
+        for (int co = cosub; co < 64; co += 4) {
+          const int rb = half * 64 + l4 * 4;
+          const float x0 = sStage[(rb + 0) * PITCH + co], x1 = sStage[(rb + 1) * PITCH + co];
+          const float x2 = sStage[(rb + 2) * PITCH + co], x3 = sStage[(rb + 3) * PITCH + co];
+          float* d4 = p.dwp + co * 576 + tap * 64 + l4 * 4;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
 // conv_band.cu: halo-reuse variant; returns 1 when it does not apply (geometry / disabled)
 int conv_band_try(int mode, const void* act, const void* wp, void* out, const void* relu_src, const float* bias, int relu,
                   int B, int H, int W, int Cin, int Cout, cudaStream_t st);
@@ -599,7 +756,29 @@ extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp
       const int tpi = (H + r - 1) / r;
       Wgrad2Params p2{B, H, W, Cin, Cout, wp, r, kr, B * tpi, tpi, dwp, db};
       cudaStream_t st2 = as_stream(stream);
-      if (Cout == 64 && Cin == 64) return launch_wgrad2<64, 64, 6>(mdy2, mx2, p2, st2);
+      if (Cout == 64 && Cin == 64) {
+        static int w3 = -1;
+        if (w3 < 0) { const char* e = getenv("MASR_CONV_WGRAD3"); w3 = (e != nullptr && e[0] == '0') ? 0 : 1; }
+        if (w3 && wp <= 124) {
+          // tap-pair variant: one image row of dY and three of X per k-block
+          CUtensorMap mdy3, mx3;
+          uint32_t by[4] = {64, uint32_t(wp), 1, 1}, bx[4] = {64, uint32_t(wp), 3, 1};
+          rc2 = make_tmap_bf16(&mdy3, dy, 4, dd, ds, by, true);
+          if (rc2 != MASR_OK) return rc2;
+          rc2 = make_tmap_bf16(&mx3, x, 4, xd, xs, bx, true);
+          if (rc2 != MASR_OK) return rc2;
+          Wgrad3Params p3{B, H, W, wp, (wp + 15) / 16 * 16, B * H, dwp, db};
+          constexpr int ST3 = 3;
+          const size_t smem3 = ST3 * (16384 + 48 * 1024) + 2048 + 256 + 1024;
+          auto kern3 = umma_conv_wgrad3_kernel<ST3>;
+          static bool attr3 = false;
+          if (!attr3) { MASR_CHECK_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem3))); attr3 = true; }
+          const int gx3 = std::max(1, std::min(p3.ntiles, sm_count()));
+          MASR_CHECK_CUDA(launch_pdl(kern3, dim3(unsigned(gx3)), dim3(CV_THREADS), smem3, st2, mdy3, mx3, p3));
+          return MASR_OK;
+        }
+        return launch_wgrad2<64, 64, 6>(mdy2, mx2, p2, st2);
+      }
       if (Cout == 128 && Cin == 64) return launch_wgrad2<128, 64, 4>(mdy2, mx2, p2, st2);
       if (Cout == 128 && Cin == 128) return launch_wgrad2<128, 128, 3>(mdy2, mx2, p2, st2);
       if (Cout == 64 && Cin == 128) return launch_wgrad2<64, 128, 4>(mdy2, mx2, p2, st2);
