@@ -55,6 +55,7 @@ struct AttnFwdParams {
   __nv_bfloat16* out; int64_t ldo;
   float* lse;
   const uint64_t* seed_ptr;      // device-resident per-step seed offset (CUDA-graph replay), may be NULL
+  int kv_stages;                 // K/V ring depth: 1 (Lk <= 128) or 2
 };
 
 __global__ void __launch_bounds__(AU_THREADS, 2)
@@ -64,8 +65,9 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* sQ = smem;                         // 16 KB
-  unsigned char* sKV = sQ + AU_T64;                 // 2 stages x (K 16 KB + V 16 KB)
-  unsigned char* sP = sKV + 4 * AU_T64;             // 32 KB
+  unsigned char* sKV = sQ + AU_T64;                 // kv_stages x (K 16 KB + V 16 KB)
+  const int kvst = p.kv_stages;                     // 1 when all keys fit one tile: 83 KB -> two CTAs per SM
+  unsigned char* sP = sKV + kvst * 2 * AU_T64;      // 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AU_T128);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                     // [2]
@@ -109,8 +111,8 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
     __syncwarp();
     for (int t = 0; t < ntiles; ++t) {
-      const int s = t & 1;
-      mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1);
+      const int s = kvst == 2 ? (t & 1) : 0;
+      mbar_wait(&kv_empty[s], ((kvst == 2 ? (t >> 1) : t) & 1) ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&kv_full[s], 2 * AU_T64);
         tma_load_2d(sKV + s * 2 * AU_T64, &map_k, &kv_full[s], h * 64, b * p.Lk + t * AU_TILE);
@@ -123,8 +125,8 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);        // O = P V   (V read MN-major)
     mbar_wait(q_full, 0);
     for (int t = 0; t < ntiles; ++t) {
-      const int s = t & 1;
-      mbar_wait(&kv_full[s], (t >> 1) & 1);
+      const int s = kvst == 2 ? (t & 1) : 0;
+      mbar_wait(&kv_full[s], (kvst == 2 ? (t >> 1) : t) & 1);
       tc_fence_after();
       const uint32_t aq = smem_u32(sQ), ak = smem_u32(sKV + s * 2 * AU_T64), av = ak + AU_T64, ap = smem_u32(sP);
       if (elect_one_sync()) {
@@ -533,11 +535,12 @@ extern "C" int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int
   rc = rows_map(&mv, v, ldv, int64_t(B) * Lk, H * 64); if (rc) return rc;
   const uint32_t thr16 = attn_drop_thr16(p_drop);
   AttnFwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? attn_drop_inv_keep(thr16) : 1.f, thr16, seed, site,
-                  static_cast<__nv_bfloat16*>(out), ldo, lse, g_seed_dev_ptr};
+                  static_cast<__nv_bfloat16*>(out), ldo, lse, g_seed_dev_ptr, Lk <= AU_TILE ? 1 : 2};
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_FWD_SMEM))); attr = true; }
   dim3 grid(unsigned(ceil_div64(Lq, AU_TILE)), unsigned(B * H));
-  MASR_CHECK_CUDA(launch_pdl(attn_fwd_umma_kernel, grid, dim3(AU_THREADS), AU_FWD_SMEM, as_stream(stream), mq, mk, mv, p));
+  const size_t smem = AU_FWD_SMEM - (p.kv_stages == 1 ? 2 * AU_T64 : 0);
+  MASR_CHECK_CUDA(launch_pdl(attn_fwd_umma_kernel, grid, dim3(AU_THREADS), smem, as_stream(stream), mq, mk, mv, p));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

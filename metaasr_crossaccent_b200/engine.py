@@ -250,15 +250,23 @@ class TransformerEngine:
         ys_out = meta[B + B * L1:].view(B, L1)
         ys_in.fill_(cfg.eos_id)
         ys_out.fill_(IGNORE_ID)
-        for b, y in enumerate(ys):
-            n = int(y.numel())
-            ys_in[b, 0] = cfg.sos_id
-            ys_in[b, 1:n + 1] = y
-            ys_out[b, :n] = y
-            ys_out[b, n] = cfg.eos_id
+        lens = [int(y.numel()) for y in ys]
+        if min(lens) == L1 - 1:                       # equal-length batch (the bucketed train loader): three copies
+            Y = torch.stack(list(ys))
+            ys_in[:, 0] = cfg.sos_id
+            ys_in[:, 1:] = Y
+            ys_out[:, :L1 - 1] = Y
+            ys_out[:, L1 - 1] = cfg.eos_id
+        else:
+            for b, y in enumerate(ys):
+                n = lens[b]
+                ys_in[b, 0] = cfg.sos_id
+                ys_in[b, 1:n + 1] = y
+                ys_out[b, :n] = y
+                ys_out[b, n] = cfg.eos_id
         if olens is not None:
             olens += 1
-        n_total = int(ys_out.ne(IGNORE_ID).sum())
+        n_total = sum(lens) + B                       # non-pad targets = every y plus its eos
         return {"x": xs_pad, "enc_lens": meta[:B], "ys_in": ys_in, "ys_out": ys_out, "meta": meta, "n_total": n_total,
                 "B": B, "T": xs_pad.shape[1], "L1": L1}
 
