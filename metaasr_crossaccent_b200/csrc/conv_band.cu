@@ -31,7 +31,7 @@
 
 namespace masr {
 
-constexpr int CB_THREADS = 224;
+constexpr int CB_THREADS = 256;               // warp 7: second MMA issuer of the resident-weight variant
 constexpr int CB_MAX_SB = 12;                 // weight ring depth is chosen at launch from the free shared memory
 
 struct BandParams {
@@ -82,14 +82,16 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* t_empty = t_full + 2;             // [2] accumulator buffer drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   float* sbias = reinterpret_cast<float*>(t_empty + 4);
-  constexpr uint32_t TMEM_COLS = (2 * NM * BN < 32) ? 32 : 2 * NM * BN;   // 128, 256 or 512
+  // RES: two accumulators per buffer (one per issuing warp)
+  constexpr uint32_t TMEM_COLS = RES ? 4 * NM * BN : ((2 * NM * BN < 32) ? 32 : 2 * NM * BN);   // 256 or 512
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_w);
-    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    // RES: two issuing warps (each commits once per chunk / tile)
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], RES ? 2 : 1); mbar_init(&t_full[s], RES ? 2 : 1); mbar_init(&t_empty[s], 4); }
     for (int s = 0; s < CB_MAX_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     fence_barrier_init();
   }
@@ -172,7 +174,7 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (RES && warp == 7)) {
     // ===== MMA issuer: the whole warp runs the loop (uniform control flow and addresses), one elected lane issues.
     // The single issuing thread is the critical resource of the N = 64 layers (a 128x64x16 MMA occupies the tensor
     // pipe for only 32 cycles): descriptors are built ONCE per (tile, chunk) and advanced by adding encoded byte
@@ -198,40 +200,60 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int ab = it & 1;
         mbar_wait(&t_empty[ab], ((it >> 1) & 1) ^ 1);            // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + uint32_t(ab * NM * BN);
+        // RES: a single thread dispatches an N = 64 MMA only every ~50 cycles (the MMA occupies the tensor pipe
+        // for 32): warp 1 issues taps 0-4 into accumulator 0, warp 7 taps 5-8 into accumulator 1; the epilogue adds them
+        const int issuer = (RES && warp == 7) ? 1 : 0;
+        const uint32_t acc0 = tmem_base + uint32_t((RES ? 2 * ab + issuer : ab) * NM * BN);
         if (RES && it == 0) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
 #pragma unroll 1
         for (int cc = 0; cc < CH; ++cc) {
           mbar_wait(&a_full[aslot], aph);
           tc_fence_after();
           const uint64_t da0 = make_smem_desc(smem_u32(sA + aslot * p.slot_bytes) + uint32_t(off) * 128u, 16, 1024);
+          if constexpr (RES) {
+            // resident weights: no barrier inside the chunk -> ONE election around all 9 x NM x 4 MMAs (the
+            // per-tap elect / reconverge / R2UR sequence costs more issue cycles than four N = 64 MMAs take)
+            if (elect_one_sync()) {
+              const int t_begin = issuer == 0 ? 0 : 5, t_end = issuer == 0 ? 5 : 9;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            uint64_t db0;
-            if (RES) {
-              db0 = db_res0 + uint64_t((cc * 9 + tap) * (B_BYTES >> 4));
-            } else {
+              for (int tap = 0; tap < 9; ++tap) {
+                if (tap < t_begin || tap >= t_end) continue;
+                const uint64_t db0 = db_res0 + uint64_t((cc * 9 + tap) * (B_BYTES >> 4));
+                const uint64_t da_tap = da0 + uint64_t(tap_rows[tap]) * 8u;
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    mma_f16_ss(acc0 + uint32_t(m * BN), da_tap + uint64_t(m * 1024 + k * 2), db0 + uint64_t(MODE == 1 ? k * 128 : k * 2),
+                               idesc, (cc > 0 || tap > t_begin || k > 0) ? 1u : 0u);
+                }
+              }
+            }
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
               const uint32_t sb = smem_u32(sB + bs * B_BYTES);
-              db0 = (MODE == 1) ? desc_mnmajor_sw128(sb, 8192) : desc_kmajor_sw128(sb);
-            }
-            const uint64_t da_tap = da0 + uint64_t(tap_rows[tap]) * 8u;
-            if (elect_one_sync()) {
+              const uint64_t db0 = (MODE == 1) ? desc_mnmajor_sw128(sb, 8192) : desc_kmajor_sw128(sb);
+              const uint64_t da_tap = da0 + uint64_t(tap_rows[tap]) * 8u;
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int m = 0; m < NM; ++m) {
+                for (int m = 0; m < NM; ++m) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  // K16 step: A +32 B; B K-major +32 B, MN-major (dgrad) +16 co-rows = +2048 B
-                  const uint64_t da = da_tap + uint64_t(m * 1024 + k * 2);
-                  const uint64_t db = db0 + uint64_t(MODE == 1 ? k * 128 : k * 2);
-                  mma_f16_ss(acc0 + uint32_t(m * BN), da, db, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k) {
+                    // K16 step: A +32 B; B K-major +32 B, MN-major (dgrad) +16 co-rows = +2048 B
+                    const uint64_t da = da_tap + uint64_t(m * 1024 + k * 2);
+                    const uint64_t db = db0 + uint64_t(MODE == 1 ? k * 128 : k * 2);
+                    mma_f16_ss(acc0 + uint32_t(m * BN), da, db, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  }
                 }
+                mma_commit(&b_empty[bs]);
               }
-              if (!RES) mma_commit(&b_empty[bs]);
+              __syncwarp();
+              if (++bs == SB) { bs = 0; bph ^= 1; }
             }
-            __syncwarp();
-            if (!RES) { if (++bs == SB) { bs = 0; bph ^= 1; } }
           }
           if (elect_one_sync()) mma_commit(&a_empty[aslot]);
           __syncwarp();
@@ -291,7 +313,8 @@ umma_conv_band_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           o.mask_at_dst_delta = true;
           o.mask_delta = reinterpret_cast<const unsigned char*>(p.relu_src) - reinterpret_cast<const unsigned char*>(p.out);
         }
-        epilogue_tile<BN, __nv_bfloat16>(tmem_base + uint32_t((ab * NM + m) * BN), q, lane, sStage, orow, BN, true, EPI_STORE, o);
+        if (RES) o.acc2_offset = uint32_t(NM * BN);
+        epilogue_tile<BN, __nv_bfloat16>(tmem_base + uint32_t(((RES ? 2 * ab : ab) * NM + m) * BN), q, lane, sStage, orow, BN, true, EPI_STORE, o);
       }
       tc_fence_before();
       __syncwarp();

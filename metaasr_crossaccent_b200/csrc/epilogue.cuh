@@ -43,6 +43,9 @@ struct EpiOpts {
   // no second pointer per row has to travel through the warp
   bool mask_at_dst_delta = false;
   long long mask_delta = 0;
+  // second accumulator (TMEM column offset from the first, 0 = none) added in phase 1: two MMA-issuing warps each
+  // own one accumulator and half of the k-blocks
+  uint32_t acc2_offset = 0;
 };
 
 // packed variant for scale == 1: v * (mask > 0 ? 1 : 0) on bf16x2 words (no fp32 round trip)
@@ -86,6 +89,15 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
       for (int j = 0; j < CB / 4; ++j) b4[j] = *reinterpret_cast<const float4*>(o.sbias + c0 + 4 * j);
     }
     umma::tmem_ld_wait();
+    if (o.acc2_offset != 0) {
+      float v2[CB];
+#pragma unroll
+      for (int h = 0; h < CB; h += 32)
+        umma::tmem_ld_32x32(tmem_acc + o.acc2_offset + (uint32_t(q * 32) << 16) + uint32_t(c0 + h), v2 + h);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < CB; ++j) v[j] += v2[j];
+    }
     if (o.sbias != nullptr) {
 #pragma unroll
       for (int j = 0; j < CB / 4; ++j) { v[4 * j] += b4[j].x; v[4 * j + 1] += b4[j].y; v[4 * j + 2] += b4[j].z; v[4 * j + 3] += b4[j].w; }
