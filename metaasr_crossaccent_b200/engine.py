@@ -273,15 +273,18 @@ class TransformerEngine:
     def _host_meta(self, numel):
         """int64 host staging buffer from a ring of 64 (pinned when CUDA is present); an entry is reused only
         after the copy that last read it has completed (event per entry)."""
-        ring = self.__dict__.setdefault("_meta_ring", {"i": 0, "bufs": [None] * 64, "evs": [None] * 64})
+        ring = self.__dict__.get("_meta_ring")
+        if ring is None:
+            # ONE pinned allocation for the whole ring (cudaHostAlloc costs milliseconds: never on the step path)
+            block = torch.empty(64 * 4096, dtype=torch.int64, pin_memory=self.device.type == "cuda")
+            ring = self._meta_ring = {"i": 0, "bufs": [block[k * 4096:(k + 1) * 4096] for k in range(64)], "evs": [None] * 64}
         i = ring["i"] = (ring["i"] + 1) % 64
         if ring["evs"][i] is not None:
             ring["evs"][i].synchronize()
         t = ring["bufs"][i]
-        if t is None or t.numel() < numel:
-            t = torch.empty(max(numel, 4096), dtype=torch.int64, pin_memory=self.device.type == "cuda")
+        if t.numel() < numel:                         # unusually large batch: private buffer for this entry
+            t = torch.empty(numel, dtype=torch.int64, pin_memory=self.device.type == "cuda")
             ring["bufs"][i] = t
-        self._meta_last = i
         return t[:numel]
 
     def _meta_copied(self, hb):
