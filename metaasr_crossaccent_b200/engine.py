@@ -352,6 +352,40 @@ class TransformerEngine:
         ppd = cfg.pos_dropout if self.training else 0.0
         P, W = self.P, self.W
 
+        # ---- decoder prefix: the target embedding and layer 0's causal self-attention block do not depend on the
+        # encoder at all -> side stream, concurrent with the conv front end / encoder
+        def dec_self(l, x):
+            pre = f"decoder.layers.{l}"
+            ws[f"d{l}.in"] = x
+            qkv = buf(f"d{l}.qkv", (Md, 3 * d))
+            be.linear_fwd(x, W[pre + ".self_attn.in_proj_weight"], P[pre + ".self_attn.in_proj_bias"], qkv)
+            ctx1 = buf(f"d{l}.ctx1", (Md, d))
+            lse1 = buf(f"d{l}.lse1", (B * H * L1,), f32)
+            be.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx1, lse1, B, H, L1, L1, None, True,
+                        pd, seed, self.site(pre + ".sa"))
+            s1 = buf(f"d{l}.s1", (Md, d))
+            be.linear_fwd(ctx1, W[pre + ".self_attn.out_proj.weight"], P[pre + ".self_attn.out_proj.bias"], s1)
+            h1 = buf(f"d{l}.h1", (Md, d))
+            be.add_layernorm_fwd(s1, x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1,
+                                 buf(f"d{l}.m1", (Md,), f32), buf(f"d{l}.r1", (Md,), f32), pd, seed, self.site(pre + ".d1"))
+            Wc, bc = W[pre + ".multihead_attn.in_proj_weight"], P[pre + ".multihead_attn.in_proj_bias"]
+            q2 = buf(f"d{l}.q2", (Md, d))
+            be.linear_fwd(h1, Wc[:d], bc[:d], q2)
+            return h1, q2
+
+        def kv_proj(l):
+            pre = f"decoder.layers.{l}"
+            Wc, bc = W[pre + ".multihead_attn.in_proj_weight"], P[pre + ".multihead_attn.in_proj_bias"]
+            be.linear_fwd(ws["mem"], Wc[d:], bc[d:], buf(f"d{l}.kv2", (Me, 2 * d)))
+
+        prefix = {}
+        if cfg.dec_layers > 0:
+            def dec_prefix():
+                x0 = buf("d.x0", (Md, d))
+                be.embed_pe_fwd(db["ys_in"].view(-1), P["pre_embed.weight"], self.pe2d, x0, L1, ppd, seed, self.site("dec.pe"))
+                prefix["h1"], prefix["q2"] = dec_self(0, x0)
+            self._fork(dec_prefix)
+
         # ---- VGG front end (NHWC)
         a1 = buf("a1", (B, T, F0, 64))
         be.conv1_fwd(db["x"], P["feat_extractor.0.weight"], P["feat_extractor.0.bias"], a1)
@@ -397,28 +431,24 @@ class TransformerEngine:
         be.add_layernorm_fwd(h, None, P["encoder.norm.weight"], P["encoder.norm.bias"], mem,
                              buf("enc.m", (Me,), f32), buf("enc.r", (Me,), f32), 0.0, seed, 0)
 
-        # ---- decoder
-        x = buf("d.x0", (Md, d))
-        be.embed_pe_fwd(db["ys_in"].view(-1), P["pre_embed.weight"], self.pe2d, x, L1, ppd, seed, self.site("dec.pe"))
+        # ---- decoder.  The memory K/V projections of layers 1.. only need `mem`: side stream, behind the prefix
+        ws["mem"] = mem
+        if cfg.dec_layers > 0:
+            kv_proj(0)
+            if cfg.dec_layers > 1:
+                self._fork(lambda: [kv_proj(l) for l in range(1, cfg.dec_layers)])
+        x = None
         for l in range(cfg.dec_layers):
             pre = f"decoder.layers.{l}"
-            ws[f"d{l}.in"] = x
-            qkv = buf(f"d{l}.qkv", (Md, 3 * d))
-            be.linear_fwd(x, W[pre + ".self_attn.in_proj_weight"], P[pre + ".self_attn.in_proj_bias"], qkv)
-            ctx1 = buf(f"d{l}.ctx1", (Md, d))
-            lse1 = buf(f"d{l}.lse1", (B * H * L1,), f32)
-            be.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx1, lse1, B, H, L1, L1, None, True,
-                        pd, seed, self.site(pre + ".sa"))
-            s1 = buf(f"d{l}.s1", (Md, d))
-            be.linear_fwd(ctx1, W[pre + ".self_attn.out_proj.weight"], P[pre + ".self_attn.out_proj.bias"], s1)
-            h1 = buf(f"d{l}.h1", (Md, d))
-            be.add_layernorm_fwd(s1, x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1,
-                                 buf(f"d{l}.m1", (Md,), f32), buf(f"d{l}.r1", (Md,), f32), pd, seed, self.site(pre + ".d1"))
-            Wc, bc = W[pre + ".multihead_attn.in_proj_weight"], P[pre + ".multihead_attn.in_proj_bias"]
-            q2 = buf(f"d{l}.q2", (Md, d))
-            be.linear_fwd(h1, Wc[:d], bc[:d], q2)
-            kv2 = buf(f"d{l}.kv2", (Me, 2 * d))
-            be.linear_fwd(mem, Wc[d:], bc[d:], kv2)
+            if l == 0:
+                if cfg.dec_layers == 1:
+                    self._join()
+                h1, q2 = prefix["h1"], prefix["q2"]       # computed on the side stream (joined below / above)
+            else:
+                h1, q2 = dec_self(l, x)
+            if l == 0 and cfg.dec_layers > 1:
+                self._join()                              # prefix + K/V projections done (they were queued long ago)
+            kv2 = ws[f"d{l}.kv2"]
             ctx2 = buf(f"d{l}.ctx2", (Md, d))
             lse2 = buf(f"d{l}.lse2", (B * H * L1,), f32)
             be.attn_fwd(q2, kv2[:, :d], kv2[:, d:], ctx2, lse2, B, H, L1, T4, db["enc_lens"], False,
@@ -437,6 +467,9 @@ class TransformerEngine:
             be.add_layernorm_fwd(s3, h2, P[pre + ".norm3.weight"], P[pre + ".norm3.bias"], h3,
                                  buf(f"d{l}.m3", (Md,), f32), buf(f"d{l}.r3", (Md,), f32), pd, seed, self.site(pre + ".d3"))
             x = h3
+        if cfg.dec_layers == 0:
+            x = buf("d.x0", (Md, d))
+            be.embed_pe_fwd(db["ys_in"].view(-1), P["pre_embed.weight"], self.pe2d, x, L1, ppd, seed, self.site("dec.pe"))
         ws["dec_last"] = x
         dout = buf("d.out", (Md, d))
         be.add_layernorm_fwd(x, None, P["decoder.norm.weight"], P["decoder.norm.bias"], dout,
