@@ -331,9 +331,10 @@ class TransformerEngine:
             self._side_busy = False
 
     # ------------------------------------------------------------------ forward
-    def forward(self, db, want_grad=True):
+    def forward(self, db, want_grad=True, mem=None):
         """Runs the network on a device batch; fills ws['logits'] [B*L1, C] fp32 and the loss
-        statistics; with want_grad also d(mean loss)/d logits."""
+        statistics; with want_grad also d(mean loss)/d logits.  `mem` (greedy decode): an encoder memory
+        [B*T', d] computed by an earlier call on the same x -- the conv front end and the encoder are skipped."""
         cfg, be = self.cfg, self.be
         self._bind_seed()
         self.prep_weights()
@@ -386,53 +387,56 @@ class TransformerEngine:
                 prefix["h1"], prefix["q2"] = dec_self(0, x0)
             self._fork(dec_prefix)
 
-        # ---- VGG front end (NHWC)
-        a1 = buf("a1", (B, T, F0, 64))
-        be.conv1_fwd(db["x"], P["feat_extractor.0.weight"], P["feat_extractor.0.bias"], a1)
-        a2 = buf("a2", (B, T, F0, 64))
-        be.conv3x3_fwd(a1, self.wp[2], P["feat_extractor.2.bias"], a2)
-        p1 = buf("p1", (B, T2, F2, 64))
-        be.maxpool_fwd(a2, p1)
-        a3 = buf("a3", (B, T2, F2, 128))
-        be.conv3x3_fwd(p1, self.wp[5], P["feat_extractor.5.bias"], a3)
-        a4 = buf("a4", (B, T2, F2, 128))
-        be.conv3x3_fwd(a3, self.wp[7], P["feat_extractor.7.bias"], a4)
-        p2 = buf("p2", (B, T4, F4, 128))
-        be.maxpool_fwd(a4, p2)
-        h = buf("h0", (Me, d))
-        be.linear_fwd(p2.view(Me, F4 * 128), self.vgg2enc_p, P["vgg2enc.bias"], h)
-        be.add_pe_dropout(h, self.pe2d, T4, ppd, seed, self.site("enc.pe"))
+        if mem is not None:
+            assert not want_grad, "a cached encoder memory is an inference-only shortcut"
+            buf("mem", (Me, d)).copy_(mem)
+        else:
+            # ---- VGG front end (NHWC)
+            a1 = buf("a1", (B, T, F0, 64))
+            be.conv1_fwd(db["x"], P["feat_extractor.0.weight"], P["feat_extractor.0.bias"], a1)
+            a2 = buf("a2", (B, T, F0, 64))
+            be.conv3x3_fwd(a1, self.wp[2], P["feat_extractor.2.bias"], a2)
+            p1 = buf("p1", (B, T2, F2, 64))
+            be.maxpool_fwd(a2, p1)
+            a3 = buf("a3", (B, T2, F2, 128))
+            be.conv3x3_fwd(p1, self.wp[5], P["feat_extractor.5.bias"], a3)
+            a4 = buf("a4", (B, T2, F2, 128))
+            be.conv3x3_fwd(a3, self.wp[7], P["feat_extractor.7.bias"], a4)
+            p2 = buf("p2", (B, T4, F4, 128))
+            be.maxpool_fwd(a4, p2)
+            h = buf("h0", (Me, d))
+            be.linear_fwd(p2.view(Me, F4 * 128), self.vgg2enc_p, P["vgg2enc.bias"], h)
+            be.add_pe_dropout(h, self.pe2d, T4, ppd, seed, self.site("enc.pe"))
 
-        # ---- encoder (post-norm)
-        for l in range(cfg.enc_layers):
-            pre = f"encoder.layers.{l}"
-            qkv = buf(f"e{l}.qkv", (Me, 3 * d))
-            be.linear_fwd(h, W[pre + ".self_attn.in_proj_weight"], P[pre + ".self_attn.in_proj_bias"], qkv)
-            ctx = buf(f"e{l}.ctx", (Me, d))
-            lse = buf(f"e{l}.lse", (B * H * T4,), f32)
-            be.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, lse, B, H, T4, T4, db["enc_lens"], False,
-                        pd, seed, self.site(pre + ".sa"))
-            s1 = buf(f"e{l}.s1", (Me, d))
-            be.linear_fwd(ctx, W[pre + ".self_attn.out_proj.weight"], P[pre + ".self_attn.out_proj.bias"], s1)
-            h1 = buf(f"e{l}.h1", (Me, d))
-            be.add_layernorm_fwd(s1, h, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1,
-                                 buf(f"e{l}.m1", (Me,), f32), buf(f"e{l}.r1", (Me,), f32), pd, seed, self.site(pre + ".d1"))
-            f1 = buf(f"e{l}.f1", (Me, ff))
-            be.linear_fwd(h1, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True,
-                          dropout=(pd, seed, self.site(pre + ".df")))
-            s2 = buf(f"e{l}.s2", (Me, d))
-            be.linear_fwd(f1, W[pre + ".linear2.weight"], P[pre + ".linear2.bias"], s2)
-            h2 = buf(f"e{l}.h2", (Me, d))
-            be.add_layernorm_fwd(s2, h1, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], h2,
-                                 buf(f"e{l}.m2", (Me,), f32), buf(f"e{l}.r2", (Me,), f32), pd, seed, self.site(pre + ".d2"))
-            h = h2
-        ws["enc_last"] = h
-        mem = buf("mem", (Me, d))
-        be.add_layernorm_fwd(h, None, P["encoder.norm.weight"], P["encoder.norm.bias"], mem,
-                             buf("enc.m", (Me,), f32), buf("enc.r", (Me,), f32), 0.0, seed, 0)
+            # ---- encoder (post-norm)
+            for l in range(cfg.enc_layers):
+                pre = f"encoder.layers.{l}"
+                qkv = buf(f"e{l}.qkv", (Me, 3 * d))
+                be.linear_fwd(h, W[pre + ".self_attn.in_proj_weight"], P[pre + ".self_attn.in_proj_bias"], qkv)
+                ctx = buf(f"e{l}.ctx", (Me, d))
+                lse = buf(f"e{l}.lse", (B * H * T4,), f32)
+                be.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, lse, B, H, T4, T4, db["enc_lens"], False,
+                            pd, seed, self.site(pre + ".sa"))
+                s1 = buf(f"e{l}.s1", (Me, d))
+                be.linear_fwd(ctx, W[pre + ".self_attn.out_proj.weight"], P[pre + ".self_attn.out_proj.bias"], s1)
+                h1 = buf(f"e{l}.h1", (Me, d))
+                be.add_layernorm_fwd(s1, h, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1,
+                                     buf(f"e{l}.m1", (Me,), f32), buf(f"e{l}.r1", (Me,), f32), pd, seed, self.site(pre + ".d1"))
+                f1 = buf(f"e{l}.f1", (Me, ff))
+                be.linear_fwd(h1, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True,
+                              dropout=(pd, seed, self.site(pre + ".df")))
+                s2 = buf(f"e{l}.s2", (Me, d))
+                be.linear_fwd(f1, W[pre + ".linear2.weight"], P[pre + ".linear2.bias"], s2)
+                h2 = buf(f"e{l}.h2", (Me, d))
+                be.add_layernorm_fwd(s2, h1, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], h2,
+                                     buf(f"e{l}.m2", (Me,), f32), buf(f"e{l}.r2", (Me,), f32), pd, seed, self.site(pre + ".d2"))
+                h = h2
+            ws["enc_last"] = h
+            mem = buf("mem", (Me, d))
+            be.add_layernorm_fwd(h, None, P["encoder.norm.weight"], P["encoder.norm.bias"], mem,
+                                 buf("enc.m", (Me,), f32), buf("enc.r", (Me,), f32), 0.0, seed, 0)
 
         # ---- decoder.  The memory K/V projections of layers 1.. only need `mem`: side stream, behind the prefix
-        ws["mem"] = mem
         if cfg.dec_layers > 0:
             kv_proj(0)
             if cfg.dec_layers > 1:

@@ -93,6 +93,27 @@ class B200Transformer(nn.Module):
         self.engine.training = bool(mode)
         return self
 
+    # -- MyTransformer.recog (:143-176): greedy decoding.  Like the reference, the decoder is re-run on the growing
+    # prefix for max(enc_lens) steps and EVERY position is re-decided each time; unlike the reference the conv
+    # front end and the encoder run once (their output is cached and handed to the later steps).
+    @torch.no_grad()
+    def recog(self, xs_pad, ilens):
+        eng = self.engine
+        eng.weights_dirty = True
+        was_training, eng.training = eng.training, False
+        B = xs_pad.shape[0]
+        out = torch.zeros((B, 0), dtype=torch.int64)
+        n_steps = int(torch.floor(ilens.to(dtype=torch.float32) / 4).max())
+        mem = None
+        for _ in range(n_steps):
+            hb = eng.prepare_batch(xs_pad, ilens, [out[b] for b in range(B)], None)
+            ws = eng.forward(eng.to_device(hb), want_grad=False, mem=mem)
+            if mem is None:
+                mem = ws["mem"].clone()
+            out = ws["argmax"].view(B, hb["L1"]).cpu()
+        eng.training = was_training
+        return out.t().contiguous()          # [L, B] like the reference
+
     # -- MyTransformer.forward (:178-208); inference-style (no autograd graph): logits on device
     @torch.no_grad()
     def forward(self, xs_pad, ilens, ys, olens):

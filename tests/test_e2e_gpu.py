@@ -155,6 +155,17 @@ def test_task_lanes_match_sequential_meta_step(dev, graphs):
     assert float((f1[:n] - f2[:n])[sig].abs().max()) <= 5e-3
 
 
+def test_greedy_decode_ids_vs_reference_golden(dev):
+    """MyTransformer.recog through the CUDA path (fp32 mode): token ids bit-exact against the live reference."""
+    z = np.load(GOLD / "run_batch_tiny.npz")
+    s = make_solver("fomaml")
+    load_tiny(s)
+    x, ilens, _, _ = load_batch(z, "in.")
+    ids = s.asr_model.recog(x, ilens)
+    assert ids.shape == z["greedy"].shape
+    assert np.array_equal(ids.numpy(), z["greedy"])
+
+
 def test_multi_step_vs_reference_golden(dev):
     z = np.load(GOLD / "multi_tiny.npz")
     s = make_solver("multi", meta=False)

@@ -211,3 +211,13 @@ def test_two_rank_meta_step_equals_sequential(tmp_path):
         ref = eng.layout.view(s._original_flat, n)
         mask = torch.from_numpy(np.abs(z[f"s0.mg.{n}#sample"]) > 1e-7)
     assert float((w0 - s._original_flat).abs().max()) <= 2.0 * lr + 1e-12
+
+
+def test_recog_greedy_ids_bit_exact_host_logic():
+    """MyTransformer.recog (greedy decode on the growing prefix, encoder memory computed once) through the engine's
+    schedule on the torch test double: token ids bit-exact against the live reference's golden."""
+    z = np.load(GOLD / "run_batch_tiny.npz")
+    s = make_solver("fomaml")
+    x, ilens, _, _ = load_batch(z, "in.")
+    ids = s.asr_model.recog(x, ilens)
+    assert np.array_equal(ids.numpy(), z["greedy"])
