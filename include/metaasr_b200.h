@@ -97,7 +97,11 @@ int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t 
  *                B tile, so no separate column-sum pass over dy is needed
  *   mask       : bf16 [M,N] (row stride ldmask): C = mask > 0 ? C * mask_scale : 0.  With mask = the stored
  *                output of ReLU(+dropout) and mask_scale = 1/(1-p): the backward of both, fused in a dgrad GEMM
- *   p_drop     : dropout on C after bias / ReLU with masr_dropout's element index m*N+n under (seed, site)  */
+ *   p_drop     : dropout on C after bias / ReLU with masr_dropout's element index m*N+n under (seed, site)
+ *   dot_src    : bf16 [M,N] (row stride lddot), N = dot_H * 64, M = batch * dot_L: dot_out[(b * dot_H + h) * dot_L + q]
+ *                = sum over the 64 columns of head h of C(m, .) * dot_src(m, .), m = b * dot_L + q.  With C = dO
+ *                (out-projection dgrad) and dot_src = O this is the D vector of the attention backward
+ *                (masr_umma_attn_bwd with dsum_ready = 1), fused into the GEMM epilogue  */
 typedef struct masr_gemm_epilogue {
   float* rowsum;
   const void* mask;
@@ -106,6 +110,11 @@ typedef struct masr_gemm_epilogue {
   float p_drop;
   uint64_t seed;
   uint32_t site;
+  const void* dot_src;
+  int64_t lddot;
+  float* dot_out;
+  int dot_L;
+  int dot_H;
 } masr_gemm_epilogue;
 int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
                       void* C, int c_dtype, int64_t ldc, const float* bias,
@@ -192,7 +201,8 @@ int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
                        float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                        int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
-                       float p_drop, uint64_t seed, uint32_t site, void* stream);
+                       float p_drop, uint64_t seed, uint32_t site, int dsum_ready, void* stream);
+/* dsum_ready != 0: dsum_ws already holds D[b,h,q] = dO . O (e.g. from masr_umma_gemm_ex's dot epilogue). */
 
 /* ------------------------------------------------------------------ kernel 3: fused elementwise
  * residual + dropout + LayerNorm (post-norm TransformerEncoder/DecoderLayer, eps 1e-5):

@@ -61,7 +61,7 @@ SIGNATURES = {
                            c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],
     "masr_umma_attn_bwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p,
                            c_p, c_i64, c_p, c_i64, c_p, c_i64,
-                           c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],
+                           c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_i, c_p],
     "masr_add_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_u64, c_u32, c_p],
     "masr_add_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_u64, c_u32, c_p],
     "masr_add_pe_dropout": [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_u64, c_u32, c_p],
@@ -89,7 +89,8 @@ EXTRA = {"masr_last_error": [], "masr_ctc_workspace_bytes": [c_i, c_i, c_i, c_i]
 class GemmEpilogue(C.Structure):
     """masr_gemm_epilogue of include/metaasr_b200.h."""
     _fields_ = [("rowsum", c_p), ("mask", c_p), ("ldmask", c_i64), ("mask_scale", c_f), ("p_drop", c_f),
-                ("seed", c_u64), ("site", c_u32)]
+                ("seed", c_u64), ("site", c_u32), ("dot_src", c_p), ("lddot", c_i64), ("dot_out", c_p),
+                ("dot_L", c_i), ("dot_H", c_i)]
 
 
 class MetaASRLibraryError(RuntimeError):

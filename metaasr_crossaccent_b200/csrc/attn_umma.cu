@@ -549,7 +549,7 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
                                   const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
                                   float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                                   int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
-                                  float p_drop, uint64_t seed, uint32_t site, void* stream) {
+                                  float p_drop, uint64_t seed, uint32_t site, int dsum_ready, void* stream) {
   if (B == 0 || H == 0) return MASR_OK;
   MASR_REQUIRE(Lk <= AU_TILE, "umma attention backward: Lk must be <= 128 (use masr_attn_bwd otherwise)");
   MASR_REQUIRE(dsum_ws != nullptr, "attention backward needs a [B*H*Lq] fp32 workspace");
@@ -562,7 +562,7 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
   rc = rows_map(&mk, k, ldk, int64_t(B) * Lk, H * 64); if (rc) return rc;
   rc = rows_map(&mv, v, ldv, int64_t(B) * Lk, H * 64); if (rc) return rc;
   rc = rows_map(&mdo, dout, lddo, int64_t(B) * Lq, H * 64); if (rc) return rc;
-  if (Lq > 0) {
+  if (Lq > 0 && !dsum_ready) {
     const int64_t rows = int64_t(B) * H * Lq;
     const int blocks = int(std::min<int64_t>(ceil_div64(rows, 8), int64_t(sm_count()) * 8));
     MASR_CHECK_CUDA(launch_pdl(attn_dsum_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(out), ldo,

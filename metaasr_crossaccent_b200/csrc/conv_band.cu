@@ -47,14 +47,11 @@ struct BandParams {
   const __nv_bfloat16* relu_src;   // dgrad: multiply by (relu_src > 0)
   const float* bias;               // fwd
   int relu;                        // fwd
-  int desc_mode;                   // 0: descriptor base offset 0; 1: base offset = (start address >> 7) & 7
 };
 
-__device__ __forceinline__ uint64_t band_a_desc(uint32_t addr, int mode) {
-  uint64_t d = umma::make_smem_desc(addr, 16, 1024);
-  if (mode == 1) d |= uint64_t((addr >> 7) & 7) << 49;
-  return d;
-}
+// Note on descriptors into the middle of a swizzled region: the matrix-descriptor "base offset" field stays 0.
+// Measured on B200: with base offset = (start address >> 7) & 7 every result is wrong, with 0 every start address
+// that is a multiple of 128 B works -- TMA and tcgen05.mma both apply the 128B swizzle to ABSOLUTE address bits.
 
 // CH = reduction channels / 64, BN = output channels, MODE 0 = forward, 1 = dgrad (weights read MN-major from the
 // forward layout), 2 = dgrad with the transposed weight layout wpt [Cin][tap][Cout] (K-major B like the forward:
@@ -374,11 +371,6 @@ static int band_rows_per_box(int nr) {
   while (nr % r != 0) --r;          // equal boxes
   return r;
 }
-static int band_desc_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MASR_CONV_BAND_DESC"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
-  return v;
-}
 
 template <int CH, int BN, int MODE, int NM, bool RES>
 static int launch_band2(const CUtensorMap& ma, const CUtensorMap& mw, const BandParams& p, const BandGeom& g, cudaStream_t st) {
@@ -425,9 +417,9 @@ int conv_band_try(int mode, const void* act, const void* wp, void* out, const vo
   if (rc != MASR_OK) return rc;
   const int kstride = mode == 2 ? Cout : Cin;              // columns per tap inside the weight rows
   static int pf = -1;
-  if (pf < 0) { const char* e = getenv("MASR_CONV_BAND_PF"); pf = e != nullptr ? atoi(e) : 2; }
+  if (pf < 0) { const char* e = getenv("MASR_CONV_BAND_PF"); pf = e != nullptr ? atoi(e) : 0; }   // measured: no effect
   BandParams p{B, H, W, g.W2, kstride, g.tiles_per_img, B * g.tiles_per_img, g.nr, g.slot_bytes, g.sb, rpb, pf,
-               static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(relu_src), bias, relu, band_desc_mode()};
+               static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(relu_src), bias, relu};
   const int key = (mode << 2) | ((Cred == 128 ? 1 : 0) << 1) | (Cn == 128 ? 1 : 0);
   switch (key) {
     case 0: return launch_band<1, 64, 0>(ma, mw, p, g, st);

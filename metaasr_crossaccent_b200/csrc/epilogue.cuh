@@ -46,6 +46,12 @@ struct EpiOpts {
   // second accumulator (TMEM column offset from the first, 0 = none) added in phase 1: two MMA-issuing warps each
   // own one accumulator and half of the k-blocks
   uint32_t acc2_offset = 0;
+  // per-64-column row dot products with a second bf16 matrix (same row, same columns): dot_out[j * dot_stride] =
+  // sum over columns [64 j, 64 j + 64) of acc * dot_row.  The attention backward needs D = rowsum(dO . O) per head;
+  // dO is the output of the out-projection dgrad GEMM, so its epilogue produces D for free (no extra kernel)
+  const __nv_bfloat16* dot_row = nullptr;
+  float* dot_out = nullptr;
+  int dot_stride = 0;
 };
 
 // packed variant for scale == 1: v * (mask > 0 ? 1 : 0) on bf16x2 words (no fp32 round trip)
@@ -110,6 +116,19 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
 #pragma unroll
       for (int j = 0; j < CB; ++j)
         v[j] *= drop_scale(o.p_drop, o.inv_keep, o.seed, o.site, uint64_t(o.drop_row_base + c0 + j));
+    }
+    if constexpr (CB == 64) {
+      if (o.dot_row != nullptr) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) {
+          float sv[8];
+          load8<__nv_bfloat16>(o.dot_row + c0 + j, sv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = fmaf(v[j + e], sv[e], acc);
+        }
+        o.dot_out[(c0 >> 6) * o.dot_stride] = acc;
+      }
     }
     if constexpr (sizeof(OutT) == 2) {
 #pragma unroll

@@ -71,6 +71,7 @@ struct UmmaGemmParams {
   float* rowsum;                   // rowsum[m] += sum_k A(m,k): a second, 16-column accumulator fed by an all-ones B tile
   const __nv_bfloat16* mask; int64_t ldmask; float mask_scale;
   float p_drop, inv_keep; uint64_t seed; const uint64_t* seed_ptr; uint32_t site;
+  const __nv_bfloat16* dot_src; int64_t lddot; float* dot_out; int dot_L, dot_H;   // per-head row dots (see EpiOpts)
 };
 
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
@@ -211,6 +212,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       o.seed = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
       o.drop_row_base = int64_t(m) * p.N + n0;
     }
+    if (p.dot_src != nullptr && m < p.M) {   // row m = b * L + q; columns n0.. = heads n0 / 64..
+      o.dot_row = p.dot_src + int64_t(m) * p.lddot + n0;
+      o.dot_out = p.dot_out + (int64_t(m / p.dot_L) * p.dot_H + (n0 >> 6)) * p.dot_L + (m % p.dot_L);
+      o.dot_stride = p.dot_L;
+    }
     o.mask_scale = p.mask_scale;      // warp-uniform: a lane drains OTHER rows' chunks in phase 2
     if (p.mask != nullptr && m < p.M) o.mask_row = p.mask + int64_t(m) * p.ldmask + n0;
     if (p.c_is_f32) {
@@ -299,7 +305,7 @@ extern "C" int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const voi
   rc = operand_map(&mb, B, ldb, N, K, b_mn != 0, BN);
   if (rc != MASR_OK) return rc;
   UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, kb_per_split, 0,
-                   nullptr, nullptr, 0, 1.f, 0.f, 1.f, 0, nullptr, 0};
+                   nullptr, nullptr, 0, 1.f, 0.f, 1.f, 0, nullptr, 0, nullptr, 0, nullptr, 1, 1};
   if (epi != nullptr) {
     MASR_REQUIRE(epi->mask == nullptr || c_dtype == MASR_BF16, "umma gemm: the output mask needs a bf16 C");
     MASR_REQUIRE(!(epi->p_drop > 0.f && (flags & MASR_GEMM_SPLITK)), "umma gemm: split-K cannot fuse dropout");
@@ -308,6 +314,13 @@ extern "C" int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const voi
     if (epi->p_drop > 0.f) {
       p.p_drop = epi->p_drop; p.inv_keep = 1.f / (1.f - epi->p_drop);
       p.seed = epi->seed; p.seed_ptr = g_seed_dev_ptr; p.site = epi->site;
+    }
+    if (epi->dot_src != nullptr) {
+      MASR_REQUIRE(epi->dot_out != nullptr && epi->dot_L > 0 && epi->dot_H > 0 && N == epi->dot_H * 64 && M % epi->dot_L == 0 &&
+                   epi->lddot % 8 == 0 && (reinterpret_cast<uintptr_t>(epi->dot_src) & 15) == 0 && !(flags & MASR_GEMM_SPLITK),
+                   "umma gemm: row-dot epilogue needs N = heads * 64, M = batch * L, 16 B aligned rows, no split-K");
+      p.dot_src = static_cast<const __nv_bfloat16*>(epi->dot_src); p.lddot = epi->lddot;
+      p.dot_out = epi->dot_out; p.dot_L = epi->dot_L; p.dot_H = epi->dot_H;
     }
   }
   cudaStream_t st = as_stream(stream);

@@ -527,11 +527,13 @@ class TransformerEngine:
         def self_attn_bwd(pre, g_o, qkv, ctx, lse, x_in, g_res, Mrows, L, klens, causal, tag, site):
             wgrad(ctx, g_o, G[pre + ".self_attn.out_proj.weight"], G[pre + ".self_attn.out_proj.bias"])
             g_ctx = buf(tag[:2] + ".g_ctx", (Mrows, d))
-            be.linear_dgrad(g_o, W[pre + ".self_attn.out_proj.weight"], g_ctx)
-            g_qkv = buf(tag + ".g_qkv", (Mrows, 3 * d))
             dsum = buf(tag[:2] + ".dsum", (B * H * L,), f32)
+            # D = rowsum(dO . O) per head comes out of the out-projection dgrad's epilogue (no separate kernel)
+            ready = be.linear_dgrad(g_o, W[pre + ".self_attn.out_proj.weight"], g_ctx, rowdot=(ctx, dsum, L, H))
+            g_qkv = buf(tag + ".g_qkv", (Mrows, 3 * d))
             be.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, g_ctx, lse, dsum,
-                        g_qkv[:, :d], g_qkv[:, d:2 * d], g_qkv[:, 2 * d:], B, H, L, L, klens, causal, pd, seed, site)
+                        g_qkv[:, :d], g_qkv[:, d:2 * d], g_qkv[:, 2 * d:], B, H, L, L, klens, causal, pd, seed, site,
+                        dsum_ready=bool(ready))
             wgrad(x_in, g_qkv, G[pre + ".self_attn.in_proj_weight"], G[pre + ".self_attn.in_proj_bias"])
             be.linear_dgrad(g_qkv, W[pre + ".self_attn.in_proj_weight"], g_res, accumulate=True)
 
@@ -568,14 +570,15 @@ class TransformerEngine:
             wgrad(ws[f"d{l}.ctx2"], g_br, G[pre + ".multihead_attn.out_proj.weight"],
                   G[pre + ".multihead_attn.out_proj.bias"])
             g_ctx = buf("gd.g_ctx", (Md, d))
-            be.linear_dgrad(g_br, W[pre + ".multihead_attn.out_proj.weight"], g_ctx)
+            dsum = buf("gd.dsum", (B * H * L1,), f32)
+            ready = be.linear_dgrad(g_br, W[pre + ".multihead_attn.out_proj.weight"], g_ctx,
+                                    rowdot=(ws[f"d{l}.ctx2"], dsum, L1, H))
             g_q2 = buf(tag + ".g_q2", (Md, d))
             g_kv2 = buf(tag + ".g_kv2", (Me, 2 * d))
-            dsum = buf("gd.dsum", (B * H * L1,), f32)
             kv2 = ws[f"d{l}.kv2"]
             be.attn_bwd(ws[f"d{l}.q2"], kv2[:, :d], kv2[:, d:], ws[f"d{l}.ctx2"], g_ctx, ws[f"d{l}.lse2"], dsum,
                         g_q2, g_kv2[:, :d], g_kv2[:, d:], B, H, L1, T4, db["enc_lens"], False,
-                        pd, seed, self.site(pre + ".ca"))
+                        pd, seed, self.site(pre + ".ca"), dsum_ready=bool(ready))
             Wc = W[pre + ".multihead_attn.in_proj_weight"]
             Gw, Gb = G[pre + ".multihead_attn.in_proj_weight"], G[pre + ".multihead_attn.in_proj_bias"]
             wgrad(ws[f"d{l}.h1"], g_q2, Gw[:d], Gb[:d])

@@ -96,15 +96,17 @@ class CudaBackend:
         return True
 
     def umma_gemm(self, A, a_mn, B, b_mn, C, bias, M, N, K, flags=0, splitk=1, rowsum=None, mask=None, mask_scale=1.0,
-                  p_drop=0.0, seed=0, site=0):
+                  p_drop=0.0, seed=0, site=0, rowdot=None):
         prof = self.prof
         if prof is not None:        # bench.py: CUDA events around every launch, on the launching stream
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         epi = None
-        if rowsum is not None or mask is not None or p_drop > 0.0:
+        if rowsum is not None or mask is not None or p_drop > 0.0 or rowdot is not None:
+            dsrc, dout, dL, dH = rowdot if rowdot is not None else (None, None, 0, 0)
             epi = _lib.GemmEpilogue(_p(rowsum), _p(mask), mask.stride(0) if mask is not None else 0, float(mask_scale),
-                                    float(p_drop), int(seed), int(site))
+                                    float(p_drop), int(seed), int(site), _p(dsrc), dsrc.stride(0) if dsrc is not None else 0,
+                                    _p(dout), int(dL), int(dH))
             epi = _lib.C.byref(epi)
         self._call("masr_umma_gemm_ex", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), _dt(C),
                    C.stride(0), _p(bias), M, N, K, flags, int(splitk), epi, self.stream)
@@ -160,7 +162,7 @@ class CudaBackend:
         if p > 0.0:
             self.dropout(y, p, seed, site)
 
-    def linear_dgrad(self, dy, w, dx, accumulate=False, relu_drop_mask=None, p=0.0):
+    def linear_dgrad(self, dy, w, dx, accumulate=False, relu_drop_mask=None, p=0.0, rowdot=None):
         """dx[M,K] (+)= dy[M,N] @ w[N,K].  relu_drop_mask = the stored forward output f of ReLU followed by
         dropout(p) whose gradient dx is: the backward of both is fused as dx = f > 0 ? dx / (1-p) : 0
         (an element of f is positive iff it passed the ReLU and was kept)."""
@@ -169,6 +171,17 @@ class CudaBackend:
         assert dx.shape == (M, K) and dy.stride(1) == 1 and w.stride(1) == 1 and dx.stride(1) == 1
         assert relu_drop_mask is None or not accumulate
         scale = 1.0 / (1.0 - p) if p > 0.0 else 1.0
+        if rowdot is not None:
+            # rowdot = (o [M, H*64] bf16, dsum [B*H*L] fp32, L, H): D = rowsum(dx . o) per head, written by the GEMM
+            # epilogue (attention backward); returns True when it was produced, False when the caller must compute it
+            o_, ds_, L_, H_ = rowdot
+            if (self._umma_ok(dy, w) and dx.dtype == torch.bfloat16 and not accumulate and relu_drop_mask is None
+                    and o_.dtype == torch.bfloat16 and o_.stride(1) == 1 and o_.stride(0) % 8 == 0 and o_.data_ptr() % 16 == 0
+                    and K == H_ * 64 and M % L_ == 0):
+                self.umma_gemm(dy, 0, w, 1, dx, None, M, K, N, 0, rowdot=rowdot)
+                return True
+            self.linear_dgrad(dy, w, dx)
+            return False
         if self._umma_ok(dy, w):
             if relu_drop_mask is not None and dx.dtype == torch.bfloat16 and relu_drop_mask.dtype == torch.bfloat16:
                 return self.umma_gemm(dy, 0, w, 1, dx, None, M, K, N, 0, mask=relu_drop_mask, mask_scale=scale)
@@ -311,13 +324,14 @@ class CudaBackend:
         self._call("masr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
                    _p(lse), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site, self.stream)
 
-    def attn_bwd(self, q, k, v, out, dout, lse, dsum, dq, dk, dv, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
+    def attn_bwd(self, q, k, v, out, dout, lse, dsum, dq, dk, dv, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0,
+                 dsum_ready=False):
         hd = out.shape[1] // H
         if Lk <= 128 and self._attn_umma_ok(hd, q, k, v, out, dout, dq, dk, dv):
             return self._call("masr_umma_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                               out.stride(0), _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0),
                               _p(dk), dk.stride(0), _p(dv), dv.stride(0), B, H, Lq, Lk, _p(klens), int(causal),
-                              float(p), seed, site, self.stream, n_kernels=2)
+                              float(p), seed, site, int(dsum_ready), self.stream, n_kernels=1 if dsum_ready else 2)
         self._call("masr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
                    _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                    _p(dv), dv.stride(0), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site,

@@ -413,3 +413,24 @@ def test_umma_gemm_fused_epilogues(dev, M, N, K):
         cb.umma_gemm(dyo, 1, x, 1, dw, None, N, K, M, GEMM_SPLITK if sk > 1 else GEMM_ACCUM, sk, rowsum=db)
         close(dw, dyo.float().t() @ x.float(), torch.float32, 2e-3, "wgrad")
         close(db - db0, dyo.float().sum(0), torch.float32, 2e-3, "fused bias gradient")
+
+
+@pytest.mark.parametrize("Bsz,L,H,N", [(32, 33, 8, 512), (4, 128, 8, 512), (3, 17, 2, 72)])
+def test_umma_gemm_rowdot_epilogue(dev, Bsz, L, H, N):
+    """Out-projection dgrad with the attention backward's D = rowsum(dO . O) per head produced by the GEMM epilogue
+    (masr_gemm_epilogue.dot_*): dx unchanged, D[b,h,q] equals the separate reduction over the head's 64 columns."""
+    from metaasr_crossaccent_b200.ops import CudaBackend
+    cb = CudaBackend(dev, torch.bfloat16, gemm="umma")
+    bf = torch.bfloat16
+    M, K = Bsz * L, H * 64
+    dy, w, o = rnd((M, N), dev, bf, 1), rnd((N, K), dev, bf, 2, 0.1), rnd((M, K), dev, bf, 3)
+    dx, dx0 = torch.empty(M, K, device=dev, dtype=bf), torch.empty(M, K, device=dev, dtype=bf)
+    dsum = torch.full((Bsz * H * L,), 9.0, device=dev)
+    ready = cb.linear_dgrad(dy, w, dx, rowdot=(o, dsum, L, H))
+    assert ready or N % 64 != 0        # the model's shapes must take the fused path
+    cb.linear_dgrad(dy, w, dx0)
+    assert torch.equal(dx, dx0)
+    if not ready:
+        return
+    ref = ((dy.float() @ w.float()) * o.float()).view(Bsz, L, H, 64).sum(-1).permute(0, 2, 1).reshape(-1)
+    close(dsum, ref, torch.float32, 5e-3, "row-dot epilogue")
