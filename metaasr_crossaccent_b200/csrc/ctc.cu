@@ -254,7 +254,6 @@ __device__ __forceinline__ float lse3_2(float a, float b, float c) {      // log
 }
 constexpr float CTC_LOG2E = 1.4426950408889634f, CTC_LN2 = 0.6931471805599453f;
 constexpr int CTC_F = 4;        // frames per warp iteration in the streaming phases
-constexpr int CTC_F3 = 2;       // frames per warp iteration in the v3 gradient phase (64 registers: 4 CTAs / SM)
 constexpr int CTC_CPL = 12;     // classes per lane held in registers (fast path: C <= 384)
 
 
@@ -583,365 +582,13 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
 #undef CTC_STAMP
 }
 
-// ====================================================================== v3: one posterior table, four CTAs per SM
-// v2 keeps alpha [T][S], beta [T][S] and the emissions [T][L+1] in shared memory (92 KB at T'=128, L=34: two CTAs
-// per SM, and for most of a CTA's life only its two recursion warps are busy).  v3 stores ONE table:
-//   * the alpha warp walks t = 0 .. Tb-1, the beta warp t = Tb-1 .. 0, concurrently as before.  Until they meet in
-//     the middle each stores its own values; after ONE 64-thread named barrier at the meeting point every frame
-//     they reach already holds the other recursion's values, so they store the combined log2 posterior
-//         P[t][s] = alpha_t(s) + beta_t(s) - E_t(s)
-//     in place (one extra shared-memory load per state, off the dependent chain);
-//   * the gradient phase reads ONE value per state (v2: three), sums the blank states by warp shuffle and finds
-//     the (few) states of each label class through a per-class linked list -- no shared-memory atomics, no
-//     per-warp scratch;
-//   * 55 KB per CTA at the BASELINE shape -> four CTAs per SM, i.e. eight recursion warps per SM hide each
-//     other's latency and the streaming phases of one CTA overlap the recursions of the others.
-template <int SPL, bool FWD>
-__device__ __forceinline__ void ctc_recur(float (&a)[SPL], const float (&e)[SPL], const bool (&skip)[SPL],
-                                          const bool (&valid)[SPL], int lane) {
-  float n1, n2;                                                            // neighbours across the lane boundary
-  if (FWD) {
-    if (SPL >= 2) { n1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1); n2 = __shfl_up_sync(0xffffffffu, a[SPL >= 2 ? SPL - 2 : 0], 1); }
-    else          { n1 = __shfl_up_sync(0xffffffffu, a[0], 1); n2 = __shfl_up_sync(0xffffffffu, a[0], 2); if (lane < 2) n2 = CTC_NEG; }
-    if (lane == 0) { n1 = CTC_NEG; n2 = CTC_NEG; }
-  } else {
-    if (SPL >= 2) { n1 = __shfl_down_sync(0xffffffffu, a[0], 1); n2 = __shfl_down_sync(0xffffffffu, a[SPL >= 2 ? 1 : 0], 1); }
-    else          { n1 = __shfl_down_sync(0xffffffffu, a[0], 1); n2 = __shfl_down_sync(0xffffffffu, a[0], 2); if (lane > 29) n2 = CTC_NEG; }
-    if (lane == 31) { n1 = CTC_NEG; n2 = CTC_NEG; }
-  }
-  float nw[SPL];
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) {
-    float x1, x2;
-    if (FWD) {
-      x1 = (i >= 1) ? a[i >= 1 ? i - 1 : 0] : n1;
-      x2 = (i >= 2) ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? n1 : n2);
-    } else {
-      x1 = (i + 1 < SPL) ? a[i + 1 < SPL ? i + 1 : 0] : n1;
-      x2 = (i + 2 < SPL) ? a[i + 2 < SPL ? i + 2 : 0] : (i + 1 < SPL ? n1 : n2);
-    }
-    x2 = skip[i] ? x2 : CTC_NEG;
-    const float m = fmaxf(a[i], fmaxf(x1, x2));
-    const float v = m + lg2f(ex2f(a[i] - m) + ex2f(x1 - m) + ex2f(x2 - m)) + e[i];
-    nw[i] = valid[i] ? fmaxf(v, CTC_NEG) : CTC_NEG;
-  }
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) a[i] = nw[i];
-}
-
-// Returns (FWD only) log2 P(labels | x) from the final alpha row held in registers.
-template <int SPL, bool FWD>
-__device__ __forceinline__ float ctc_chain3(float* __restrict__ P, const float* __restrict__ E2, const int* __restrict__ tg,
-                                            int lane, int L, int S, int Tb, int Sstride, int L1stride, int blank) {
-  float a[SPL], e[SPL];
-  bool skip[SPL], valid[SPL];
-  int ecol[SPL];
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) {
-    const int s = lane * SPL + i;
-    const int j = s >> 1;
-    const bool odd = s & 1;
-    valid[i] = s < S;
-    ecol[i] = (odd && j < L) ? j : L;
-    if (FWD) skip[i] = odd && s > 1 && s < S && tg[j] != blank && tg[j] != tg[j - 1];
-    else     skip[i] = odd && s + 2 < S && tg[j] != blank && tg[j] != tg[j + 1];
-  }
-  const int mid = Tb >> 1;
-  const int npre = FWD ? mid : Tb - mid;           // frames this warp reaches first
-  const int tstep = FWD ? 1 : -1;
-  const int t0 = FWD ? 0 : Tb - 1;
-  const float* Et = E2 + t0 * L1stride;
-  float* dst = P + t0 * Sstride + lane * SPL;
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) {
-    const int s = lane * SPL + i;
-    e[i] = Et[ecol[i]];
-    const bool start = FWD ? (s <= 1) : (s >= S - 2);
-    a[i] = (start && valid[i]) ? e[i] : CTC_NEG;
-  }
-  for (int k = 0; k < Tb; ++k) {
-    // a[], e[] belong to frame t0 + k * tstep; fetch the next frame's emissions first
-    float en[SPL];
-    const bool more = k + 1 < Tb;
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) en[i] = more ? Et[tstep * L1stride + ecol[i]] : 0.f;
-    if (k == npre) bar_sync_named(1, 64);          // everything the other warp stored so far is visible from here on
-    if (k < npre) {
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) if (valid[i]) dst[i] = a[i];
-    } else {
-      float o[SPL];
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) o[i] = valid[i] ? dst[i] : 0.f;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) if (valid[i]) dst[i] = a[i] + o[i] - e[i];
-    }
-    if (more) {
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) e[i] = en[i];
-      ctc_recur<SPL, FWD>(a, e, skip, valid, lane);
-      Et += tstep * L1stride;
-      dst += tstep * Sstride;
-    }
-  }
-  if (npre >= Tb) bar_sync_named(1, 64);           // Tb == 1: the beta warp owns the only frame
-  float ll2 = 0.f;
-  if (FWD) {
-    float m = CTC_NEG;
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) { const int s = lane * SPL + i; if (valid[i] && s >= S - 2) m = fmaxf(m, a[i]); }
-    m = warp_max(m);
-    float se = 0.f;
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) { const int s = lane * SPL + i; if (valid[i] && s >= S - 2) se += ex2f(a[i] - m); }
-    se = warp_sum(se);
-    ll2 = se > 0.f ? m + lg2f(se) : CTC_NEG;
-  }
-  return ll2;
-}
-
-template <int SPL>
-__global__ void __launch_bounds__(CTC_THREADS, 4)
-ctc_fwd_bwd_v3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
-                      const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
-                      const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-                      int Lmax, int blank, int zero_infinity, float grad_scale,
-                      float* __restrict__ nll_out, float* __restrict__ loss_out, float* __restrict__ grad,
-                      long long* __restrict__ dbg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = CTC_THREADS / 32;
-#define CTC_STAMP(i) do { if (dbg != nullptr && b == 0 && tid == 0) dbg[i] = clock64(); } while (0)
-  CTC_STAMP(0);
-  const int Sstride = 2 * Lmax + 1, L1stride = Lmax + 1;
-
-  float* logZ2 = reinterpret_cast<float*>(smem_raw);                 // [T]
-  float* red = logZ2 + T;                                            // [4]
-  float* E2 = red + 4;                                               // [T][L1stride]  emissions, log2 domain
-  float* P = E2 + size_t(T) * L1stride;                              // [T][Sstride]   alpha / beta, then log2 posteriors
-  int* tg = reinterpret_cast<int*>(P + size_t(T) * Sstride);         // [Lmax]
-  short* nxt = reinterpret_cast<short*>(tg + Lmax);                  // [Lmax]  next position with the same class, -1 = none
-  short* cmap = nxt + Lmax;                                          // [C]     class -> first position, -1 none, -2 blank
-
-  const int L = int(tgt_lens[b]);
-  const int Tb = min(T, int(in_lens[b]));
-  const int S = 2 * L + 1;
-  const int64_t toff = tgt_offsets[b];
-
-  for (int j = tid; j < L; j += CTC_THREADS) tg[j] = int(targets[toff + j]);
-  for (int c = tid; c < C; c += CTC_THREADS) cmap[c] = (c == blank) ? short(-2) : short(-1);
-  __syncthreads();
-  bool mine_blank = false;
-  for (int j = tid; j < L; j += CTC_THREADS) {
-    const int cls = tg[j];
-    int nx = -1;
-    if (cls == blank) {
-      mine_blank = true;            // a label equal to the blank class (legal for ATen) joins the blank sum
-    } else {
-      bool first = true;
-      for (int i = 0; i < j; ++i) if (tg[i] == cls) { first = false; break; }
-      for (int i = j + 1; i < L; ++i) if (tg[i] == cls) { nx = i; break; }
-      if (first) cmap[cls] = short(j);
-    }
-    nxt[j] = short(nx);
-  }
-  const bool blank_labels = __syncthreads_or(mine_blank ? 1 : 0) != 0;
-
-  CTC_STAMP(1);
-  // ---- phase 0: log2-domain normaliser and emission table (as v2)
-  const bool fast_c = C <= 32 * CTC_CPL;
-  if (fast_c) {
-    for (int t0 = warp * CTC_F; t0 < Tb; t0 += NW * CTC_F) {
-      float x[CTC_F][CTC_CPL];
-#pragma unroll
-      for (int f = 0; f < CTC_F; ++f) {
-        const float* row = acts + (int64_t(min(t0 + f, Tb - 1)) * B + b) * C;
-#pragma unroll
-        for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; x[f][k] = c < C ? __ldg(row + c) : CTC_NEG; }
-      }
-      float z2[CTC_F];
-#pragma unroll
-      for (int f = 0; f < CTC_F; ++f) {
-        z2[f] = 0.f;
-        if (!is_logprob) {
-          float mx = CTC_NEG;
-#pragma unroll
-          for (int k = 0; k < CTC_CPL; ++k) mx = fmaxf(mx, x[f][k]);
-          mx = warp_max(mx);
-          float se = 0.f;
-#pragma unroll
-          for (int k = 0; k < CTC_CPL; ++k) se += ex2f((x[f][k] - mx) * CTC_LOG2E);
-          se = warp_sum(se);
-          z2[f] = mx * CTC_LOG2E + lg2f(se);
-        }
-      }
-      // emission gather: the rows were just read, these hit L1; all CTC_F frames' loads are issued together
-      for (int j = lane; j <= L; j += 32) {
-        const int cls = j < L ? tg[j] : blank;
-        float ev[CTC_F];
-#pragma unroll
-        for (int f = 0; f < CTC_F; ++f) ev[f] = __ldg(acts + (int64_t(min(t0 + f, Tb - 1)) * B + b) * C + cls);
-#pragma unroll
-        for (int f = 0; f < CTC_F; ++f) if (t0 + f < Tb) E2[size_t(t0 + f) * L1stride + j] = ev[f] * CTC_LOG2E - z2[f];
-      }
-      if (lane < CTC_F && t0 + lane < Tb) {
-        float z = z2[0];
-#pragma unroll
-        for (int f = 1; f < CTC_F; ++f) if (lane == f) z = z2[f];
-        logZ2[t0 + lane] = z;
-      }
-    }
-  } else {
-    for (int t = warp; t < Tb; t += NW) {
-      const float* row = acts + (int64_t(t) * B + b) * C;
-      float z2 = 0.f;
-      if (!is_logprob) {
-        float mx = CTC_NEG_INF;
-        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int c = lane; c < C; c += 32) se += ex2f((row[c] - mx) * CTC_LOG2E);
-        se = warp_sum(se);
-        z2 = mx * CTC_LOG2E + lg2f(se);
-      }
-      if (lane == 0) logZ2[t] = z2;
-      float* Et = E2 + size_t(t) * L1stride;
-      for (int j = lane; j <= L; j += 32) Et[j] = row[j < L ? tg[j] : blank] * CTC_LOG2E - z2;
-    }
-  }
-  __syncthreads();
-
-  CTC_STAMP(2);
-  // ---- phase 1: alpha in warp 0, beta in warp 1, meeting in the middle
-  if (Tb > 0 && warp < 2) {
-    if (warp == 0) {
-      const float v = ctc_chain3<SPL, true>(P, E2, tg, lane, L, S, Tb, Sstride, L1stride, blank);
-      if (lane == 0) red[0] = v;
-    } else {
-      ctc_chain3<SPL, false>(P, E2, tg, lane, L, S, Tb, Sstride, L1stride, blank);
-    }
-  } else if (Tb == 0 && tid == 0) {
-    red[0] = (S == 1) ? 0.f : CTC_NEG;
-  }
-  __syncthreads();
-  CTC_STAMP(3);
-
-  const float ll2 = red[0];
-  const bool feasible = (ll2 > 0.5f * CTC_NEG);
-  if (tid == 0) {
-    float nll = feasible ? -ll2 * CTC_LN2 : INFINITY;
-    if (!feasible && zero_infinity) nll = 0.f;
-    nll_out[b] = nll;
-    if (loss_out != nullptr) atomicAdd(loss_out, nll / float(max(L, 1)) / float(B));
-  }
-  if (grad == nullptr) return;
-  const float scale = grad_scale / (float(B) * float(max(L, 1)));
-
-  // ---- phase 3: gradient rows, CTC_F3 frames per warp iteration.  grad[t][c] = (softmax_t(c) - Gamma_t(c)) * scale with
-  // Gamma_t(c) = sum over the states of class c of 2^(P[t][s] - ll2): blank = all even states (shuffle sum), a label
-  // class = its positions' odd states (linked list from cmap / nxt).
-  constexpr int NEV = SPL / 2 + 1;             // even states per lane: L + 1 <= 16 SPL + 1
-  int ucls[CTC_CPL];
-#pragma unroll
-  for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; ucls[k] = (fast_c && c < C) ? int(cmap[c]) : -1; }
-  for (int t0 = warp * CTC_F3; t0 < T; t0 += NW * CTC_F3) {
-    bool live[CTC_F3];
-    const float* Pt[CTC_F3];
-#pragma unroll
-    for (int f = 0; f < CTC_F3; ++f) {
-      live[f] = feasible && t0 + f < Tb;
-      Pt[f] = P + size_t(live[f] ? t0 + f : 0) * Sstride;
-    }
-    float x[CTC_F3][CTC_CPL];
-    if (fast_c) {
-#pragma unroll
-      for (int f = 0; f < CTC_F3; ++f) {
-        const float* row = acts + (int64_t(live[f] ? t0 + f : 0) * B + b) * C;
-#pragma unroll
-        for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; x[f][k] = (live[f] && c < C) ? __ldg(row + c) : 0.f; }
-      }
-    }
-    float bs[CTC_F3];
-#pragma unroll
-    for (int f = 0; f < CTC_F3; ++f) bs[f] = 0.f;
-    if (live[0]) {
-#pragma unroll
-      for (int i = 0; i < NEV; ++i) {
-        const int m = lane + 32 * i;
-        if (m <= L) {
-#pragma unroll
-          for (int f = 0; f < CTC_F3; ++f) bs[f] += ex2f(Pt[f][2 * m] - ll2);
-        }
-      }
-      if (blank_labels) {
-        for (int j = lane; j < L; j += 32) {
-          if (tg[j] == blank) {
-#pragma unroll
-            for (int f = 0; f < CTC_F3; ++f) bs[f] += ex2f(Pt[f][2 * j + 1] - ll2);
-          }
-        }
-      }
-#pragma unroll
-      for (int f = 0; f < CTC_F3; ++f) bs[f] = warp_sum(bs[f]);
-    }
-    float z2[CTC_F3], fill[CTC_F3];
-#pragma unroll
-    for (int f = 0; f < CTC_F3; ++f) {
-      z2[f] = live[f] ? logZ2[t0 + f] : 0.f;
-      // beyond the input length ATen writes zeros; an infeasible utterance under zero_infinity too (without
-      // zero_infinity the loss is inf and the gradient NaN, as in ATen)
-      fill[f] = (!feasible && !zero_infinity && t0 + f < Tb) ? NAN : 0.f;
-    }
-    if (fast_c) {
-#pragma unroll
-      for (int k = 0; k < CTC_CPL; ++k) {
-        const int c = lane + 32 * k;
-        if (c >= C) continue;
-        float occ[CTC_F3];
-        const int u = ucls[k];
-#pragma unroll
-        for (int f = 0; f < CTC_F3; ++f) occ[f] = (u == -2) ? bs[f] : 0.f;
-        if (u >= 0 && live[0]) {
-          int j = u;
-          do {
-#pragma unroll
-            for (int f = 0; f < CTC_F3; ++f) occ[f] += ex2f(Pt[f][2 * j + 1] - ll2);
-            j = nxt[j];
-          } while (j >= 0);
-        }
-#pragma unroll
-        for (int f = 0; f < CTC_F3; ++f) {
-          const int t = t0 + f;
-          if (t < T) {
-            const float pr = ex2f(x[f][k] * CTC_LOG2E - z2[f]);
-            grad[(int64_t(t) * B + b) * C + c] = live[f] ? (pr - occ[f]) * scale : fill[f];
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int f = 0; f < CTC_F3; ++f) {
-        const int t = t0 + f;
-        if (t >= T) continue;
-        float* grow = grad + (int64_t(t) * B + b) * C;
-        if (!live[f]) { for (int c = lane; c < C; c += 32) grow[c] = fill[f]; continue; }
-        const float* row = acts + (int64_t(t) * B + b) * C;
-        for (int c = lane; c < C; c += 32) {
-          const float pr = ex2f(row[c] * CTC_LOG2E - z2[f]);
-          const int u = cmap[c];
-          float occ = (u == -2) ? bs[f] : 0.f;
-          for (int j = u; j >= 0; j = nxt[j]) occ += ex2f(Pt[f][2 * j + 1] - ll2);
-          grow[c] = (pr - occ) * scale;
-        }
-      }
-    }
-  }
-  CTC_STAMP(5);
-#undef CTC_STAMP
-}
-
 static long long* g_ctc_dbg = nullptr;
+
+// ctc3.cu: v3 kernel (single posterior table); returns CTC3_NOT_APPLICABLE when the shape does not fit shared memory
+constexpr int CTC3_NOT_APPLICABLE = 12345;
+int ctc3_try(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+             const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
+             float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st);
 
 static size_t ctc2_small_bytes(int T, int Lmax, int C) {
   return sizeof(float) * size_t(T) + sizeof(int) * (size_t(Lmax) + (Lmax + 1) + C) +
@@ -960,24 +607,6 @@ static int launch_ctc2(const float* acts, int T, int B, int C, int is_logprob, c
   ctc_fwd_bwd_v2_kernel<SPL><<<B, CTC_THREADS, smem, st>>>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens,
                                                            Lmax, blank, zero_infinity, grad_scale, nll, loss, grad, ws,
                                                            in_smem ? 1 : 0, g_ctc_dbg);
-  MASR_LAUNCH_CHECK();
-  return MASR_OK;
-}
-
-static size_t ctc3_bytes(int T, int Lmax, int C) {
-  const size_t b = sizeof(float) * (size_t(T) + 4 + size_t(T) * (Lmax + 1) + size_t(T) * (2 * size_t(Lmax) + 1)) +
-                   sizeof(int) * size_t(Lmax) + sizeof(short) * (size_t(Lmax) + C);
-  return (b + 15) / 16 * 16;
-}
-
-template <int SPL>
-static int launch_ctc3(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets,
-                       const int64_t* tgt_offsets, const int64_t* in_lens, const int64_t* tgt_lens, int Lmax,
-                       int blank, int zero_infinity, float grad_scale, float* nll, float* loss, float* grad,
-                       size_t smem, cudaStream_t st) {
-  MASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_fwd_bwd_v3_kernel<SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  ctc_fwd_bwd_v3_kernel<SPL><<<B, CTC_THREADS, smem, st>>>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens,
-                                                           Lmax, blank, zero_infinity, grad_scale, nll, loss, grad, g_ctc_dbg);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
@@ -1018,20 +647,12 @@ extern "C" int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_
     // tables in the workspace) whenever the extended label sequence fits 32 lanes x 12 states
     const int S = 2 * max_tgt_len + 1;
     const int spl = (S + 31) / 32;
-    const size_t smem3 = ctc3_bytes(T, max_tgt_len, C);
     static int ctc_ver = -1;
-    if (ctc_ver < 0) { const char* e = getenv("MASR_CTC_VERSION"); ctc_ver = e != nullptr ? atoi(e) : 2; }
-    if (spl <= 12 && smem3 <= 227 * 1024 && max_tgt_len < 32000 && ctc_ver >= 3) {
-#define CTC3_CASE(N) return launch_ctc3<N>(acts, T, B, C, act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens, max_tgt_len, \
-                                           blank, zero_infinity, grad_scale, nll, loss, grad, smem3, st)
-      if (spl <= 1) CTC3_CASE(1);
-      if (spl <= 2) CTC3_CASE(2);
-      if (spl <= 3) CTC3_CASE(3);
-      if (spl <= 4) CTC3_CASE(4);
-      if (spl <= 6) CTC3_CASE(6);
-      if (spl <= 8) CTC3_CASE(8);
-      CTC3_CASE(12);
-#undef CTC3_CASE
+    if (ctc_ver < 0) { const char* e = getenv("MASR_CTC_VERSION"); ctc_ver = e != nullptr ? atoi(e) : 3; }
+    if (ctc_ver >= 3) {
+      const int rc3 = ctc3_try(acts, T, B, C, act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens, max_tgt_len, blank,
+                               zero_infinity, grad_scale, nll, loss, grad, g_ctc_dbg, st);
+      if (rc3 != CTC3_NOT_APPLICABLE) return rc3;
     }
     const size_t small2 = ctc2_small_bytes(T, max_tgt_len, C), tables2 = ctc2_table_bytes(T, max_tgt_len);
     const bool fits = small2 + tables2 <= CTC_SMEM_LIMIT;
