@@ -285,11 +285,11 @@ def run_ours(args):
 def ctc_bandwidth(be, peaks):
     """Kernel 1 (CTC alpha-beta forward-backward, src/blstm_trainer.py:22,55-70): achieved HBM GB/s on the
     algorithmic bytes B*T'*C*(4+4) at the BASELINE shape (latency regime, 32 utterances on 148 SMs) and in the
-    bandwidth regime (2048 utterances), CUDA events over 10 launches each."""
+    bandwidth regime (2048 and 8192 utterances: 0.77 / 3.1 GB per launch, far beyond L2), CUDA events over 10 launches each."""
     dev = be.device
     res = {}
     hbm = float(peaks.get("hbm_gbs", 6650.0))
-    for (T, B, C, L) in [(128, 32, 367, 34), (128, 2048, 367, 34)]:
+    for (T, B, C, L) in [(128, 32, 367, 34), (128, 2048, 367, 34), (128, 8192, 367, 34)]:
         lg = torch.randn(T, B, C, device=dev)
         tg = torch.randint(1, C, (B * L,), device=dev)
         offs = torch.arange(B, device=dev, dtype=torch.int64) * L

@@ -140,7 +140,7 @@ ctc_fwd_bwd_kernel(const float* __restrict__ acts, int T, int B, int C, int is_l
           const bool odd = s & 1;
           const float a = prev[s];
           const float bb = s > 0 ? prev[s - 1] : CTC_NEG_INF;
-          const float c = (odd && s > 1 && tg[j] != blank && tg[j] != tg[j - 1]) ? prev[s - 2] : CTC_NEG_INF;
+          const float c = (odd && s > 1 && tg[j] != tg[j - 1]) ? prev[s - 2] : CTC_NEG_INF;
           cur[s] = lse3(a, bb, c) + (odd ? Et[j] : Et[L]);
         }
         bar_sync_named(1, CTC_HALF);
@@ -167,7 +167,7 @@ ctc_fwd_bwd_kernel(const float* __restrict__ acts, int T, int B, int C, int is_l
           const bool odd = s & 1;
           const float a = nxt[s];
           const float bb = s + 1 < S ? nxt[s + 1] : CTC_NEG_INF;
-          const float c = (odd && s + 2 < S && tg[j] != blank && tg[j] != tg[j + 1]) ? nxt[s + 2] : CTC_NEG_INF;
+          const float c = (odd && s + 2 < S && tg[j] != tg[j + 1]) ? nxt[s + 2] : CTC_NEG_INF;
           cur[s] = lse3(a, bb, c) + (odd ? Et[j] : Et[L]);
         }
         bar_sync_named(2, CTC_HALF);
@@ -274,8 +274,8 @@ __device__ __forceinline__ void ctc_chain(float* __restrict__ tab, const float* 
     const bool odd = s & 1;
     valid[i] = s < S;
     ecol[i] = (odd && j < L) ? j : L;
-    if (FWD) skip[i] = odd && s > 1 && s < S && tg[j] != blank && tg[j] != tg[j - 1];
-    else     skip[i] = odd && s + 2 < S && tg[j] != blank && tg[j] != tg[j + 1];
+    if (FWD) skip[i] = odd && s > 1 && s < S && tg[j] != tg[j - 1];
+    else     skip[i] = odd && s + 2 < S && tg[j] != tg[j + 1];
   }
   const int tstep = FWD ? 1 : -1;
   int t = FWD ? 0 : Tb - 1;

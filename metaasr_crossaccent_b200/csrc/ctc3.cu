@@ -93,8 +93,8 @@ __device__ __forceinline__ float chain(float* __restrict__ P, const float* __res
     valid[i] = s < S;
     pe[i] = E2 + ((odd && j < L) ? int(cmap[tg[j]]) : L) * TP + t0;
     bool skip;
-    if (FWD) skip = odd && s > 1 && s < S && tg[j] != blank && tg[j] != tg[j - 1];
-    else     skip = odd && s + 2 < S && tg[j] != blank && tg[j] != tg[j + 1];
+    if (FWD) skip = odd && s > 1 && s < S && tg[j] != tg[j - 1];
+    else     skip = odd && s + 2 < S && tg[j] != tg[j + 1];
     skipadd[i] = skip ? 0.f : NEG;
     validadd[i] = valid[i] ? 0.f : NEG;
   }
@@ -453,29 +453,30 @@ int launch(const float* acts, int T, int B, int C, int is_logprob, const int64_t
   return MASR_OK;
 }
 
-}  // namespace
-
-int ctc3_try(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
-             const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
-             float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
+template <int F0, int F3>
+static int dispatch(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+                    const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
+                    float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
   const int S = 2 * Lmax + 1;
   const int spl = (S + 31) / 32;
-  constexpr int F0 = 2, F3 = 2;
   if (spl > 12) return CTC3_NOT_APPLICABLE;
   const int spld = spl <= 4 ? spl : (spl <= 6 ? 6 : (spl <= 8 ? 8 : 12));
   size_t smem = smem_bytes<F3>(T, Lmax, C, spld);
-  if ( smem > 227 * 1024 || Lmax > 30000 || C > 32000) return CTC3_NOT_APPLICABLE;
+  if (smem > 227 * 1024 || Lmax > 30000 || C > 32000) return CTC3_NOT_APPLICABLE;
   static int pad = -1;              // MASR_CTC_SMEM_PAD: extra bytes per CTA (occupancy experiments)
   if (pad < 0) { const char* e = getenv("MASR_CTC_SMEM_PAD"); pad = e != nullptr ? atoi(e) : 0; }
   if (smem + size_t(pad) <= 227 * 1024) smem += size_t(pad);
-  static int minb = -1;             // MASR_CTC_MINB=4: 64-register build (four CTAs per SM); default 3 (80 registers)
-  if (minb < 0) { const char* e = getenv("MASR_CTC_MINB"); minb = e != nullptr ? atoi(e) : 3; }
+  // 64-register build (four CTAs per SM) while the whole batch fits one wave of it, else the 80-register build
+  // (three CTAs per SM, no spills): equal at 2 048 utterances, 94 vs 111 us at 512.  MASR_CTC_MINB=3|4 overrides.
+  static int minb_env = -1;
+  if (minb_env < 0) { const char* e = getenv("MASR_CTC_MINB"); minb_env = e != nullptr ? atoi(e) : 0; }
+  const int minb = minb_env != 0 ? minb_env : (B <= 4 * sm_count() ? 4 : 3);
 #define CTC3_CASE(N)                                                                                                         \
   do {                                                                                                                       \
-    if (minb == 3)                                                                                                           \
-      return launch<N, F0, F3, 3>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,         \
+    if (minb == 4)                                                                                                           \
+      return launch<N, F0, F3, 4>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,         \
                                   zero_infinity, grad_scale, nll, loss, grad, dbg, smem, st);                               \
-    return launch<N, F0, F3, 4>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,           \
+    return launch<N, F0, F3, 3>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,           \
                                 zero_infinity, grad_scale, nll, loss, grad, dbg, smem, st);                                 \
   } while (0)
   if (spl <= 1) CTC3_CASE(1);
@@ -486,6 +487,16 @@ int ctc3_try(const float* acts, int T, int B, int C, int is_logprob, const int64
   if (spl <= 8) CTC3_CASE(8);
   CTC3_CASE(12);
 #undef CTC3_CASE
+}
+
+}  // namespace
+
+int ctc3_try(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+             const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
+             float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
+  // frames per warp iteration (emission, gradient) = (2, 2): measured best of (2,2) / (3,3) / (4,2) at 80 registers
+  return dispatch<2, 2>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, zero_infinity,
+                        grad_scale, nll, loss, grad, dbg, st);
 }
 
 }  // namespace masr

@@ -102,3 +102,68 @@ def test_ctc_infeasible_and_large_workspace(dev):
     assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
     gtol = max(2e-4, 8 * 1.2e-7 * float(nll.abs().max()))
     assert float((grad - lg.grad).abs().max()) <= gtol * float(lg.grad.abs().max())
+
+
+def _torch_ref(logits, targets, in_lens, tl, dev):
+    lg = logits.double().requires_grad_(True)
+    ref = F.ctc_loss(F.log_softmax(lg, -1), targets.to(dev), in_lens, tl, blank=0, reduction='mean', zero_infinity=True)
+    ref.backward()
+    return ref, lg.grad
+
+
+@pytest.mark.parametrize("case", ["triple_repeats", "many_repeats", "blank_as_label", "tb1_and_short", "same_label_run"])
+def test_ctc_v3_label_structure_edge_cases(dev, case):
+    """The single-table kernel (ctc3.cu) treats a class's first / second occurrence in registers-free tables, later
+    occurrences and labels equal to the blank class through a side list, and falls back to its generic gradient path
+    when that list overflows: every one of those routes against F.ctc_loss in float64."""
+    from metaasr_crossaccent_b200.ctc import ctc_fwd_bwd
+    g = torch.Generator().manual_seed(11)
+    C = 367
+    if case == "triple_repeats":            # a few classes occur 3-5 times: side list
+        T, ys = 96, [torch.tensor([5, 9, 5, 7, 5, 9, 9, 5, 11, 5, 12, 9]), torch.tensor([3, 3, 3, 3]), torch.tensor([8, 2, 8])]
+    elif case == "many_repeats":            # 60 labels over 3 classes: the side list overflows -> generic path
+        T, ys = 160, [torch.randint(1, 4, (60,), generator=g), torch.randint(1, 4, (50,), generator=g)]
+    elif case == "blank_as_label":          # legal for ATen: a target id equal to the blank index
+        T, ys = 40, [torch.tensor([4, 0, 6, 0, 0, 4]), torch.tensor([0]), torch.tensor([7, 7, 0])]
+    elif case == "tb1_and_short":           # one-frame inputs, empty target, odd input lengths
+        T, ys = 9, [torch.tensor([5]), torch.tensor([], dtype=torch.int64), torch.tensor([6, 2, 6]), torch.tensor([4])]
+    else:                                   # runs of one label (no skip transitions anywhere)
+        T, ys = 64, [torch.full((20,), 17), torch.full((31,), 200)]
+    B = len(ys)
+    logits = (torch.randn(T, B, C, generator=g) * 3).to(dev)
+    in_lens = torch.tensor([T - 2 * b for b in range(B)], dtype=torch.int64)
+    if case == "tb1_and_short":
+        in_lens = torch.tensor([1, 1, 7, 5], dtype=torch.int64)
+    targets = torch.cat(ys)
+    tl = torch.tensor([len(y) for y in ys], dtype=torch.int64)
+    ref, gref = _torch_ref(logits, targets, in_lens, tl, dev)
+    loss, nll, grad = ctc_fwd_bwd(logits, targets, in_lens, tl)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-7
+    scale = float(gref.abs().max())
+    gtol = max(2e-4, 8 * 1.2e-7 * float(nll.abs().max()))
+    assert float((grad - gref).abs().max()) <= gtol * scale + 1e-9
+    for b in range(B):
+        assert float(grad[int(in_lens[b]):, b].abs().max() if int(in_lens[b]) < T else 0.0) == 0.0
+
+
+def test_ctc_full_batch_properties_at_baseline_shape(dev):
+    """B = 2048 utterances at the BASELINE shape (T'=128, C=367, L+2=34): full-size property checks (gradient rows sum
+    to zero, loss equals the mean of nll / length) and agreement with F.ctc_loss on a slice of the batch."""
+    from metaasr_crossaccent_b200.ctc import ctc_fwd_bwd
+    T, B, C, L = 128, 2048, 367, 34
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(T, B, C, generator=g).to(dev)
+    targets = torch.randint(1, C, (B * L,), generator=g)
+    in_lens = torch.full((B,), T, dtype=torch.int64)
+    tl = torch.full((B,), L, dtype=torch.int64)
+    loss, nll, grad = ctc_fwd_bwd(logits, targets, in_lens, tl)
+    assert abs(float(loss) - float((nll / L).mean())) <= 1e-5 * abs(float(loss))
+    assert float(grad.sum(-1).abs().max()) <= 1e-5 * float(grad.abs().max()) * C
+    sl = slice(1000, 1016)
+    ref, gref = _torch_ref(logits[:, sl].contiguous(), targets.view(B, L)[sl].reshape(-1), in_lens[sl], tl[sl], dev)
+    assert abs(float((nll[sl] / L).mean()) - float(ref)) <= 1e-5 * abs(float(ref))
+    # the kernel's gradient carries 1/B of the FULL batch; the slice reference 1/16
+    gs = grad[:, sl].double() * (B / 16.0)
+    # alpha/beta are fp32 log-probabilities of magnitude ~|nll|: posteriors carry ~8 ulp(|nll|) relative error
+    gtol = max(2e-4, 8 * 1.2e-7 * float(nll.abs().max()))
+    assert float((gs - gref).abs().max()) <= gtol * float(gref.abs().max())

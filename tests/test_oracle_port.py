@@ -126,3 +126,20 @@ def test_ctc_port_matches_reference_call_site():
 def test_noam_lr():
     assert math.isclose(port.noam_lr(1, 1.0, 512, 25000), 1.118e-8, rel_tol=1e-3)
     assert math.isclose(port.inner_lr(1.0, 512, 25000), 2.795e-4, rel_tol=1e-3)
+
+
+def test_port_ctc_blank_as_label_matches_aten():
+    """ATen allows a target id equal to the blank index and compares only the extended labels for the skip
+    transition (a blank-valued label after a different label may be skipped to): the oracle follows that."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1)
+    T, B, C = 12, 2, 8
+    lg = torch.randn(T, B, C, generator=g, dtype=torch.float64)
+    tg = torch.tensor([4, 0, 6, 0, 0, 4, 0, 3])
+    il, tl = torch.tensor([T, T - 1]), torch.tensor([6, 2])
+    l = lg.clone().requires_grad_(True)
+    ref = F.ctc_loss(F.log_softmax(l, -1), tg, il, tl, blank=0, reduction='mean', zero_infinity=True)
+    ref.backward()
+    onll, oloss, ograd = port.ctc_alpha_beta(lg.float(), tg, il, tl)
+    assert abs(float(oloss) - float(ref.detach())) <= 1e-6 * abs(float(ref.detach()))
+    assert float((ograd - l.grad).abs().max()) <= 1e-6
