@@ -113,6 +113,29 @@ def test_fomaml_meta_step_vs_reference_golden(dev):
         check_adam_weights(z, "s0.w.", ["s0.mg."], n, s._original[n], s.meta_opt.lr)
 
 
+def test_reptile_meta_step_vs_definition(dev):
+    """Reptile (no reference implementation, `fo_meta_interface.py:195-198` raises; parity unpinned):
+    `_updates += theta - phi` after meta_k inner steps, then the same noam-Adam -- through the CUDA path
+    (masr_mt_reptile_delta) against the oracle's restatement of that definition on identical weights and batches."""
+    z = np.load(GOLD / "fomaml_tiny.npz")
+    s = make_solver("reptile")
+    load_tiny(s)
+    ml = port.MetaLearner(load_weights(tiny_cfg()), tiny_cfg(), algo="reptile", k=0.02, warmup=4)
+    tasks, otasks = [], []
+    for acc in range(2):
+        tr = [load_batch(z, f"s0.a{acc}.tr{j}.") for j in range(2)]
+        te = load_batch(z, f"s0.a{acc}.te.")
+        otasks.append(([tuple(t if not isinstance(t, list) else [y.clone() for y in t] for t in b) for b in tr], te))
+        tasks.append(([(acc, load_batch(z, f"s0.a{acc}.tr{j}.")) for j in range(2)], (acc, load_batch(z, f"s0.a{acc}.te."))))
+    s.meta_step_on_tasks(tasks)
+    ml.meta_step(otasks)
+    for n in ml.meta_names:
+        g = ml.last_meta_grad[n]
+        mask = g.abs() > 1e-7             # Adam (eps 1e-9) turns a ~0 pseudo-gradient into a +-lr step of arbitrary sign
+        err = (s._original[n].cpu() - ml.original[n]).abs()[mask]
+        assert err.numel() == 0 or float(err.max()) <= 3e-2 * s.meta_opt.lr, n
+
+
 @pytest.mark.parametrize("graphs", [False, True])
 def test_task_lanes_match_sequential_meta_step(dev, graphs):
     """asr_model.task_lanes = 2 runs the two accents of the golden meta-step concurrently on two CUDA streams
