@@ -3,6 +3,8 @@
     FOMetaASRInterface  (src/fo_meta_interface.py:18-302)   FOMAML  (+ Reptile, which the
                          reference accepts on the CLI but raises on, :195-198 -- SURVEY 8a row R)
     MultiASRInterface   (src/multi_interface.py:17-192)     multi-task
+    MonoASRInterface    (src/mono_interface.py:18-230)      fine-tune / mono-accent loop (filter_model,
+                         freeze_module, per-epoch checkpoint) -- SURVEY 8f #2
 
 They keep the reference's hook names and behaviour (`load_model`, `run_task`,
 `_partial_meta_update`, `_final_meta_update`, `train`, `save_per_steps`, `_original`,
@@ -467,10 +469,242 @@ class MultiMixin:
             self.dashboard.set_status('pretrained')
 
 
+# ======================================================================================= fine-tune / mono
+class TrainHost:
+    """Minimal stand-alone equivalent of TrainInterface (src/train_interface.py:15-175): config fields, vocabulary,
+    pretrain-model path, log-dir layout `LOG_DIR/<train_type>/<setting>/<algo>/<pretrain_suffix>/<eval_suffix>/<accent>/<runs>`,
+    resume files (`snapshot.latest`, `optimizer.latest`, `info_dict.latest`, `epoch`, `global_step`, `best_{cer,wer}`).
+    `self.train_set` / `self.dev_set` are iterables of (x, ilens, ys, olens) (io/dataset.py get_loader)."""
+
+    def __init__(self, config, paras, id2accent):
+        self.config, self.paras = config, paras
+        self.train_type = 'evaluation'
+        s = config['solver']
+        self.eval_ival, self.log_ival = s['eval_ival'], s['log_ival']
+        self.half_batch_ilen, self.dev_max_ilen = s.get('half_batch_ilen'), s.get('dev_max_ilen', 1 << 30)
+        self.best_cer = self.best_wer = INIT_BEST_ER
+        units = [SOS_SYMBOL]
+        mapping = Path(s.get('spm_mapping', ''))
+        if mapping.is_file():
+            with open(mapping) as fin:
+                units += [line.rstrip().split(' ')[0] for line in fin.readlines()]
+        else:
+            units += [f"<u{i}>" for i in range(1, int(s.get('n_units', 365)) + 1)]
+        units.append(EOS_SYMBOL)
+        self.id2units = self.id2ch = units
+        self.metric_observer = None
+        self.save_verbose = getattr(paras, 'save_verbose', False)
+        root = Path(getattr(paras, 'log_root', None) or Path.cwd())
+        if getattr(paras, 'pretrain', False):
+            if getattr(paras, 'pretrain_model_path', None):
+                self.pretrain_model_path = Path(paras.pretrain_model_path)
+            else:
+                self.pretrain_model_path = Path(root, LOG_DIR, 'pretrain', paras.pretrain_setting, paras.algo,
+                                                paras.pretrain_suffix, id2accent[paras.pretrain_tgt_accent],
+                                                str(paras.pretrain_runs), f"snapshot.step.{paras.pretrain_step}")
+            assert self.pretrain_model_path.exists(), f"Pretrain model path {self.pretrain_model_path} not exists"
+            self.pretrain_module = s['pretrain_module']
+        self.accent = id2accent[paras.accent]
+        self.log_dir = None
+        self.train_info = RunningAvgDict(decay_rate=0.99)
+        self.global_step, self.ep = 1, 0
+        if getattr(paras, 'log_root', None) is not None and D.rank() == 0:
+            self.log_dir = Path(root, LOG_DIR, self.train_type, s['setting'], paras.algo, str(paras.pretrain_suffix),
+                                str(getattr(paras, 'eval_suffix', None)), self.accent, str(paras.runs))
+            if getattr(paras, 'resume', False):
+                self.resume_model_path = self.log_dir.joinpath('snapshot.latest')
+                self.optimizer_path = self.log_dir.joinpath('optimizer.latest')
+                assert self.optimizer_path.exists(), f"Optimizer state {self.optimizer_path} not exists..."
+                assert self.resume_model_path.exists(), f"{self.resume_model_path} not exists..."
+                self.ep = int(self.log_dir.joinpath('epoch').read_text().strip())
+                self.global_step = int(self.log_dir.joinpath('global_step').read_text().strip())
+                for t in ('wer', 'cer'):
+                    f = self.log_dir.joinpath(f'best_{t}')
+                    if f.exists():
+                        setattr(self, f'best_{t}', float(f.read_text().strip().split(' ')[1]))
+                with open(self.log_dir.joinpath('info_dict.latest'), 'rb') as fin:
+                    self.train_info = pickle.load(fin)
+            else:
+                self.log_dir.mkdir(parents=True, exist_ok=True)
+        self.dashboard = _NullDashboard()
+        self.train_set, self.dev_set = [], []
+
+    def load_data(self):
+        pass
+
+    def write_log(self, k, v):
+        if self.log_dir is not None:
+            with open(self.log_dir.joinpath(k), 'a') as fout:
+                print(f"{self.global_step} {v}", file=fout)
+
+    def log_msg(self, lr=None):
+        pass
+
+    def write_logs(self, dev_info):
+        for k, v in dev_info.items():
+            self.write_log(f"dev_{k}", float(v))
+
+
+class MonoMixin:
+    """Hot hooks of MonoASRInterface (src/mono_interface.py:18-178): the fine-tune / mono-accent loop that follows
+    pretraining in every experiment script.  One step = run_batch -> clip_grad_norm_(5) -> optimizer step on the flat
+    arenas (same kernels as the multi-task step); `filter_model` / `freeze_module` / the per-epoch checkpoint keep the
+    reference's names, files and state-dict keys."""
+
+    def _mono_init(self):
+        self.asr_model, self.asr_opt, self.lr_scheduler = None, None, None
+        self.eval_every_epoch = getattr(self.paras, 'eval_every_epoch', False)
+        self.max_epoch = self.config['solver'].get('total_epochs', 0)
+        self._train = partial(self.run_batch, train=True)
+        self._eval = partial(self.run_batch, train=False)
+        self._frozen = []                    # (offset, numel) arena segments of frozen modules
+
+    # ---- checkpoints (mono_interface.py:34-73)
+    def save_per_epoch(self):
+        if self.log_dir is None:
+            return
+        sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.asr_model.state_dict().items())
+        if self.save_verbose:
+            torch.save(sd, self.log_dir.joinpath(f"snapshot.ep.{self.ep}"))
+        torch.save(sd, self.log_dir.joinpath("snapshot.latest"))
+        # the reference pickles its TransformerOptimizer object; here the optimizer is a flat-arena object whose
+        # state_dict (step, lr, Adam m / v as CPU tensors) is what can be restored
+        osd = self.asr_opt.state_dict()
+        if isinstance(self.asr_opt, FlatNoamAdam):
+            osd = {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in osd.items()}
+            with open(self.log_dir.joinpath("optimizer.latest"), "wb") as fout:
+                pickle.dump(osd, fout)
+        else:
+            torch.save(osd, self.log_dir.joinpath("optimizer.latest"))
+        with open(self.log_dir.joinpath("info_dict.latest"), 'wb') as fout:
+            pickle.dump(self.train_info, fout)
+        with open(self.log_dir.joinpath("global_step"), 'w') as fout:
+            print(self.global_step, file=fout)
+        with open(self.log_dir.joinpath("epoch"), 'w') as fout:
+            print(self.ep, file=fout)
+
+    def save_best_model(self, tpe='wer', only_stat=False):
+        if self.log_dir is None:
+            return
+        if not only_stat:
+            sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.asr_model.state_dict().items())
+            torch.save(sd, self.log_dir.joinpath(f'model.{tpe}.best'))
+        with open(self.log_dir.joinpath(f'best_{tpe}'), 'w') as fout:
+            print('{} {}'.format(self.global_step, getattr(self, f'best_{tpe}')), file=fout)
+
+    def save_init(self):
+        if self.log_dir is not None:
+            torch.save(OrderedDict((k, v.detach().cpu().clone()) for k, v in self.asr_model.state_dict().items()),
+                       self.log_dir.joinpath("snapshot.init"))
+
+    # ---- model loading (mono_interface.py:75-116)
+    def filter_model(self, state_dict):
+        ret = OrderedDict()
+        for k, v in state_dict.items():
+            if k.split('.')[0] in self.pretrain_module:
+                ret[k] = v
+        return ret
+
+    def load_model(self):
+        eng = self.asr_model.engine
+        self._gnorm = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        if getattr(self.paras, 'resume', False):
+            self.asr_model.load_state_dict(torch.load(self.resume_model_path))
+            if isinstance(self.asr_opt, FlatNoamAdam):
+                with open(self.optimizer_path, 'rb') as fin:
+                    self.asr_opt.load_state_dict(pickle.load(fin))
+            else:
+                self.asr_opt.load_state_dict(torch.load(self.optimizer_path))
+        elif getattr(self.paras, 'pretrain', False):
+            model_dict = OrderedDict((k, v.detach().clone()) for k, v in self.asr_model.state_dict().items())
+            model_dict.update(self.filter_model(torch.load(self.pretrain_model_path)))
+            self.asr_model.load_state_dict(model_dict)
+            if 'freeze_module' in self.config['solver']:
+                self.freeze_module(self.config['solver']['freeze_module'])
+
+    def freeze_module(self, modules):
+        """`p.requires_grad = False` for the module's parameters (mono_interface.py:109-116).  On the flat arenas a
+        frozen tensor is a gradient segment that is zeroed before the norm / the optimizer: with Adam moments at 0
+        the update of that segment is exactly 0, i.e. the parameter is skipped like in the reference."""
+        eng = self.asr_model.engine
+        for module in modules:
+            for p in getattr(self.asr_model, module).parameters():
+                p.requires_grad = False
+            names = [n for n in eng.layout.offsets if n.split('.')[0] == module]
+            if module == 'pre_embed' and 'pre_embed.weight' not in eng.layout.offsets:
+                names.append('char_trans.weight')     # tied matrix: ONE Parameter in the reference, one arena tensor here
+            for name in names:
+                self._frozen.append((eng.layout.offsets[name], eng.layout.view(eng.grads, name).numel()))
+
+    # ---- one step (mono_interface.py:131-148)
+    def mono_step(self, cur_b, x, ilens, ys, olens, sync=True):
+        eng = self.asr_model.engine
+        info = self.run_batch(cur_b, x, ilens, ys, olens, train=True, sync=sync)
+        for off, n in self._frozen:
+            eng.grads[off:off + n].zero_()
+        n = eng.layout.total
+        eng.be.mt_sumsq(eng.grads[:n], self._gnorm)
+        if isinstance(self.asr_opt, FlatNoamAdam):
+            self.asr_opt.step(self._gnorm, GRAD_CLIP)       # NaN norm skips the step on the device
+        else:                                               # any torch optimizer: reference semantics
+            eng.be.mt_clip(eng.grads[:n], self._gnorm, GRAD_CLIP)
+            if not math.isnan(float(self._gnorm.item())):
+                self.asr_opt.step()
+            eng.weights_dirty = True
+        return info
+
+    def check_evaluate(self):
+        if self.global_step % self.eval_ival == 0:
+            self.asr_opt.zero_grad()
+            self.evaluate()
+
+    def train(self):
+        self.evaluate()
+        try:
+            if self.save_verbose:
+                self.save_init()
+            while self.ep < self.max_epoch:
+                for cur_b, (x, ilens, ys, olens) in enumerate(self.train_set):
+                    info = self.mono_step(cur_b, x, ilens, ys, olens)
+                    self.train_info.add(info, len(ys))
+                    self.log_msg(getattr(self.asr_opt, 'lr', None))
+                    self.check_evaluate()
+                    self.global_step += 1
+                    self.dashboard.step()
+                self.ep += 1
+                self.save_per_epoch()
+                self.dashboard.check()
+                if self.eval_every_epoch:
+                    self.evaluate()
+        except KeyboardInterrupt:
+            self.evaluate()
+            self.dashboard.set_status('trained(SIGINT)')
+        else:
+            self.dashboard.set_status('trained')
+
+    def evaluate(self):
+        """Dev-set loop of mono_interface.py:180-230: run_batch(train=False) under no_grad, running averages, best
+        CER / WER bookkeeping when the trainer reports them (the scorer itself is host-side and out of scope)."""
+        self.asr_model.eval()
+        dev_info = RunningAvgDict(decay_rate=1.)
+        with torch.no_grad():
+            for cur_b, (x, ilens, ys, olens) in enumerate(self.dev_set):
+                if int(ilens.max()) > self.dev_max_ilen:
+                    continue
+                dev_info.add(self._eval(cur_b, x, ilens, ys, olens), len(ys))
+        self.write_logs(dev_info)
+        for t in ('cer', 'wer'):
+            if t in dev_info and float(dev_info[t]) < getattr(self, f'best_{t}'):
+                setattr(self, f'best_{t}', float(dev_info[t]))
+                self.save_best_model(t)
+        self.asr_model.train()
+        return dev_info
+
+
 def fused(mixin, base):
     """Graft the fused hot hooks onto an interface base class (the reference's own
-    FOMetaASRInterface / MultiASRInterface, or PretrainHost)."""
-    init_name = '_fo_init' if mixin is FOMetaMixin else '_multi_init'
+    FOMetaASRInterface / MultiASRInterface / MonoASRInterface, or PretrainHost / TrainHost)."""
+    init_name = {FOMetaMixin: '_fo_init', MultiMixin: '_multi_init', MonoMixin: '_mono_init'}[mixin]
 
     class Fused(mixin, base):
         def __init__(self, config, paras, id2accent):
@@ -483,3 +717,4 @@ def fused(mixin, base):
 
 FOMetaASRInterface = fused(FOMetaMixin, PretrainHost)
 MultiASRInterface = fused(MultiMixin, PretrainHost)
+MonoASRInterface = fused(MonoMixin, TrainHost)

@@ -173,6 +173,45 @@ def golden_multi():
     print("multi_tiny done")
 
 
+def golden_mono_freeze():
+    """Fine-tune loop body of MonoASRInterface (mono_interface.py:75-116,131-148) run with the reference's own code:
+    `filter_model` of a 'pretrained' state dict over pretrain_module, `freeze_module(['encoder'])`, then three
+    steps of run_batch -> clip_grad_norm_(5) -> noam-Adam on the reference's model / optimizer objects."""
+    from types import SimpleNamespace
+    from torch import nn
+    cfg = H.base_config(**TINY, dropout=0.0, warmup_steps=4, k=0.02, meta=False)
+    solver = H.build_reference_solver(cfg, H.make_paras("multi"))
+    from src.mono_interface import MonoASRInterface
+    g = torch.Generator().manual_seed(11)
+    out = {"n_steps": 3, "warmup_steps": 4, "k": 0.02}
+    # a "pretrained" snapshot: the init weights plus a seeded perturbation; only pretrain_module entries are taken
+    pre = {n: (t.detach().clone() + 0.01 * torch.randn(t.shape, generator=g) if n != "pos_encoder.pe" else t.detach().clone())
+           for n, t in solver.asr_model.state_dict().items()}
+    pre["pre_embed.weight"] = pre["char_trans.weight"]          # tied in the checkpoint like in the model
+    sd_to_np("pre.", pre, out)
+    solver.pretrain_module = ["feat_extractor", "vgg2enc", "encoder"]
+    model_dict = solver.asr_model.state_dict()
+    model_dict.update(MonoASRInterface.filter_model(solver, pre))
+    solver.asr_model.load_state_dict(model_dict)
+    MonoASRInterface.freeze_module(solver, ["encoder"])
+    out["pretrain_module"] = np.array(solver.pretrain_module)
+    out["freeze_module"] = np.array(["encoder"])
+    for step in range(3):
+        b = synth_batch(g, 3, [33, 33, 26], [4, 6, 2])
+        pack_batch(f"s{step}.", b, out)
+        info = solver._train(0, *clone_batch(b), accent_idx=0)
+        gn = nn.utils.clip_grad_norm_(solver.asr_model.parameters(), 5)
+        solver.asr_opt.step()
+        out[f"s{step}.loss"] = np.float64(info["loss"])
+        out[f"s{step}.gnorm"] = np.float64(float(gn))
+        out[f"s{step}.lr"] = np.float64(solver.asr_opt.lr)
+        summarize(f"s{step}.w.", solver.asr_model.state_dict(), out)
+        summarize(f"s{step}.g.", {n: (p.grad if p.grad is not None else torch.zeros_like(p))
+                                  for n, p in solver.asr_model.named_parameters()}, out)
+    np.savez_compressed(GOLD / "mono_freeze_tiny.npz", **out)
+    print("mono_freeze_tiny done")
+
+
 def golden_ctc():
     """The CTC call site of src/blstm_trainer.py:55-70 on synthetic encoder outputs:
     targets [366]+y+[366], blank 0, reduction='mean', zero_infinity=True.  Cases: ragged
@@ -219,4 +258,5 @@ if __name__ == "__main__":
     golden_run_batch()
     golden_fomaml()
     golden_multi()
+    golden_mono_freeze()
     golden_ctc()

@@ -76,3 +76,65 @@ def check_adam_weights(z, wprefix, gprefixes, name, t, lr, tol_lr=3e-2, gmin=1e-
     err = np.abs(s - gs)[mask]
     assert mask.sum() == 0 or err.max() <= tol_lr * lr, \
         f"{wprefix}{name}: max err {err.max():.3e} = {err.max() / lr:.3f} lr over {mask.sum()} elems"
+
+
+def mono_paras(tmp_path, pre_path, **kw):
+    """argparse.Namespace of train.py for the fine-tune loop (pretrained snapshot given by path)."""
+    import argparse
+    d = dict(accent="hk", runs=0, seed=531, algo="fomaml", pretrain=True, pretrain_model_path=str(pre_path),
+             pretrain_suffix="t", eval_suffix="ft", resume=False, overwrite=True, save_verbose=False,
+             eval_every_epoch=False, log_root=str(tmp_path), model_name="transformer")
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def run_mono_freeze_check(make_solver_fn, z, tmp_path, loss_rtol, tol_lr=3e-2):
+    """Shared by the host-logic (CPU double) and CUDA tests: the fine-tune steps of tests/golden/mono_freeze_tiny.npz."""
+    import numpy as np
+    import torch
+    from collections import OrderedDict
+    pre = OrderedDict((k[len("pre."):], torch.from_numpy(z[k].copy())) for k in z.files if k.startswith("pre."))
+    pre_path = tmp_path / "snapshot.step.100"
+    torch.save(pre, pre_path)
+    s = make_solver_fn(pre_path)
+    sd0 = {n: t.detach().cpu().clone() for n, t in s.asr_model.state_dict().items()}
+    init = load_weights(tiny_cfg())
+    # filter_model: pretrain_module entries come from the snapshot, the rest keep their initial values
+    for n, t in sd0.items():
+        if n == "pos_encoder.pe":
+            continue
+        src = pre[n] if n.split(".")[0] in ("feat_extractor", "vgg2enc", "encoder") else init[n]
+        assert torch.equal(t, src), n
+    assert all(not p.requires_grad for p in s.asr_model.encoder.parameters())
+    assert all(p.requires_grad for p in s.asr_model.decoder.parameters())
+    for step in range(int(z["n_steps"])):
+        info = s.mono_step(step, *load_batch(z, f"s{step}."))
+        ref = float(z[f"s{step}.loss"])
+        assert abs(info["loss"] - ref) <= loss_rtol * abs(ref), (step, info["loss"], ref)
+        assert abs(s.asr_opt.lr - float(z[f"s{step}.lr"])) < 1e-15
+        for n, t in s.asr_model.state_dict().items():
+            if n in ("pos_encoder.pe", "pre_embed.weight"):
+                continue
+            if n.split(".")[0] == "encoder":                     # frozen: bit-identical to the loaded snapshot
+                assert torch.equal(t.detach().cpu(), sd0[n]), n
+            else:
+                check_adam_weights(z, f"s{step}.w.", [f"s{i}.g." for i in range(step + 1)], n, t.detach().cpu(),
+                                   float(z[f"s{step}.lr"]), tol_lr=tol_lr)
+    return s
+
+
+def set_model_from_tiny_init(s):
+    """set_model() with the golden's initial weights in place BEFORE load_model() overlays the pretrained modules
+    (the reference initialises in MyTransformer.__init__, then TransformerTrainer.set_model calls load_model)."""
+    from metaasr_crossaccent_b200 import interfaces as I
+    orig = I.MonoMixin.load_model
+
+    def load_with_init(self):
+        self.asr_model.load_state_dict(load_weights(tiny_cfg()))
+        orig(self)
+    I.MonoMixin.load_model = load_with_init
+    try:
+        s.set_model()
+    finally:
+        I.MonoMixin.load_model = orig
+    return s

@@ -232,3 +232,20 @@ def test_hkust_run_batch_vs_oracle_port(dev, dtype, gemm):
         worst = max(worst, rel)
         assert rel <= (2e-3 if dtype == "fp32" else 1.5e-1), (n, rel)   # bf16: the first conv sees every rounding of the net
     print(f"[{dtype}/{gemm}] loss {info['loss']:.6f} vs oracle {oinfo['loss']:.6f}; worst grad rel-L2 {worst:.2e}")
+
+
+def test_mono_finetune_steps_vs_reference_golden(dev, tmp_path):
+    """Fine-tune loop (MonoASRInterface, mono_interface.py:75-148) through the CUDA path: filter_model over
+    pretrain_module, freeze_module(['encoder']), three steps of run_batch -> clip -> noam-Adam against the golden
+    produced by the reference's own methods; frozen tensors stay bit-identical."""
+    from metaasr_crossaccent_b200 import interfaces as I
+    from metaasr_crossaccent_b200.trainer import get_trainer
+    from tests.helpers import mono_paras, run_mono_freeze_check, set_model_from_tiny_init
+    z = np.load(GOLD / "mono_freeze_tiny.npz")
+
+    def mk(pre_path):
+        cfg = make_config(meta=False)
+        cfg["solver"].update({"pretrain_module": ["feat_extractor", "vgg2enc", "encoder"], "freeze_module": ["encoder"],
+                              "total_epochs": 1})
+        return set_model_from_tiny_init(get_trainer(I.MonoASRInterface, cfg, mono_paras(tmp_path, pre_path), ID2ACCENT))
+    run_mono_freeze_check(mk, z, tmp_path, loss_rtol=2e-4)

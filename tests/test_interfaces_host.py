@@ -221,3 +221,45 @@ def test_recog_greedy_ids_bit_exact_host_logic():
     x, ilens, _, _ = load_batch(z, "in.")
     ids = s.asr_model.recog(x, ilens)
     assert np.array_equal(ids.numpy(), z["greedy"])
+
+
+# ---------------------------------------------------------------------------- fine-tune loop
+def _mono_solver(pre_path, tmp_path, backend_factory, **am_extra):
+    from tests.helpers import mono_paras
+    cfg = make_config(meta=False)
+    cfg["asr_model"].update(am_extra)
+    cfg["solver"].update({"pretrain_module": ["feat_extractor", "vgg2enc", "encoder"], "freeze_module": ["encoder"],
+                          "total_epochs": 2})
+    paras = mono_paras(tmp_path, pre_path, backend_factory=backend_factory)
+    s = get_trainer(I.MonoASRInterface, cfg, paras, ID2ACCENT)
+    return s
+
+
+def test_mono_finetune_filter_freeze_steps_match_reference(tmp_path):
+    """MonoASRInterface (mono_interface.py:75-148): filter_model over pretrain_module, freeze_module, then
+    run_batch -> clip -> noam-Adam, against the golden made with the reference's own methods."""
+    from tests.helpers import run_mono_freeze_check, set_model_from_tiny_init
+    z = np.load(GOLD / "mono_freeze_tiny.npz")
+
+    def mk(pre_path):
+        return set_model_from_tiny_init(_mono_solver(pre_path, tmp_path, lambda dt: TorchBackend("cpu", dt)))
+    s = run_mono_freeze_check(mk, z, tmp_path, loss_rtol=5e-4)
+    # per-epoch checkpoint + resume: files of mono_interface.py:34-59, state restored exactly
+    s.train_set = [load_batch(z, "s0."), load_batch(z, "s1.")]
+    s.max_epoch = 1
+    s.train()
+    for f in ("snapshot.latest", "optimizer.latest", "info_dict.latest", "global_step", "epoch"):
+        assert s.log_dir.joinpath(f).exists(), f
+    sd = torch.load(s.log_dir.joinpath("snapshot.latest"))
+    assert list(sd.keys()) == list(s.asr_model.state_dict().keys())
+    from tests.helpers import mono_paras
+    cfg = make_config(meta=False)
+    cfg["solver"].update({"pretrain_module": ["encoder"], "total_epochs": 2})
+    paras = mono_paras(tmp_path, tmp_path / "snapshot.step.100", resume=True,
+                       backend_factory=lambda dt: TorchBackend("cpu", dt))
+    r = get_trainer(I.MonoASRInterface, cfg, paras, ID2ACCENT)
+    r.set_model()
+    assert r.ep == 1 and r.global_step == s.global_step and r.asr_opt.step_num == s.asr_opt.step_num
+    for (n, a), (_, b) in zip(r.asr_model.state_dict().items(), s.asr_model.state_dict().items()):
+        assert torch.equal(a, b), n
+    assert torch.equal(r.asr_opt.state.m, s.asr_opt.state.m) and torch.equal(r.asr_opt.state.v, s.asr_opt.state.v)
