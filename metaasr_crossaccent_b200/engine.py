@@ -301,8 +301,8 @@ class TransformerEngine:
     def to_device(self, hb):
         """H2D of one prepared batch: x and the packed int64 block (two asynchronous copies)."""
         x = hb["x"]
-        if self.device.type == "cuda" and not x.is_pinned():
-            x = x.pin_memory()
+        if self.device.type == "cuda" and x.device.type == "cpu" and not x.is_pinned():
+            x = x.pin_memory()        # (a loader with device= hands over features that are already resident)
         B, L1 = hb["B"], hb["L1"]
         meta = hb["meta"].to(self.device, non_blocking=True)
         self._meta_copied(hb)

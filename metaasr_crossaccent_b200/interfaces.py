@@ -103,9 +103,22 @@ class PretrainHost:
         self.global_step = 1
         self.dashboard = _NullDashboard()
         self.data_container = None
+        self.data_dirs = ([Path(s['data_root'], a) for a in self.accents] if 'data_root' in s else [])
 
     def load_data(self):
-        pass
+        """pretrain_interface.py:110-126: one endless bucketed train iterator and one dev loader per accent
+        (data.DataContainer keeps the reference's on-disk format and batch order); synthetic runs and tests inject
+        `self.data_container` themselves and leave `solver.data_root` out."""
+        self.id2ch = self.id2units
+        if not self.data_dirs:
+            return
+        from .data import DataContainer
+        s = self.config['solver']
+        self.data_container = DataContainer(self.data_dirs, batch_size=s['batch_size'], dev_batch_size=s['dev_batch_size'],
+                                            is_memmap=getattr(self.paras, 'is_memmap', True),
+                                            is_bucket=getattr(self.paras, 'is_bucket', True),
+                                            num_workers=getattr(self.paras, 'njobs', 0), min_ilen=s.get('min_ilen'),
+                                            max_ilen=s.get('max_ilen'), half_batch_ilen=s.get('half_batch_ilen'))
 
     def write_log(self, k, v):
         if self.log_dir is not None:
@@ -528,9 +541,22 @@ class TrainHost:
                 self.log_dir.mkdir(parents=True, exist_ok=True)
         self.dashboard = _NullDashboard()
         self.train_set, self.dev_set = [], []
+        self.data_dir = Path(s['data_root'], self.accent) if 'data_root' in s else None
 
     def load_data(self):
-        pass
+        """train_interface.py:129-154: bucketed train loader and sequential dev loader of the target accent."""
+        self.id2ch = self.id2units
+        if self.data_dir is None:
+            return
+        from .data import get_loader
+        s = self.config['solver']
+        memmap, njobs = getattr(self.paras, 'is_memmap', True), getattr(self.paras, 'njobs', 0)
+        self.train_set = get_loader(self.data_dir.joinpath('train'), batch_size=s['batch_size'], min_ilen=s.get('min_ilen'),
+                                    max_ilen=s.get('max_ilen'), half_batch_ilen=s.get('half_batch_ilen'),
+                                    bucket_reverse=False, is_memmap=memmap,
+                                    is_bucket=getattr(self.paras, 'is_bucket', True), num_workers=njobs)
+        self.dev_set = get_loader(self.data_dir.joinpath('dev'), batch_size=s['dev_batch_size'], is_memmap=memmap,
+                                  is_bucket=False, shuffle=False, num_workers=njobs)
 
     def write_log(self, k, v):
         if self.log_dir is not None:

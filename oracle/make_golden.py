@@ -212,6 +212,54 @@ def golden_mono_freeze():
     print("mono_freeze_tiny done")
 
 
+def golden_loader():
+    """Batch sequences of the reference's own input pipeline (src/io/dataset.py: BucketSampler + collate_fn +
+    DataLoader, num_workers=0, and DataContainer.get_item) on synthetic accent directories that the test
+    regenerates from the same seeds (tests/helpers.make_synth_accent_dir): per batch the dataset indices (marked in
+    feat[first frame, 0]), ilens, olens and a checksum of the padded features."""
+    import random
+    import tempfile
+    from pathlib import Path
+    from tests.helpers import make_synth_accent_dir
+    H.install_stubs()
+    from src.io.dataset import DataContainer, get_loader
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        dirs = [make_synth_accent_dir(Path(td, f"acc{a}"), seed=100 + a) for a in range(2)]
+
+        def record(prefix, batches):
+            out[prefix + "n"] = np.int64(len(batches))
+            for i, (x, ilens, ys, olens) in enumerate(batches):
+                out[f"{prefix}{i}.idx"] = x[:, 0, 0].numpy().astype(np.int64)
+                out[f"{prefix}{i}.ilens"] = ilens.numpy()
+                out[f"{prefix}{i}.olens"] = olens.numpy()
+                out[f"{prefix}{i}.xsum"] = np.float64(x.double().sum().item())
+                out[f"{prefix}{i}.ysum"] = np.int64(sum(int(y.sum()) for y in ys))
+                out[f"{prefix}{i}.shape"] = np.array(x.shape)
+        # (1) bucketed train loader, two epochs, half batch beyond 50 frames, max_ilen cut
+        random.seed(7); np.random.seed(7); torch.manual_seed(7)
+        ld = get_loader(dirs[0] / "train", batch_size=8, is_memmap=True, is_bucket=True, num_workers=0, min_ilen=None,
+                        max_ilen=70, half_batch_ilen=50)
+        record("bucket.e0.", list(ld))
+        record("bucket.e1.", list(ld))
+        # (2) dev loader: sequential, no buckets
+        record("dev.", list(get_loader(dirs[0] / "dev", batch_size=5, is_memmap=True, is_bucket=False, shuffle=False)))
+        # (3) plain shuffled loader (torch RandomSampler)
+        random.seed(9); np.random.seed(9); torch.manual_seed(9)
+        record("shuf.", list(get_loader(dirs[1] / "train", batch_size=16, is_memmap=True, is_bucket=False, shuffle=True)))
+        # (4) DataContainer.get_item: per-accent draws that run past the end of an epoch, then multi-task draws
+        random.seed(11); np.random.seed(11); torch.manual_seed(11)
+        dc = DataContainer(dirs, batch_size=8, dev_batch_size=5, is_memmap=True, is_bucket=True, num_workers=0,
+                           max_ilen=70, half_batch_ilen=50)
+        seq = [dc.get_item(accent_idx=a % 2, num=1)[0] for a in range(60)]
+        seq += [it for _ in range(10) for it in dc.get_item(num=2)]
+        out["dc.accents"] = np.array([a for a, _ in seq], dtype=np.int64)
+        out["dc.reload_cnt"] = np.int64(dc.reload_cnt)
+        record("dc.", [b for _, b in seq])
+    np.savez_compressed(GOLD / "loader.npz", **out)
+    print("loader done", len(out))
+
+
 def golden_ctc():
     """The CTC call site of src/blstm_trainer.py:55-70 on synthetic encoder outputs:
     targets [366]+y+[366], blank 0, reduction='mean', zero_infinity=True.  Cases: ragged
@@ -259,4 +307,5 @@ if __name__ == "__main__":
     golden_fomaml()
     golden_multi()
     golden_mono_freeze()
+    golden_loader()
     golden_ctc()

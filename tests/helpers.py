@@ -138,3 +138,28 @@ def set_model_from_tiny_init(s):
     finally:
         I.MonoMixin.load_model = orig
     return s
+
+
+def make_synth_accent_dir(root, seed, n_train=160, n_dev=24, idim=83):
+    """Synthetic accent directory in the reference's on-disk format: <root>/{train,dev}/
+    feat.dat (npy format), ilens.npy, label.npy, olens.npy.  Input lengths cluster on a few values so that the
+    1-frame buckets of the train loader hold several utterances; feat[first frame of utterance i, 0] = i marks
+    the utterance so that a batch reveals the dataset indices it was built from."""
+    import numpy as np
+    from pathlib import Path
+    rng = np.random.default_rng(seed)
+    for split, n in (("train", n_train), ("dev", n_dev)):
+        d = Path(root, split)
+        d.mkdir(parents=True, exist_ok=True)
+        ilens = rng.choice(np.array([37, 40, 41, 44, 52, 53, 60, 75]), size=n).astype(np.int64)
+        olens = rng.integers(1, 9, size=n).astype(np.int64)
+        feat = rng.standard_normal((int(ilens.sum()), idim)).astype(np.float32)
+        ptr = np.concatenate([[0], np.cumsum(ilens)])
+        feat[ptr[:-1], 0] = np.arange(n, dtype=np.float32)
+        label = rng.integers(1, 366, size=int(olens.sum())).astype(np.int64)
+        with open(d / "feat.dat", "wb") as f:
+            np.save(f, feat)
+        np.save(d / "ilens.npy", ilens)
+        np.save(d / "label.npy", label)
+        np.save(d / "olens.npy", olens)
+    return Path(root)
