@@ -60,6 +60,15 @@ class RunningAvgDict(dict):
                 self[k] = self.decay_rate * self[k] + (1 - self.decay_rate) * v
 
 
+def _make_metric(solver_cfg, units):
+    """Metric(spm_model, id2units, sos, eos) as in train_interface.py:37-41 / pretrain_interface.py:43-48 when
+    `solver.spm_mapping` was readable (real vocabulary); synthetic runs score nothing (cer / wer = nan)."""
+    if not Path(solver_cfg.get('spm_mapping', '')).is_file():
+        return None
+    from .metric import Metric
+    return Metric(solver_cfg.get('spm_model'), units, 0, len(units) - 1)
+
+
 class _NullDashboard:
     def __getattr__(self, name):
         return lambda *a, **k: None
@@ -88,7 +97,7 @@ class PretrainHost:
         units.append(EOS_SYMBOL)
         self.id2units = units
         self.id2ch = units
-        self.metric_observer = None               # CER/WER stays host-side and out of scope
+        self.metric_observer = _make_metric(s, units)   # CER / WER scoring when the sentencepiece files are configured
         self.accents = [id2accent[a] for a in paras.pretrain_accents]
         self.num_pretrain = paras.num_pretrain
         self.tgt_accent = id2accent.get(getattr(paras, 'tgt_accent', None), 'none')
@@ -136,8 +145,50 @@ class PretrainHost:
         if self.global_step % self.eval_ival == 0:
             self.evaluate()
 
+    def write_dev_logs(self, prefix, info):
+        for k, v in info.items():
+            self.write_log(f"{prefix}_{k}", float(v))
+
+    def save_best_model(self, tpe='wer', only_stat=False):
+        """pretrain_interface / fo_meta_interface.py:56-68: model.<tpe>.best + the best_<tpe> stat file."""
+        if self.log_dir is None:
+            return
+        if not only_stat:
+            sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.asr_model.state_dict().items())
+            torch.save(sd, self.log_dir.joinpath(f'model.{tpe}.best'))
+        with open(self.log_dir.joinpath(f'best_{tpe}'), 'w') as fout:
+            print('{} {}'.format(self.global_step, getattr(self, f'best_{tpe}')), file=fout)
+
     def evaluate(self):
+        """fo_meta_interface.py:253-298 / multi_interface.py:142-192: dev loop per pretraining accent with
+        run_batch(train=False) under no_grad, per-accent and averaged logs, best WER / CER bookkeeping (when a scorer
+        is configured: cer / wer are nan for synthetic vocabularies and nothing is ranked)."""
         self.write_tr_logs()
+        dc = self.data_container
+        if dc is None or not getattr(dc, 'dev_loaders', None) or not hasattr(self, '_eval'):
+            return
+        self.asr_model.eval()
+        dev_info_ls = [RunningAvgDict(decay_rate=1.) for _ in range(self.num_pretrain)]
+        for idx, dev_loader in enumerate(dc.dev_loaders):
+            with torch.no_grad():
+                for cur_b, (x, ilens, ys, olens) in enumerate(dev_loader):
+                    if self.dev_max_ilen and int(ilens.max()) > self.dev_max_ilen:
+                        continue
+                    dev_info_ls[idx].add(self._eval(idx, x, ilens, ys, olens), len(ys))
+            self.write_dev_logs(f"dev_{self.accents[idx]}", dev_info_ls[idx])
+        dev_avg_info = RunningAvgDict(decay_rate=1.0)
+        for dev_info in dev_info_ls:
+            dev_avg_info.add({k: float(v) for k, v in dev_info.items()})
+        self.write_dev_logs("dev_avg", dev_avg_info)
+        cur_cer, cur_wer = float(dev_avg_info.get('cer', float('nan'))), float(dev_avg_info.get('wer', float('nan')))
+        if cur_wer < self.best_wer:
+            self.best_wer = cur_wer
+            self.save_best_model()
+        if cur_cer < self.best_cer:
+            self.best_cer = cur_cer
+            self.save_best_model('cer', only_stat=True)
+        self.asr_model.train()
+        return dev_avg_info
 
     def save_per_steps(self):
         """snapshot.latest / snapshot.step.N / info_dict.latest / global_step, rank 0 only
@@ -505,7 +556,7 @@ class TrainHost:
             units += [f"<u{i}>" for i in range(1, int(s.get('n_units', 365)) + 1)]
         units.append(EOS_SYMBOL)
         self.id2units = self.id2ch = units
-        self.metric_observer = None
+        self.metric_observer = _make_metric(s, units)
         self.save_verbose = getattr(paras, 'save_verbose', False)
         root = Path(getattr(paras, 'log_root', None) or Path.cwd())
         if getattr(paras, 'pretrain', False):
@@ -710,7 +761,7 @@ class MonoMixin:
 
     def evaluate(self):
         """Dev-set loop of mono_interface.py:180-230: run_batch(train=False) under no_grad, running averages, best
-        CER / WER bookkeeping when the trainer reports them (the scorer itself is host-side and out of scope)."""
+        CER / WER bookkeeping when a scorer (metric.Metric) is configured."""
         self.asr_model.eval()
         dev_info = RunningAvgDict(decay_rate=1.)
         with torch.no_grad():

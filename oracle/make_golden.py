@@ -260,6 +260,52 @@ def golden_loader():
     print("loader done", len(out))
 
 
+def golden_metric():
+    """CER / WER of the reference's own Metric (src/monitor/metric.py, with its sentencepiece model and the repo's
+    unigram150 unit list): attention-mode scores of seeded logits against padded references, CTC-mode scores of
+    frame-level id sequences; the unit strings travel inside the fixture."""
+    H.install_stubs()
+    from src.monitor.metric import Metric
+    data = H.REFERENCE_ROOT / "data"
+    units = ['<s>'] + [l.rstrip().split(' ')[0] for l in open(data / "valid_train_en_unigram150_units.txt")] + ['</s>']
+    m = Metric(str(data / "valid_train_en_unigram150.model"), units, 0, len(units) - 1)
+    g = torch.Generator().manual_seed(17)
+    B, L1, C = 6, 12, len(units)
+    out = {"units": np.array(units)}
+    # attention mode: hypotheses that partly agree with the references (so that the rates are not all > 100)
+    ys = torch.full((B, L1), -1, dtype=torch.int64)
+    for b in range(B):
+        n = int(torch.randint(1, L1 - 1, (1,), generator=g))
+        ys[b, :n] = torch.randint(2, C - 1, (n,), generator=g)
+        ys[b, n] = C - 1
+    logits = torch.randn(B, L1, C, generator=g)
+    for b in range(B):
+        for t in range(L1):
+            if ys[b, t] >= 0 and float(torch.rand((), generator=g)) < 0.7:
+                logits[b, t, ys[b, t]] += 8.0
+    out["att.pred_ids"] = torch.argmax(logits, -1).numpy()
+    out["att.ys"] = ys.numpy()
+    out["att.logits"] = logits.numpy()
+    out["att.cer"] = np.float64(m.batch_cal_er(logits, ys, ['att'], ['cer'])['att_cer'])
+    out["att.wer"] = np.float64(m.batch_cal_er(logits, ys, ['att'], ['wer'])['att_wer'])
+    out["att.cer_each"] = np.array([m.cal_att_cer(p, y) for p, y in zip(torch.argmax(logits, -1), ys)])
+    out["att.wer_each"] = np.array([m.cal_att_wer(p, y) for p, y in zip(torch.argmax(logits, -1), ys)])
+    # CTC mode (blstm vocabulary: <blank> first): frame-level ids with repeats and blanks
+    cunits = ['<blank>'] + units[1:]
+    mc = Metric(str(data / "valid_train_en_unigram150.model"), cunits, len(cunits) - 1, len(cunits) - 1)
+    preds = torch.randint(0, C, (B, 30), generator=g)
+    preds[:, ::3] = 0
+    preds[:, 1::3] = preds[:, 2::3]
+    refs = [torch.randint(2, C - 1, (int(torch.randint(1, 9, (1,), generator=g)),), generator=g) for _ in range(B)]
+    out["ctc.pred_ids"] = preds.numpy()
+    out["ctc.ref_lens"] = np.array([len(r) for r in refs])
+    out["ctc.refs"] = torch.cat(refs).numpy()
+    out["ctc.cer_each"] = np.array([mc.cal_ctc_cer(p, y) for p, y in zip(preds, refs)])
+    out["ctc.wer_each"] = np.array([mc.cal_ctc_wer(p, y) for p, y in zip(preds, refs)])
+    np.savez_compressed(GOLD / "metric.npz", **out)
+    print("metric done", out["att.cer"], out["att.wer"])
+
+
 def golden_ctc():
     """The CTC call site of src/blstm_trainer.py:55-70 on synthetic encoder outputs:
     targets [366]+y+[366], blank 0, reduction='mean', zero_infinity=True.  Cases: ragged
@@ -308,4 +354,5 @@ if __name__ == "__main__":
     golden_multi()
     golden_mono_freeze()
     golden_loader()
+    golden_metric()
     golden_ctc()

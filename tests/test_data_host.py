@@ -87,13 +87,16 @@ def test_pretrain_then_finetune_from_files(dirs, tmp_path):
     from tests.torch_backend import TorchBackend
     root = dirs[0].parent
     id2accent = {"a0": "acc0", "a1": "acc1"}
+    mapping = tmp_path / "units.txt"           # a real unit inventory switches the CER / WER scorer on (metric.Metric)
+    mapping.write_text("".join(f"{'▁' if i % 3 == 0 else ''}{chr(0x61 + i % 26)}{i % 7} {i}\n" for i in range(1, 366)))
     am = {"idim": 83, "nheads": 4, "d_model": 32, "d_inner": 64, "dropout": 0.0, "tgt_share_weight": 1,
           "encoder": {"nlayers": 1}, "decoder": {"nlayers": 1}, "pos_dropout": 0.0,
           "inner_optimizer_cls": "SGD", "inner_optimizer_opt": {"momentum": 0.9, "nesterov": True},
           "meta_opt_cls": "noam", "meta": {"optimizer_opt": {"k": 0.02, "warmup_steps": 4}}}
     solver = {"setting": "t", "total_steps": 4, "label_smoothing": 0.2, "eval_ival": 3, "log_ival": 1, "save_ival": 3,
               "data_root": str(root), "batch_size": 4, "dev_batch_size": 4, "min_ilen": None, "max_ilen": 70,
-              "half_batch_ilen": 50, "spm_mapping": "/nonexistent"}
+              "half_batch_ilen": 50, "spm_mapping": str(mapping), "spm_model": "/nonexistent.model",
+              "dev_max_ilen": 1000}
     paras = argparse.Namespace(pretrain_accents=["a0", "a1"], num_pretrain=2, tgt_accent="a1", runs=0, seed=531, meta_k=2,
                                meta_batch_size=2, sample_strategy="normal", max_step=0, resume=False, algo="fomaml",
                                pretrain_suffix="t", log_root=str(tmp_path), is_memmap=True, is_bucket=True, njobs=1,
@@ -106,6 +109,10 @@ def test_pretrain_then_finetune_from_files(dirs, tmp_path):
     assert s.global_step == 4 and not torch.equal(w0, s._original_flat)
     snap = s.log_dir / "snapshot.step.3"
     assert snap.exists() and s.data_container.num_datasets == 2
+    # evaluate() ran at step 3: per-accent and averaged dev logs, scored hypotheses, best-model bookkeeping
+    for f in ("dev_acc0_loss", "dev_acc1_cer", "dev_avg_wer", "best_wer", "best_cer", "model.wer.best", "train_loss"):
+        assert (s.log_dir / f).exists(), f
+    assert 0.0 < s.best_cer < 200.0 and 0.0 < s.best_wer < 200.0
     # fine-tune on accent a1 from that snapshot
     am2 = {k: v for k, v in am.items() if not k.startswith(("inner_", "meta"))}
     am2.update({"optimizer_cls": "noam", "optimizer_opt": {"k": 0.02, "warmup_steps": 4}})
@@ -123,4 +130,4 @@ def test_pretrain_then_finetune_from_files(dirs, tmp_path):
     n_batches = len(f.train_set)
     f.exec()
     assert f.ep == 1 and f.global_step == 1 + n_batches and (f.log_dir / "snapshot.latest").exists()
-    assert (f.log_dir / "dev_loss").exists()
+    assert (f.log_dir / "dev_loss").exists() and (f.log_dir / "dev_cer").exists() and (f.log_dir / "model.wer.best").exists()
