@@ -306,6 +306,30 @@ def golden_metric():
     print("metric done", out["att.cer"], out["att.wer"])
 
 
+def golden_decode():
+    """Tester.trim / write_hyp (src/tester.py:189-207,271-273) on seeded hypotheses: the trimmed id lists for both
+    model names and the bytes of the resulting `best-hyp` file."""
+    import random
+    import tempfile
+    from pathlib import Path
+    from types import SimpleNamespace
+    H.install_stubs()
+    from src.tester import Tester
+    random.seed(3)
+    hyps = [[random.choice([0, 5, 9, 366, 366, 12]) for _ in range(random.randint(0, 8))] for _ in range(200)]
+    out = {"hyp_flat": np.array([x for h in hyps for x in h], dtype=np.int64), "hyp_lens": np.array([len(h) for h in hyps])}
+    for mn in ("transformer", "blstm"):
+        tr = [Tester.trim(SimpleNamespace(model_name=mn, eos_id=366), list(h)) for h in hyps]
+        out[f"{mn}.flat"] = np.array([x for h in tr for x in h], dtype=np.int64)
+        out[f"{mn}.lens"] = np.array([len(h) for h in tr])
+    with tempfile.TemporaryDirectory() as td:
+        for i, h in enumerate(hyps[:40]):
+            Tester.write_hyp(SimpleNamespace(decode_dir=td), [1 + i, 2, 3], Tester.trim(SimpleNamespace(model_name="transformer", eos_id=366), list(h)))
+        out["best_hyp_bytes"] = np.frombuffer(Path(td, "best-hyp").read_bytes(), dtype=np.uint8)
+    np.savez_compressed(GOLD / "decode.npz", **out)
+    print("decode done")
+
+
 def golden_ctc():
     """The CTC call site of src/blstm_trainer.py:55-70 on synthetic encoder outputs:
     targets [366]+y+[366], blank 0, reduction='mean', zero_infinity=True.  Cases: ragged
@@ -355,4 +379,5 @@ if __name__ == "__main__":
     golden_mono_freeze()
     golden_loader()
     golden_metric()
+    golden_decode()
     golden_ctc()

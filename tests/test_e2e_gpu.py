@@ -249,3 +249,19 @@ def test_mono_finetune_steps_vs_reference_golden(dev, tmp_path):
                               "total_epochs": 1})
         return set_model_from_tiny_init(get_trainer(I.MonoASRInterface, cfg, mono_paras(tmp_path, pre_path), ID2ACCENT))
     run_mono_freeze_check(mk, z, tmp_path, loss_rtol=2e-4)
+
+
+def test_batch_greedy_decode_writes_reference_best_hyp(dev, tmp_path):
+    """Tester.batch_greedy_decode (src/tester.py:210-239) through the CUDA recog: the `best-hyp` lines are the
+    trimmed greedy ids of the live reference (golden) in the reference's wire format."""
+    from metaasr_crossaccent_b200.decode import batch_greedy_decode, trim
+    z = np.load(GOLD / "run_batch_tiny.npz")
+    s = make_solver("fomaml")
+    load_tiny(s)
+    x, ilens, ys, olens = load_batch(z, "in.")
+    batch_greedy_decode(s.asr_model, x, ilens, ys, tmp_path)
+    lines = (tmp_path / "best-hyp").read_text().splitlines()
+    ref_ids = torch.from_numpy(z["greedy"]).transpose(0, 1).tolist()          # [L, B] -> per utterance
+    assert len(lines) == len(ys)
+    for line, y, hyp in zip(lines, ys, ref_ids):
+        assert line == " ".join(str(i) for i in y.tolist()) + "\t" + " ".join(str(i) for i in trim(hyp, "transformer", s.asr_model.eos_id))

@@ -59,3 +59,16 @@ def test_run_batch_eval_scores_from_ce_kernel_argmax():
     ref = s.metric_observer.batch_cal_er(torch.from_numpy(z["logit"]), torch.from_numpy(z["gold"]), ['att'], ['cer', 'wer'])
     assert info["cer"] == ref["att_cer"] and info["wer"] == ref["att_wer"]
     assert info["cer"] > 0 and info["wer"] > 0
+
+
+def test_trim_and_best_hyp_format_match_reference_tester(tmp_path):
+    """decode.trim / write_hyp against src/tester.py:189-207,271-273 (tests/golden/decode.npz)."""
+    from metaasr_crossaccent_b200.decode import trim, write_hyp
+    z = np.load(GOLD / "decode.npz")
+    hyps = [h.tolist() for h in np.split(z["hyp_flat"], np.cumsum(z["hyp_lens"])[:-1])]
+    for mn in ("transformer", "blstm"):
+        ref = [h.tolist() for h in np.split(z[f"{mn}.flat"], np.cumsum(z[f"{mn}.lens"])[:-1])]
+        assert [trim(list(h), mn, 366) for h in hyps] == ref
+    for i, h in enumerate(hyps[:40]):
+        write_hyp(tmp_path, [1 + i, 2, 3], trim(list(h), "transformer", 366))
+    assert (tmp_path / "best-hyp").read_bytes() == z["best_hyp_bytes"].tobytes()
