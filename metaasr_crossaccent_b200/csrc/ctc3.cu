@@ -149,9 +149,131 @@ __device__ __forceinline__ float chain(float* __restrict__ P, const float* __res
   return ll2;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined variant (ctc3p_kernel): the two recursion warps run CONCURRENTLY with the six streaming warps of the
+// same CTA instead of between two block barriers.
+//   emission frames are produced from both ends towards the middle (what alpha / beta consume first) and announced
+//   per frame (erdy[t]); the recursions poll the flag of the frame they are about to load;
+//   at the meeting point the alpha warp knows log2 P(labels | x) already (sum over s of alpha_t(s) beta_t(s) / y_t(s)
+//   is the same for every t) and publishes it; from then on every step finalises one frame per recursion warp and
+//   bumps a counter (fin[0] alpha side, fin[1] beta side); the streaming warps turn into gradient workers that take
+//   finalised frame pairs outward from the middle.
+struct PipeSync {
+  volatile unsigned char* erdy;      // [T]  emission column of frame t is complete
+  volatile int* fin;                 // [0] frames finalised by alpha (mid, mid+1, ..), [1] by beta (mid-1, mid-2, ..), [2] ll ready
+  float* red;                        // [0] log2 likelihood
+};
+
+__device__ __forceinline__ void wait_frame(const PipeSync& ps, int t) {
+  while (ps.erdy[t] == 0) __nanosleep(20);
+  __threadfence_block();
+}
+// frames t + tstep .. t + n * tstep (n <= 8) at once: lane l polls one flag, one vote and one fence per eight steps
+// keep the flag round trip off the per-frame dependent chain
+__device__ __forceinline__ void wait_ahead(const PipeSync& ps, int t, int tstep, int n, int lane) {
+  const bool mine = lane < n;
+  const int tf = mine ? t + (lane + 1) * tstep : t;
+  while (!__all_sync(0xffffffffu, !mine || ps.erdy[tf] != 0)) __nanosleep(20);
+  __threadfence_block();
+}
+
+template <int SPL, bool FWD>
+__device__ __forceinline__ void chain_pipe(float* __restrict__ P, const float* __restrict__ E2, const int* __restrict__ tg,
+                                           const short* __restrict__ cmap, int lane, int L, int S, int Tb, int Sstride,
+                                           int TP, const PipeSync ps) {
+  float a[SPL], e[SPL], skipadd[SPL], validadd[SPL];
+  bool valid[SPL];
+  const float* pe[SPL];
+  const int t0 = FWD ? 0 : Tb - 1;
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    const int j = s >> 1;
+    const bool odd = s & 1;
+    valid[i] = s < S;
+    pe[i] = E2 + ((odd && j < L) ? int(cmap[tg[j]]) : L) * TP + t0;
+    bool skip;
+    if (FWD) skip = odd && s > 1 && s < S && tg[j] != tg[j - 1];
+    else     skip = odd && s + 2 < S && tg[j] != tg[j + 1];
+    skipadd[i] = skip ? 0.f : NEG;
+    validadd[i] = valid[i] ? 0.f : NEG;
+  }
+  const int mid = Tb >> 1;
+  const int npre = FWD ? mid : Tb - mid;
+  const int tstep = FWD ? 1 : -1, sstep = FWD ? Sstride : -Sstride;
+  float* dst = P + t0 * Sstride + lane * SPL;
+  int t = t0;
+  wait_frame(ps, t);
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    e[i] = *pe[i];
+    const bool start = FWD ? (s <= 1) : (s >= S - 2);
+    a[i] = (start && valid[i]) ? e[i] : NEG;
+  }
+  int k = 0;
+  for (; k < npre; ++k) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) if (valid[i]) dst[i] = a[i];
+    if (k + 1 < Tb) {
+      if ((k & 7) == 0) wait_ahead(ps, t, tstep, min(8, Tb - 1 - k), lane);
+      dst += sstep;
+      t += tstep;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) { pe[i] += tstep; e[i] = *pe[i]; }
+      recur<SPL, FWD>(a, e, skipadd, validadd, lane);
+    }
+  }
+  bar_sync_named(1, 64);
+  for (; k < Tb; ++k) {
+    float o[SPL], pc[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) o[i] = valid[i] ? dst[i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) { pc[i] = (a[i] - e[i]) + o[i]; if (valid[i]) dst[i] = pc[i]; }
+    if (FWD && k == npre) {
+      // log2 P(labels | x) = log2 sum_s 2^(alpha + beta - E) at the meeting frame
+      float m = NEG;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) if (valid[i]) m = fmaxf(m, pc[i]);
+      m = warp_max(m);
+      float se = 0.f;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) if (valid[i]) se += ex2f(fmaxf(pc[i], 2.f * NEG) - m);
+      se = warp_sum(se);
+      if (lane == 0) ps.red[0] = se > 0.f ? fmaxf(m + lg2f(se), NEG) : NEG;
+    }
+    // progress is published per frame PAIR (what a gradient worker takes) and at the last frame
+    const int nfin = k - npre + 1;
+    if ((FWD && k == npre) || (nfin & 1) == 0 || k + 1 == Tb) {
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (FWD && k == npre) ps.fin[2] = 1;
+        ps.fin[FWD ? 0 : 1] = nfin;
+      }
+    }
+    if (k + 1 < Tb) {
+      if ((k & 7) == 0) wait_ahead(ps, t, tstep, min(8, Tb - 1 - k), lane);
+      dst += sstep;
+      t += tstep;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) { pe[i] += tstep; e[i] = *pe[i]; }
+      recur<SPL, FWD>(a, e, skipadd, validadd, lane);
+    }
+  }
+}
+
 constexpr int EXMAX = 32;           // label positions beyond a class's second occurrence (or equal to the blank class)
 
 __host__ __device__ inline int ctc3_tp(int T, int F3) { const int t = T > NW * F3 ? T : NW * F3; return t | 1; }
+
+__host__ __device__ inline size_t smem_bytes_dev(int T, int Lmax, int C, int spl_dispatched) {
+  const size_t npos = 32 * size_t(spl_dispatched / 2 + 1);
+  const size_t b = sizeof(float) * (size_t(T) + 4 + size_t(Lmax + 3) * ctc3_tp(T, 2) + size_t(T) * (2 * size_t(Lmax) + 2)) +
+                   sizeof(int) * size_t(Lmax + 1) + sizeof(short) * (size_t(C) + 3 * npos + 2 * EXMAX);
+  return (b + 15) / 16 * 16;
+}
 
 template <int F3>
 inline size_t smem_bytes(int T, int Lmax, int C, int spl_dispatched) {
@@ -437,6 +559,304 @@ ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
 #undef CTC_STAMP
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+inline size_t smem_bytes_pipe(int T, int Lmax, int C, int spl_dispatched) {
+  return smem_bytes<2>(T, Lmax, C, spl_dispatched) + sizeof(float) * size_t(NW * 2 * (Lmax + 3)) + size_t((T + 15) / 16 * 16) + 16;
+}
+
+template <int SPL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
+             const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
+             const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+             int Lmax, int blank, int zero_infinity, float grad_scale,
+             float* __restrict__ nll_out, float* __restrict__ loss_out, float* __restrict__ grad,
+             long long* __restrict__ dbg) {
+  constexpr int F = 2;               // frames per worker iteration (emission and gradient)
+  constexpr int NWK = NW - 2;        // streaming warps
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#define CTC_STAMP(i) do { if (dbg != nullptr && b == 0 && tid == 0) dbg[i] = clock64(); } while (0)
+  CTC_STAMP(0);
+  const int Sstride = 2 * Lmax + 2, NEGCOL = 2 * Lmax + 1;
+  const int NSLOT = Lmax + 3, DUMMY = Lmax + 1, TRASH = Lmax + 2;
+  const int TP = ctc3_tp(T, F);
+  constexpr int NJ = SPL / 2 + 1;
+
+  float* logZ2 = reinterpret_cast<float*>(smem_raw);             // [T]
+  float* red = logZ2 + T;                                        // [4]
+  float* E2 = red + 4;                                           // [NSLOT][TP]
+  float* P = E2 + size_t(NSLOT) * TP;                            // [T][Sstride]
+  int* tg = reinterpret_cast<int*>(P + size_t(T) * Sstride);     // [Lmax]
+  int* nextra = tg + Lmax;                                       // [1]
+  short* cmap = reinterpret_cast<short*>(nextra + 1);            // [C]
+  short* colA = cmap + C;
+  short* colB = colA + 32 * NJ;
+  short* gslot = colB + 32 * NJ;
+  short* excol = gslot + 32 * NJ;
+  short* exslot = excol + EXMAX;
+  // pipeline extras behind the (16 B rounded) v3 layout
+  unsigned char* xtra = smem_raw + smem_bytes_dev(T, Lmax, C, SPL);
+  float* Gall = reinterpret_cast<float*>(xtra);                  // [NW][F][NSLOT] class posteriors per warp
+  int* fin = reinterpret_cast<int*>(Gall + NW * F * NSLOT);      // [4]
+  unsigned char* erdy = reinterpret_cast<unsigned char*>(fin + 4);   // [T]
+
+  const int L = int(tgt_lens[b]);
+  const int Tb = min(T, int(in_lens[b]));
+  const int S = 2 * L + 1;
+  const int64_t toff = tgt_offsets[b];
+
+  for (int j = tid; j < L; j += THREADS) tg[j] = int(targets[toff + j]);
+  for (int c = tid; c < C; c += THREADS) cmap[c] = short(c == blank ? L : DUMMY);
+  for (int t = tid; t < T; t += THREADS) erdy[t] = 0;
+  if (tid < 4) fin[tid] = 0;
+  if (tid == 0) *nextra = 0;
+  __syncthreads();
+  for (int j = tid; j < 32 * NJ; j += THREADS) {
+    int ca = NEGCOL, cb = NEGCOL, gs = TRASH;
+    if (j < L) {
+      const int cls = tg[j];
+      int firstpos = j, rank = 0, nx = -1;
+      if (cls != blank) {
+        for (int i = j - 1; i >= 0; --i) if (tg[i] == cls) { firstpos = i; ++rank; }
+        if (rank == 0) {
+          for (int i = j + 1; i < L; ++i) if (tg[i] == cls) { nx = i; break; }
+          cmap[cls] = short(j);
+          ca = 2 * j + 1; gs = j;
+          if (nx >= 0) cb = 2 * nx + 1;
+        }
+      } else {
+        firstpos = L; rank = 2;
+      }
+      if (rank >= 2) {
+        const int e = atomicAdd(nextra, 1);
+        if (e < EXMAX) { excol[e] = short(2 * j + 1); exslot[e] = short(firstpos); }
+      }
+    }
+    colA[j] = short(ca); colB[j] = short(cb); gslot[j] = short(gs);
+  }
+  for (int t = tid; t < T; t += THREADS) P[t * Sstride + NEGCOL] = NEG;
+  __syncthreads();
+  const int nex = *nextra;
+  const bool fast_c = C >= 32 && C <= 32 * CPL;
+  const bool pipe0 = fast_c && Tb >= 4;                          // emission frames from both ends, two at a time
+  const bool pipe3 = pipe0 && nex <= EXMAX && grad != nullptr;   // gradient rows by the workers, behind the recursions
+  const int mid = Tb >> 1;
+  const float scale = grad_scale / (float(B) * float(max(L, 1)));
+  const PipeSync ps{erdy, fin, red};
+  CTC_STAMP(1);
+
+  const int cw = (__popc(unsigned(b)) & 1) * 2;                  // recursion warps {0,1} or {2,3}
+  if (warp == cw || warp == cw + 1) {
+    // =========================================================== recursion warps
+    if (Tb > 0) {
+      if (warp == cw) chain_pipe<SPL, true>(P, E2, tg, cmap, lane, L, S, Tb, Sstride, TP, ps);
+      else            chain_pipe<SPL, false>(P, E2, tg, cmap, lane, L, S, Tb, Sstride, TP, ps);
+      CTC_STAMP(2);                  // CTA 0: warp 0 is the alpha warp -> [1..2] = recursion, [2..3] = gradient tail
+    } else if (warp == cw && lane == 0) {
+      red[0] = (S == 1) ? 0.f : NEG;
+    }
+  } else {
+    // =========================================================== streaming warps
+    const int wi = warp - (warp > cw ? 2 : 0);                   // 0 .. NWK-1
+    // ---- emissions
+    if (pipe0) {
+      float* ek[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { const int c = lane + 32 * k; ek[k] = E2 + (c < C ? int(cmap[c]) : DUMMY) * TP; }
+      const int nfront = (mid + 1) / 2, nback = (Tb - mid + 1) / 2;      // nfront <= nback <= nfront + 1
+      for (int q = wi; q < nfront + nback; q += NWK) {
+        int t0;
+        if (q < 2 * nfront && (q & 1) == 0) { t0 = 2 * (q >> 1); if (t0 + 1 >= mid) t0 = mid - 2; }       // front, upward
+        else { const int i = q < 2 * nfront ? (q >> 1) : nfront; t0 = Tb - 2 - 2 * i; if (t0 < mid) t0 = mid; }   // back, downward
+        float x[F][CPL];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float* row = acts + (int64_t(t0 + f) * B + b) * C + lane;
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldg(row + 32 * k) : NEG;
+        }
+        float z2[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          z2[f] = 0.f;
+          if (!is_logprob) {
+            float mx = x[f][0];
+#pragma unroll
+            for (int k = 1; k < CPL; ++k) mx = fmaxf(mx, x[f][k]);
+            mx = warp_max(mx) * LOG2E;
+            float se = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) se += ex2f(fmaf(x[f][k], LOG2E, -mx));
+            se = warp_sum(se);
+            z2[f] = mx + lg2f(se);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          float* d = ek[k] + t0;
+#pragma unroll
+          for (int f = 0; f < F; ++f) d[f] = fmaf(x[f][k], LOG2E, -z2[f]);
+        }
+        if (lane < F) logZ2[t0 + lane] = lane == 0 ? z2[0] : z2[1];
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); ps.erdy[t0] = 1; ps.erdy[t0 + 1] = 1; }
+      }
+    } else {
+      for (int t = wi; t < Tb; t += NWK) {
+        const float* row = acts + (int64_t(t) * B + b) * C;
+        float z2 = 0.f;
+        if (!is_logprob) {
+          float mx = -INFINITY;
+          for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+          mx = warp_max(mx);
+          float se = 0.f;
+          for (int c = lane; c < C; c += 32) se += ex2f((row[c] - mx) * LOG2E);
+          se = warp_sum(se);
+          z2 = mx * LOG2E + lg2f(se);
+        }
+        if (lane == 0) logZ2[t] = z2;
+        for (int j = lane; j <= L; j += 32) {
+          const int cls = j < L ? tg[j] : blank;
+          if (j == L || int(cmap[cls]) == j) E2[j * TP + t] = row[cls] * LOG2E - z2;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); ps.erdy[t] = 1; }
+      }
+    }
+    // ---- gradient rows of finalised frames, outward from the meeting point
+    if (pipe3) {
+      while (ps.fin[2] == 0) __nanosleep(100);      // (volatile view: the plain pointer would be hoisted)
+      __threadfence_block();
+      const float ll2 = red[0];
+      if (ll2 > 0.5f * NEG) {
+        float* Gw = Gall + warp * (F * NSLOT);
+        if (lane < F) Gw[DUMMY * F + lane] = 0.f;
+        const float* gk[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { const int c = lane + 32 * k; gk[k] = Gw + (c < C ? int(cmap[c]) : DUMMY) * F; }
+        __syncwarp();
+        const int nA = (Tb - mid + 1) / 2, nB = (mid + 1) / 2;           // nB <= nA <= nB + 1
+        for (int q = wi; q < nA + nB; q += NWK) {
+          int t0, need, side;
+          if (q < 2 * nB && (q & 1) == 1) { side = 1; const int j = q >> 1; t0 = mid - 2 - 2 * j; need = 2 * j + 2; if (t0 < 0) { t0 = 0; need = mid; } }
+          else { side = 0; const int j = q < 2 * nB ? (q >> 1) : nB; t0 = mid + 2 * j; need = 2 * j + 2; if (t0 + 1 >= Tb) { t0 = Tb - 2; need = Tb - mid; } }
+          float x[F][CPL];
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const float* row = acts + (int64_t(t0 + f) * B + b) * C + lane;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldcs(row + 32 * k) : 0.f;
+          }
+          while (ps.fin[side] < need) __nanosleep(100);
+          __threadfence_block();
+          const float* Pt = P + t0 * Sstride;
+          float bs[F];
+#pragma unroll
+          for (int f = 0; f < F; ++f) bs[f] = 0.f;
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) {
+            const int m = lane + 32 * i;
+            const int ca = colA[m], cb = colB[m], gs = gslot[m];
+            const int ce = m <= L ? 2 * m : NEGCOL;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+              const float* Pf = Pt + f * Sstride;
+              Gw[gs * F + f] = (ex2f(Pf[ca] - ll2) + ex2f(Pf[cb] - ll2)) * scale;
+              bs[f] += ex2f(Pf[ce] - ll2);
+            }
+          }
+#pragma unroll
+          for (int f = 0; f < F; ++f) bs[f] = warp_sum(bs[f]);
+          if (lane == 0) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) Gw[L * F + f] = bs[f] * scale;
+          }
+          __syncwarp();
+          if (nex > 0) {
+            if (lane < F) {
+              const float* Pf = Pt + lane * Sstride;
+              for (int e = 0; e < nex; ++e) Gw[int(exslot[e]) * F + lane] += ex2f(Pf[excol[e]] - ll2) * scale;
+            }
+            __syncwarp();
+          }
+          float z2[F];
+#pragma unroll
+          for (int f = 0; f < F; ++f) z2[f] = logZ2[t0 + f];
+          float* grow = grad + (int64_t(t0) * B + b) * C + lane;
+          const int64_t fstride = int64_t(B) * C;
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            if (lane + 32 * k < C) {
+#pragma unroll
+              for (int f = 0; f < F; ++f) {
+                const float pr = ex2f(fmaf(x[f][k], LOG2E, -z2[f]));
+                __stcs(grow + f * fstride + 32 * k, fmaf(pr, scale, -gk[k][f]));
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  CTC_STAMP(3);
+
+  const float ll2 = red[0];
+  const bool feasible = (ll2 > 0.5f * NEG);
+  if (tid == 0) {
+    float nll = feasible ? -ll2 * LN2 : INFINITY;
+    if (!feasible && zero_infinity) nll = 0.f;
+    nll_out[b] = nll;
+    if (loss_out != nullptr) atomicAdd(loss_out, nll / float(max(L, 1)) / float(B));
+  }
+  if (grad == nullptr) return;
+  // ---- what the pipeline did not cover: padded frames; everything for infeasible / odd-shaped utterances
+  const bool done_live = pipe3 && feasible;
+  for (int t = (done_live ? Tb : 0) + warp; t < T; t += NW) {
+    float* grow = grad + (int64_t(t) * B + b) * C;
+    if (!feasible || t >= Tb) {
+      const float fill = (!feasible && !zero_infinity && t < Tb) ? NAN : 0.f;
+      for (int c = lane; c < C; c += 32) grow[c] = fill;
+      continue;
+    }
+    const float* row = acts + (int64_t(t) * B + b) * C;
+    const float* Pt = P + t * Sstride;
+    float bsum = 0.f;
+    for (int m = lane; m <= L; m += 32) bsum += ex2f(Pt[2 * m] - ll2);
+    for (int j = lane; j < L; j += 32) if (int(cmap[tg[j]]) == L) bsum += ex2f(Pt[2 * j + 1] - ll2);
+    bsum = warp_sum(bsum);
+    const float z2 = logZ2[t];
+    for (int c = lane; c < C; c += 32) {
+      const float pr = ex2f(row[c] * LOG2E - z2);
+      const int u = int(cmap[c]);
+      float occ = (u == L) ? bsum : 0.f;
+      if (u < L) for (int j = u; j < L; ++j) if (tg[j] == c) occ += ex2f(Pt[2 * j + 1] - ll2);
+      grow[c] = (pr - occ) * scale;
+    }
+  }
+  CTC_STAMP(5);
+#undef CTC_STAMP
+}
+
+template <int SPL, int MINB>
+int launch_pipe(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+                const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
+                float* nll, float* loss, float* grad, long long* dbg, size_t smem, cudaStream_t st) {
+  auto kern = ctc3p_kernel<SPL, MINB>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_smem = smem;
+  }
+  kern<<<B, THREADS, smem, st>>>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,
+                                 zero_infinity, grad_scale, nll, loss, grad, dbg);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
 template <int SPL, int F0, int F3, int MINB>
 int launch(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
            const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
@@ -463,6 +883,23 @@ static int dispatch(const float* acts, int T, int B, int C, int is_logprob, cons
   const int spld = spl <= 4 ? spl : (spl <= 6 ? 6 : (spl <= 8 ? 8 : 12));
   size_t smem = smem_bytes<F3>(T, Lmax, C, spld);
   if (smem > 227 * 1024 || Lmax > 30000 || C > 32000) return CTC3_NOT_APPLICABLE;
+  static int pipe = -1;             // MASR_CTC_PIPE=0: the block-barrier kernel instead of the pipelined one
+  if (pipe < 0) { const char* e = getenv("MASR_CTC_PIPE"); pipe = e != nullptr ? atoi(e) : 1; }
+  if (pipe && F0 == 2 && F3 == 2) {
+    const size_t smem_p = smem_bytes_pipe(T, Lmax, C, spld);
+    if (smem_p <= 227 * 1024) {
+#define CTC3P_CASE(N) return launch_pipe<N, 3>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, \
+                                               zero_infinity, grad_scale, nll, loss, grad, dbg, smem_p, st)
+      if (spl <= 1) CTC3P_CASE(1);
+      if (spl <= 2) CTC3P_CASE(2);
+      if (spl <= 3) CTC3P_CASE(3);
+      if (spl <= 4) CTC3P_CASE(4);
+      if (spl <= 6) CTC3P_CASE(6);
+      if (spl <= 8) CTC3P_CASE(8);
+      CTC3P_CASE(12);
+#undef CTC3P_CASE
+    }
+  }
   static int pad = -1;              // MASR_CTC_SMEM_PAD: extra bytes per CTA (occupancy experiments)
   if (pad < 0) { const char* e = getenv("MASR_CTC_SMEM_PAD"); pad = e != nullptr ? atoi(e) : 0; }
   if (smem + size_t(pad) <= 227 * 1024) smem += size_t(pad);

@@ -153,7 +153,9 @@ def main():
             be.lib.masr_ctc_debug_read(buf)
             be.lib.masr_ctc_debug_enable(0)
             st = list(buf)
-            tab.append(f"    CTA0 cycles: setup {st[1]-st[0]}, emissions {st[2]-st[1]}, recursions {st[3]-st[2]}, posteriors+grad {st[5]-st[3]}")
+            # block-barrier kernels (v2, MASR_CTC_PIPE=0): emissions | recursions | gradient phase; pipelined kernel:
+            # [1..2] = the alpha recursion running alongside the emission / gradient workers, [2..3] = their tail
+            tab.append(f"    CTA0 cycles: setup {st[1]-st[0]}, [1..2] {st[2]-st[1]}, [2..3] {st[3]-st[2]}, [3..end] {st[5]-st[3]}")
     print("\n".join(tab))
 
 
