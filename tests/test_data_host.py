@@ -81,10 +81,22 @@ def test_pretrain_then_finetune_from_files(dirs, tmp_path):
     """The whole user-facing flow of pretrain.py / train.py on files in the reference's format, with the CPU test
     double as kernel backend: load_data() -> set_model() -> exec() for FOMAML (3 meta-steps, snapshot written), then
     the fine-tune loop that loads encoder modules from that snapshot and runs one epoch."""
+    from tests.torch_backend import TorchBackend
+    run_files_flow(dirs, tmp_path, lambda dt: TorchBackend("cpu", dt))
+
+
+@pytest.mark.gpu
+def test_pretrain_then_finetune_from_files_cuda(dirs, tmp_path):
+    """Same flow on the CUDA path (C ABI kernels, pinned loader buffers, scorer fed by the CE kernel's argmax)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    run_files_flow(dirs, tmp_path, None)
+
+
+def run_files_flow(dirs, tmp_path, backend_factory):
     import argparse
     from metaasr_crossaccent_b200 import interfaces as I
     from metaasr_crossaccent_b200.trainer import get_trainer
-    from tests.torch_backend import TorchBackend
     root = dirs[0].parent
     id2accent = {"a0": "acc0", "a1": "acc1"}
     mapping = tmp_path / "units.txt"           # a real unit inventory switches the CER / WER scorer on (metric.Metric)
@@ -100,7 +112,7 @@ def test_pretrain_then_finetune_from_files(dirs, tmp_path):
     paras = argparse.Namespace(pretrain_accents=["a0", "a1"], num_pretrain=2, tgt_accent="a1", runs=0, seed=531, meta_k=2,
                                meta_batch_size=2, sample_strategy="normal", max_step=0, resume=False, algo="fomaml",
                                pretrain_suffix="t", log_root=str(tmp_path), is_memmap=True, is_bucket=True, njobs=1,
-                               backend_factory=lambda dt: TorchBackend("cpu", dt))
+                               backend_factory=backend_factory)
     seed(5)
     s = get_trainer(I.FOMetaASRInterface, {"asr_model": am, "solver": solver}, paras, id2accent)
     s.load_data(); s.set_model()
@@ -121,12 +133,12 @@ def test_pretrain_then_finetune_from_files(dirs, tmp_path):
     p2 = argparse.Namespace(accent="a1", runs=0, seed=531, algo="fomaml", pretrain=True, pretrain_model_path=str(snap),
                             pretrain_suffix="t", eval_suffix="ft", resume=False, save_verbose=False, eval_every_epoch=False,
                             log_root=str(tmp_path), is_memmap=True, is_bucket=True, njobs=0,
-                            backend_factory=lambda dt: TorchBackend("cpu", dt))
+                            backend_factory=backend_factory)
     seed(6)
     f = get_trainer(I.MonoASRInterface, {"asr_model": am2, "solver": solver2}, p2, id2accent)
     f.load_data(); f.set_model()
     pre = torch.load(snap)
-    assert torch.equal(f.asr_model.state_dict()["encoder.layers.0.linear1.weight"], pre["encoder.layers.0.linear1.weight"])
+    assert torch.equal(f.asr_model.state_dict()["encoder.layers.0.linear1.weight"].cpu(), pre["encoder.layers.0.linear1.weight"].cpu())
     n_batches = len(f.train_set)
     f.exec()
     assert f.ep == 1 and f.global_step == 1 + n_batches and (f.log_dir / "snapshot.latest").exists()
