@@ -164,9 +164,12 @@ struct PipeSync {
   float* red;                        // [0] log2 likelihood
 };
 
+// acquire / release at CTA scope (lighter than __threadfence_block(), which is a sequentially consistent fence)
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 __device__ __forceinline__ void wait_frame(const PipeSync& ps, int t) {
   while (ps.erdy[t] == 0) __nanosleep(20);
-  __threadfence_block();
+  fence_cta();
 }
 // frames t + tstep .. t + n * tstep (n <= 8) at once: lane l polls one flag, one vote and one fence per eight steps
 // keep the flag round trip off the per-frame dependent chain
@@ -174,7 +177,7 @@ __device__ __forceinline__ void wait_ahead(const PipeSync& ps, int t, int tstep,
   const bool mine = lane < n;
   const int tf = mine ? t + (lane + 1) * tstep : t;
   while (!__all_sync(0xffffffffu, !mine || ps.erdy[tf] != 0)) __nanosleep(20);
-  __threadfence_block();
+  fence_cta();
 }
 
 template <int SPL, bool FWD>
@@ -248,7 +251,7 @@ __device__ __forceinline__ void chain_pipe(float* __restrict__ P, const float* _
     if ((FWD && k == npre) || (nfin & 1) == 0 || k + 1 == Tb) {
       __syncwarp();
       if (lane == 0) {
-        __threadfence_block();
+        fence_cta();
         if (FWD && k == npre) ps.fin[2] = 1;
         ps.fin[FWD ? 0 : 1] = nfin;
       }
@@ -573,7 +576,6 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
              float* __restrict__ nll_out, float* __restrict__ loss_out, float* __restrict__ grad,
              long long* __restrict__ dbg) {
   constexpr int F = 2;               // frames per worker iteration (emission and gradient)
-  constexpr int NWK = NW - 2;        // streaming warps
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -659,6 +661,9 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
     }
   } else {
     // =========================================================== streaming warps
+    // (measured: leaving the two warps that share a scheduler with a recursion warp idle does not speed the
+    // recursion up -- 57 k vs 55 k cycles -- and costs 20 % throughput: the contention is SM-wide, MIO / LSU)
+    constexpr int NWK = NW - 2;
     const int wi = warp - (warp > cw ? 2 : 0);                   // 0 .. NWK-1
     // ---- emissions
     if (pipe0) {
@@ -701,7 +706,7 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
         }
         if (lane < F) logZ2[t0 + lane] = lane == 0 ? z2[0] : z2[1];
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); ps.erdy[t0] = 1; ps.erdy[t0 + 1] = 1; }
+        if (lane == 0) { fence_cta(); ps.erdy[t0] = 1; ps.erdy[t0 + 1] = 1; }
       }
     } else {
       for (int t = wi; t < Tb; t += NWK) {
@@ -722,13 +727,13 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
           if (j == L || int(cmap[cls]) == j) E2[j * TP + t] = row[cls] * LOG2E - z2;
         }
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); ps.erdy[t] = 1; }
+        if (lane == 0) { fence_cta(); ps.erdy[t] = 1; }
       }
     }
     // ---- gradient rows of finalised frames, outward from the meeting point
     if (pipe3) {
       while (ps.fin[2] == 0) __nanosleep(100);      // (volatile view: the plain pointer would be hoisted)
-      __threadfence_block();
+      fence_cta();
       const float ll2 = red[0];
       if (ll2 > 0.5f * NEG) {
         float* Gw = Gall + warp * (F * NSLOT);
@@ -750,7 +755,7 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
             for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldcs(row + 32 * k) : 0.f;
           }
           while (ps.fin[side] < need) __nanosleep(100);
-          __threadfence_block();
+          fence_cta();
           const float* Pt = P + t0 * Sstride;
           float bs[F];
 #pragma unroll
