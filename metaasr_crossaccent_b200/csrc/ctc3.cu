@@ -158,6 +158,25 @@ __device__ __forceinline__ float chain(float* __restrict__ P, const float* __res
 //   is the same for every t) and publishes it; from then on every step finalises one frame per recursion warp and
 //   bumps a counter (fin[0] alpha side, fin[1] beta side); the streaming warps turn into gradient workers that take
 //   finalised frame pairs outward from the middle.
+// Cheaper warp reductions for the streaming warps of the pipelined kernel (their shuffles share the MIO pipe with
+// the recursion warps' shuffles): max through one integer REDUX (order-preserving float <-> int map), the sums of two
+// frames through a transposed butterfly (lanes 0-15 reduce frame 0, lanes 16-31 frame 1: 5 shuffles instead of 10).
+__device__ __forceinline__ float warp_max_redux(float v) {
+  int i = __float_as_int(v);
+  i ^= (i >> 31) & 0x7fffffff;
+  i = __reduce_max_sync(0xffffffffu, i);
+  i ^= (i >> 31) & 0x7fffffff;
+  return __int_as_float(i);
+}
+// returns the total of a (lanes 0-15) / of b (lanes 16-31)
+__device__ __forceinline__ float warp_sum2_split(float a, float b, int lane) {
+  const bool hi = (lane & 16) != 0;
+  float r = (hi ? b : a) + __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
 struct PipeSync {
   volatile unsigned char* erdy;      // [T]  emission column of frame t is complete
   volatile int* fin;                 // [0] frames finalised by alpha (mid, mid+1, ..), [1] by beta (mid-1, mid-2, ..), [2] ll ready
@@ -682,21 +701,24 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
 #pragma unroll
           for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldg(row + 32 * k) : NEG;
         }
-        float z2[F];
+        float z2[F] = {0.f, 0.f};
+        if (!is_logprob) {
+          float mx[F], se[F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-          z2[f] = 0.f;
-          if (!is_logprob) {
-            float mx = x[f][0];
+          for (int f = 0; f < F; ++f) {
+            mx[f] = x[f][0];
 #pragma unroll
-            for (int k = 1; k < CPL; ++k) mx = fmaxf(mx, x[f][k]);
-            mx = warp_max(mx) * LOG2E;
-            float se = 0.f;
+            for (int k = 1; k < CPL; ++k) mx[f] = fmaxf(mx[f], x[f][k]);
+            mx[f] = warp_max_redux(mx[f]) * LOG2E;
+            se[f] = 0.f;
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) se += ex2f(fmaf(x[f][k], LOG2E, -mx));
-            se = warp_sum(se);
-            z2[f] = mx + lg2f(se);
+            for (int k = 0; k < CPL; ++k) se[f] += ex2f(fmaf(x[f][k], LOG2E, -mx[f]));
           }
+          const float mine = warp_sum2_split(se[0], se[1], lane);          // frame 0 in lanes 0-15, frame 1 in 16-31
+          const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+          const bool hi = (lane & 16) != 0;
+          z2[0] = mx[0] + lg2f(hi ? other : mine);
+          z2[1] = mx[1] + lg2f(hi ? mine : other);
         }
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
@@ -772,11 +794,9 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
               bs[f] += ex2f(Pf[ce] - ll2);
             }
           }
-#pragma unroll
-          for (int f = 0; f < F; ++f) bs[f] = warp_sum(bs[f]);
-          if (lane == 0) {
-#pragma unroll
-            for (int f = 0; f < F; ++f) Gw[L * F + f] = bs[f] * scale;
+          {
+            const float tot = warp_sum2_split(bs[0], bs[1], lane);
+            if ((lane & 15) == 0) Gw[L * F + (lane >> 4)] = tot * scale;
           }
           __syncwarp();
           if (nex > 0) {
