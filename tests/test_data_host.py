@@ -143,3 +143,39 @@ def run_files_flow(dirs, tmp_path, backend_factory):
     f.exec()
     assert f.ep == 1 and f.global_step == 1 + n_batches and (f.log_dir / "snapshot.latest").exists()
     assert (f.log_dir / "dev_loss").exists() and (f.log_dir / "dev_cer").exists() and (f.log_dir / "model.wer.best").exists()
+
+
+@pytest.mark.gpu
+def test_device_staging_loader_matches_host_loader_and_feeds_run_batch(dirs):
+    """get_loader(device=...): the features are staged on the GPU by the loader's own stream (with and without the
+    background thread); same batches as the host loader, and run_batch takes the resident features as they are."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import argparse
+    from metaasr_crossaccent_b200 import interfaces as I
+    from metaasr_crossaccent_b200.trainer import get_trainer
+    kw = dict(batch_size=8, is_memmap=True, is_bucket=True, half_batch_ilen=50)
+    seed(31)
+    host = [tuple(t if not torch.is_tensor(t) else t.clone() for t in b) for b in get_loader(dirs[0] / "train", num_workers=0, **kw)]
+    for nw in (0, 2):
+        seed(31)
+        devb = list(get_loader(dirs[0] / "train", num_workers=nw, device="cuda:0", **kw))
+        assert len(devb) == len(host)
+        for (x1, i1, y1, o1), (x2, i2, y2, o2) in zip(host, devb):
+            assert x2.is_cuda and torch.equal(x1, x2.cpu()) and torch.equal(i1, i2) and torch.equal(o1, o2)
+            assert all(torch.equal(u, v) for u, v in zip(y1, y2))
+    am = {"idim": 83, "nheads": 4, "d_model": 32, "d_inner": 64, "dropout": 0.0, "tgt_share_weight": 1,
+          "encoder": {"nlayers": 1}, "decoder": {"nlayers": 1}, "pos_dropout": 0.0,
+          "optimizer_cls": "noam", "optimizer_opt": {"k": 0.02, "warmup_steps": 4}}
+    solver = {"setting": "t", "total_steps": 4, "label_smoothing": 0.2, "eval_ival": 100, "log_ival": 100, "save_ival": 100}
+    paras = argparse.Namespace(pretrain_accents=["a0"], num_pretrain=1, tgt_accent="a0", runs=0, seed=531, max_step=0,
+                               resume=False, algo="multi", pretrain_suffix="t", log_root=None)
+    s = get_trainer(I.MultiASRInterface, {"asr_model": am, "solver": solver}, paras, {"a0": "acc0"})
+    s.set_model()
+    sd = {k: v.clone() for k, v in s.asr_model.state_dict().items()}
+    xh, ih, yh, oh = host[0]
+    a = s.run_batch(0, xh, ih, [y.clone() for y in yh], oh.clone(), train=True)
+    s.asr_model.load_state_dict(sd)
+    xd, idv, yd, od = devb[0]
+    b = s.run_batch(0, xd, idv, [y.clone() for y in yd], od.clone(), train=True)
+    assert a["loss"] == b["loss"] and a["acc"] == b["acc"]
