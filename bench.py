@@ -316,6 +316,12 @@ def ctc_bandwidth(be, peaks):
         us = e0.elapsed_time(e1) * 1e3 / 10
         gbs = T * B * C * 8 / us / 1e3
         res[f"B{B}_T{T}_C{C}_L{L}"] = {"us": round(us, 1), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 3)}
+    tj = ROOT / "profiles" / "r1_traffic.json"
+    if tj.exists():                  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+        for key, v in json.loads(tj.read_text()).get("ctc", {}).items():
+            if key in res and isinstance(v, dict):
+                res[key]["traffic"] = v.get("dram_bytes")
+                res[key]["algorithmic_bytes"] = v.get("algorithmic_bytes")
     return res
 
 
