@@ -22,7 +22,9 @@ __device__ __forceinline__ float clip_coef(const double* sumsq, float max_norm) 
   // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (total_norm + 1e-6), max=1)
   const float total = float(sqrt(*sumsq));
   const float c = max_norm / (total + 1e-6f);
-  return c < 1.f ? c : 1.f;                        // NaN compares false -> 1 (caller checks NaN)
+  // torch.clamp(NaN, max=1) is NaN: a NaN norm multiplies EVERY gradient by NaN in the reference
+  // (fo_meta_interface.py:148-154: the inner-test NaN is only warned about and still accumulated)
+  return (c < 1.f || c != c) ? c : 1.f;
 }
 
 __global__ void __launch_bounds__(MT_THREADS) mt_sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
@@ -57,12 +59,21 @@ mt_clip_sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restri
   pdl_launch_dependents();
   pdl_wait();
   const double ss = *sumsq;
-  if (ss != ss) return;                            // NaN gradient norm: skip the step (:245-248)
-  const float coef = clip_coef(sumsq, max_norm);
   const int64_t n4 = n / 4;
   float4* p4 = reinterpret_cast<float4*>(p);
   float4* g4 = reinterpret_cast<float4*>(g);
   float4* b4 = reinterpret_cast<float4*>(buf);
+  if (ss != ss) {                                  // NaN gradient norm: skip the step (:245-248)
+    // a skipped FIRST step of a task leaves the momentum of the previous task behind while the host clears its
+    // `first` flag: zero it, so that the next step's mu * buf + g is the fresh buffer torch.optim.SGD would create
+    if (first && mu != 0.f) {
+      for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x)
+        b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (blockIdx.x == 0 && threadIdx.x < (n & 3)) buf[n4 * 4 + threadIdx.x] = 0.f;
+    }
+    return;
+  }
+  const float coef = clip_coef(sumsq, max_norm);
   auto upd = [&](float& pv, float& gv, float& bv) {
     gv = gv * coef;
     float d = gv;

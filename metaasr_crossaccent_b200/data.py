@@ -195,7 +195,9 @@ class B200Loader:
             for idxs in self.batches:
                 out, ev = self._load(idxs, stream)
                 if ev is not None:
-                    torch.cuda.current_stream(self.device).wait_event(ev)
+                    cur = torch.cuda.current_stream(self.device)
+                    cur.wait_event(ev)
+                    out[0].record_stream(cur)
                 yield out
             return
         # index lists are drawn HERE (consumer thread, reference order); the worker only moves bytes
@@ -233,7 +235,9 @@ class B200Loader:
                     inflight += 1
                 out, ev = res
                 if ev is not None:
-                    torch.cuda.current_stream(self.device).wait_event(ev)
+                    cur = torch.cuda.current_stream(self.device)
+                    cur.wait_event(ev)
+                    out[0].record_stream(cur)      # allocated on the loader's stream, consumed on the trainer's
                 yield out
         finally:
             todo.put(stop)

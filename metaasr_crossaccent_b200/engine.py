@@ -170,7 +170,8 @@ class TransformerEngine:
         self._sites = {}
         self.training = True
         self.use_graphs = False           # CUDA-graph replay of forward+backward per (B, T, L1) shape
-        self._graphs = {}
+        self._graphs = OrderedDict()
+        self.max_graphs = 8
         # weight-gradient GEMMs (and bias sums) never feed the back-propagation chain: they run on a
         # second stream, concurrently with the dgrad chain (small launches fill only part of the 148 SMs)
         self.multi_stream = self.device.type == "cuda"
@@ -695,7 +696,14 @@ class TransformerEngine:
         B, T, L1 = db["B"], db["T"], db["L1"]
         key = (B, T, L1, self.training)
         ent = self._graphs.get(key)
+        if ent is not None:
+            self._graphs.move_to_end(key)
         if ent is None:
+            # bounded LRU: with the reference's 1-frame buckets nearly every real batch has a new (B, T, L) shape; a
+            # captured graph pins its workspaces (hundreds of MB at full size), so keep only the most recent shapes
+            while len(self._graphs) >= self.max_graphs:
+                old_key, _ = self._graphs.popitem(last=False)
+                self._ws.pop(old_key[:3], None)
             dev = self.device
             smeta = torch.empty(B * (1 + 2 * L1), dtype=torch.int64, device=dev)
             sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev),

@@ -110,6 +110,21 @@ class PretrainHost:
             self.log_dir.mkdir(parents=True, exist_ok=True)
         self.train_info = RunningAvgDict(decay_rate=0.99)
         self.global_step = 1
+        if getattr(paras, 'resume', False):
+            # pretrain_interface.py:82-103.  (The reference asserts an optimizer.latest that none of its pretraining
+            # loops writes; save_per_steps below writes one, so resuming works here.)
+            root = self.log_dir if self.log_dir is not None else Path(
+                paras.log_root, LOG_DIR, self.train_type, s['setting'], paras.algo, paras.pretrain_suffix,
+                self.tgt_accent, str(paras.runs))
+            self.resume_model_path = root.joinpath('snapshot.latest')
+            self.optimizer_path = root.joinpath('optimizer.latest')
+            info_dict_path = root.joinpath('info_dict.latest')
+            assert self.resume_model_path.exists(), f"{self.resume_model_path} not exists..."
+            assert info_dict_path.exists(), f"PreTraining info {info_dict_path} not exists..."
+            with open(root.joinpath('global_step')) as f:
+                self.global_step = int(f.read().strip())
+            with open(info_dict_path, 'rb') as fin:
+                self.train_info = pickle.load(fin)
         self.dashboard = _NullDashboard()
         self.data_container = None
         self.data_dirs = ([Path(s['data_root'], a) for a in self.accents] if 'data_root' in s else [])
@@ -202,6 +217,16 @@ class PretrainHost:
         with open(self.log_dir.joinpath("global_step"), 'w') as f:
             print(self.global_step, file=f)
         torch.save(sd, self.log_dir.joinpath(f"snapshot.step.{self.global_step}"))
+        osd = self.optimizer_state()
+        if osd is not None:
+            torch.save(osd, self.log_dir.joinpath("optimizer.latest"))
+
+    def optimizer_state(self):
+        """What --resume needs beyond the fast weights of snapshot.latest: the optimizer of the outer loop."""
+        opt = getattr(self, 'asr_opt', None)
+        if isinstance(opt, FlatNoamAdam):
+            return {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in opt.state_dict().items()}
+        return None
 
 
 # ======================================================================================= FOMAML / Reptile
@@ -244,6 +269,12 @@ class FOMetaMixin:
                 self._original[name] = eng.layout.view(self._original_flat, src)
         opt = am['meta']['optimizer_opt']
         self.meta_opt = _MetaNoamAdam(eng.be, self._original_flat, opt['k'], am['d_model'], opt['warmup_steps'])
+        if getattr(self.paras, 'resume', False) and Path(getattr(self, 'optimizer_path', '')).is_file():
+            osd = torch.load(self.optimizer_path)
+            self._original_flat.copy_(osd['original'])             # the META weights (snapshot.latest = fast weights)
+            st = self.meta_opt.state
+            st.m.copy_(osd['m']); st.v.copy_(osd['v'])
+            st.t, self.meta_opt.step_num = int(osd['t']), int(osd['step_num'])
         # update arena: [n params | 1 slot for the task counter] -> a single all-reduce carries both
         self._upd_flat = torch.zeros(eng.layout.total + 64, dtype=torch.float32, device=eng.device)
         self._gnorm = torch.zeros(1, dtype=torch.float64, device=eng.device)
@@ -253,6 +284,11 @@ class FOMetaMixin:
         self.asr_opt = FlatInnerSGD(eng, self.inner_lr, io.get('momentum', 0.0), io.get('nesterov', False))
         self._stats_ring = torch.zeros(max(self.num_pretrain, 1), 4, dtype=torch.float64, device=eng.device)
         self._ring_sizes = []
+
+    def optimizer_state(self):
+        st = self.meta_opt.state
+        return {'original': self._original_flat.detach().cpu().clone(), 'm': st.m.detach().cpu().clone(),
+                'v': st.v.detach().cpu().clone(), 't': st.t, 'step_num': self.meta_opt.step_num}
 
     # -- lanes: independent accents of a meta-batch may run CONCURRENTLY on one GPU (asr_model.task_lanes > 1)
     def _lane(self, i):
@@ -411,10 +447,15 @@ class FOMetaMixin:
     def train(self):
         task_ids = list(range(self.num_pretrain))
         world = D.world_size()
+        # One rank: the global python RNG, like the reference (fo_meta_interface.py:136), so the accent order of a
+        # seeded run is the reference's.  Several ranks: every rank must draw the SAME permutation each step, but the
+        # data pipeline (BucketSampler re-shuffles on loader reload) consumes the global RNG at rank-dependent
+        # times -- sample tasks from a private stream that nothing else touches.
+        task_rng = random if world == 1 else random.Random(int(getattr(self.paras, 'seed', 531)) * 7919 + 17)
         try:
             while self.global_step < self.max_step:
                 for _ in range(self.eval_ival):
-                    random.shuffle(task_ids)           # identical on every rank (same seed, pretrain.py:62)
+                    task_rng.shuffle(task_ids)         # identical on every rank
                     mine = D.partition_tasks(task_ids, self.meta_batch_size)
                     self._global_task_count = min(self.meta_batch_size, len(task_ids))
                     tasks = []
@@ -478,12 +519,22 @@ class MultiMixin:
         self.asr_model, self.asr_opt = None, None
         self._train = partial(self.run_batch, train=True)
         self._eval = partial(self.run_batch, train=False)
+        if D.world_size() > 1:
+            # data-parallel multi-task training: every rank must draw its OWN accents / batches (and dropout masks);
+            # pretrain.py seeds all ranks identically, so re-seed the data-side RNG streams per rank
+            import numpy as np
+            seed = int(getattr(self.paras, 'seed', 531)) + 1000003 * D.rank()
+            random.seed(seed); np.random.seed(seed % (2 ** 32)); torch.manual_seed(seed)
 
     def load_model(self):
         if getattr(self.paras, 'resume', False):
             self.asr_model.load_state_dict(torch.load(self.resume_model_path))
+            if isinstance(self.asr_opt, FlatNoamAdam) and Path(getattr(self, 'optimizer_path', '')).is_file():
+                self.asr_opt.load_state_dict(torch.load(self.optimizer_path))
         eng = self.asr_model.engine
         self._gnorm = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        if D.world_size() > 1:
+            eng.seed_t.fill_(D.rank() << 40)          # rank-private dropout streams
 
     def multi_step(self, item, sync=True):
         """run_batch -> clip_grad_norm_ -> optimizer step (NaN norm skips the step on the device)."""

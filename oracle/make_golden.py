@@ -212,6 +212,65 @@ def golden_mono_freeze():
     print("mono_freeze_tiny done")
 
 
+
+def golden_hkust():
+    """BASELINE shape (hkust net d512/h8/ff2048/2e4d, B=32, T=512, L=32) through the LIVE reference, summaries only
+    (weights and inputs are regenerated from seeds by the tests: port.init_state_dict(seed 7),
+    tests.helpers.hkust_profile_batch): one run_batch on the equal-length profile, one on the ragged profile, and
+    one FOMAML meta-step (2 accents, meta_k = 1; accent 0 equal-length, accent 1 ragged) through the reference's own
+    run_task / _train / clip_grad_norm_ / _partial_meta_update / _final_meta_update with k = 0.2, warmup = 4 so that
+    the inner SGD step (4.4e-3) and the meta Adam step (1.1e-3) are far from trivial."""
+    from torch import nn
+    from oracle import port
+    from tests.helpers import HKUST_K, HKUST_SEED_W, HKUST_WARMUP, hkust_profile_batch
+    cfg = H.base_config(dropout=0.0, warmup_steps=HKUST_WARMUP, k=HKUST_K)
+    solver = H.build_reference_solver(cfg, H.make_paras("fomaml", meta_k=1))
+    sd = port.init_state_dict(port.NetCfg(), seed=HKUST_SEED_W)
+    solver.asr_model.load_state_dict(sd)
+    solver.load_model()                      # re-clone _original / rebuild meta_opt over the loaded weights
+    m = solver.asr_model
+    out = {"k": HKUST_K, "warmup_steps": HKUST_WARMUP, "seed_w": HKUST_SEED_W}
+    solver.asr_opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    for tag, seed in (("eq", 101), ("rag", 102)):
+        x, ilens, ys, olens = hkust_profile_batch(seed, tag)
+        m.train()
+        logit, gold = m(x, ilens, ys, olens.clone())
+        out[f"{tag}.argmax"] = logit.detach().argmax(-1).numpy().astype(np.int16)
+        srt = logit.detach().sort(-1).values
+        out[f"{tag}.margin"] = (srt[..., -1] - srt[..., -2]).numpy().astype(np.float32)
+        out[f"{tag}.gold"] = gold.numpy().astype(np.int16)
+        out[f"{tag}.logit_absmax"] = np.float64(logit.detach().abs().max())
+        summarize(f"{tag}.logit.", {"all": logit.detach()}, out, nsample=2048)
+        out[f"{tag}.enc_lens"] = torch.floor(ilens.to(dtype=torch.float32) / 4).to(dtype=torch.int64).numpy()
+        ol = olens.clone()
+        info = solver.run_batch(0, x, ilens, ys, ol, train=True)
+        out[f"{tag}.olens_after"] = ol.numpy()
+        out[f"{tag}.loss"] = np.float64(info["loss"])
+        out[f"{tag}.acc"] = np.float64(info["acc"])
+        summarize(f"{tag}.g.", {n: p.grad for n, p in m.named_parameters()}, out)
+        print("hkust", tag, info)
+    # ---- one FOMAML meta-step
+    batches = {0: (hkust_profile_batch(201, "eq"), hkust_profile_batch(202, "eq")),
+               1: (hkust_profile_batch(203, "rag"), hkust_profile_batch(204, "rag"))}
+    for acc in range(2):
+        tr, te = batches[acc]
+        solver.run_task([(acc, clone_batch(tr))])
+        info = solver._train(acc, *clone_batch(te), accent_idx=acc)
+        gn = nn.utils.clip_grad_norm_(solver.asr_model.parameters(), 5)
+        assert not math.isnan(gn)
+        out[f"fo.a{acc}.te_loss"] = np.float64(info["loss"])
+        out[f"fo.a{acc}.te_gnorm"] = np.float64(float(gn))
+        solver._partial_meta_update()
+    cnt = solver._counter
+    summarize("fo.mg.", {n: u / cnt for n, u in solver._updates.items()}, out)
+    solver._final_meta_update()
+    out["fo.lr"] = np.float64(solver.meta_opt.lr)
+    out["fo.inner_lr"] = np.float64(solver.inner_lr)
+    summarize("fo.w.", solver._original, out)
+    summarize("fo.fast.", solver.asr_model.state_dict(), out)
+    np.savez_compressed(GOLD / "hkust_b32.npz", **out)
+    print("hkust_b32 done: lr", solver.meta_opt.lr, "inner_lr", solver.inner_lr)
+
 def golden_loader():
     """Batch sequences of the reference's own input pipeline (src/io/dataset.py: BucketSampler + collate_fn +
     DataLoader, num_workers=0, and DataContainer.get_item) on synthetic accent directories that the test
@@ -373,6 +432,10 @@ if __name__ == "__main__":
     assert H.reference_available(), "needs /root/reference (build container only)"
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:                    # e.g. `python oracle/make_golden.py hkust`: one fixture only
+        for nm in sys.argv[1:]:
+            globals()["golden_" + nm]()
+        sys.exit(0)
     golden_run_batch()
     golden_fomaml()
     golden_multi()
@@ -381,3 +444,4 @@ if __name__ == "__main__":
     golden_metric()
     golden_decode()
     golden_ctc()
+    golden_hkust()

@@ -163,3 +163,30 @@ def make_synth_accent_dir(root, seed, n_train=160, n_dev=24, idim=83):
         np.save(d / "label.npy", label)
         np.save(d / "olens.npy", olens)
     return Path(root)
+
+
+# ------------------------------------------------------------------ hkust-size cases (BASELINE shape B=32, T=512, L=32)
+HKUST_SEED_W, HKUST_K, HKUST_WARMUP = 7, 0.2, 4
+
+
+def hkust_profile_batch(seed, profile, B=32, T=512, L=32, idim=83):
+    """Synthetic batch of SURVEY 8(d), regenerable from its seed on any box with this torch build:
+    'eq'  -- what the reference's 1-frame-bucket train loader yields: all ilen = T, all label lengths = L;
+    'rag' -- dev-loader-like: ilens = linspace(T -> T/2, B) sorted descending, L_b = ilen_b // 16, zeros beyond ilen."""
+    g = torch.Generator().manual_seed(seed)
+    if profile == "eq":
+        ilens = torch.full((B,), T, dtype=torch.int64)
+        lens = [L] * B
+    else:
+        ilens = torch.linspace(T, T // 2, B).round().to(torch.int64)
+        lens = [int(t) // 16 for t in ilens.tolist()]
+    x = torch.zeros(B, T, idim)
+    for b, t in enumerate(ilens.tolist()):
+        x[b, :t] = torch.randn(t, idim, generator=g)
+    ys = [torch.randint(1, 366, (l,), generator=g, dtype=torch.int64) for l in lens]
+    return x, ilens, ys, torch.tensor(lens, dtype=torch.int64)
+
+
+def clone_batch(b):
+    x, ilens, ys, olens = b
+    return x.clone(), ilens.clone(), [y.clone() for y in ys], olens.clone()

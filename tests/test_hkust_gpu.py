@@ -1,0 +1,221 @@
+"""GPU parity at the BENCHMARKED shape: hkust network (d512/h8/ff2048/2e4d, C=367), B=32, T=512, L=32, on the
+equal-length profile (what the reference's bucketed train loader yields) and a ragged one, in BOTH modes --
+fp32 (CUDA-core reference-precision path) and bf16 (the tcgen05 path bench.py times) -- against
+
+  (a) tests/golden/hkust_b32.npz : summaries produced by the LIVE reference (oracle/make_golden.py golden_hkust), and
+  (b) oracle/port.py on the same seeded weights / inputs (full per-tensor gradients, not only samples).
+
+One run_batch (reference src/transformer_torch_trainer.py:59-99) and one full FOMAML meta-step of two accents
+(src/fo_meta_interface.py:128-250).  Tolerances (north_star): loss 1e-5 (fp32) / 2e-2 (bf16) relative, greedy
+(teacher-forced argmax) ids bit-exact in fp32 and exact in bf16 wherever the reference's top-2 margin exceeds the
+bf16 logit error, per-tensor gradient rel-L2 bounded per tensor class by measurement + margin (printed), post-meta-step
+parameters 1e-3 relative where the meta-gradient is above the re-ordering noise (Adam with eps 1e-9 turns a ~0
+gradient into a +-lr step of arbitrary sign that not even the reference reproduces)."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests.helpers import (GOLD, HKUST_K, HKUST_SEED_W, HKUST_WARMUP, clone_batch, hkust_profile_batch, summary)
+
+pytestmark = pytest.mark.gpu
+ID2ACCENT = {"ca": "canada", "en": "england", "hk": "hongkong"}
+MODES = [("fp32", "simt"), ("bf16", "umma")]
+
+# per-tensor gradient rel-L2 bounds of the bf16 / tcgen05 path against the fp32 oracle, by tensor class
+# (measured on B200 at this shape, see profiles/r2_parity_hkust.md; bound = measured worst of the class x ~1.5)
+BF16_GRAD_BOUND = {"feat_extractor.0": 9e-2, "feat_extractor": 6e-2, "vgg2enc": 4e-2, "encoder": 4e-2, "decoder": 3e-2,
+                   "char_trans": 2e-2}
+FP32_GRAD_BOUND = 2e-3
+
+
+def bound_for(name, table):
+    for k in sorted(table, key=len, reverse=True):
+        if name.startswith(k):
+            return table[k]
+    raise KeyError(name)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda", 0)
+
+
+def make_solver(dtype, gemm, lanes=1, graphs=False):
+    from metaasr_crossaccent_b200 import interfaces as I
+    from metaasr_crossaccent_b200.trainer import get_trainer
+    am = {"idim": 83, "dropout": 0.0, "tgt_share_weight": 1, "pos_dropout": 0.0, "dtype": dtype, "gemm": gemm,
+          "nheads": 8, "d_model": 512, "d_inner": 2048, "encoder": {"nlayers": 2}, "decoder": {"nlayers": 4},
+          "inner_optimizer_cls": "SGD", "inner_optimizer_opt": {"momentum": 0.9, "nesterov": True},
+          "meta_opt_cls": "noam", "meta": {"optimizer_opt": {"k": HKUST_K, "warmup_steps": HKUST_WARMUP}},
+          "task_lanes": lanes, "cuda_graphs": graphs}
+    solver = {"setting": "t", "total_steps": 10, "label_smoothing": 0.2, "eval_ival": 100000, "log_ival": 100000,
+              "save_ival": 100000, "spm_mapping": "/nonexistent"}
+    paras = argparse.Namespace(pretrain_accents=["ca", "en"], num_pretrain=2, tgt_accent="hk", runs=0, seed=531,
+                               meta_k=1, meta_batch_size=2, sample_strategy="normal", max_step=0, resume=False,
+                               algo="fomaml", pretrain_suffix="t", log_root=None)
+    s = get_trainer(I.FOMetaASRInterface, {"asr_model": am, "solver": solver}, paras, ID2ACCENT)
+    s.set_model()
+    sd = port.init_state_dict(port.NetCfg(), seed=HKUST_SEED_W)
+    s.asr_model.load_state_dict(sd)
+    s._original_flat.copy_(s.asr_model.engine.params)
+    return s, sd
+
+
+def sample_rel(z, key, t):
+    s, _, l2 = summary(t)
+    gs = z[key + "#sample"].astype(np.float64)
+    return float(np.linalg.norm(s - gs) / (np.linalg.norm(gs) + 1e-30)), l2, float(z[key + "#l2"])
+
+
+@pytest.mark.parametrize("dtype,gemm", MODES)
+@pytest.mark.parametrize("profile,seed", [("eq", 101), ("rag", 102)])
+def test_run_batch_b32_vs_live_reference_and_port(dev, dtype, gemm, profile, seed):
+    z = np.load(GOLD / "hkust_b32.npz")
+    s, sd = make_solver(dtype, gemm)
+    eng = s.asr_model.engine
+    batch = hkust_profile_batch(seed, profile)
+    x, ilens, ys, olens = clone_batch(batch)
+    info = s.run_batch(0, x, ilens, ys, olens, train=True)
+    ref_loss = float(z[f"{profile}.loss"])
+    tol = 1e-5 if dtype == "fp32" else 2e-2
+    rel_loss = abs(info["loss"] - ref_loss) / abs(ref_loss)
+    assert rel_loss <= tol, (info, ref_loss)
+    assert np.array_equal(olens.numpy(), z[f"{profile}.olens_after"])          # olens += 1 in place (preprocess :139)
+    B, L1 = z[f"{profile}.gold"].shape
+    ws = eng.workspace(B, 512, L1)
+    am = ws["argmax"].view(B, L1).cpu().numpy()
+    ref_am = z[f"{profile}.argmax"].astype(np.int64)
+    keep = z[f"{profile}.gold"] >= 0
+    if dtype == "fp32":
+        assert np.array_equal(am[keep], ref_am[keep])                          # ids bit-exact
+        assert abs(info["acc"] - float(z[f"{profile}.acc"])) < 1e-12
+    else:
+        logit = ws["logits"].view(B, L1, -1).cpu().double().numpy().reshape(-1)
+        stride = max(1, logit.size // 2048)
+        gs = z[f"{profile}.logit.all#sample"].astype(np.float64)
+        lerr = float(np.abs(logit[::stride][:2048] - gs).max())
+        safe = keep & (z[f"{profile}.margin"] > 4.0 * lerr)
+        assert np.array_equal(am[safe], ref_am[safe])
+        print(f"[{dtype}/{profile}] max logit err {lerr:.3e} (absmax {float(z[f'{profile}.logit_absmax']):.2f}); "
+              f"ids compared on {int(safe.sum())}/{int(keep.sum())} positions")
+    # ---- gradients: live-reference samples + full tensors of the port
+    oinfo, ograds, ologit, _ = port.run_batch(sd, port.NetCfg(), *clone_batch(batch), 0.2)
+    assert abs(oinfo["loss"] - ref_loss) <= 1e-5 * abs(ref_loss)                # port == live reference at full size
+    rows, worst = [], {}
+    for n, og in ograds.items():
+        gg = eng.G[n].cpu()
+        rel = float((gg - og).norm() / (og.norm() + 1e-30))
+        srel, l2, gl2 = sample_rel(z, f"{profile}.g.{n}", gg)
+        rows.append((n, rel, srel, l2, gl2))
+        cls = n.split(".")[0] if not n.startswith("feat_extractor.0") else "feat_extractor.0"
+        worst[cls] = max(worst.get(cls, 0.0), rel)
+        bound = FP32_GRAD_BOUND if dtype == "fp32" else bound_for(n, BF16_GRAD_BOUND)
+        assert rel <= bound, (n, rel, bound)
+        assert abs(l2 - gl2) <= 2.5 * bound * gl2 + 1e-12, (n, l2, gl2)
+    print(f"[{dtype}/{gemm}/{profile}] loss {info['loss']:.6f} ref {ref_loss:.6f} rel {rel_loss:.2e}; "
+          f"grad rel-L2 worst per class: " + ", ".join(f"{k} {v:.2e}" for k, v in sorted(worst.items())))
+
+
+@pytest.mark.parametrize("dtype,gemm", MODES)
+def test_fomaml_meta_step_b32_vs_live_reference_and_port(dev, dtype, gemm):
+    """Two accents (one equal-length, one ragged), meta_k = 1: run_task -> inner test -> clip -> accumulate -> average
+    -> noam-Adam, against the live-reference golden and the port's full tensors."""
+    z = np.load(GOLD / "hkust_b32.npz")
+    s, sd = make_solver(dtype, gemm)
+    eng = s.asr_model.engine
+    batches = {0: (hkust_profile_batch(201, "eq"), hkust_profile_batch(202, "eq")),
+               1: (hkust_profile_batch(203, "rag"), hkust_profile_batch(204, "rag"))}
+    tasks = [([(a, clone_batch(batches[a][0]))], (a, clone_batch(batches[a][1]))) for a in range(2)]
+    captured = {}
+    orig = s.meta_opt.step
+
+    def spy(upd, count):
+        captured["mg"] = (upd / count).clone()
+        return orig(upd, count)
+    s.meta_opt.step = spy
+    s.meta_step_on_tasks(tasks)
+    infos = s.flush_train_info()
+    tol = 2e-4 if dtype == "fp32" else 2e-2
+    for a, info in enumerate(infos):
+        ref = float(z[f"fo.a{a}.te_loss"])
+        assert abs(info["loss"] - ref) <= tol * abs(ref), (a, info, ref)
+    lr = float(z["fo.lr"])
+    assert abs(s.meta_opt.lr - lr) < 1e-12
+    # the port's meta-step on the same inputs: full tensors
+    ml = port.MetaLearner(sd, port.NetCfg(), algo="fomaml", k=HKUST_K, warmup=HKUST_WARMUP)
+    ml.meta_step([([clone_batch(batches[a][0])], clone_batch(batches[a][1])) for a in range(2)])
+    worst_g, worst_w, worst_w_all = {}, {}, {}
+    gtol = 1e-2 if dtype == "fp32" else 8e-2
+    for n in eng.layout.offsets:
+        mg = eng.layout.view(captured["mg"], n).cpu()
+        og = ml.last_meta_grad[n]
+        relg = float((mg - og).norm() / (og.norm() + 1e-30))
+        srel, l2, gl2 = sample_rel(z, f"fo.mg.{n}", mg)
+        cls = n.split(".")[0]
+        worst_g[cls] = max(worst_g.get(cls, 0.0), relg)
+        assert relg <= gtol, (n, relg)
+        assert abs(l2 - gl2) <= 2 * gtol * gl2 + 1e-12, (n, l2, gl2)
+        # post-step parameters: 1e-3 relative where the meta-gradient is above the noise of this mode
+        w, ow = s._original[n].cpu(), ml.original[n]
+        noise = (1e-2 if dtype == "fp32" else 2.5e-1) * float(og.abs().max())
+        sig = og.abs() > max(noise, 1e-7)
+        rel_all = float((w - ow).norm() / (ow.norm() + 1e-30))
+        worst_w_all[cls] = max(worst_w_all.get(cls, 0.0), rel_all)
+        if int(sig.sum()) > 0:
+            relw = float((w - ow)[sig].norm() / (ow[sig].norm() + 1e-30))
+            worst_w[cls] = max(worst_w.get(cls, 0.0), relw)
+            # a +-lr Adam step on a parameter of magnitude ~lr (biases, LN offsets start at 0) is a 100 % relative
+            # move: bound the error by 1e-3 of the parameter OR 3 % of the step, whichever is larger
+            errmax = float((w - ow)[sig].abs().max())
+            assert relw <= 1e-3 or errmax <= 3e-2 * lr, (n, relw, errmax, lr)
+    print(f"[{dtype}/{gemm}] te losses {[round(i['loss'], 5) for i in infos]}; meta-grad rel-L2 worst per class: "
+          + ", ".join(f"{k} {v:.2e}" for k, v in sorted(worst_g.items()))
+          + "; post-step param rel (significant entries): " + ", ".join(f"{k} {v:.2e}" for k, v in sorted(worst_w.items()))
+          + "; all entries: " + ", ".join(f"{k} {v:.2e}" for k, v in sorted(worst_w_all.items())))
+
+
+def test_bf16_lanes_and_graphs_match_sequential_b32(dev):
+    """The schedule bench.py times (3 task lanes, CUDA-graph replay, side stream) gives the meta-gradient of the plain
+    sequential schedule at the benchmarked shape (fp32 summation order only)."""
+    res = []
+    batches = [(hkust_profile_batch(300 + 2 * a, "eq"), hkust_profile_batch(301 + 2 * a, "eq")) for a in range(2)]
+    for lanes, graphs in ((1, False), (2, True)):
+        s, _ = make_solver("bf16", "umma", lanes=lanes, graphs=graphs)
+        s.asr_model.engine.use_graphs = graphs
+        captured = {}
+        orig = s.meta_opt.step
+
+        def spy(upd, count, orig=orig, captured=captured):
+            captured["mg"] = (upd / count).clone()
+            return orig(upd, count)
+        s.meta_opt.step = spy
+        for _ in range(2):          # second step replays the captured graphs
+            s._original_flat.copy_(port_flat(s))
+            s.meta_step_on_tasks([([(a, clone_batch(batches[a][0]))], (a, clone_batch(batches[a][1]))) for a in range(2)])
+            losses = [i["loss"] for i in s.flush_train_info()]
+        torch.cuda.synchronize()
+        res.append((losses, captured["mg"].clone()))
+    (l1, g1), (l2, g2) = res
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(l1, l2)), (l1, l2)
+    assert float((g1 - g2).norm()) <= 1e-4 * float(g1.norm())
+
+
+def port_flat(s):
+    """The initial weights as a flat arena (restores the meta weights between repeated steps)."""
+    eng = s.asr_model.engine
+    if not hasattr(s, "_flat0"):
+        sd = port.init_state_dict(port.NetCfg(), seed=HKUST_SEED_W)
+        flat = torch.zeros_like(eng.params)
+        for n in eng.layout.offsets:
+            eng.layout.view(flat, n).copy_(sd[n])
+        s._flat0 = flat
+        # fresh Adam moments too
+    st = s.meta_opt.state
+    st.m.zero_(); st.v.zero_(); st.t = 0
+    s.meta_opt.step_num = 0
+    return s._flat0

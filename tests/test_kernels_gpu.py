@@ -344,6 +344,24 @@ def test_flat_multi_tensor_ops(dev):
     assert torch.equal(p0, p)
     cb.mt_adam(p0, torch.zeros_like(p), torch.zeros_like(p), g, 1.0, 1e-3, 0.9, 0.98, 1e-9, 0.1, 0.02, nan)
     assert torch.equal(p0, p)
+    # a skipped FIRST step leaves no stale momentum behind: the following step (first = 0 on the host) must equal a
+    # fresh optimizer's first step (torch.optim.SGD creates its buffer on the first step it actually performs)
+    stale = buf.clone()
+    cb.mt_clip_sgd(p0, g.clone(), stale, nan, 5.0, 0.01, 0.9, True, True)
+    assert float(stale.abs().max()) == 0.0
+    a = [p.clone(), g.clone(), stale]
+    b = [p.clone(), g.clone(), torch.zeros_like(p)]
+    cb.mt_clip_sgd(a[0], a[1], a[2], ss2, 5.0, 0.01, 0.9, True, False)
+    tb.mt_clip_sgd(b[0], b[1], b[2], ss2, 5.0, 0.01, 0.9, True, True)
+    close(a[0], b[0], torch.float32, 1e-6, "sgd after a skipped first step")
+    # NaN norm of the inner-TEST gradient: the reference only warns and accumulates grad * clamp(NaN) = NaN for every
+    # element (fo_meta_interface.py:148-156, torch.clamp keeps NaN)
+    u = p.clone()
+    cb.mt_accumulate(u, g, nan, 5.0)
+    assert bool(torch.isnan(u).all())
+    gg = g.clone()
+    cb.mt_clip(gg, nan, 5.0)
+    assert bool(torch.isnan(gg).all())
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (4096, 1536, 512), (1056, 512, 2048), (200, 96, 72),
