@@ -119,6 +119,16 @@ typedef struct masr_gemm_epilogue {
 int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
                       void* C, int c_dtype, int64_t ldc, const float* bias,
                       int M, int N, int K, int flags, int splitk, const masr_gemm_epilogue* epi, void* stream);
+/* The same contract on the PERSISTENT CTA-PAIR kernel (tcgen05.mma.cta_group::2: two CTAs of a cluster compute one
+ * 256 x bn tile, each staging its own 128 rows of A and half of B; accumulator double-buffered in TMEM so that the
+ * epilogue of a tile overlaps the MMAs of the next).  masr_umma_gemm / _ex dispatch to it by problem size (encoder /
+ * front-end sized problems: nn.Linear of mono_transformer_torch.py:62,74-85 at M = B T/4 rows and their backward);
+ * this entry selects it explicitly.  bn: 128 | 256 | 0 (choose); splitk <= 0: choose (with MASR_GEMM_SPLITK). */
+int masr_umma_gemm_pair(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                        void* C, int c_dtype, int64_t ldc, const float* bias,
+                        int M, int N, int K, int flags, int splitk, int bn, const masr_gemm_epilogue* epi, void* stream);
+/* mode 0: masr_umma_gemm* never use the CTA-pair kernel; 1 (default): by problem size (A/B measurements). */
+int masr_gemm_set_pair_mode(int mode);
 /* Convenience form of the above: A [M,K] and B [N,K] both K-major ("TN"). */
 int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
                       void* C, int c_dtype, int64_t ldc, const float* bias,

@@ -11,9 +11,7 @@
 // B[K_out, N_red]; wgrad: dy[M,N], x[M,K] reduced over M) -- the latter only changes the TMA box, the smem
 // descriptor (LBO/SBO) and two bits of the instruction descriptor, the data are never transposed in memory.
 #include <type_traits>
-#include "common.cuh"
-#include "umma.cuh"
-#include "epilogue.cuh"
+#include "gemm_common.cuh"
 
 namespace masr {
 
@@ -56,23 +54,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }
 
 // ------------------------------------------------------------------ kernel
-constexpr int UG_BM = 128;         // UMMA M
-constexpr int UG_BK = 64;          // k-block: 64 bf16 = one 128 B swizzle row
 constexpr int UG_THREADS = 192;
-
-struct UmmaGemmParams {
-  int M, N, K;                     // C[M,N] = sum_k A(m,k) B(n,k)
-  void* C; int64_t ldc; int c_is_f32;
-  const float* bias;
-  int flags;
-  int kb_per_split;                // k-blocks per blockIdx.z slice (split-K: fp32 atomics into C)
-  int stages;                      // depth of the TMA->MMA ring (host: deep when one CTA owns an SM)
-  // fused extras (masr_gemm_epilogue)
-  float* rowsum;                   // rowsum[m] += sum_k A(m,k): a second, 16-column accumulator fed by an all-ones B tile
-  const __nv_bfloat16* mask; int64_t ldmask; float mask_scale;
-  float p_drop, inv_keep; uint64_t seed; const uint64_t* seed_ptr; uint32_t site;
-  const __nv_bfloat16* dot_src; int64_t lddot; float* dot_out; int dot_L, dot_H;   // per-head row dots (see EpiOpts)
-};
 
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(UG_THREADS, 2)
@@ -193,7 +175,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4; staged through shared memory (epilogue.cuh) =====
     const int q = warp & 3;
     const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
-    const bool relu = p.flags & MASR_GEMM_RELU, accum = p.flags & MASR_GEMM_ACCUM, splitk = p.flags & MASR_GEMM_SPLITK;
+    const bool splitk = p.flags & MASR_GEMM_SPLITK;
     const bool use_bias = p.bias != nullptr && (!splitk || blockIdx.z == 0);
     if (use_bias) {
       for (int i = et; i < BN; i += 128) sbias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
@@ -202,33 +184,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int m = m0 + q * 32 + lane;
-    const int ncols = min(BN, p.N - n0);
-    const int mode = splitk ? EPI_ATOMIC : (accum ? EPI_ACCUM : EPI_STORE);
-    EpiOpts o;
-    o.sbias = use_bias ? sbias : nullptr;
-    o.relu = relu;
-    if (p.p_drop > 0.f) {
-      o.p_drop = p.p_drop; o.inv_keep = p.inv_keep; o.site = p.site;
-      o.seed = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
-      o.drop_row_base = int64_t(m) * p.N + n0;
-    }
-    if (p.dot_src != nullptr && m < p.M) {   // row m = b * L + q; columns n0.. = heads n0 / 64..
-      o.dot_row = p.dot_src + int64_t(m) * p.lddot + n0;
-      o.dot_out = p.dot_out + (int64_t(m / p.dot_L) * p.dot_H + (n0 >> 6)) * p.dot_L + (m % p.dot_L);
-      o.dot_stride = p.dot_L;
-    }
-    o.mask_scale = p.mask_scale;      // warp-uniform: a lane drains OTHER rows' chunks in phase 2
-    if (p.mask != nullptr && m < p.M) o.mask_row = p.mask + int64_t(m) * p.ldmask + n0;
-    if (p.c_is_f32) {
-      float* row = (m < p.M) ? static_cast<float*>(p.C) + int64_t(m) * p.ldc + n0 : nullptr;
-      const bool vec_ok = ncols == BN && (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) + size_t(n0) * 4) & 15) == 0;
-      epilogue_tile<BN, float>(tmem_base, q, lane, smem, row, ncols, vec_ok, mode, o);
-    } else {
-      __nv_bfloat16* row = (m < p.M) ? static_cast<__nv_bfloat16*>(p.C) + int64_t(m) * p.ldc + n0 : nullptr;
-      const bool vec_ok = ncols == BN && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) + size_t(n0) * 2) & 15) == 0 &&
-                          (p.mask == nullptr || ((p.ldmask & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.mask) + size_t(n0) * 2) & 15) == 0));
-      epilogue_tile<BN, __nv_bfloat16>(tmem_base, q, lane, smem, row, ncols, vec_ok, mode, o);
-    }
+    gemm_epilogue_piece<BN>(p, tmem_base, q, lane, m, n0, smem, sbias, use_bias);
     if (rowsum) {                   // column 0 of the ones-accumulator = sum_k A(m, k)
       float v[32];
       tmem_ld_32x32(tmem_base + BN + (uint32_t(q * 32) << 16), v);
@@ -268,7 +224,7 @@ static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmPar
 }
 
 // operand map: K-major  -> dims {K, rows}, box {64, tile_rows};  MN-major -> dims {rows(MN), K}, box {64, 64}
-static int operand_map(CUtensorMap* out, const void* base, int64_t ld_elems, int rows_mn, int K, bool mn_major, int tile_rows) {
+int gemm_operand_map(CUtensorMap* out, const void* base, int64_t ld_elems, int rows_mn, int K, bool mn_major, int tile_rows) {
   MASR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "umma: operand base must be 16-byte aligned");
   MASR_REQUIRE(ld_elems % 8 == 0, "umma: operand leading dimension must be a multiple of 8 elements");
   uint64_t dims[2]; uint64_t strides[1]; uint32_t box[2];
@@ -300,9 +256,9 @@ extern "C" int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const voi
   const int64_t tiles128 = ceil_div64(M, UG_BM) * ceil_div64(N, 128) * ceil_div64(total_kb, kb_per_split);
   const int BN = (N <= 64 || (tiles128 * 3 < sm_count() * 2 && kb_per_split <= 16)) ? 64 : 128;
   CUtensorMap ma, mb;
-  int rc = operand_map(&ma, A, lda, M, K, a_mn != 0, UG_BM);
+  int rc = gemm_operand_map(&ma, A, lda, M, K, a_mn != 0, UG_BM);
   if (rc != MASR_OK) return rc;
-  rc = operand_map(&mb, B, ldb, N, K, b_mn != 0, BN);
+  rc = gemm_operand_map(&mb, B, ldb, N, K, b_mn != 0, BN);
   if (rc != MASR_OK) return rc;
   UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, kb_per_split, 0,
                    nullptr, nullptr, 0, 1.f, 0.f, 1.f, 0, nullptr, 0, nullptr, 0, nullptr, 1, 1};
@@ -324,6 +280,9 @@ extern "C" int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const voi
     }
   }
   cudaStream_t st = as_stream(stream);
+  // large problems: persistent CTA-pair kernel (256-row tiles, cta_group::2, double-buffered TMEM), gemm_pair_umma.cu
+  if (umma_pair_preferred(M, N, K))
+    return launch_umma_pair(A, lda, a_mn, B, ldb, b_mn, p, (flags & MASR_GEMM_SPLITK) ? -1 : 1, 0, st);
   const int key = (BN == 64 ? 0 : 4) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
   switch (key) {
     case 0: return launch_umma<64, 4, false, false>(ma, mb, p, st);
@@ -347,4 +306,35 @@ extern "C" int masr_umma_gemm_tn(const void* A, int64_t lda, const void* B, int6
                                  void* C, int c_dtype, int64_t ldc, const float* bias,
                                  int M, int N, int K, int flags, void* stream) {
   return masr_umma_gemm(A, lda, 0, B, ldb, 0, C, c_dtype, ldc, bias, M, N, K, flags, 1, stream);
+}
+
+/* Explicit entry to the CTA-pair kernel (tests / probes): bn = 128 or 256 (0 = choose), splitk <= 0 = choose. */
+extern "C" int masr_umma_gemm_pair(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                                   void* C, int c_dtype, int64_t ldc, const float* bias,
+                                   int M, int N, int K, int flags, int splitk, int bn, const masr_gemm_epilogue* epi, void* stream) {
+  MASR_REQUIRE(M > 0 && N > 0 && K > 0, "pair gemm: empty problem");
+  MASR_REQUIRE(!(flags & MASR_GEMM_SPLITK) || c_dtype == MASR_F32, "pair gemm: split-K needs an fp32 C");
+  MASR_REQUIRE(!((flags & MASR_GEMM_SPLITK) && (flags & MASR_GEMM_RELU)), "pair gemm: split-K cannot fuse ReLU");
+  MASR_REQUIRE(bn == 0 || bn == 128 || bn == 256, "pair gemm: bn must be 0, 128 or 256");
+  UmmaGemmParams p{M, N, K, C, ldc, c_dtype == MASR_F32 ? 1 : 0, bias, flags, 0, 0,
+                   nullptr, nullptr, 0, 1.f, 0.f, 1.f, 0, nullptr, 0, nullptr, 0, nullptr, 1, 1};
+  if (epi != nullptr) {
+    p.rowsum = epi->rowsum;
+    p.mask = static_cast<const __nv_bfloat16*>(epi->mask); p.ldmask = epi->ldmask; p.mask_scale = epi->mask_scale;
+    if (epi->p_drop > 0.f) {
+      p.p_drop = epi->p_drop; p.inv_keep = 1.f / (1.f - epi->p_drop);
+      p.seed = epi->seed; p.seed_ptr = g_seed_dev_ptr; p.site = epi->site;
+    }
+    if (epi->dot_src != nullptr) {
+      p.dot_src = static_cast<const __nv_bfloat16*>(epi->dot_src); p.lddot = epi->lddot;
+      p.dot_out = epi->dot_out; p.dot_L = epi->dot_L; p.dot_H = epi->dot_H;
+    }
+  }
+  return launch_umma_pair(A, lda, a_mn, B, ldb, b_mn, p, splitk, bn, as_stream(stream));
+}
+
+/* 0: masr_umma_gemm* never uses the CTA-pair kernel; 1 (default): by problem size.  For A/B measurements. */
+extern "C" int masr_gemm_set_pair_mode(int mode) {
+  set_pair_mode(mode);
+  return MASR_OK;
 }

@@ -115,6 +115,20 @@ class CudaBackend:
             kind = ("fwd", "dgrad", "a_mn", "wgrad")[int(a_mn) * 2 + int(b_mn)]
             prof.setdefault((kind, M, N, K), []).append((e0, e1))
 
+    def umma_gemm_pair(self, A, a_mn, B, b_mn, C, bias, M, N, K, flags=0, splitk=0, bn=0, rowsum=None, mask=None,
+                       mask_scale=1.0, p_drop=0.0, seed=0, site=0, rowdot=None):
+        """Explicit entry to the persistent CTA-pair kernel (masr_umma_gemm_pair); umma_gemm reaches the same kernel
+        through the size-based dispatch of masr_umma_gemm_ex."""
+        epi = None
+        if rowsum is not None or mask is not None or p_drop > 0.0 or rowdot is not None:
+            dsrc, dout, dL, dH = rowdot if rowdot is not None else (None, None, 0, 0)
+            epi = _lib.GemmEpilogue(_p(rowsum), _p(mask), mask.stride(0) if mask is not None else 0, float(mask_scale),
+                                    float(p_drop), int(seed), int(site), _p(dsrc), dsrc.stride(0) if dsrc is not None else 0,
+                                    _p(dout), int(dL), int(dH))
+            epi = _lib.C.byref(epi)
+        self._call("masr_umma_gemm_pair", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), _dt(C),
+                   C.stride(0), _p(bias), M, N, K, flags, int(splitk), int(bn), epi, self.stream)
+
     def _conv_umma_ok(self, *ts):
         """implicit-GEMM tcgen05 convolution: bf16, contiguous, 16 B aligned, channels 64 / 128."""
         if self.gemm_path != "umma":

@@ -452,3 +452,83 @@ def test_umma_gemm_rowdot_epilogue(dev, Bsz, L, H, N):
         return
     ref = ((dy.float() @ w.float()) * o.float()).view(Bsz, L, H, 64).sum(-1).permute(0, 2, 1).reshape(-1)
     close(dsum, ref, torch.float32, 5e-3, "row-dot epilogue")
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 2048, 512), (4096, 512, 2048), (1000, 367, 520), (512, 2560, 4096), (300, 136, 200),
+                                   (2304, 1536, 512)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("bn", [128, 256])
+def test_umma_gemm_pair(dev, M, N, K, a_mn, b_mn, bn):
+    """Persistent CTA-pair GEMM (tcgen05.mma.cta_group::2, 256 x bn tiles, double-buffered TMEM accumulator) against an
+    fp32 matmul of the same bf16 operands: forward / dgrad / wgrad operand majors, bf16 and fp32 outputs, bias / ReLU /
+    accumulate / split-K, ragged M / N / K (TMA zero fill, partial tiles), several tiles per pair (M = 4096: 128 items)."""
+    from metaasr_crossaccent_b200.ops import CudaBackend, GEMM_ACCUM, GEMM_RELU, GEMM_SPLITK
+    cb = CudaBackend(dev, torch.bfloat16, gemm="umma")
+    Mp, Np, Kp = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
+    bf = torch.bfloat16
+    A = rnd((Kp, Mp) if a_mn else (Mp, Kp), dev, bf, 1)
+    B = rnd((Kp, Np) if b_mn else (Np, Kp), dev, bf, 2, 0.1)
+    Af = (A[:K, :M].t() if a_mn else A[:M, :K]).float()
+    Bf = (B[:K, :N].t() if b_mn else B[:N, :K]).float()
+    bias = rnd((N,), dev, torch.float32, 3)
+    ref = Af @ Bf.t()
+    Av = A[:K] if a_mn else A[:M]
+    Bv = B[:K] if b_mn else B[:N]
+    C = torch.full((M, Np), 7.0, device=dev)
+    cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, C[:, :N], bias, M, N, K, GEMM_RELU, bn=bn)
+    close(C[:, :N], torch.relu(ref + bias), torch.float32, 2e-3, "pair f32 relu")
+    assert float((C[:, N:] - 7.0).abs().max() if Np > N else 0.0) == 0.0
+    C0 = rnd((M, Np), dev, bf, 4)
+    C1 = C0.clone()
+    cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, C1[:, :N], None, M, N, K, GEMM_ACCUM, bn=bn)
+    close(C1[:, :N], ref + C0[:, :N].float(), bf, what="pair bf16 accum")
+    Cb = torch.empty(M, Np, device=dev, dtype=bf)
+    cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, Cb[:, :N], bias, M, N, K, 0, bn=bn)
+    close(Cb[:, :N], ref + bias, bf, what="pair bf16 store")
+    for sk in (0, 3):
+        C2 = torch.zeros(M, Np, device=dev)
+        cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, C2[:, :N], None, M, N, K, GEMM_SPLITK, splitk=sk, bn=bn)
+        close(C2[:, :N], ref, torch.float32, 2e-3, f"pair split-K {sk}")
+    # repeated launches reuse nothing stale (barrier phases, TMEM stages): same result twice in a row
+    C3 = torch.empty(M, Np, device=dev, dtype=bf)
+    cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, C3[:, :N], bias, M, N, K, 0, bn=bn)
+    assert torch.equal(C3[:, :N], Cb[:, :N])
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 2048, 512), (1056, 2048, 512)])
+def test_umma_gemm_pair_fused_epilogues(dev, M, N, K):
+    """The fused extras on the pair kernel: ReLU + dropout forward (same mask as masr_dropout), ReLU/dropout backward
+    mask in a dgrad, tensor-core row sums (bias gradient) of a split-K wgrad, per-head row dots of an out-projection dgrad."""
+    from metaasr_crossaccent_b200.ops import CudaBackend, GEMM_ACCUM, GEMM_RELU, GEMM_SPLITK
+    cb = CudaBackend(dev, torch.bfloat16, gemm="umma")
+    bf = torch.bfloat16
+    x, w, bias = rnd((M, K), dev, bf, 1), rnd((N, K), dev, bf, 2, 0.1), rnd((N,), dev, torch.float32, 3)
+    y1, y2 = torch.empty(M, N, device=dev, dtype=bf), torch.empty(M, N, device=dev, dtype=bf)
+    cb.umma_gemm_pair(x, 0, w, 0, y1, bias, M, N, K, GEMM_RELU, p_drop=0.1, seed=77, site=5)
+    cb.umma_gemm_pair(x, 0, w, 0, y2, bias, M, N, K, GEMM_RELU)
+    cb.dropout(y2, 0.1, 77, 5)
+    assert torch.equal(y1 == 0, y2 == 0)
+    close(y1, y2, bf, what="pair fused relu+dropout forward")
+    dy = rnd((M, K), dev, bf, 4)
+    w2 = rnd((K, N), dev, bf, 5, 0.1)
+    g1 = torch.full((M, N), 3.0, device=dev, dtype=bf)
+    cb.umma_gemm_pair(dy, 0, w2, 1, g1, None, M, N, K, 0, mask=y1, mask_scale=1.0 / 0.9)
+    close(g1, (dy.float() @ w2.float()) * (y1.float() > 0) / 0.9, bf, what="pair fused relu/dropout backward")
+    dyo = rnd((M, N), dev, bf, 6)
+    for sk in (1, 0):
+        dw, db = torch.zeros(N, K, device=dev), rnd((N,), dev, torch.float32, 7)
+        db0 = db.clone()
+        cb.umma_gemm_pair(dyo, 1, x, 1, dw, None, N, K, M, GEMM_SPLITK if sk != 1 else GEMM_ACCUM, splitk=sk, rowsum=db)
+        close(dw, dyo.float().t() @ x.float(), torch.float32, 2e-3, "pair wgrad")
+        close(db - db0, dyo.float().sum(0), torch.float32, 2e-3, "pair fused bias gradient")
+    # row dots: out-projection dgrad of an attention block, 8 heads of 64
+    H, L = 8, 33 if M % 33 == 0 else 128
+    o = rnd((M, 512), dev, bf, 8)
+    wo = rnd((N, 512), dev, bf, 9, 0.1)
+    dx = torch.empty(M, 512, device=dev, dtype=bf)
+    dsum = torch.full((M // L * H * L,), 9.0, device=dev)
+    cb.umma_gemm_pair(dyo, 0, wo, 1, dx, None, M, 512, N, 0, rowdot=(o, dsum, L, H))
+    refdx = dyo.float() @ wo.float()
+    close(dx, refdx, bf, what="pair dgrad with row dots")
+    ref = (refdx * o.float()).view(M // L, L, H, 64).sum(-1).permute(0, 2, 1).reshape(-1)
+    close(dsum, ref, torch.float32, 5e-3, "pair row-dot epilogue")
