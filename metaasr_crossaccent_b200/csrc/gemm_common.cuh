@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "epilogue.cuh"
+#include "epilogue_tma.cuh"
 
 namespace masr {
 
@@ -62,6 +63,56 @@ __device__ __forceinline__ void gemm_epilogue_piece(const UmmaGemmParams& p, uin
   }
 }
 
+// Epilogue flavours (kernel template parameter: each instantiation carries only its own code -- the epilogue of the
+// K = 512 problems is instruction-cache sensitive)
+enum GemmEpi {
+  GEPI_LEGACY = 0,      // epilogue.cuh: any alignment / dtype / mode (staged, per-thread global stores)
+  GEPI_TMA_BF16 = 1,    // bf16 C through bulk tensor stores; bias / ReLU only
+  GEPI_TMA_BF16_X = 2,  // + dropout / backward mask / row dots / += old C
+  GEPI_TMA_F32 = 3      // fp32 C: bulk store, or bulk reduce-add for split-K (bias on the first slice)
+};
+
+// One warp's 32 rows x `width` columns of a tile through the TMA epilogue.  m_warp0: global row of the warp's lane 0.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_tma_piece(const UmmaGemmParams& p, const CUtensorMap* map_c, uint32_t tmem_acc, int q,
+                                                        int lane, int m_warp0, int n0, int width, unsigned char* wstage,
+                                                        const float* sbias, bool use_bias, int& boxsel) {
+  const int ncols = min(width, p.N - n0);
+  if (ncols <= 0) return;
+  const int m = m_warp0 + lane;
+  EptOpts o;
+  o.sbias = use_bias ? sbias : nullptr;
+  o.relu = p.flags & MASR_GEMM_RELU;
+  if constexpr (EPI == GEPI_TMA_F32) {
+    if (p.flags & (MASR_GEMM_SPLITK | MASR_GEMM_ACCUM)) epilogue_tma_f32<true>(map_c, tmem_acc, q, lane, m_warp0, n0, width / 32, ncols, wstage, boxsel, o);
+    else epilogue_tma_f32<false>(map_c, tmem_acc, q, lane, m_warp0, n0, width / 32, ncols, wstage, boxsel, o);
+  } else {
+    const bool row_valid = m < p.M;
+    if constexpr (EPI == GEPI_TMA_BF16_X) {
+      if (p.p_drop > 0.f) {
+        o.p_drop = p.p_drop; o.inv_keep = p.inv_keep; o.site = p.site;
+        o.seed = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
+        o.drop_row_base = int64_t(m) * p.N + n0;
+      }
+      if (p.dot_src != nullptr && row_valid) {
+        o.dot_row = p.dot_src + int64_t(m) * p.lddot + n0;
+        o.dot_out = p.dot_out + (int64_t(m / p.dot_L) * p.dot_H + (n0 >> 6)) * p.dot_L + (m % p.dot_L);
+        o.dot_stride = p.dot_L;
+      }
+      o.mask_scale = p.mask_scale;
+      if (p.mask != nullptr && row_valid) o.mask_row = p.mask + int64_t(m) * p.ldmask + n0;
+      if ((p.flags & MASR_GEMM_ACCUM) && row_valid) o.old_row = static_cast<const __nv_bfloat16*>(p.C) + int64_t(m) * p.ldc + n0;
+    }
+    epilogue_tma_bf16<EPI == GEPI_TMA_BF16_X>(map_c, tmem_acc, q, lane, m_warp0, n0, width / 64, ncols, row_valid, wstage, boxsel, o);
+  }
+}
+
+// host: which epilogue flavour serves this problem (GEPI_LEGACY when C cannot be described by a tensor map or a side
+// input is not 16-byte addressable)
+int gemm_pick_epilogue(const UmmaGemmParams& p);
+// host: tensor map of C for the TMA epilogues: box = 32 rows x 128 bytes, 128B swizzle
+int gemm_c_map(CUtensorMap* out, const UmmaGemmParams& p);
+
 // host: operand tensor map.  K-major -> dims {K, rows}, box {64, tile_rows};  MN-major -> dims {rows(MN), K}, box {64, 64}
 int gemm_operand_map(CUtensorMap* out, const void* base, int64_t ld_elems, int rows_mn, int K, bool mn_major, int tile_rows);
 
@@ -69,7 +120,7 @@ int gemm_operand_map(CUtensorMap* out, const void* base, int64_t ld_elems, int r
 int launch_umma_pair(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, UmmaGemmParams p,
                      int splitk, int force_bn, cudaStream_t st);
 // host: true when the pair kernel is the better choice for this problem (large M, enough tiles)
-bool umma_pair_preferred(int M, int N, int K);
+bool umma_pair_preferred(int M, int N, int K, int flags);
 void set_pair_mode(int mode);
 
 }  // namespace masr

@@ -67,8 +67,11 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// Remote arrive WITHOUT a memory fence: what is handed over is a TMEM accumulator stage, ordered by the tcgen05 fences.
+// (.release.cluster compiles to MEMBAR.ALL.CTA + ERRBAR, which waits for all of the warp's outstanding global stores:
+// a third of the epilogue warps' time in the first version of this kernel.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // barrier with remote arrivals
   asm volatile(
@@ -108,10 +111,10 @@ struct PairSmem {
   static_assert(EpiLayout<128, float>::BYTES % 1024 == 0 && EpiLayout<128, __nv_bfloat16>::BYTES % 1024 == 0, "ones tile alignment");
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UP_THREADS, 1)
-umma_pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaGemmParams p,
-                      PairSched sch) {
+umma_pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_c, UmmaGemmParams p, PairSched sch) {
   using namespace umma;
   using SM = PairSmem<BN>;
   constexpr uint32_t A_BYTES = SM::A_BYTES, B_BYTES = SM::B_BYTES, STAGE_BYTES = SM::STAGE_BYTES;
@@ -138,6 +141,7 @@ umma_pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
+    if (EPI != GEPI_LEGACY) prefetch_tmap(&map_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
     fence_barrier_init();
@@ -251,6 +255,7 @@ umma_pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const bool splitk = p.flags & MASR_GEMM_SPLITK;
     const uint32_t te_leader = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     int as = 0; uint32_t aph = 0;
+    int boxsel = 0;
     for (int w = pair; w < sch.total; w += npairs) {
       int m0, n0, kb_begin, num_kb;
       decode(w, m0, n0, kb_begin, num_kb);
@@ -264,9 +269,14 @@ umma_pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       tc_fence_after();
       const uint32_t acc_addr = tmem_base + uint32_t(as * UP_ACC_STRIDE);
       const int m = m0 + int(rank) * 128 + q * 32 + lane;
+      if constexpr (EPI == GEPI_LEGACY) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 128; ++c)
-        gemm_epilogue_piece<128>(p, acc_addr + uint32_t(c * 128), q, lane, m, n0 + c * 128, staging, sbias + c * 128, use_bias);
+        for (int c = 0; c < BN / 128; ++c)
+          gemm_epilogue_piece<128>(p, acc_addr + uint32_t(c * 128), q, lane, m, n0 + c * 128, staging, sbias + c * 128, use_bias);
+      } else {
+        gemm_epilogue_tma_piece<EPI>(p, &map_c, acc_addr, q, lane, m0 + int(rank) * 128 + q * 32, n0, BN,
+                                     staging + q * EPT_WARP_BYTES, sbias, use_bias, boxsel);
+      }
       if (want_rowsum && n0 == 0) {                            // column 0 of the ones-accumulator = sum_k A(m, k)
         float v[32];
         tmem_ld_32x32(acc_addr + BN + (uint32_t(q * 32) << 16), v);
@@ -279,6 +289,7 @@ umma_pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       if (lane == 0) mbar_arrive_cluster(te_leader + uint32_t(as * 8));
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if constexpr (EPI != GEPI_LEGACY) epilogue_tma_drain(lane);      // bulk stores have left shared memory and landed
   }
   // teardown: nobody leaves (or frees TMEM) while the peer may still read this CTA's shared memory / signal its barriers
   tc_fence_before();
@@ -287,12 +298,13 @@ umma_pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmParams p, PairSched sch, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, UmmaGemmParams p, PairSched sch,
+                       cudaStream_t st) {
   using SM = PairSmem<BN>;
-  auto kern = umma_pair_gemm_kernel<BN, A_MN, B_MN>;
-  const bool f32 = p.c_is_f32 != 0;
-  int stages = int((226 * 1024 - SM::staging(f32) - SM::TAIL - 1024) / SM::STAGE_BYTES);
+  auto kern = umma_pair_gemm_kernel<BN, A_MN, B_MN, EPI>;
+  const uint32_t staging = EPI == GEPI_LEGACY ? SM::staging(p.c_is_f32 != 0) : uint32_t(EPT_CTA_BYTES);
+  int stages = int((226 * 1024 - staging - SM::TAIL - 1024) / SM::STAGE_BYTES);
   stages = std::max(2, std::min(stages, UP_MAX_STAGES));
   static bool attr_set = false;
   if (!attr_set) {
@@ -300,29 +312,54 @@ static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmPar
     attr_set = true;
   }
   p.stages = stages;
-  sch.staging_bytes = int(SM::staging(f32));
+  sch.staging_bytes = int(staging);
   const int pairs = std::max(1, std::min(sch.total, sm_count() / 2));
-  MASR_CHECK_CUDA(launch_pdl(kern, dim3(unsigned(2 * pairs)), dim3(UP_THREADS), SM::bytes(stages, f32), st, ma, mb, p, sch));
+  const size_t smem = size_t(stages) * SM::STAGE_BYTES + staging + SM::TAIL + 1024;
+  MASR_CHECK_CUDA(launch_pdl(kern, dim3(unsigned(2 * pairs)), dim3(UP_THREADS), smem, st, ma, mb, mc, p, sch));
   return MASR_OK;
 }
 
-// Work items per pair-round and a relative cost per item decide between 256 x 128 and 256 x 256 tiles.
+template <int BN>
+static int launch_pair_bn(int a_mn, int b_mn, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                          const UmmaGemmParams& p, const PairSched& sch, cudaStream_t st) {
+  // forward (K-major x K-major) and dgrad (K-major x MN-major) produce bf16 activations / gradients; wgrad (MN x MN)
+  // produces fp32 split-K sums
+  if (!a_mn && !b_mn) {
+    if (epi == GEPI_TMA_BF16) return launch_pair<BN, false, false, GEPI_TMA_BF16>(ma, mb, mc, p, sch, st);
+    if (epi == GEPI_TMA_BF16_X) return launch_pair<BN, false, false, GEPI_TMA_BF16_X>(ma, mb, mc, p, sch, st);
+    if (epi == GEPI_TMA_F32) return launch_pair<BN, false, false, GEPI_TMA_F32>(ma, mb, mc, p, sch, st);
+    return launch_pair<BN, false, false, GEPI_LEGACY>(ma, mb, mc, p, sch, st);
+  }
+  if (!a_mn && b_mn) {
+    if (epi == GEPI_TMA_BF16) return launch_pair<BN, false, true, GEPI_TMA_BF16>(ma, mb, mc, p, sch, st);
+    if (epi == GEPI_TMA_BF16_X) return launch_pair<BN, false, true, GEPI_TMA_BF16_X>(ma, mb, mc, p, sch, st);
+    return launch_pair<BN, false, true, GEPI_LEGACY>(ma, mb, mc, p, sch, st);
+  }
+  if (a_mn && b_mn) {
+    if (epi == GEPI_TMA_F32) return launch_pair<BN, true, true, GEPI_TMA_F32>(ma, mb, mc, p, sch, st);
+    return launch_pair<BN, true, true, GEPI_LEGACY>(ma, mb, mc, p, sch, st);
+  }
+  return launch_pair<BN, true, false, GEPI_LEGACY>(ma, mb, mc, p, sch, st);
+}
+
+// 256 x 256 tiles halve the operand bytes per flop but leave pairs idle unless the problem has many of them; measured
+// in a replayed graph (profiles/r2_gemm_probe.md): N = 2048 9.4 vs 9.8 us, N = 1536 8.8 vs 8.5 us, N <= 1024 worse.
 static int pair_pick_bn(int M, int N, int nsplit) {
-  const int pairs = std::max(1, sm_count() / 2);
-  const int64_t tm = ceil_div64(M, 256);
-  auto rounds = [&](int bn) { return ceil_div64(tm * ceil_div64(N, bn) * nsplit, pairs); };
-  if (N <= 128) return 128;
-  // a 256-wide item costs ~1.85x a 128-wide one (half the operand bytes per flop, one epilogue set-up instead of two)
-  return double(rounds(256)) * 1.85 <= double(rounds(128)) ? 256 : 128;
+  (void)M; (void)nsplit;
+  return (N >= 2048 && N % 256 == 0) ? 256 : 128;
 }
 
 static int g_pair_mode = 1;            // 0 = never, 1 = by problem size (default)
-void set_pair_mode(int mode) { g_pair_mode = mode; }
+int g_force_legacy_epilogue = 0;       // mode bit 2: staged epilogue everywhere (A/B measurements)
+void set_pair_mode(int mode) { g_pair_mode = mode & 1; g_force_legacy_epilogue = (mode >> 1) & 1; }
 
-bool umma_pair_preferred(int M, int N, int K) {
+bool umma_pair_preferred(int M, int N, int K, int flags) {
   if (g_pair_mode == 0) return false;
-  // decoder-sized problems (M = B (L+1) ~ 1 k rows, a handful of tiles) stay on the one-CTA-per-tile kernel
-  return M >= 512 && N >= 128 && K >= 128 && int64_t(M) * N >= int64_t(1024) * 512;
+  // measured crossover (replayed graph, B200): wide outputs of the M = B T/4 = 4096-row problems and the long-reduction
+  // weight gradients win 20-35 %; N <= 1024 forward / dgrad problems and everything decoder-sized (M = B (L+1) ~ 1 k rows)
+  // are as fast or faster on the one-CTA-per-tile kernel
+  if (flags & MASR_GEMM_SPLITK) return K >= 2048 && int64_t(M) * N >= int64_t(512) * 512 && M >= 256 && N >= 256;
+  return M >= 2048 && N >= 1536 && K >= 256;
 }
 
 int launch_umma_pair(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, UmmaGemmParams p,
@@ -355,17 +392,14 @@ int launch_umma_pair(const void* A, int64_t lda, int a_mn, const void* B, int64_
   if (rc != MASR_OK) return rc;
   rc = gemm_operand_map(&mb, B, ldb, p.N, p.K, b_mn != 0, BN / 2);
   if (rc != MASR_OK) return rc;
-  const int key = (BN == 128 ? 0 : 4) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
-  switch (key) {
-    case 0: return launch_pair<128, false, false>(ma, mb, p, sch, st);
-    case 1: return launch_pair<128, false, true>(ma, mb, p, sch, st);
-    case 2: return launch_pair<128, true, false>(ma, mb, p, sch, st);
-    case 3: return launch_pair<128, true, true>(ma, mb, p, sch, st);
-    case 4: return launch_pair<256, false, false>(ma, mb, p, sch, st);
-    case 5: return launch_pair<256, false, true>(ma, mb, p, sch, st);
-    case 6: return launch_pair<256, true, false>(ma, mb, p, sch, st);
-    default: return launch_pair<256, true, true>(ma, mb, p, sch, st);
+  CUtensorMap mc = ma;
+  int epi = g_force_legacy_epilogue ? GEPI_LEGACY : gemm_pick_epilogue(p);
+  if (epi != GEPI_LEGACY) {
+    rc = gemm_c_map(&mc, p);
+    if (rc != MASR_OK) return rc;
   }
+  return BN == 128 ? launch_pair_bn<128>(a_mn, b_mn, epi, ma, mb, mc, p, sch, st)
+                   : launch_pair_bn<256>(a_mn, b_mn, epi, ma, mb, mc, p, sch, st);
 }
 
 }  // namespace masr

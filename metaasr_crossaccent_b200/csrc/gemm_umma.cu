@@ -32,14 +32,22 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, bool swizzle128) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle128);
+}
+
+static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
   PFN_encodeTiled enc = get_encode();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MASR_E_CUDA; }
   cuuint64_t gdim[5]; cuuint64_t gstr[5]; cuuint32_t bx[5]; cuuint32_t estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];       // stride of dim i+1
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bx, estr,
+  CUresult r = enc(out, dt, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bx, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -56,9 +64,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // ------------------------------------------------------------------ kernel
 constexpr int UG_THREADS = 192;
 
-template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
+template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(UG_THREADS, 2)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, UmmaGemmParams p) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, UmmaGemmParams p) {
   using namespace umma;
   constexpr uint32_t A_BYTES = UG_BM * UG_BK * 2;          // 16 KB
   constexpr uint32_t B_BYTES = BN * UG_BK * 2;
@@ -74,6 +83,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* sbias = reinterpret_cast<float*>(tmem_full_bar + 2);          // BN floats, 16 B aligned
   static_assert(MIN_STAGES * STAGE_BYTES >= EpiLayout<BN, float>::BYTES, "staging tile must fit in the pipeline stages");
+  static_assert(MIN_STAGES * STAGE_BYTES >= EPT_CTA_BYTES, "TMA epilogue boxes must fit in the pipeline stages");
   pdl_launch_dependents();          // the next kernel's prologue may overlap this kernel (see common.cuh)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,6 +95,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
+    if (EPI != GEPI_LEGACY) prefetch_tmap(&map_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -184,7 +195,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int m = m0 + q * 32 + lane;
-    gemm_epilogue_piece<BN>(p, tmem_base, q, lane, m, n0, smem, sbias, use_bias);
+    if constexpr (EPI == GEPI_LEGACY) {
+      gemm_epilogue_piece<BN>(p, tmem_base, q, lane, m, n0, smem, sbias, use_bias);
+    } else {
+      // the accumulator is complete, i.e. every MMA has read its operands: the pipeline stages are free for the boxes
+      int boxsel = 0;
+      gemm_epilogue_tma_piece<EPI>(p, &map_c, tmem_base, q, lane, m0 + q * 32, n0, BN, smem + q * EPT_WARP_BYTES, sbias,
+                                   use_bias, boxsel);
+      epilogue_tma_drain(lane);
+    }
     if (rowsum) {                   // column 0 of the ones-accumulator = sum_k A(m, k)
       float v[32];
       tmem_ld_32x32(tmem_base + BN + (uint32_t(q * 32) << 16), v);
@@ -197,11 +216,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-template <int BN, int MIN_STAGES, bool A_MN, bool B_MN>
-static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmParams p, cudaStream_t st) {
+template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
+static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, UmmaGemmParams p, cudaStream_t st) {
   constexpr size_t STAGE = size_t(UG_BM * UG_BK * 2 + BN * UG_BK * 2);
   constexpr int MAX_STAGES = int((198 * 1024) / STAGE);
-  auto kern = umma_gemm_kernel<BN, MIN_STAGES, A_MN, B_MN>;
+  auto kern = umma_gemm_kernel<BN, MIN_STAGES, A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -219,8 +238,30 @@ static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, UmmaGemmPar
   stages = std::max(MIN_STAGES, std::min(stages, std::min(p.kb_per_split, total_kb)));
   p.stages = stages;
   const size_t smem = size_t(stages) * STAGE + 2048 + 1024 + 512 + BN * 4;
-  MASR_CHECK_CUDA(launch_pdl(kern, grid, dim3(UG_THREADS), smem, st, ma, mb, p));
+  MASR_CHECK_CUDA(launch_pdl(kern, grid, dim3(UG_THREADS), smem, st, ma, mb, mc, p));
   return MASR_OK;
+}
+
+// forward (K-major x K-major) and dgrad (K-major x MN-major): bf16 or fp32 C; wgrad (MN x MN): fp32 split-K sums
+template <int BN, int MIN_STAGES>
+static int launch_umma_bn(int a_mn, int b_mn, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                          const UmmaGemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) {
+    if (epi == GEPI_TMA_BF16) return launch_umma<BN, MIN_STAGES, false, false, GEPI_TMA_BF16>(ma, mb, mc, p, st);
+    if (epi == GEPI_TMA_BF16_X) return launch_umma<BN, MIN_STAGES, false, false, GEPI_TMA_BF16_X>(ma, mb, mc, p, st);
+    if (epi == GEPI_TMA_F32) return launch_umma<BN, MIN_STAGES, false, false, GEPI_TMA_F32>(ma, mb, mc, p, st);
+    return launch_umma<BN, MIN_STAGES, false, false, GEPI_LEGACY>(ma, mb, mc, p, st);
+  }
+  if (!a_mn && b_mn) {
+    if (epi == GEPI_TMA_BF16) return launch_umma<BN, MIN_STAGES, false, true, GEPI_TMA_BF16>(ma, mb, mc, p, st);
+    if (epi == GEPI_TMA_BF16_X) return launch_umma<BN, MIN_STAGES, false, true, GEPI_TMA_BF16_X>(ma, mb, mc, p, st);
+    return launch_umma<BN, MIN_STAGES, false, true, GEPI_LEGACY>(ma, mb, mc, p, st);
+  }
+  if (a_mn && b_mn) {
+    if (epi == GEPI_TMA_F32) return launch_umma<BN, MIN_STAGES, true, true, GEPI_TMA_F32>(ma, mb, mc, p, st);
+    return launch_umma<BN, MIN_STAGES, true, true, GEPI_LEGACY>(ma, mb, mc, p, st);
+  }
+  return launch_umma<BN, MIN_STAGES, true, false, GEPI_LEGACY>(ma, mb, mc, p, st);
 }
 
 // operand map: K-major  -> dims {K, rows}, box {64, tile_rows};  MN-major -> dims {rows(MN), K}, box {64, 64}
@@ -233,6 +274,34 @@ int gemm_operand_map(CUtensorMap* out, const void* base, int64_t ld_elems, int r
   strides[0] = uint64_t(ld_elems) * 2;
   return make_tmap_bf16(out, base, 2, dims, strides, box, true);
 }
+
+int gemm_pick_epilogue(const UmmaGemmParams& p) {
+  const size_t es = p.c_is_f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(p.C) & 15) != 0 || (size_t(p.ldc) * es) % 16 != 0) return GEPI_LEGACY;
+  // a bulk tensor store clips rows exactly but writes whole 16-byte units along the row (measured: the element after a
+  // row end that is not 16-byte aligned is overwritten with zero): such outputs keep the staged epilogue
+  if ((size_t(p.N) * es) % 16 != 0) return GEPI_LEGACY;
+  const bool extras = p.p_drop > 0.f || p.mask != nullptr || p.dot_src != nullptr;
+  if (p.c_is_f32) return extras ? GEPI_LEGACY : GEPI_TMA_F32;          // store, or reduce-add for split-K / accumulate
+  const bool accum = p.flags & MASR_GEMM_ACCUM;
+  if (!extras && !accum) return GEPI_TMA_BF16;
+  if (p.N % 8 != 0) return GEPI_LEGACY;                                // side inputs are read as 8-element vectors
+  if (p.mask != nullptr && ((reinterpret_cast<uintptr_t>(p.mask) & 15) != 0 || p.ldmask % 8 != 0)) return GEPI_LEGACY;
+  if (p.dot_src != nullptr && ((reinterpret_cast<uintptr_t>(p.dot_src) & 15) != 0 || p.lddot % 8 != 0)) return GEPI_LEGACY;
+  if (accum && p.ldc % 8 != 0) return GEPI_LEGACY;
+  return GEPI_TMA_BF16_X;
+}
+
+int gemm_c_map(CUtensorMap* out, const UmmaGemmParams& p) {
+  const uint64_t es = p.c_is_f32 ? 4 : 2;
+  uint64_t dims[2] = {uint64_t(p.N), uint64_t(p.M)};
+  uint64_t strides[1] = {uint64_t(p.ldc) * es};
+  uint32_t box[2] = {uint32_t(128 / es), 32};
+  return make_tmap_typed(out, p.c_is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.C, 2, dims,
+                         strides, box, true);
+}
+
+extern int g_force_legacy_epilogue;
 
 }  // namespace masr
 
@@ -281,19 +350,16 @@ extern "C" int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const voi
   }
   cudaStream_t st = as_stream(stream);
   // large problems: persistent CTA-pair kernel (256-row tiles, cta_group::2, double-buffered TMEM), gemm_pair_umma.cu
-  if (umma_pair_preferred(M, N, K))
+  if (umma_pair_preferred(M, N, K, flags))
     return launch_umma_pair(A, lda, a_mn, B, ldb, b_mn, p, (flags & MASR_GEMM_SPLITK) ? -1 : 1, 0, st);
-  const int key = (BN == 64 ? 0 : 4) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
-  switch (key) {
-    case 0: return launch_umma<64, 4, false, false>(ma, mb, p, st);
-    case 1: return launch_umma<64, 4, false, true>(ma, mb, p, st);
-    case 2: return launch_umma<64, 4, true, false>(ma, mb, p, st);
-    case 3: return launch_umma<64, 4, true, true>(ma, mb, p, st);
-    case 4: return launch_umma<128, 3, false, false>(ma, mb, p, st);
-    case 5: return launch_umma<128, 3, false, true>(ma, mb, p, st);
-    case 6: return launch_umma<128, 3, true, false>(ma, mb, p, st);
-    default: return launch_umma<128, 3, true, true>(ma, mb, p, st);
+  CUtensorMap mc = ma;
+  const int epi_kind = g_force_legacy_epilogue ? GEPI_LEGACY : gemm_pick_epilogue(p);
+  if (epi_kind != GEPI_LEGACY) {
+    rc = gemm_c_map(&mc, p);
+    if (rc != MASR_OK) return rc;
   }
+  return BN == 64 ? launch_umma_bn<64, 4>(a_mn, b_mn, epi_kind, ma, mb, mc, p, st)
+                  : launch_umma_bn<128, 3>(a_mn, b_mn, epi_kind, ma, mb, mc, p, st);
 }
 
 extern "C" int masr_umma_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,

@@ -458,12 +458,17 @@ def test_umma_gemm_rowdot_epilogue(dev, Bsz, L, H, N):
                                    (2304, 1536, 512)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("bn", [128, 256])
-def test_umma_gemm_pair(dev, M, N, K, a_mn, b_mn, bn):
+@pytest.mark.parametrize("legacy_epilogue", [False, True])
+def test_umma_gemm_pair(dev, M, N, K, a_mn, b_mn, bn, legacy_epilogue, request):
     """Persistent CTA-pair GEMM (tcgen05.mma.cta_group::2, 256 x bn tiles, double-buffered TMEM accumulator) against an
     fp32 matmul of the same bf16 operands: forward / dgrad / wgrad operand majors, bf16 and fp32 outputs, bias / ReLU /
     accumulate / split-K, ragged M / N / K (TMA zero fill, partial tiles), several tiles per pair (M = 4096: 128 items)."""
     from metaasr_crossaccent_b200.ops import CudaBackend, GEMM_ACCUM, GEMM_RELU, GEMM_SPLITK
     cb = CudaBackend(dev, torch.bfloat16, gemm="umma")
+    # both epilogues: bulk tensor stores / reduce-adds (epilogue_tma.cuh, default) and the staged one (epilogue.cuh, which
+    # also serves outputs a tensor map cannot describe)
+    cb.lib.masr_gemm_set_pair_mode(3 if legacy_epilogue else 1)
+    request.addfinalizer(lambda: cb.lib.masr_gemm_set_pair_mode(1))
     Mp, Np, Kp = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
     bf = torch.bfloat16
     A = rnd((Kp, Mp) if a_mn else (Mp, Kp), dev, bf, 1)
@@ -489,6 +494,10 @@ def test_umma_gemm_pair(dev, M, N, K, a_mn, b_mn, bn):
         C2 = torch.zeros(M, Np, device=dev)
         cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, C2[:, :N], None, M, N, K, GEMM_SPLITK, splitk=sk, bn=bn)
         close(C2[:, :N], ref, torch.float32, 2e-3, f"pair split-K {sk}")
+    C4 = rnd((M, Np), dev, torch.float32, 5)
+    C40 = C4.clone()
+    cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, C4[:, :N], bias, M, N, K, GEMM_ACCUM, bn=bn)
+    close(C4[:, :N], ref + bias + C40[:, :N], torch.float32, 2e-3, "pair f32 accumulate")
     # repeated launches reuse nothing stale (barrier phases, TMEM stages): same result twice in a row
     C3 = torch.empty(M, Np, device=dev, dtype=bf)
     cb.umma_gemm_pair(Av, a_mn, Bv, b_mn, C3[:, :N], bias, M, N, K, 0, bn=bn)
