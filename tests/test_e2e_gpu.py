@@ -190,14 +190,20 @@ def test_greedy_decode_ids_vs_reference_golden(dev):
 
 
 def test_multi_step_vs_reference_golden(dev):
+    """MultiASRInterface loop body (multi_interface.py:100-114) on the CUDA path (fp32): run_batch -> clip -> noam-Adam,
+    three steps; losses, lr schedule and the POST-STEP parameters against the live-reference golden."""
     z = np.load(GOLD / "multi_tiny.npz")
     s = make_solver("multi", meta=False)
     load_tiny(s)
-    for step in range(2):
+    for step in range(int(z["n_steps"])):
         info = s.multi_step((0, load_batch(z, f"s{step}.")))
         ref = float(z[f"s{step}.loss"])
-        assert abs(info["loss"] - ref) <= (1e-5 if step == 0 else 5e-3) * abs(ref)
-    lr = port.noam_lr(1, 0.02, 32, 4)
+        assert abs(info["loss"] - ref) <= (1e-5 if step == 0 else 5e-3) * abs(ref), (step, info["loss"], ref)
+        lr = port.noam_lr(step + 1, float(z["k"]), 32, int(z["warmup_steps"]))
+        assert abs(s.asr_opt.lr - lr) < 1e-15
+        for n, t in s.asr_model.state_dict().items():
+            if n not in ("pos_encoder.pe", "pre_embed.weight"):
+                check_adam_weights(z, f"s{step}.w.", [f"s{i}.g." for i in range(step + 1)], n, t, lr)
 
 
 def synth_batch(g, B, T, L):
@@ -265,3 +271,61 @@ def test_batch_greedy_decode_writes_reference_best_hyp(dev, tmp_path):
     assert len(lines) == len(ys)
     for line, y, hyp in zip(lines, ys, ref_ids):
         assert line == " ".join(str(i) for i in y.tolist()) + "\t" + " ".join(str(i) for i in trim(hyp, "transformer", s.asr_model.eos_id))
+
+
+# ---------------------------------------------------------------------------- eval path
+def _units():
+    return ['<s>'] + [('▁' if i % 3 == 0 else '') + chr(0x61 + i % 26) + str(i % 7) for i in range(365)] + ['</s>']
+
+
+def test_eval_run_batch_vs_reference_golden(dev):
+    """run_batch(train=False) on the CUDA path (transformer_torch_trainer.py:94-99): {'cer','wer','loss','acc'} with the
+    rates scored from the CE kernel's argmax ids equal the Metric applied to the LIVE reference's logits of the batch."""
+    from metaasr_crossaccent_b200.metric import Metric
+    z = np.load(GOLD / "run_batch_tiny.npz")
+    s = make_solver("fomaml", dtype="fp32")
+    load_tiny(s)
+    units = _units()
+    s.metric_observer = Metric(None, units, 0, len(units) - 1)
+    x, ilens, ys, olens = load_batch(z, "in.")
+    g_before = s.asr_model.engine.grads.clone()
+    info = s.run_batch(0, x, ilens, ys, olens, train=False)
+    assert set(info) == {"cer", "wer", "loss", "acc"}
+    assert abs(info["loss"] - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))       # dropout 0: train == eval
+    assert info["acc"] == float(z["acc"])
+    ref = s.metric_observer.batch_cal_er(torch.from_numpy(z["logit"]), torch.from_numpy(z["gold"]), ['att'], ['cer', 'wer'])
+    assert info["cer"] == ref["att_cer"] and info["wer"] == ref["att_wer"] and info["cer"] > 0
+    assert np.array_equal(olens.numpy(), z["olens_after"])
+    assert torch.equal(s.asr_model.engine.grads, g_before)                            # no backward in eval
+
+
+@pytest.mark.parametrize("dtype,gemm", [("fp32", "simt"), ("bf16", "umma")])
+def test_eval_run_batch_hkust_vs_oracle_port(dev, dtype, gemm):
+    """Eval batch at the hkust network size, ragged dev-loader-like batch, dropout 0.1 configured (must be OFF in eval):
+    loss / acc / CER / WER of the CUDA path against the oracle port's eval-mode logits."""
+    from metaasr_crossaccent_b200.metric import Metric
+    from tests.helpers import hkust_profile_batch, clone_batch
+    s = make_solver("fomaml", dtype=dtype, tiny=False, gemm=gemm)
+    s.asr_model.engine.cfg.dropout = s.asr_model.engine.cfg.pos_dropout = 0.1
+    cfg = port.NetCfg(dropout=0.1, pos_dropout=0.1)
+    sd = port.init_state_dict(cfg, seed=7)
+    s.asr_model.load_state_dict(sd)
+    units = _units()
+    s.metric_observer = Metric(None, units, 0, len(units) - 1)
+    b = hkust_profile_batch(77, "rag", B=8, T=256, L=16)
+    x, ilens, ys, olens = clone_batch(b)
+    with torch.no_grad():
+        logit, gold = port.forward(sd, cfg, *clone_batch(b), training=False)
+        loss, n_correct, n_total = port.ls_ce(logit, gold, 0.2)
+    infos = [s.run_batch(0, *clone_batch(b), train=False) for _ in range(2)]
+    assert infos[0] == infos[1]                                                      # deterministic: no dropout in eval
+    info = infos[0]
+    tol = 1e-5 if dtype == "fp32" else 2e-2
+    assert abs(info["loss"] - float(loss)) <= tol * abs(float(loss)), (info, float(loss))
+    ref = s.metric_observer.batch_cal_er(logit, gold, ['att'], ['cer', 'wer'])
+    if dtype == "fp32":
+        assert info["acc"] == float(n_correct) / n_total
+        assert info["cer"] == ref["att_cer"] and info["wer"] == ref["att_wer"]
+    else:       # bf16 may flip an argmax whose top-2 margin is below the rounding error: rates within 2 points
+        assert abs(info["acc"] - float(n_correct) / n_total) <= 0.02
+        assert abs(info["cer"] - ref["att_cer"]) <= 2.0 and abs(info["wer"] - ref["att_wer"]) <= 2.0

@@ -213,6 +213,53 @@ def test_two_rank_meta_step_equals_sequential(tmp_path):
     assert float((w0 - s._original_flat).abs().max()) <= 2.0 * lr + 1e-12
 
 
+def _multi_worker(rank, world, port_no, out):
+    os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank),
+                       "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port_no)})
+    torch.set_num_threads(2)
+    from metaasr_crossaccent_b200 import dist as D
+    D.init_from_env("gloo")
+    z = np.load(GOLD / "multi_tiny.npz")
+    s = make_solver("multi", meta=False)
+    infos = []
+    for step in range(2):                      # rank r trains on batch s{2*step + r} of the golden file's inputs
+        infos.append(s.multi_step((0, load_batch(z, f"s{(2 * step + rank) % 3}."))))
+    torch.save({"w": s.asr_model.engine.params.clone(), "loss": [i["loss"] for i in infos],
+                "lr": s.asr_opt.lr, "step_num": s.asr_opt.step_num}, f"{out}/m{rank}.pt")
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_multi_task_gradient_dp_equals_mean_gradient_step(tmp_path):
+    """Multi-task data parallelism (loop body multi_interface.py:100-114): two ranks draw
+    different batches, one all-reduce of the flat gradient arena, then clip_grad_norm_(5) and noam-Adam on the
+    MEAN gradient.  Replicas end bit-identical and equal a single process stepping on the averaged gradient."""
+    port_no = _free_port()
+    mp.spawn(_multi_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "m0.pt"), torch.load(tmp_path / "m1.pt")
+    assert torch.equal(r0["w"], r1["w"]) and r0["lr"] == r1["lr"] and r0["step_num"] == r1["step_num"] == 2
+    z = np.load(GOLD / "multi_tiny.npz")
+    s = make_solver("multi", meta=False)
+    eng = s.asr_model.engine
+    n = eng.layout.total
+    for step in range(2):
+        losses, gsum = [], torch.zeros_like(eng.grads)
+        for r in range(2):
+            info = s.run_batch(0, *load_batch(z, f"s{(2 * step + r) % 3}."), train=True, accent_idx=0)
+            losses.append(info["loss"])
+            gsum += eng.grads
+        eng.grads.copy_(gsum / 2)
+        eng.be.mt_sumsq(eng.grads[:n], s._gnorm)
+        s.asr_opt.step(s._gnorm, I.GRAD_CLIP)
+        assert abs(losses[0] - r0["loss"][step]) <= 1e-6 * abs(losses[0])      # each rank saw its own batch
+        assert abs(losses[1] - r1["loss"][step]) <= 1e-6 * abs(losses[1])
+    assert abs(s.asr_opt.lr - r0["lr"]) < 1e-15
+    # Adam(eps 1e-9) amplifies fp32 re-ordering noise on ~0 gradients to +-lr: compare in units of lr
+    diff = (eng.params - r0["w"]).abs()
+    assert float(diff.max()) <= 2.0 * s.asr_opt.lr + 1e-12
+    assert float((diff > 3e-2 * s.asr_opt.lr).float().mean()) < 0.02
+
+
 def test_recog_greedy_ids_bit_exact_host_logic():
     """MyTransformer.recog (greedy decode on the growing prefix, encoder memory computed once) through the engine's
     schedule on the torch test double: token ids bit-exact against the live reference's golden."""
