@@ -60,6 +60,15 @@ int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_is_logprob,
                      int blank, int zero_infinity, float grad_scale,
                      float* nll, float* loss, float* grad,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with explicit element strides of the activation / gradient tensors: acts(t, b, c) = acts[t*st_t + b*st_b + c].
+ * (st_t, st_b) = (B*C, C) is nn.CTCLoss's [T, B, C]; (C, T*C) reads the batch-first [B, T, C] output of a CTC head
+ * GEMM in place (joint CTC / attention training: the `ctc_weight` extension, no transpose pass). */
+int masr_ctc_fwd_bwd_ex(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int act_is_logprob,
+                        const int64_t* targets, const int64_t* tgt_offsets,
+                        const int64_t* in_lens, const int64_t* tgt_lens, int max_tgt_len,
+                        int blank, int zero_infinity, float grad_scale,
+                        float* nll, float* loss, float* grad,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* Profiling hook: record SM-clock timestamps of CTA 0 at the phase boundaries of the following CTC launches
  * (start, setup done, emissions done, recursions done, -, end) and read them back (out6: 6 x int64). */
 int masr_ctc_debug_enable(int on);
@@ -259,6 +268,17 @@ int masr_permute_cf(const void* src, int src_dtype, void* dst, int dst_dtype, in
 int masr_ls_ce_fwd_bwd(const float* logits, const int64_t* gold, int N, int C, float eps, float inv_n,
                        const float* inv_n_dev, double* stats, int64_t* argmax, void* dlogits, int dl_dtype,
                        int64_t ld_dl, void* stream);
+
+/* CTC-weight mixing (north_star kernel 3; espnet-style joint CTC / attention objective, an EXTENSION: the reference
+ * carries only dead config for it, config/transformer/mono-test.yaml:44-50):
+ *   total = (1 - w) * attention LS-CE + w * CTC.  The gradient scales are folded into the producing kernels
+ *   (masr_ls_ce_fwd_bwd's inv_n = (1-w)/n, masr_ctc_fwd_bwd's grad_scale = w); this entry stores the CTC term next to
+ *   the CE statistics so that one device->host read returns both: stats[3] = *ctc_loss, stats[4] = w. */
+int masr_loss_mix(double* stats, const float* ctc_loss, float w, void* stream);
+/* dst[r, 0:cols] = src[r, 0:cols] (dtype conversion), dst[r, cols:ld_dst] = 0: pads the fp32 CTC gradient rows to the
+ * 16-byte row pitch the tcgen05 GEMMs need. */
+int masr_cast_pad2d(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
+                    int rows, int cols, void* stream);
 
 /* Dropout seeds: every dropout site draws from (seed + *dev_ptr, site, element index).  dev_ptr (set once per
  * process; NULL = offset 0) lives in device memory so a captured CUDA graph of the step replays with fresh

@@ -31,6 +31,10 @@ SIGNATURES = {
     "masr_init": [c_i],
     "masr_ctc_fwd_bwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p,
                          c_p, c_sz, c_p],
+    "masr_ctc_fwd_bwd_ex": [c_p, c_i, c_i, c_i, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p,
+                            c_p, c_sz, c_p],
+    "masr_loss_mix": [c_p, c_p, c_f, c_p],
+    "masr_cast_pad2d": [c_p, c_i, c_i64, c_p, c_i, c_i64, c_i, c_i, c_p],
     "masr_ctc_debug_enable": [c_i],
     "masr_ctc_debug_read": [c_p],
     "masr_gemm": [c_p, c_i, c_i64, c_i64, c_p, c_i, c_i64, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p],

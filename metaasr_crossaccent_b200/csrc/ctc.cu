@@ -42,7 +42,7 @@ struct CtcTables {
 };
 
 __global__ void __launch_bounds__(CTC_THREADS)
-ctc_fwd_bwd_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
+ctc_fwd_bwd_kernel(const float* __restrict__ acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob,
                    const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
                    const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                    int Lmax, int blank, int zero_infinity, float grad_scale,
@@ -98,7 +98,7 @@ ctc_fwd_bwd_kernel(const float* __restrict__ acts, int T, int B, int C, int is_l
 
   // ---- phase 0: normalisers + emission gather (+ zero G)
   for (int t = warp; t < Tb; t += nwarps) {
-    const float* row = acts + (int64_t(t) * B + b) * C;
+    const float* row = acts + (int64_t(t) * st_t + b * st_b);
     float z = 0.f;
     if (!is_logprob) {
       float mx = CTC_NEG_INF;
@@ -215,7 +215,7 @@ ctc_fwd_bwd_kernel(const float* __restrict__ acts, int T, int B, int C, int is_l
 
   // ---- phase 3: gradient rows
   for (int t = warp; t < T; t += nwarps) {
-    float* grow = grad + (int64_t(t) * B + b) * C;
+    float* grow = grad + (int64_t(t) * st_t + b * st_b);
     if (t >= Tb || (!feasible)) {
       // beyond the input length ATen writes zeros; an infeasible utterance under zero_infinity too
       // (without zero_infinity the loss is inf and the gradient NaN, as in ATen)
@@ -223,7 +223,7 @@ ctc_fwd_bwd_kernel(const float* __restrict__ acts, int T, int B, int C, int is_l
       for (int c = lane; c < C; c += 32) grow[c] = fill;
       continue;
     }
-    const float* row = acts + (int64_t(t) * B + b) * C;
+    const float* row = acts + (int64_t(t) * st_t + b * st_b);
     const float z = logZ[t];
     const float* Gt = tb.G + size_t(t) * L1stride;
     for (int c = lane; c < C; c += 32) {
@@ -339,7 +339,7 @@ __device__ __forceinline__ void ctc_chain(float* __restrict__ tab, const float* 
 
 template <int SPL>
 __global__ void __launch_bounds__(CTC_THREADS)
-ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
+ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob,
                       const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
                       const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
                       int Lmax, int blank, int zero_infinity, float grad_scale,
@@ -399,7 +399,7 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
       float x[CTC_F][CTC_CPL];
 #pragma unroll
       for (int f = 0; f < CTC_F; ++f) {
-        const float* row = acts + (int64_t(min(t0 + f, Tb - 1)) * B + b) * C;
+        const float* row = acts + (int64_t(min(t0 + f, Tb - 1)) * st_t + b * st_b);
 #pragma unroll
         for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; x[f][k] = c < C ? __ldg(row + c) : CTC_NEG; }
       }
@@ -423,7 +423,7 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
       for (int f = 0; f < CTC_F; ++f) {
         const int t = t0 + f;
         if (t < Tb) {
-          const float* row = acts + (int64_t(t) * B + b) * C;
+          const float* row = acts + (int64_t(t) * st_t + b * st_b);
           if (lane == 0) logZ2[t] = z2[f];
           float* Et = E2 + size_t(t) * L1stride;
           for (int j = lane; j <= L; j += 32) Et[j] = __ldg(row + (j < L ? tg[j] : blank)) * CTC_LOG2E - z2[f];
@@ -432,7 +432,7 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
     }
   } else {
     for (int t = warp; t < Tb; t += NW) {
-      const float* row = acts + (int64_t(t) * B + b) * C;
+      const float* row = acts + (int64_t(t) * st_t + b * st_b);
       float z2 = 0.f;
       if (!is_logprob) {
         float mx = CTC_NEG_INF;
@@ -506,7 +506,7 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
       for (int f = 0; f < CTC_F; ++f) {
         const int t = t0 + f;
         const bool live = feasible && t < Tb;
-        const float* row = acts + (int64_t(live ? t : 0) * B + b) * C;
+        const float* row = acts + (int64_t(live ? t : 0) * st_t + b * st_b);
 #pragma unroll
         for (int k = 0; k < CTC_CPL; ++k) { const int c = lane + 32 * k; x[f][k] = (live && c < C) ? __ldg(row + c) : 0.f; }
       }
@@ -549,7 +549,7 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
     for (int f = 0; f < CTC_F; ++f) {
       const int t = t0 + f;
       if (t >= T) continue;
-      float* grow = grad + (int64_t(t) * B + b) * C;
+      float* grow = grad + (int64_t(t) * st_t + b * st_b);
       if (t >= Tb || !feasible) {
         const float fill = (!feasible && !zero_infinity && t < Tb) ? NAN : 0.f;
         for (int c = lane; c < C; c += 32) grow[c] = fill;
@@ -567,7 +567,7 @@ ctc_fwd_bwd_v2_kernel(const float* __restrict__ acts, int T, int B, int C, int i
           }
         }
       } else {
-        const float* row = acts + (int64_t(t) * B + b) * C;
+        const float* row = acts + (int64_t(t) * st_t + b * st_b);
         for (int c = lane; c < C; c += 32) {
           const float pr = ex2f(row[c] * CTC_LOG2E - z2);
           const int u = cmap[c];
@@ -586,7 +586,7 @@ static long long* g_ctc_dbg = nullptr;
 
 // ctc3.cu: v3 kernel (single posterior table); returns CTC3_NOT_APPLICABLE when the shape does not fit shared memory
 constexpr int CTC3_NOT_APPLICABLE = 12345;
-int ctc3_try(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+int ctc3_try(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
              const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
              float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st);
 
@@ -599,12 +599,12 @@ static size_t ctc2_table_bytes(int T, int Lmax) {
 }
 
 template <int SPL>
-static int launch_ctc2(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets,
+static int launch_ctc2(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets,
                        const int64_t* tgt_offsets, const int64_t* in_lens, const int64_t* tgt_lens, int Lmax,
                        int blank, int zero_infinity, float grad_scale, float* nll, float* loss, float* grad,
                        float* ws, bool in_smem, size_t smem, cudaStream_t st) {
   MASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_fwd_bwd_v2_kernel<SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  ctc_fwd_bwd_v2_kernel<SPL><<<B, CTC_THREADS, smem, st>>>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens,
+  ctc_fwd_bwd_v2_kernel<SPL><<<B, CTC_THREADS, smem, st>>>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens,
                                                            Lmax, blank, zero_infinity, grad_scale, nll, loss, grad, ws,
                                                            in_smem ? 1 : 0, g_ctc_dbg);
   MASR_LAUNCH_CHECK();
@@ -637,7 +637,18 @@ extern "C" int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_
                                 int blank, int zero_infinity, float grad_scale,
                                 float* nll, float* loss, float* grad,
                                 void* workspace, size_t workspace_bytes, void* stream) {
+  return masr_ctc_fwd_bwd_ex(acts, T, B, C, int64_t(B) * C, int64_t(C), act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens,
+                             max_tgt_len, blank, zero_infinity, grad_scale, nll, loss, grad, workspace, workspace_bytes, stream);
+}
+
+extern "C" int masr_ctc_fwd_bwd_ex(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int act_is_logprob,
+                                   const int64_t* targets, const int64_t* tgt_offsets,
+                                   const int64_t* in_lens, const int64_t* tgt_lens, int max_tgt_len,
+                                   int blank, int zero_infinity, float grad_scale,
+                                   float* nll, float* loss, float* grad,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   MASR_REQUIRE(T >= 0 && B >= 0 && C > 0 && max_tgt_len >= 0, "ctc: bad sizes");
+  MASR_REQUIRE(st_t >= C && st_b >= C, "ctc: frame / utterance strides must be >= C (rows are contiguous)");
   MASR_REQUIRE(blank >= 0 && blank < C, "ctc: blank out of range");
   cudaStream_t st = as_stream(stream);
   if (loss != nullptr) { ctc_zero_kernel<<<1, 1, 0, st>>>(loss); MASR_LAUNCH_CHECK(); }
@@ -650,7 +661,7 @@ extern "C" int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_
     static int ctc_ver = -1;
     if (ctc_ver < 0) { const char* e = getenv("MASR_CTC_VERSION"); ctc_ver = e != nullptr ? atoi(e) : 3; }
     if (ctc_ver >= 3) {
-      const int rc3 = ctc3_try(acts, T, B, C, act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens, max_tgt_len, blank,
+      const int rc3 = ctc3_try(acts, T, B, C, st_t, st_b, act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens, max_tgt_len, blank,
                                zero_infinity, grad_scale, nll, loss, grad, g_ctc_dbg, st);
       if (rc3 != CTC3_NOT_APPLICABLE) return rc3;
     }
@@ -660,7 +671,7 @@ extern "C" int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_
     if (spl <= 12 && small2 <= 100 * 1024 && (fits || ws_ok)) {
       const size_t smem2 = fits ? small2 + tables2 : small2;
       float* wsf = static_cast<float*>(workspace);
-#define CTC2_CASE(N) return launch_ctc2<N>(acts, T, B, C, act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens, max_tgt_len, \
+#define CTC2_CASE(N) return launch_ctc2<N>(acts, T, B, C, st_t, st_b, act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens, max_tgt_len, \
                                            blank, zero_infinity, grad_scale, nll, loss, grad, wsf, fits, smem2, st)
       if (spl <= 1) CTC2_CASE(1);
       if (spl <= 2) CTC2_CASE(2);
@@ -681,7 +692,7 @@ extern "C" int masr_ctc_fwd_bwd(const float* acts, int T, int B, int C, int act_
   }
   const size_t smem = in_smem ? small + tables : small;
   MASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  ctc_fwd_bwd_kernel<<<B, CTC_THREADS, smem, st>>>(acts, T, B, C, act_is_logprob, targets, tgt_offsets, in_lens,
+  ctc_fwd_bwd_kernel<<<B, CTC_THREADS, smem, st>>>(acts, T, B, C, st_t, st_b, act_is_logprob, targets, tgt_offsets, in_lens,
                                                    tgt_lens, max_tgt_len, blank, zero_infinity, grad_scale,
                                                    nll, loss, grad, static_cast<float*>(workspace), in_smem ? 1 : 0);
   MASR_LAUNCH_CHECK();

@@ -308,7 +308,7 @@ inline size_t smem_bytes(int T, int Lmax, int C, int spl_dispatched) {
 // F0 / F3: frames per warp iteration in the emission / gradient phase; MINB: CTAs per SM the register budget allows
 template <int SPL, int F0, int F3, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
+ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob,
             const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
             const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
             int Lmax, int blank, int zero_infinity, float grad_scale,
@@ -389,7 +389,7 @@ ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
       const bool full = t0 + F0 <= Tb;
 #pragma unroll
       for (int f = 0; f < F0; ++f) {
-        const float* row = acts + (int64_t(full ? t0 + f : min(t0 + f, Tb - 1)) * B + b) * C + lane;
+        const float* row = acts + (int64_t(full ? t0 + f : min(t0 + f, Tb - 1)) * st_t + b * st_b) + lane;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldg(row + 32 * k) : NEG;
       }
@@ -434,7 +434,7 @@ ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
     }
   } else {
     for (int t = warp; t < Tb; t += NW) {
-      const float* row = acts + (int64_t(t) * B + b) * C;
+      const float* row = acts + (int64_t(t) * st_t + b * st_b);
       float z2 = 0.f;
       if (!is_logprob) {
         float mx = -INFINITY;
@@ -496,7 +496,7 @@ ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
       float x[F3][CPL];
 #pragma unroll
       for (int f = 0; f < F3; ++f) {
-        const float* row = acts + (int64_t(t0 + f) * B + b) * C + lane;
+        const float* row = acts + (int64_t(t0 + f) * st_t + b * st_b) + lane;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldcs(row + 32 * k) : 0.f;
       }
@@ -533,8 +533,8 @@ ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
       float z2[F3];
 #pragma unroll
       for (int f = 0; f < F3; ++f) z2[f] = logZ2[t0 + f];
-      float* grow = grad + (int64_t(t0) * B + b) * C + lane;
-      const int64_t fstride = int64_t(B) * C;
+      float* grow = grad + (int64_t(t0) * st_t + b * st_b) + lane;
+      const int64_t fstride = st_t;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
         if (lane + 32 * k < C) {
@@ -552,7 +552,7 @@ ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
       for (int f = 0; f < F3; ++f) {
         const int t = t0 + f;
         if (t >= T) break;
-        float* grow = grad + (int64_t(t) * B + b) * C;
+        float* grow = grad + (int64_t(t) * st_t + b * st_b);
         if (!feasible || t >= Tb) {
           // beyond the input length ATen writes zeros; an infeasible utterance under zero_infinity too (without
           // zero_infinity the loss is inf and the gradient NaN, as in ATen)
@@ -560,7 +560,7 @@ ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
           for (int c = lane; c < C; c += 32) grow[c] = fill;
           continue;
         }
-        const float* row = acts + (int64_t(t) * B + b) * C;
+        const float* row = acts + (int64_t(t) * st_t + b * st_b);
         const float* Pt = P + t * Sstride;
         float bsum = 0.f;
         for (int m = lane; m <= L; m += 32) bsum += ex2f(Pt[2 * m] - ll2);
@@ -588,7 +588,7 @@ inline size_t smem_bytes_pipe(int T, int Lmax, int C, int spl_dispatched) {
 
 template <int SPL, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob,
+ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob,
              const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
              const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
              int Lmax, int blank, int zero_infinity, float grad_scale,
@@ -697,7 +697,7 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
         float x[F][CPL];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          const float* row = acts + (int64_t(t0 + f) * B + b) * C + lane;
+          const float* row = acts + (int64_t(t0 + f) * st_t + b * st_b) + lane;
 #pragma unroll
           for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldg(row + 32 * k) : NEG;
         }
@@ -732,7 +732,7 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
       }
     } else {
       for (int t = wi; t < Tb; t += NWK) {
-        const float* row = acts + (int64_t(t) * B + b) * C;
+        const float* row = acts + (int64_t(t) * st_t + b * st_b);
         float z2 = 0.f;
         if (!is_logprob) {
           float mx = -INFINITY;
@@ -772,7 +772,7 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
           float x[F][CPL];
 #pragma unroll
           for (int f = 0; f < F; ++f) {
-            const float* row = acts + (int64_t(t0 + f) * B + b) * C + lane;
+            const float* row = acts + (int64_t(t0 + f) * st_t + b * st_b) + lane;
 #pragma unroll
             for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldcs(row + 32 * k) : 0.f;
           }
@@ -809,8 +809,8 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
           float z2[F];
 #pragma unroll
           for (int f = 0; f < F; ++f) z2[f] = logZ2[t0 + f];
-          float* grow = grad + (int64_t(t0) * B + b) * C + lane;
-          const int64_t fstride = int64_t(B) * C;
+          float* grow = grad + (int64_t(t0) * st_t + b * st_b) + lane;
+          const int64_t fstride = st_t;
 #pragma unroll
           for (int k = 0; k < CPL; ++k) {
             if (lane + 32 * k < C) {
@@ -841,13 +841,13 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
   // ---- what the pipeline did not cover: padded frames; everything for infeasible / odd-shaped utterances
   const bool done_live = pipe3 && feasible;
   for (int t = (done_live ? Tb : 0) + warp; t < T; t += NW) {
-    float* grow = grad + (int64_t(t) * B + b) * C;
+    float* grow = grad + (int64_t(t) * st_t + b * st_b);
     if (!feasible || t >= Tb) {
       const float fill = (!feasible && !zero_infinity && t < Tb) ? NAN : 0.f;
       for (int c = lane; c < C; c += 32) grow[c] = fill;
       continue;
     }
-    const float* row = acts + (int64_t(t) * B + b) * C;
+    const float* row = acts + (int64_t(t) * st_t + b * st_b);
     const float* Pt = P + t * Sstride;
     float bsum = 0.f;
     for (int m = lane; m <= L; m += 32) bsum += ex2f(Pt[2 * m] - ll2);
@@ -867,7 +867,7 @@ ctc3p_kernel(const float* __restrict__ acts, int T, int B, int C, int is_logprob
 }
 
 template <int SPL, int MINB>
-int launch_pipe(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+int launch_pipe(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
                 const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
                 float* nll, float* loss, float* grad, long long* dbg, size_t smem, cudaStream_t st) {
   auto kern = ctc3p_kernel<SPL, MINB>;
@@ -876,14 +876,14 @@ int launch_pipe(const float* acts, int T, int B, int C, int is_logprob, const in
     MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr_smem = smem;
   }
-  kern<<<B, THREADS, smem, st>>>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,
+  kern<<<B, THREADS, smem, st>>>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,
                                  zero_infinity, grad_scale, nll, loss, grad, dbg);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
 
 template <int SPL, int F0, int F3, int MINB>
-int launch(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+int launch(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
            const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
            float* nll, float* loss, float* grad, long long* dbg, size_t smem, cudaStream_t st) {
   auto kern = ctc3_kernel<SPL, F0, F3, MINB>;
@@ -892,14 +892,14 @@ int launch(const float* acts, int T, int B, int C, int is_logprob, const int64_t
     MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr_smem = smem;
   }
-  kern<<<B, THREADS, smem, st>>>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,
+  kern<<<B, THREADS, smem, st>>>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,
                                  zero_infinity, grad_scale, nll, loss, grad, dbg);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }
 
 template <int F0, int F3>
-static int dispatch(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+static int dispatch(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
                     const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
                     float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
   const int S = 2 * Lmax + 1;
@@ -913,7 +913,7 @@ static int dispatch(const float* acts, int T, int B, int C, int is_logprob, cons
   if (pipe && F0 == 2 && F3 == 2) {
     const size_t smem_p = smem_bytes_pipe(T, Lmax, C, spld);
     if (smem_p <= 227 * 1024) {
-#define CTC3P_CASE(N) return launch_pipe<N, 3>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, \
+#define CTC3P_CASE(N) return launch_pipe<N, 3>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, \
                                                zero_infinity, grad_scale, nll, loss, grad, dbg, smem_p, st)
       if (spl <= 1) CTC3P_CASE(1);
       if (spl <= 2) CTC3P_CASE(2);
@@ -936,9 +936,9 @@ static int dispatch(const float* acts, int T, int B, int C, int is_logprob, cons
 #define CTC3_CASE(N)                                                                                                         \
   do {                                                                                                                       \
     if (minb == 4)                                                                                                           \
-      return launch<N, F0, F3, 4>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,         \
+      return launch<N, F0, F3, 4>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,         \
                                   zero_infinity, grad_scale, nll, loss, grad, dbg, smem, st);                               \
-    return launch<N, F0, F3, 3>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,           \
+    return launch<N, F0, F3, 3>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,           \
                                 zero_infinity, grad_scale, nll, loss, grad, dbg, smem, st);                                 \
   } while (0)
   if (spl <= 1) CTC3_CASE(1);
@@ -953,11 +953,11 @@ static int dispatch(const float* acts, int T, int B, int C, int is_logprob, cons
 
 }  // namespace
 
-int ctc3_try(const float* acts, int T, int B, int C, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
+int ctc3_try(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
              const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
              float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
   // frames per warp iteration (emission, gradient) = (2, 2): measured best of (2,2) / (3,3) / (4,2) at 80 registers
-  return dispatch<2, 2>(acts, T, B, C, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, zero_infinity,
+  return dispatch<2, 2>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, zero_infinity,
                         grad_scale, nll, loss, grad, dbg, st);
 }
 

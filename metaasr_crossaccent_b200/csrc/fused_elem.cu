@@ -401,6 +401,26 @@ __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, in
     dst[i] = from_f<TD>(to_f<TS>(src[i]));
 }
 
+// dst[r, 0:cols] = src[r, 0:cols], dst[r, cols:ld_dst] = 0
+template <typename TS, typename TD>
+__global__ void cast_pad2d_kernel(const TS* __restrict__ src, int64_t ld_src, TD* __restrict__ dst, int64_t ld_dst,
+                                  int64_t rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t n = rows * ld_dst;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = int(i - r * ld_dst);
+    dst[i] = c < cols ? from_f<TD>(to_f<TS>(src[r * ld_src + c])) : from_f<TD>(0.f);
+  }
+}
+
+__global__ void loss_mix_kernel(double* __restrict__ stats, const float* __restrict__ ctc_loss, float w) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) { stats[3] = double(*ctc_loss); stats[4] = double(w); }
+}
+
 // forward: dst[r, f*C + c] = src[r, c*F + f]; inverse_add: dst[r, c*F + f] += src[r, f*C + c]
 template <typename TS, typename TD>
 __global__ void permute_cf_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t rows, int C, int F, int inverse_add) {
@@ -625,6 +645,31 @@ extern "C" int masr_cast(const void* src, int src_dtype, void* dst, int dst_dtyp
   else if (src_dtype == MASR_BF16 && dst_dtype == MASR_BF16)
     launch_pdl(cast_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n);
   else { set_error("masr_cast: bad dtype"); return MASR_E_INVALID; }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_cast_pad2d(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
+                               int rows, int cols, void* stream) {
+  MASR_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= cols, "cast_pad2d: bad sizes");
+  const int64_t n = int64_t(rows) * ld_dst;
+  if (n == 0) return MASR_OK;
+  cudaStream_t st = as_stream(stream);
+  const int g = grid_for(n, 256);
+  if (src_dtype == MASR_F32 && dst_dtype == MASR_BF16)
+    launch_pdl(cast_pad2d_kernel<float, __nv_bfloat16>, dim3(g), dim3(256), 0, st, static_cast<const float*>(src), ld_src,
+               static_cast<__nv_bfloat16*>(dst), ld_dst, int64_t(rows), cols);
+  else if (src_dtype == MASR_F32 && dst_dtype == MASR_F32)
+    launch_pdl(cast_pad2d_kernel<float, float>, dim3(g), dim3(256), 0, st, static_cast<const float*>(src), ld_src,
+               static_cast<float*>(dst), ld_dst, int64_t(rows), cols);
+  else { set_error("masr_cast_pad2d: fp32 source, fp32 / bf16 destination"); return MASR_E_INVALID; }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_loss_mix(double* stats, const float* ctc_loss, float w, void* stream) {
+  MASR_REQUIRE(stats != nullptr && ctc_loss != nullptr, "loss_mix: null pointer");
+  launch_pdl(loss_mix_kernel, dim3(1), dim3(32), 0, as_stream(stream), stats, ctc_loss, w);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -32,11 +32,16 @@ class NetConfig:
     """asr_model block of the reference YAMLs (config/transformer/pretrain/fometa-hkust.yaml:13-26)."""
 
     def __init__(self, idim=83, d_model=512, nheads=8, d_inner=2048, enc_layers=2, dec_layers=4,
-                 odim=367, dropout=0.1, pos_dropout=0.1, tie=True):
+                 odim=367, dropout=0.1, pos_dropout=0.1, tie=True, ctc_weight=0.0):
         self.idim, self.d_model, self.nheads, self.d_inner = idim, d_model, nheads, d_inner
         self.enc_layers, self.dec_layers, self.odim = enc_layers, dec_layers, odim
         self.dropout, self.pos_dropout, self.tie = float(dropout), float(pos_dropout), bool(tie)
         self.sos_id, self.eos_id = 0, odim - 1
+        # joint CTC / attention objective (north_star kernel 3; an EXTENSION -- the reference only carries dead config for
+        # it, config/transformer/mono-test.yaml:44-50): total = (1-w) * LS-CE + w * CTC(ctc_lo(encoder memory), ys),
+        # blank = index 0.  w = 0 (default): no CTC head, state dict and numerics are exactly the reference's.
+        self.ctc_weight = float(ctc_weight)
+        assert 0.0 <= self.ctc_weight < 1.0
         self.vgg_ch = 128
         self.f4 = idim // 4
         self.vgg_o_dim = self.vgg_ch * self.f4
@@ -46,7 +51,7 @@ class NetConfig:
     def from_yaml(am: dict, odim: int):
         return NetConfig(am["idim"], am["d_model"], am["nheads"], am["d_inner"], am["encoder"]["nlayers"],
                          am["decoder"]["nlayers"], odim, am.get("dropout", 0.0), am.get("pos_dropout", 0.0),
-                         am.get("tgt_share_weight", 1) != 0)
+                         am.get("tgt_share_weight", 1) != 0, am.get("ctc_weight", 0.0))
 
 
 def param_shapes(cfg: NetConfig) -> "OrderedDict[str, tuple]":
@@ -89,6 +94,9 @@ def param_shapes(cfg: NetConfig) -> "OrderedDict[str, tuple]":
         ffn_norms(f"decoder.layers.{l}", 3)
     s["decoder.norm.weight"] = (d,)
     s["decoder.norm.bias"] = (d,)
+    if cfg.ctc_weight > 0.0:          # appended LAST: every reference tensor keeps its arena offset
+        s["ctc_lo.weight"] = (cfg.odim, d)
+        s["ctc_lo.bias"] = (cfg.odim,)
     return s
 
 
@@ -160,7 +168,8 @@ class TransformerEngine:
         self.vgg2enc_p = torch.zeros(cfg.d_model, cfg.vgg_o_dim, dtype=self.act_dtype, device=self.device)
         self.d_vgg2enc_p = torch.zeros(cfg.d_model, cfg.vgg_o_dim, dtype=torch.float32, device=self.device)
         self.weights_dirty = True
-        self.stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        # [sum of row losses, n_correct, n_non_pad, CTC term, ctc_weight, -, -, -]
+        self.stats = torch.zeros(8, dtype=torch.float64, device=self.device)
         # device-resident dropout seed offset of THIS engine (kernels add it to every dropout seed; a captured
         # CUDA graph bumps it at replay).  Per engine, so that engines running concurrently on different
         # streams cannot change each other's masks between a forward and its backward.
@@ -245,10 +254,11 @@ class TransformerEngine:
         # enc_lens | ys_in | ys_out live back to back in ONE int64 host buffer (pinned on a GPU box, taken from a
         # small ring): a single asynchronous H2D copy per batch.  Pageable sources would make every copy block
         # the host until the stream drains, which serialises the lanes / the run-ahead of the launch thread.
-        meta = self._host_meta(B * (1 + 2 * L1))
+        ctc = cfg.ctc_weight > 0.0
+        meta = self._host_meta(B * (1 + 2 * L1) + (2 * B if ctc else 0))
         meta[:B] = enc_lens
         ys_in = meta[B:B + B * L1].view(B, L1)
-        ys_out = meta[B + B * L1:].view(B, L1)
+        ys_out = meta[B + B * L1:B + 2 * B * L1].view(B, L1)
         ys_in.fill_(cfg.eos_id)
         ys_out.fill_(IGNORE_ID)
         lens = [int(y.numel()) for y in ys]
@@ -268,8 +278,12 @@ class TransformerEngine:
         if olens is not None:
             olens += 1
         n_total = sum(lens) + B                       # non-pad targets = every y plus its eos
-        return {"x": xs_pad, "enc_lens": meta[:B], "ys_in": ys_in, "ys_out": ys_out, "meta": meta, "n_total": n_total,
-                "B": B, "T": xs_pad.shape[1], "L1": L1}
+        if ctc:       # CTC reads its targets in place from ys_out (row b holds y_b first): per-utterance length / offset
+            meta[B + 2 * B * L1:2 * B + 2 * B * L1] = torch.tensor(lens, dtype=torch.int64)
+            meta[2 * B + 2 * B * L1:] = torch.arange(B, dtype=torch.int64) * L1
+        hb = {"x": xs_pad, "meta": meta, "n_total": n_total, "B": B, "T": xs_pad.shape[1], "L1": L1}
+        hb.update(self._meta_views(meta, B, L1))
+        return hb
 
     def _host_meta(self, numel):
         """int64 host staging buffer from a ring of 64 (pinned when CUDA is present); an entry is reused only
@@ -307,10 +321,18 @@ class TransformerEngine:
         B, L1 = hb["B"], hb["L1"]
         meta = hb["meta"].to(self.device, non_blocking=True)
         self._meta_copied(hb)
-        dev = {"x": x.to(self.device, non_blocking=True), "meta": meta, "enc_lens": meta[:B],
-               "ys_in": meta[B:B + B * L1].view(B, L1), "ys_out": meta[B + B * L1:].view(B, L1)}
+        dev = {"x": x.to(self.device, non_blocking=True), "meta": meta}
+        dev.update(self._meta_views(meta, B, L1))
         dev.update({k: hb[k] for k in ("n_total", "B", "T", "L1")})
         return dev
+
+    def _meta_views(self, meta, B, L1):
+        v = {"enc_lens": meta[:B], "ys_in": meta[B:B + B * L1].view(B, L1),
+             "ys_out": meta[B + B * L1:B + 2 * B * L1].view(B, L1)}
+        if self.cfg.ctc_weight > 0.0:
+            v["ctc_tl"] = meta[B + 2 * B * L1:2 * B + 2 * B * L1]
+            v["ctc_offs"] = meta[2 * B + 2 * B * L1:3 * B + 2 * B * L1]
+        return v
 
     # ------------------------------------------------------------------ side stream (fork / join)
     def _fork(self, fn):
@@ -388,6 +410,7 @@ class TransformerEngine:
                 prefix["h1"], prefix["q2"] = dec_self(0, x0)
             self._fork(dec_prefix)
 
+        mem_given = mem is not None
         if mem is not None:
             assert not want_grad, "a cached encoder memory is an inference-only shortcut"
             buf("mem", (Me, d)).copy_(mem)
@@ -437,6 +460,7 @@ class TransformerEngine:
             be.add_layernorm_fwd(h, None, P["encoder.norm.weight"], P["encoder.norm.bias"], mem,
                                  buf("enc.m", (Me,), f32), buf("enc.r", (Me,), f32), 0.0, seed, 0)
 
+        ctc_here = cfg.ctc_weight > 0.0 and not mem_given
         # ---- decoder.  The memory K/V projections of layers 1.. only need `mem`: side stream, behind the prefix
         if cfg.dec_layers > 0:
             kv_proj(0)
@@ -453,6 +477,9 @@ class TransformerEngine:
                 h1, q2 = dec_self(l, x)
             if l == 0 and cfg.dec_layers > 1:
                 self._join()                              # prefix + K/V projections done (they were queued long ago)
+            if l == 0 and ctc_here:
+                self._fork(lambda: self._ctc_head(db, ws, want_grad))     # overlaps the rest of the decoder
+                ctc_here = False
             kv2 = ws[f"d{l}.kv2"]
             ctx2 = buf(f"d{l}.ctx2", (Md, d))
             lse2 = buf(f"d{l}.lse2", (B * H * L1,), f32)
@@ -475,6 +502,8 @@ class TransformerEngine:
         if cfg.dec_layers == 0:
             x = buf("d.x0", (Md, d))
             be.embed_pe_fwd(db["ys_in"].view(-1), P["pre_embed.weight"], self.pe2d, x, L1, ppd, seed, self.site("dec.pe"))
+        if ctc_here:
+            self._ctc_head(db, ws, want_grad)
         ws["dec_last"] = x
         dout = buf("d.out", (Md, d))
         be.add_layernorm_fwd(x, None, P["decoder.norm.weight"], P["decoder.norm.bias"], dout,
@@ -491,9 +520,26 @@ class TransformerEngine:
         if want_grad:
             dlogits = buf("dlogits", (Md, (C + 7) // 8 * 8))[:, :C]
             ws["dlogits_v"] = dlogits
-        be.ls_ce(logits, db["ys_out"].view(-1), self.eps_ls, 1.0 / max(db["n_total"], 1), self.stats, argmax, dlogits,
+        w = cfg.ctc_weight
+        be.ls_ce(logits, db["ys_out"].view(-1), self.eps_ls, (1.0 - w) / max(db["n_total"], 1), self.stats, argmax, dlogits,
                  db.get("inv_n_dev"))
+        if w > 0.0 and not mem_given:
+            self._join()
+            be.loss_mix(self.stats, ws["ctc.loss"], w)
         return ws
+
+    def _ctc_head(self, db, ws, want_grad):
+        """CTC branch of the joint objective: logits = ctc_lo(encoder memory) [B*T', C] fp32, fused log-softmax + alpha-beta
+        forward-backward (kernel 1) reading the batch-first rows in place; the gradient leaves already scaled by w."""
+        cfg, be = self.cfg, self.be
+        B, T, L1, T2, F2, T4, F4, Me, Md = ws["dims"]
+        C = cfg.odim
+        f32 = torch.float32
+        cl = self._buf(ws, "ctc.logits", (Me, C), f32)
+        be.linear_fwd(ws["mem"], self.W["ctc_lo.weight"], self.P["ctc_lo.bias"], cl)
+        g = self._buf(ws, "ctc.grad", (Me, C), f32) if want_grad else None
+        be.ctc_joint(cl, B, T4, C, db["ys_out"].view(-1), db["ctc_offs"], db["enc_lens"], db["ctc_tl"], L1 - 1,
+                     cfg.ctc_weight, self._buf(ws, "ctc.nll", (B,), f32), self._buf(ws, "ctc.loss", (1,), f32), g)
 
     # ------------------------------------------------------------------ backward
     def backward(self, db, ws):
@@ -607,6 +653,15 @@ class TransformerEngine:
         cur = 0
         if cfg.dec_layers == 0:
             be.zero_(g_mem)
+        if cfg.ctc_weight > 0.0:
+            gc = ws["ctc.grad"]
+            if self.act_dtype != torch.float32:       # bf16 rows padded to a 16-byte pitch for the tcgen05 GEMMs
+                C8 = (C + 7) // 8 * 8
+                gcb = buf("ctc.grad_c", (Me, C8))
+                be.cast_pad2d(gc, gcb, C)
+                gc = gcb[:, :C]
+            wgrad(ws["mem"], gc, G["ctc_lo.weight"], G["ctc_lo.bias"])
+            be.linear_dgrad(gc, W["ctc_lo.weight"], g_mem, accumulate=True)
         be.add_layernorm_bwd(g_mem, ws["enc_last"], ws["enc.m"], ws["enc.r"], P["encoder.norm.weight"], ge[cur], False,
                              None, G["encoder.norm.weight"], G["encoder.norm.bias"])
         for l in reversed(range(cfg.enc_layers)):
@@ -705,12 +760,11 @@ class TransformerEngine:
                 old_key, _ = self._graphs.popitem(last=False)
                 self._ws.pop(old_key[:3], None)
             dev = self.device
-            smeta = torch.empty(B * (1 + 2 * L1), dtype=torch.int64, device=dev)
-            sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev),
-                   "meta": smeta, "enc_lens": smeta[:B],
-                   "ys_in": smeta[B:B + B * L1].view(B, L1), "ys_out": smeta[B + B * L1:].view(B, L1),
+            smeta = torch.empty(B * (1 + 2 * L1) + (2 * B if self.cfg.ctc_weight > 0.0 else 0), dtype=torch.int64, device=dev)
+            sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev), "meta": smeta,
                    "inv_n_dev": torch.empty(1, dtype=torch.float32, device=dev),
                    "n_total": 1, "B": B, "T": T, "L1": L1}
+            sdb.update(self._meta_views(smeta, B, L1))
             self._load_static(sdb, db)
             cur = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev)
@@ -736,12 +790,22 @@ class TransformerEngine:
             if db["meta"].device.type == "cpu":
                 self._meta_copied(db)
         else:
-            for k in ("enc_lens", "ys_in", "ys_out"):
-                sdb[k].copy_(db[k], non_blocking=True)
-        sdb["inv_n_dev"].fill_(1.0 / max(db["n_total"], 1))
+            for k in ("enc_lens", "ys_in", "ys_out", "ctc_tl", "ctc_offs"):
+                if k in sdb:
+                    sdb[k].copy_(db[k], non_blocking=True)
+        sdb["inv_n_dev"].fill_((1.0 - self.cfg.ctc_weight) / max(db["n_total"], 1))
 
     def read_stats(self):
         """The single device->host read of a step: {'loss', 'acc'} like run_batch's info dict."""
-        s = self.stats.tolist()
+        return self.stats_to_info(self.stats.tolist())
+
+    @staticmethod
+    def stats_to_info(s):
+        """[sum of row losses, n_correct, n_non_pad, CTC term, w, ...] -> {'loss','acc'}; w = 0 unless the joint
+        CTC / attention objective is on, in which case loss = (1-w) * LS-CE + w * CTC and both terms are reported."""
         n = max(s[2], 1.0)
-        return {"loss": s[0] / n, "acc": s[1] / n}
+        att = s[0] / n
+        w = s[4] if len(s) > 4 else 0.0
+        if w > 0.0:
+            return {"loss": (1.0 - w) * att + w * s[3], "acc": s[1] / n, "att_loss": att, "ctc_loss": s[3]}
+        return {"loss": att, "acc": s[1] / n}

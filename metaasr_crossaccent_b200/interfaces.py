@@ -282,7 +282,7 @@ class FOMetaMixin:
         if am.get('inner_optimizer_cls', 'SGD') != 'SGD':
             raise NotImplementedError("fused inner loop implements torch.optim.SGD (fometa-hkust.yaml:2-6)")
         self.asr_opt = FlatInnerSGD(eng, self.inner_lr, io.get('momentum', 0.0), io.get('nesterov', False))
-        self._stats_ring = torch.zeros(max(self.num_pretrain, 1), 4, dtype=torch.float64, device=eng.device)
+        self._stats_ring = torch.zeros(max(self.num_pretrain, 1), 8, dtype=torch.float64, device=eng.device)
         self._ring_sizes = []
 
     def optimizer_state(self):
@@ -373,15 +373,33 @@ class FOMetaMixin:
             raise ValueError(f"Not support meta algo {self.paras.algo}")
 
     # -- fo_meta_interface.py:200-221 (+ the one collective of the path)
-    def _final_meta_update(self):
+    def _reduce_updates(self):
+        """The one collective of the path: all-reduce(SUM) of the flat update arena (+ the task counter in its last
+        slot).  Returns the number of tasks that contributed over all ranks."""
         eng = self.asr_model.engine
         n = eng.layout.total
+        self._mark('reduce0')
         if D.is_dist():
             self._upd_flat[n] = float(self._counter)
             D.all_reduce_sum_(self._upd_flat)
             count = float(self._global_task_count) if self._global_task_count else float(self._upd_flat[n].item())
         else:
             count = float(self._counter)
+        self._mark('reduce1')
+        return count
+
+    _phase_log = None            # list -> (tag, CUDA event) per phase boundary of a meta-step (bench.py: phase split)
+
+    def _mark(self, tag):
+        if self._phase_log is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._phase_log.append((tag, ev))
+
+    def _final_meta_update(self):
+        eng = self.asr_model.engine
+        n = eng.layout.total
+        count = self._reduce_updates()
         if self.paras.algo == 'reptile' and self.reptile_outer == 'interp':
             eng.be.mt_axpy(self._original_flat[:n], self._upd_flat[:n], -self.reptile_eps / max(count, 1.0))
             self.meta_opt.lr = self.reptile_eps
@@ -389,6 +407,7 @@ class FOMetaMixin:
             self.meta_opt.step(self._upd_flat[:n], max(count, 1.0))
         eng.be.zero_(self._upd_flat)
         self._counter, self._updates = 0, None
+        self._mark('adam1')
 
     _global_task_count = 0       # tasks of the meta-batch over ALL ranks (0: read it from the all-reduce)
 
@@ -400,9 +419,12 @@ class FOMetaMixin:
         self._ring_sizes = []
         n_lanes = min(int(self.config['asr_model'].get('task_lanes', 1)), len(tasks))
         if n_lanes <= 1 or self.asr_model.engine.device.type != 'cuda':
+            self._mark('step0')
             for tr_batches, val_batch in tasks:
                 self.run_task(tr_batches)
+                self._mark('train1')
                 self.inner_test(val_batch)
+                self._mark('test1')
         else:
             # Accents are independent given the meta weights: run them on n_lanes CUDA streams so that the
             # small-kernel phases of one accent (decoder, LayerNorm, attention: a fraction of the 148 SMs)
@@ -430,14 +452,19 @@ class FOMetaMixin:
                 eng0.be.zero_(l.upd)
         self._final_meta_update()
 
+    def replica_checksum(self):
+        """(sum, sum of squares) of the meta weights in float64, on the device: replicas of a multi-GPU run must agree
+        bit for bit (every rank applies the identical average+Adam kernel to the identical all-reduced arena)."""
+        w = self._original_flat.double()
+        return torch.stack([w.sum(), (w * w).sum()])
+
     def flush_train_info(self):
         """The single device->host read of a meta-step: per-task inner-test loss/acc."""
         k = len(self._ring_sizes)
         infos = []
         if k:
             for row, bs in zip(self._stats_ring[:k].tolist(), self._ring_sizes):
-                nn_ = max(row[2], 1.0)
-                info = {'loss': row[0] / nn_, 'acc': row[1] / nn_}
+                info = self.asr_model.engine.stats_to_info(row)
                 infos.append(info)
                 self.train_info.add(info, bs)
         self._ring_sizes = []

@@ -396,6 +396,23 @@ class CudaBackend:
                    _p(argmax), _p(dlogits), _dt(dlogits) if dlogits is not None else F32,
                    dlogits.stride(0) if dlogits is not None else Cc, self.stream)
 
+    # -------------------------------------------------------------- joint CTC / attention (ctc_weight extension)
+    def ctc_joint(self, logits, B, T, Cc, targets, offs, in_lens, tgt_lens, lmax, w, nll, loss, grad):
+        """Kernel 1 on the batch-first CTC-head output logits [B*T, C] fp32 (row b*T + t), log-softmax fused, blank 0,
+        reduction 'mean', zero_infinity; grad (or None) = w * d loss / d logits in the same layout."""
+        wsb = self.lib.masr_ctc_workspace_bytes(T, B, Cc, lmax)
+        ws = self.scratch(("ctc_ws", self.scratch_tag), wsb // 4 + 1, torch.float32) if wsb else None
+        self._call("masr_ctc_fwd_bwd_ex", _p(logits), T, B, Cc, logits.stride(0), T * logits.stride(0), 0, _p(targets),
+                   _p(offs), _p(in_lens), _p(tgt_lens), int(lmax), 0, 1, float(w), _p(nll), _p(loss), _p(grad), _p(ws), wsb,
+                   self.stream, n_kernels=2)
+
+    def cast_pad2d(self, src, dst, cols):
+        self._call("masr_cast_pad2d", _p(src), _dt(src), src.stride(0), _p(dst), _dt(dst), dst.stride(0), src.shape[0],
+                   int(cols), self.stream)
+
+    def loss_mix(self, stats, ctc_loss, w):
+        self._call("masr_loss_mix", _p(stats), _p(ctc_loss), float(w), self.stream)
+
     def set_seed_ptr(self, t):
         """Device-resident dropout seed offset (uint64 stored in an int64 tensor); see masr_set_seed_ptr."""
         self._seed_t = t

@@ -21,8 +21,9 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def make_config(meta=True, k=0.02, warmup=4, dtype="fp32", tiny=True, gemm="simt"):
-    am = {"idim": 83, "dropout": 0.0, "tgt_share_weight": 1, "pos_dropout": 0.0, "dtype": dtype, "gemm": gemm}
+def make_config(meta=True, k=0.02, warmup=4, dtype="fp32", tiny=True, gemm="simt", ctc_weight=0.0, graphs=False):
+    am = {"idim": 83, "dropout": 0.0, "tgt_share_weight": 1, "pos_dropout": 0.0, "dtype": dtype, "gemm": gemm,
+          "ctc_weight": ctc_weight, "cuda_graphs": graphs}
     if tiny:
         am.update({"nheads": 4, "d_model": 32, "d_inner": 64, "encoder": {"nlayers": 2}, "decoder": {"nlayers": 2}})
     else:
@@ -329,3 +330,36 @@ def test_eval_run_batch_hkust_vs_oracle_port(dev, dtype, gemm):
     else:       # bf16 may flip an argmax whose top-2 margin is below the rounding error: rates within 2 points
         assert abs(info["acc"] - float(n_correct) / n_total) <= 0.02
         assert abs(info["cer"] - ref["att_cer"]) <= 2.0 and abs(info["wer"] - ref["att_wer"]) <= 2.0
+
+
+# ---------------------------------------------------------------------------- joint CTC / attention (north_star kernel 3)
+@pytest.mark.parametrize("dtype,gemm,graphs", [("fp32", "simt", False), ("bf16", "umma", False), ("bf16", "umma", True)])
+def test_joint_ctc_attention_run_batch_vs_torch_restatement(dev, dtype, gemm, graphs):
+    """ctc_weight = 0.3 at the hkust network size on a ragged batch (parity unpinned: the reference has no joint
+    objective; checked against oracle/port.run_batch_joint = autograd over F.ctc_loss + the pinned attention path):
+    mixed loss and both terms, and the gradient of every tensor incl. the CTC head, on the CUDA path (CTC kernel reading
+    the batch-first head output in place, its gradient entering the encoder next to the decoder's)."""
+    from tests.helpers import hkust_profile_batch, clone_batch
+    w = 0.3
+    s = make_solver("multi", meta=False, dtype=dtype, tiny=False, gemm=gemm, ctc_weight=w, graphs=graphs)
+    cfg = port.NetCfg()
+    sd = port.init_state_dict(cfg, seed=7)
+    g = torch.Generator().manual_seed(5)
+    sd["ctc_lo.weight"] = (torch.rand(367, 512, generator=g) * 2 - 1) * (6.0 / (367 + 512)) ** 0.5
+    sd["ctc_lo.bias"] = torch.zeros(367)
+    s.asr_model.load_state_dict(sd)
+    assert len(s.asr_model.state_dict()) == 116
+    b = hkust_profile_batch(21, "rag", B=6, T=192, L=10)
+    oinfo, ograds, _, _ = port.run_batch_joint(sd, cfg, *clone_batch(b), 0.2, w, training=False)
+    for rep in range(2 if graphs else 1):          # second pass = graph replay
+        info = s.run_batch(0, *clone_batch(b), train=True)
+    tol = 1e-5 if dtype == "fp32" else 2e-2
+    for k in ("loss", "att_loss", "ctc_loss"):
+        assert abs(info[k] - oinfo[k]) <= tol * abs(oinfo[k]), (k, info, oinfo)
+    eng = s.asr_model.engine
+    worst = 0.0
+    for n, og in ograds.items():
+        rel = float((eng.G[n].cpu() - og).norm() / (og.norm() + 1e-12))
+        worst = max(worst, rel)
+        assert rel <= (2e-3 if dtype == "fp32" else 1.5e-1), (n, rel)
+    print(f"[joint {dtype}/{gemm}] loss {info['loss']:.6f} vs {oinfo['loss']:.6f} (att {info['att_loss']:.4f} ctc {info['ctc_loss']:.4f}); worst grad rel-L2 {worst:.2e}")

@@ -208,6 +208,27 @@ class TorchBackend:
             (g,) = torch.autograd.grad(tot * inv_n, lz)
             dlogits.copy_(g)
 
+    def ctc_joint(self, logits, B, T, Cc, targets, offs, in_lens, tgt_lens, lmax, w, nll, loss, grad):
+        """Torch restatement of the joint objective's CTC branch (espnet-style): F.ctc_loss(log_softmax(logits)) with
+        blank 0, reduction 'mean', zero_infinity on the batch-first logits."""
+        lg = logits.detach().double().view(B, T, Cc).requires_grad_(True)
+        lp = torch.log_softmax(lg, -1).transpose(0, 1)
+        tl = tgt_lens.cpu().long()
+        tg = torch.cat([targets[int(offs[b]):int(offs[b]) + int(tl[b])] for b in range(B)]).long().cpu()
+        l = torch.nn.functional.ctc_loss(lp, tg, in_lens.cpu().long(), tl, blank=0, reduction='mean', zero_infinity=True)
+        loss.copy_(l.detach().float().view(1))
+        if grad is not None:
+            (g,) = torch.autograd.grad(l, lg)
+            grad.copy_((w * g).float().view(B * T, Cc))
+
+    def cast_pad2d(self, src, dst, cols):
+        dst.zero_()
+        dst[:, :cols].copy_(src[:, :cols])
+
+    def loss_mix(self, stats, ctc_loss, w):
+        stats[3] = float(ctc_loss)
+        stats[4] = w
+
     def zero_(self, t):
         t.zero_()
 
