@@ -35,7 +35,7 @@ extern "C" {
 #define MASR_F32 0
 #define MASR_BF16 1
 
-#define MASR_ABI_VERSION 2
+#define MASR_ABI_VERSION 3
 
 int masr_abi_version(void);
 const char* masr_last_error(void);
@@ -211,8 +211,10 @@ int masr_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
                   float p_drop, uint64_t seed, uint32_t site, void* stream);
 
 /* tcgen05 fast path of the two calls above: bf16, head dim 64, rows 16 B aligned (ld % 8 == 0).
- * Forward handles any Lk (online soft-max over 128-key tiles); backward requires Lk <= 128 (one key
- * tile per (batch, head); longer memories use masr_attn_bwd). */
+ * Forward handles any Lk (online soft-max over 128-key tiles).  Backward: one CTA per 128-key tile of a (batch, head);
+ * with Lk <= 128 dQ is written directly, with longer memories (utterances up to max_ilen 1500 -> 375 keys) the key tiles
+ * add their dQ partials into dq_ws ([B*Lq, H*64] fp32, zeroed by the call) and a cast pass rounds the sum (dq_ws may be
+ * NULL when Lk <= 128). */
 int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                        void* out, int64_t ldo, float* lse, int B, int H, int Lq, int Lk,
                        const int64_t* klens, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
@@ -220,7 +222,7 @@ int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
                        float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                        int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
-                       float p_drop, uint64_t seed, uint32_t site, int dsum_ready, void* stream);
+                       float p_drop, uint64_t seed, uint32_t site, int dsum_ready, float* dq_ws, void* stream);
 /* dsum_ready != 0: dsum_ws already holds D[b,h,q] = dO . O (e.g. from masr_umma_gemm_ex's dot epilogue). */
 
 /* ------------------------------------------------------------------ kernel 3: fused elementwise

@@ -67,7 +67,7 @@ SIGNATURES = {
                            c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],
     "masr_umma_attn_bwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p,
                            c_p, c_i64, c_p, c_i64, c_p, c_i64,
-                           c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_i, c_p],
+                           c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_i, c_p, c_p],
     "masr_add_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_u64, c_u32, c_p],
     "masr_add_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_u64, c_u32, c_p],
     "masr_add_pe_dropout": [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_u64, c_u32, c_p],

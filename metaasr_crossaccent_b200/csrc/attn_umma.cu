@@ -281,10 +281,27 @@ struct AttnBwdParams {
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
   const uint64_t* seed_ptr;
+  float* dq_ws;                  // [B*Lq, H*64] fp32, zeroed: dQ partials of the key tiles when Lk > 128 (else NULL)
 };
 
-// Single key tile per (batch, head) CTA column: requires Lk <= 128 * gridDim.x with dQ written directly only
-// when gridDim.x == 1 (the host falls back to the CUDA-core kernels otherwise).
+// fp32 dQ partial sums -> bf16 dQ (memories longer than one key tile)
+__global__ void attn_dq_cast_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ dq, int64_t lddq, int64_t rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t n8 = rows * (cols / 8);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / (cols / 8);
+    const int c = int(i - r * (cols / 8)) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(ws + r * cols + c), b = *reinterpret_cast<const float4*>(ws + r * cols + c + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    store8<__nv_bfloat16>(dq + r * lddq + c, v);
+  }
+}
+
+// One CTA = one 128-key tile of one (batch, head), looping over the query tiles: dK / dV accumulate in TMEM.  dQ of a
+// query tile is complete when the memory fits ONE key tile (gridDim.x == 1: written directly as bf16); for longer
+// memories (utterances up to max_ilen 1500 -> 375 keys) every key tile adds its partial to the fp32 workspace with
+// vector reductions and attn_dq_cast_kernel rounds the sum once.
 __global__ void __launch_bounds__(AU_THREADS, 1)
 attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do, AttnBwdParams p) {
@@ -463,9 +480,17 @@ attn_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tmem_ld_32x32(tm_dQ + lane_addr + half * 32, v);
         tmem_ld_wait();
         if (qok) {
-          __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64 + half * 32;
+          if (gridDim.x == 1) {
+            __nv_bfloat16* drow = p.dq + (int64_t(b) * p.Lq + qi) * p.lddq + h * 64 + half * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) store8<__nv_bfloat16>(drow + j, v + j);
+            for (int j = 0; j < 32; j += 8) store8<__nv_bfloat16>(drow + j, v + j);
+          } else {
+            float* wrow = p.dq_ws + (int64_t(b) * p.Lq + qi) * (int64_t(p.H) * 64) + h * 64 + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                           "f"(v[j + 3]) : "memory");
+          }
         }
       }
       tc_fence_before();
@@ -549,9 +574,10 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
                                   const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
                                   float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                                   int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
-                                  float p_drop, uint64_t seed, uint32_t site, int dsum_ready, void* stream) {
+                                  float p_drop, uint64_t seed, uint32_t site, int dsum_ready, float* dq_ws, void* stream) {
   if (B == 0 || H == 0) return MASR_OK;
-  MASR_REQUIRE(Lk <= AU_TILE, "umma attention backward: Lk must be <= 128 (use masr_attn_bwd otherwise)");
+  const int nkt = int(ceil_div64(std::max(Lk, 1), AU_TILE));
+  MASR_REQUIRE(nkt == 1 || dq_ws != nullptr, "umma attention backward: Lk > 128 needs the [B*Lq, H*64] fp32 dq workspace");
   MASR_REQUIRE(dsum_ws != nullptr, "attention backward needs a [B*H*Lq] fp32 workspace");
   MASR_REQUIRE(lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && ldo % 2 == 0 && lddo % 2 == 0 &&
                ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0,
@@ -571,11 +597,19 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
   const uint32_t thr16 = attn_drop_thr16(p_drop);
   AttnBwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? attn_drop_inv_keep(thr16) : 1.f, thr16, seed, site,
                   lse, dsum_ws, static_cast<__nv_bfloat16*>(dq), lddq, static_cast<__nv_bfloat16*>(dk), lddk,
-                  static_cast<__nv_bfloat16*>(dv), lddv, g_seed_dev_ptr};
+                  static_cast<__nv_bfloat16*>(dv), lddv, g_seed_dev_ptr, nkt > 1 ? dq_ws : nullptr};
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_BWD_SMEM))); attr = true; }
-  dim3 grid(1, unsigned(B * H));
+  if (nkt > 1 && Lq > 0) MASR_CHECK_CUDA(cudaMemsetAsync(dq_ws, 0, sizeof(float) * size_t(B) * Lq * H * 64, st));
+  dim3 grid(unsigned(nkt), unsigned(B * H));
   MASR_CHECK_CUDA(launch_pdl(attn_bwd_umma_kernel, grid, dim3(AU_THREADS), AU_BWD_SMEM, st, mq, mk, mv, mdo, p));
   MASR_LAUNCH_CHECK();
+  if (nkt > 1 && Lq > 0) {
+    const int64_t rows = int64_t(B) * Lq;
+    const int blocks = int(std::min<int64_t>(ceil_div64(rows * H * 8, 256), int64_t(sm_count()) * 8));
+    MASR_CHECK_CUDA(launch_pdl(attn_dq_cast_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(dq_ws),
+                               static_cast<__nv_bfloat16*>(dq), lddq, rows, H * 64));
+    MASR_LAUNCH_CHECK();
+  }
   return MASR_OK;
 }

@@ -358,6 +358,47 @@ class TransformerEngine:
         """Runs the network on a device batch; fills ws['logits'] [B*L1, C] fp32 and the loss
         statistics; with want_grad also d(mean loss)/d logits.  `mem` (greedy decode): an encoder memory
         [B*T', d] computed by an earlier call on the same x -- the conv front end and the encoder are skipped."""
+        if mem is None:
+            self.forward_conv(db)
+        return self.forward_rest(db, want_grad, mem)
+
+    def _dims(self, db):
+        cfg = self.cfg
+        B, T, L1 = db["B"], db["T"], db["L1"]
+        T2, F2 = T // 2, cfg.idim // 2
+        T4, F4 = T2 // 2, F2 // 2
+        ws = self.workspace(B, T, L1)
+        ws["dims"] = (B, T, L1, T2, F2, T4, F4, B * T4, B * L1)
+        return ws
+
+    def forward_conv(self, db):
+        """Segment 1 of a batch: derived weight copies + the VGG front end (NHWC) up to the second pool.  These are
+        the long, GPU-filling launches; the lock-step scheduler of the meta-step queues them back to back for all
+        task lanes (interfaces.FOMetaMixin._meta_lockstep)."""
+        cfg, be = self.cfg, self.be
+        self._bind_seed()
+        self.prep_weights()
+        ws = self._dims(db)
+        B, T, L1, T2, F2, T4, F4, Me, Md = ws["dims"]
+        F0 = cfg.idim
+        P = self.P
+        buf = lambda n, shape, dt=None: self._buf(ws, n, shape, dt)
+        a1 = buf("a1", (B, T, F0, 64))
+        be.conv1_fwd(db["x"], P["feat_extractor.0.weight"], P["feat_extractor.0.bias"], a1)
+        a2 = buf("a2", (B, T, F0, 64))
+        be.conv3x3_fwd(a1, self.wp[2], P["feat_extractor.2.bias"], a2)
+        p1 = buf("p1", (B, T2, F2, 64))
+        be.maxpool_fwd(a2, p1)
+        a3 = buf("a3", (B, T2, F2, 128))
+        be.conv3x3_fwd(p1, self.wp[5], P["feat_extractor.5.bias"], a3)
+        a4 = buf("a4", (B, T2, F2, 128))
+        be.conv3x3_fwd(a3, self.wp[7], P["feat_extractor.7.bias"], a4)
+        p2 = buf("p2", (B, T4, F4, 128))
+        be.maxpool_fwd(a4, p2)
+        return ws
+
+    def forward_rest(self, db, want_grad=True, mem=None):
+        """Segment 2a: vgg2enc, encoder, decoder, output projection, loss (everything after the conv front end)."""
         cfg, be = self.cfg, self.be
         self._bind_seed()
         self.prep_weights()
@@ -367,8 +408,7 @@ class TransformerEngine:
         T4, F4 = T2 // 2, F2 // 2
         d, ff, H, C = cfg.d_model, cfg.d_inner, cfg.nheads, cfg.odim
         Me, Md = B * T4, B * L1
-        ws = self.workspace(B, T, L1)
-        ws["dims"] = (B, T, L1, T2, F2, T4, F4, Me, Md)
+        ws = self._dims(db)
         buf = lambda n, shape, dt=None: self._buf(ws, n, shape, dt)
         f32 = torch.float32
         seed = self.step_seed
@@ -415,19 +455,8 @@ class TransformerEngine:
             assert not want_grad, "a cached encoder memory is an inference-only shortcut"
             buf("mem", (Me, d)).copy_(mem)
         else:
-            # ---- VGG front end (NHWC)
-            a1 = buf("a1", (B, T, F0, 64))
-            be.conv1_fwd(db["x"], P["feat_extractor.0.weight"], P["feat_extractor.0.bias"], a1)
-            a2 = buf("a2", (B, T, F0, 64))
-            be.conv3x3_fwd(a1, self.wp[2], P["feat_extractor.2.bias"], a2)
-            p1 = buf("p1", (B, T2, F2, 64))
-            be.maxpool_fwd(a2, p1)
-            a3 = buf("a3", (B, T2, F2, 128))
-            be.conv3x3_fwd(p1, self.wp[5], P["feat_extractor.5.bias"], a3)
-            a4 = buf("a4", (B, T2, F2, 128))
-            be.conv3x3_fwd(a3, self.wp[7], P["feat_extractor.7.bias"], a4)
-            p2 = buf("p2", (B, T4, F4, 128))
-            be.maxpool_fwd(a4, p2)
+            # ---- vgg2enc on the pooled conv output of forward_conv
+            p2 = ws["p2"]
             h = buf("h0", (Me, d))
             be.linear_fwd(p2.view(Me, F4 * 128), self.vgg2enc_p, P["vgg2enc.bias"], h)
             be.add_pe_dropout(h, self.pe2d, T4, ppd, seed, self.site("enc.pe"))
@@ -545,7 +574,14 @@ class TransformerEngine:
     def backward(self, db, ws):
         """Back-propagates ws['dlogits'] through the whole network; gradients are ACCUMULATED into
         self.grads (zeroed here first, as run_batch's asr_opt.zero_grad() does)."""
+        self.backward_rest(db, ws, join=False)
+        self.backward_conv(db, ws)
+
+    def backward_rest(self, db, ws, join=True):
+        """Segment 2b: output projection, decoder, encoder and vgg2enc backward, down to the gradient of the pooled conv
+        output (ws['g.p2'])."""
         cfg, be = self.cfg, self.be
+        self._bind_seed()
         B, T, L1, T2, F2, T4, F4, Me, Md = ws["dims"]
         F0 = cfg.idim
         d, ff, H, C = cfg.d_model, cfg.d_inner, cfg.nheads, cfg.odim
@@ -696,6 +732,19 @@ class TransformerEngine:
         fork(vgg2enc_wgrad)
         g_p2 = buf("g.p2", (B, T4, F4, 128))
         be.linear_dgrad(g_h0, self.vgg2enc_p, g_p2.view(Me, F4 * 128))
+        if join:                  # a segment that is captured / scheduled on its own must end with its side work joined
+            self._join()
+
+    def backward_conv(self, db, ws):
+        """Segment 3: VGG front end backward (pool / dgrad chain on the stream, weight gradients on the side stream)."""
+        cfg, be = self.cfg, self.be
+        self._bind_seed()
+        B, T, L1, T2, F2, T4, F4, Me, Md = ws["dims"]
+        F0 = cfg.idim
+        buf = lambda n, shape, dt=None: self._buf(ws, n, shape, dt)
+        G = self.G
+        fork = self._fork
+        g_p2 = ws["g.p2"]
         g_a4 = buf("g.a4", (B, T2, F2, 128))
         be.maxpool_bwd(ws["a4"], g_p2, g_a4, True)
 
@@ -721,67 +770,98 @@ class TransformerEngine:
         self._join()
 
     # ------------------------------------------------------------------ public step
+    N_SEGMENTS = 3
+
     def forward_backward(self, db):
         """One run_batch(train=True) worth of device work.  Returns the workspace; the loss
-        statistics stay on the device in self.stats = [sum of row losses, n_correct, n_non_pad].
-        With use_graphs the whole kernel schedule of a (B, T, L1) shape is captured once into a CUDA
-        graph and replayed: inputs are copied into static buffers, the dropout seed offset and 1/n live
-        in device memory, so a replay is one launch instead of ~270."""
+        statistics stay on the device in self.stats = [sum of row losses, n_correct, n_non_pad, ...].
+        The work is issued as THREE segments -- conv front end forward | everything between | conv front end backward
+        -- here back to back on the current stream; the lock-step meta-step scheduler issues the segments of several
+        task lanes on different streams (fb_begin / fb_segment).  With use_graphs each segment of a (B, T, L1) shape is
+        captured once into a CUDA graph and replayed: inputs are copied into static buffers, the dropout seed offset
+        and 1/n live in device memory, so a batch is three launches instead of ~240."""
+        h = self.fb_begin(db)
+        for i in range(self.N_SEGMENTS):
+            self.fb_segment(h, i)
+        return h["ws"] if h["ws"] is not None else self.workspace(db["B"], db["T"], db["L1"])
+
+    def fb_begin(self, db):
+        """Stages the inputs of a batch on the CURRENT stream and returns the handle fb_segment takes."""
         if self.use_graphs and self.device.type == "cuda":
-            return self._forward_backward_graphed(db)
-        return self._forward_backward_eager(db)
+            ent = self._graph_entry(db)
+            graphs, sdb, ws = ent
+            self._load_static(sdb, db)
+            return {"graphs": graphs, "db": sdb, "ws": ws}
+        return {"graphs": None, "db": db, "ws": None}
+
+    def fb_segment(self, h, i):
+        """Issues segment i (0: conv forward, 1: the rest of forward + backward down to the conv output, 2: conv
+        backward) of the batch on the current stream."""
+        if h["graphs"] is not None:
+            h["graphs"][i].replay()
+        else:
+            self._segment_eager(h["db"], i, join=True)
 
     def _bind_seed(self):
         self.be.scratch_tag = (id(self), "main")   # backend scratch buffers are private to this engine
         if hasattr(self.be, "set_seed_ptr"):
             self.be.set_seed_ptr(self.seed_t)  # kernels launched from here on read this engine's offset
 
-    def _forward_backward_eager(self, db):
-        self.weights_dirty = True             # training: the master weights may have moved since the last batch
-        self._bind_seed()
-        if hasattr(self.be, "seed_bump"):
-            self.be.seed_bump(1)              # fresh dropout masks: device-resident seed offset += 1
+    def _segment_eager(self, db, i, join):
+        if i == 0:
+            self.weights_dirty = True         # training: the master weights may have moved since the last batch
+            self._bind_seed()
+            if hasattr(self.be, "seed_bump"):
+                self.be.seed_bump(1)          # fresh dropout masks: device-resident seed offset += 1
+            else:
+                self.step_seed += 1
+            self.forward_conv(db)
+        elif i == 1:
+            ws = self.forward_rest(db, want_grad=True)
+            self.backward_rest(db, ws, join=join)
         else:
-            self.step_seed += 1
-        ws = self.forward(db, want_grad=True)
-        self.backward(db, ws)
-        return ws
+            self.backward_conv(db, self.workspace(db["B"], db["T"], db["L1"]))
 
-    def _forward_backward_graphed(self, db):
+    def _forward_backward_eager(self, db):
+        for i in range(self.N_SEGMENTS):
+            self._segment_eager(db, i, join=False)
+        return self.workspace(db["B"], db["T"], db["L1"])
+
+    def _graph_entry(self, db):
         B, T, L1 = db["B"], db["T"], db["L1"]
         key = (B, T, L1, self.training)
         ent = self._graphs.get(key)
         if ent is not None:
             self._graphs.move_to_end(key)
-        if ent is None:
-            # bounded LRU: with the reference's 1-frame buckets nearly every real batch has a new (B, T, L) shape; a
-            # captured graph pins its workspaces (hundreds of MB at full size), so keep only the most recent shapes
-            while len(self._graphs) >= self.max_graphs:
-                old_key, _ = self._graphs.popitem(last=False)
-                self._ws.pop(old_key[:3], None)
-            dev = self.device
-            smeta = torch.empty(B * (1 + 2 * L1) + (2 * B if self.cfg.ctc_weight > 0.0 else 0), dtype=torch.int64, device=dev)
-            sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev), "meta": smeta,
-                   "inv_n_dev": torch.empty(1, dtype=torch.float32, device=dev),
-                   "n_total": 1, "B": B, "T": T, "L1": L1}
-            sdb.update(self._meta_views(smeta, B, L1))
-            self._load_static(sdb, db)
-            cur = torch.cuda.current_stream(dev)
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):         # allocate workspaces / set kernel attributes eagerly first
-                self._forward_backward_eager(sdb)
-            cur.wait_stream(side)
-            torch.cuda.synchronize(dev)
+            return ent
+        # bounded LRU: with the reference's 1-frame buckets nearly every real batch has a new (B, T, L) shape; a
+        # captured graph pins its workspaces (hundreds of MB at full size), so keep only the most recent shapes
+        while len(self._graphs) >= self.max_graphs:
+            old_key, _ = self._graphs.popitem(last=False)
+            self._ws.pop(old_key[:3], None)
+        dev = self.device
+        smeta = torch.empty(B * (1 + 2 * L1) + (2 * B if self.cfg.ctc_weight > 0.0 else 0), dtype=torch.int64, device=dev)
+        sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev), "meta": smeta,
+               "inv_n_dev": torch.empty(1, dtype=torch.float32, device=dev),
+               "n_total": 1, "B": B, "T": T, "L1": L1}
+        sdb.update(self._meta_views(smeta, B, L1))
+        self._load_static(sdb, db)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):         # allocate workspaces / set kernel attributes eagerly first
+            self._forward_backward_eager(sdb)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graphs = []
+        for i in range(self.N_SEGMENTS):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                ws = self._forward_backward_eager(sdb)
-            ent = (g, sdb, ws)
-            self._graphs[key] = ent
-        g, sdb, ws = ent
-        self._load_static(sdb, db)
-        g.replay()
-        return ws
+                self._segment_eager(sdb, i, join=True)
+            graphs.append(g)
+        ent = (graphs, sdb, self.workspace(B, T, L1))
+        self._graphs[key] = ent
+        return ent
 
     def _load_static(self, sdb, db):
         sdb["x"].copy_(db["x"], non_blocking=True)

@@ -352,8 +352,9 @@ class FOMetaMixin:
             self._train_batch(lane, idx, x, ilens, ys, olens, accent_idx=idx)
             be.mt_sumsq(eng.grads[:eng.layout.total], lane.gnorm)
         else:   # reptile: the held-out batch only produces logging statistics (no gradient needed)
-            hb = eng.prepare_batch(x, ilens, ys, olens)
-            eng.forward(eng.to_device(hb), want_grad=False)
+            db = x if isinstance(x, dict) else eng.to_device(eng.prepare_batch(x, ilens, ys, olens))
+            eng.weights_dirty = True
+            eng.forward(db, want_grad=False)
         if slot is None:
             slot = len(self._ring_sizes)
             self._ring_sizes.append(len(ys))
@@ -425,6 +426,8 @@ class FOMetaMixin:
                 self._mark('train1')
                 self.inner_test(val_batch)
                 self._mark('test1')
+        elif bool(self.config['asr_model'].get('lockstep', True)):
+            self._meta_lockstep(tasks, n_lanes)
         else:
             # Accents are independent given the meta weights: run them on n_lanes CUDA streams so that the
             # small-kernel phases of one accent (decoder, LayerNorm, attention: a fraction of the 148 SMs)
@@ -457,6 +460,112 @@ class FOMetaMixin:
         bit for bit (every rank applies the identical average+Adam kernel to the identical all-reduced arena)."""
         w = self._original_flat.double()
         return torch.stack([w.sum(), (w * w).sum()])
+
+    def _meta_lockstep(self, tasks, n_lanes):
+        """Lock-step schedule of the tasks of a meta-step over n_lanes task lanes (private engines).
+
+        A batch is three segments (engine.fb_segment): conv front end forward | encoder + decoder forward / backward |
+        conv front end backward.  The conv segments are long launches that fill all 148 SMs; the middle segment is a
+        dependent chain of ~150 launches of 36-150 CTAs each (latency bound).  Free-running lanes serialise: a
+        persistent conv kernel of one lane leaves no SM for the other lanes' small kernels.  Here every round (the
+        k-th inner-train batch of all lanes, then the inner-test batch) queues the conv segments of ALL lanes back to
+        back on ONE stream and runs the middle segments CONCURRENTLY on the lanes' own streams, so the small kernels of
+        different accents fill the machine together.  Same arithmetic per task as run_task / inner_test; the LAST task
+        runs on lane 0 (asr_model ends the meta-step with its fast weights, fo_meta_interface.py:70-88)."""
+        eng0 = self.asr_model.engine
+        dev = eng0.device
+        main = torch.cuda.current_stream(dev)
+        if '_conv_stream' not in self.__dict__:
+            self._conv_stream = torch.cuda.Stream(dev)
+        if '_lane0_stream' not in self.__dict__:
+            self._lane0_stream = torch.cuda.Stream(dev)
+        conv = self._conv_stream
+        lanes = [self._lane(i) for i in range(n_lanes)]
+        streams = [self._lane0_stream] + [l.stream for l in lanes[1:]]
+        for st in streams + [conv]:
+            st.wait_stream(main)
+        self._ring_sizes = [len(t[1][1][2]) for t in tasks]
+        fomaml = self.paras.algo == 'fomaml'
+        n = eng0.layout.total
+        indexed = list(enumerate(tasks))
+        for g0 in range(0, len(indexed), n_lanes):
+            group = indexed[g0:g0 + n_lanes]
+            assign = []
+            for j, (slot, task) in enumerate(group):
+                li = (len(group) - 1 - j) % n_lanes
+                assign.append((lanes[li], streams[li], slot, task))
+            for lane, st, slot, task in assign:                 # run_task prologue: load_state_dict(_original), fresh SGD
+                with torch.cuda.stream(st):
+                    self._counter += 1
+                    lane.eng.be.copy_(lane.eng.params, self._original_flat)
+                    lane.eng.weights_dirty = True
+                    lane.eng.training = True
+                    lane.sgd.reset()
+            n_train = max(len(t[0]) for _, _, _, t in assign)
+            for rnd in range(n_train + 1):
+                test = rnd == n_train
+                live = []
+                for lane, st, slot, (tr, te) in assign:
+                    if not test and rnd >= len(tr):
+                        continue
+                    idx, (x, ilens, ys, olens) = te if test else tr[rnd]
+                    eng = lane.eng
+                    with torch.cuda.stream(st):
+                        if test and not fomaml:             # reptile: forward-only logging batch, then theta - phi
+                            self.inner_test((idx, (x, ilens, ys, olens)), lane, slot=slot)
+                            continue
+                        if isinstance(x, dict):
+                            db = x
+                        else:
+                            hb = eng.prepare_batch(x, ilens, ys, olens)
+                            db = hb if eng.use_graphs else eng.to_device(hb)
+                        eng.weights_dirty = True
+                        h = eng.fb_begin(db)
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                    live.append((lane, st, slot, h, ev))
+                ev1s = []
+                for lane, st, slot, h, ev in live:              # conv forward of every lane, back to back
+                    conv.wait_event(ev)
+                    with torch.cuda.stream(conv):
+                        lane.eng.fb_segment(h, 0)
+                        e1 = torch.cuda.Event()
+                        e1.record(conv)
+                    ev1s.append(e1)
+                ev2s = []
+                strict = bool(self.config['asr_model'].get('lockstep_strict', True))
+                for (lane, st, slot, h, ev), e1 in zip(live, ev1s):   # the small-kernel chains, concurrently
+                    # strict phases: no chain starts before the LAST conv segment is done -- a persistent conv kernel
+                    # holds every SM, chains interleaved with it crawl one launch per conv kernel and delay its CTAs
+                    st.wait_event(ev1s[-1] if strict else e1)
+                    with torch.cuda.stream(st):
+                        lane.eng.fb_segment(h, 1)
+                        e2 = torch.cuda.Event()
+                        e2.record(st)
+                    ev2s.append(e2)
+                if strict:
+                    for e2 in ev2s:
+                        conv.wait_event(e2)
+                for (lane, st, slot, h, ev), e2 in zip(live, ev2s):   # conv backward, back to back again
+                    conv.wait_event(e2)
+                    with torch.cuda.stream(conv):
+                        lane.eng.fb_segment(h, 2)
+                        e3 = torch.cuda.Event()
+                        e3.record(conv)
+                    st.wait_event(e3)
+                    eng = lane.eng
+                    with torch.cuda.stream(st):
+                        eng.be.mt_sumsq(eng.grads[:n], lane.gnorm)          # clip_grad_norm_ (device-side norm)
+                        if test:
+                            self._stats_ring[slot].copy_(eng.stats)
+                            self._partial_meta_update(lane)
+                        else:
+                            lane.sgd.step(lane.gnorm, GRAD_CLIP)
+        for st in streams + [conv]:
+            main.wait_stream(st)
+        for l in lanes[1:]:                      # combine the lanes' accumulators (then clear them)
+            eng0.be.mt_axpy(self._upd_flat[:n], l.upd[:n], 1.0)
+            eng0.be.zero_(l.upd)
 
     def flush_train_info(self):
         """The single device->host read of a meta-step: per-task inner-test loss/acc."""

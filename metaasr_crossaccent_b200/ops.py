@@ -140,13 +140,13 @@ class CudaBackend:
                 return False
         return True
 
-    def _timed_call(self, key, name, *args):
+    def _timed_call(self, key, name, *args, n_kernels=1):
         prof = self.prof
         if prof is None:
-            return self._call(name, *args)
+            return self._call(name, *args, n_kernels=n_kernels)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        self._call(name, *args)
+        self._call(name, *args, n_kernels=n_kernels)
         e1.record()
         prof.setdefault(key, []).append((e0, e1))
 
@@ -332,7 +332,7 @@ class CudaBackend:
     def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
         hd = out.shape[1] // H
         if self._attn_umma_ok(hd, q, k, v, out):
-            return self._call("masr_umma_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+            return self._timed_call(("attn_fwd", B * H, Lq, Lk), "masr_umma_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                               out.stride(0), _p(lse), B, H, Lq, Lk, _p(klens), int(causal), float(p), seed, site,
                               self.stream)
         self._call("masr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
@@ -341,11 +341,14 @@ class CudaBackend:
     def attn_bwd(self, q, k, v, out, dout, lse, dsum, dq, dk, dv, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0,
                  dsum_ready=False):
         hd = out.shape[1] // H
-        if Lk <= 128 and self._attn_umma_ok(hd, q, k, v, out, dout, dq, dk, dv):
-            return self._call("masr_umma_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+        if self._attn_umma_ok(hd, q, k, v, out, dout, dq, dk, dv):
+            # memories longer than one 128-key tile: the key tiles reduce their dQ partials in an fp32 workspace
+            dq_ws = self.scratch(("attn_dq", self.scratch_tag), B * Lq * H * 64, torch.float32) if Lk > 128 else None
+            return self._timed_call(("attn_bwd", B * H, Lq, Lk), "masr_umma_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                               out.stride(0), _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0),
                               _p(dk), dk.stride(0), _p(dv), dv.stride(0), B, H, Lq, Lk, _p(klens), int(causal),
-                              float(p), seed, site, int(dsum_ready), self.stream, n_kernels=1 if dsum_ready else 2)
+                              float(p), seed, site, int(dsum_ready), _p(dq_ws), self.stream,
+                              n_kernels=(1 if dsum_ready else 2) + (2 if Lk > 128 else 0))
         self._call("masr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
                    _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                    _p(dv), dv.stride(0), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     bound = set(_lib.SIGNATURES) | set(_lib.EXTRA)
     assert set(names) == bound, (set(names) ^ bound)
-    assert lib.masr_abi_version() == 2
+    assert lib.masr_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
