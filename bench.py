@@ -716,7 +716,7 @@ def main():
                     help="headline line only: skip the short runs of the other configs and the long CTC sweep")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-graphs", dest="no_graphs", action="store_true", help="launch every kernel from the host")
-    ap.add_argument("--lanes", type=int, default=8,
+    ap.add_argument("--lanes", type=int, default=4,
                     help="accents of a rank's share that run concurrently on one GPU (asr_model.task_lanes)")
     args = ap.parse_args()
     if args.impl == "reference":

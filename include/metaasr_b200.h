@@ -136,6 +136,10 @@ int masr_umma_gemm_ex(const void* A, int64_t lda, int a_mn, const void* B, int64
 int masr_umma_gemm_pair(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
                         void* C, int c_dtype, int64_t ldc, const float* bias,
                         int M, int N, int K, int flags, int splitk, int bn, const masr_gemm_epilogue* epi, void* stream);
+/* Upper bound of the TMA operand ring depth of masr_umma_gemm* (0 = default policy: the whole shared memory when the
+ * grid fits one wave).  The lock-step meta-step sets 3 while several task lanes run their small GEMMs concurrently, so
+ * that two CTAs of different lanes fit one SM. */
+int masr_gemm_set_stage_cap(int stages);
 /* mode 0: masr_umma_gemm* never use the CTA-pair kernel; 1 (default): by problem size (A/B measurements). */
 int masr_gemm_set_pair_mode(int mode);
 /* Convenience form of the above: A [M,K] and B [N,K] both K-major ("TN"). */

@@ -216,6 +216,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+// masr_gemm_set_stage_cap: upper bound of the operand ring depth.  A lone CTA per SM wants the whole shared memory as a
+// deep ring; when several task lanes run their small GEMMs concurrently (lock-step meta-step) a 192 KB CTA would keep
+// every other lane off its SM -- three stages (96 KB) leave room for a second CTA.
+static int g_stage_cap = 0;
+
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
 static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, UmmaGemmParams p, cudaStream_t st) {
   constexpr size_t STAGE = size_t(UG_BM * UG_BK * 2 + BN * UG_BK * 2);
@@ -235,6 +240,7 @@ static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   // overlaps the main loop of the other)
   const int64_t ctas = int64_t(grid.x) * grid.y * grid.z;
   int stages = (ctas <= sm_count()) ? MAX_STAGES : MIN_STAGES;
+  if (g_stage_cap > 0) stages = std::min(stages, g_stage_cap);
   stages = std::max(MIN_STAGES, std::min(stages, std::min(p.kb_per_split, total_kb)));
   p.stages = stages;
   const size_t smem = size_t(stages) * STAGE + 2048 + 1024 + 512 + BN * 4;
@@ -397,6 +403,11 @@ extern "C" int masr_umma_gemm_pair(const void* A, int64_t lda, int a_mn, const v
     }
   }
   return launch_umma_pair(A, lda, a_mn, B, ldb, b_mn, p, splitk, bn, as_stream(stream));
+}
+
+extern "C" int masr_gemm_set_stage_cap(int stages) {
+  g_stage_cap = stages > 0 ? stages : 0;
+  return MASR_OK;
 }
 
 /* 0: masr_umma_gemm* never uses the CTA-pair kernel; 1 (default): by problem size.  For A/B measurements. */

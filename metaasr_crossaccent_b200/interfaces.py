@@ -419,6 +419,9 @@ class FOMetaMixin:
             self._global_task_count = global_task_count
         self._ring_sizes = []
         n_lanes = min(int(self.config['asr_model'].get('task_lanes', 1)), len(tasks))
+        be0 = self.asr_model.engine.be
+        if hasattr(be0, 'gemm_stage_cap'):         # concurrent lanes share SMs: shallower operand rings (two CTAs per SM)
+            be0.gemm_stage_cap(3 if n_lanes > 1 else 0)
         if n_lanes <= 1 or self.asr_model.engine.device.type != 'cuda':
             self._mark('step0')
             for tr_batches, val_batch in tasks:

@@ -86,6 +86,12 @@ class CudaBackend:
         self._call("masr_gemm", _p(A), _dt(A), sam, sak, _p(B), _dt(B), sbn, sbk, _p(C), _dt(C), ldc, _p(bias),
                    M, N, K, flags, splitk, self.stream)
 
+    def gemm_stage_cap(self, stages):
+        """Operand-ring depth bound of the tcgen05 GEMMs (masr_gemm_set_stage_cap); 0 restores the default policy."""
+        if getattr(self, "_stage_cap", 0) != stages:
+            self.lib.masr_gemm_set_stage_cap(int(stages))
+            self._stage_cap = stages
+
     def _umma_ok(self, *ts):
         """tcgen05 path: bf16 operands, 16 B aligned bases, leading dimensions multiple of 8."""
         if self.gemm_path != "umma":

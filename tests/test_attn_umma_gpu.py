@@ -20,8 +20,10 @@ def dev():
     (3, 8, 33, 33, True, False, True),        # decoder causal self-attention
     (3, 8, 33, 128, False, True, True),       # decoder cross-attention with memory key padding
     (2, 4, 200, 100, False, True, True),      # two query tiles
-    (2, 4, 70, 300, False, True, False),      # three key tiles (forward: online soft-max)
-    (1, 2, 150, 150, True, False, False),     # causal over two tiles (forward)
+    (2, 4, 70, 300, False, True, True),       # three key tiles (forward: online soft-max; backward: dQ partials reduced in fp32)
+    (1, 2, 150, 150, True, False, True),      # causal over two tiles
+    (4, 8, 375, 375, False, True, True),      # encoder self-attention at max_ilen 1500 (fometa-hkust.yaml:45-47): T' = 375
+    (4, 8, 33, 375, False, True, True),       # decoder cross-attention over a 375-frame memory
 ])
 def test_umma_attention(dev, B, H, Lq, Lk, causal, use_klens, bwd):
     from metaasr_crossaccent_b200.ops import CudaBackend
