@@ -222,6 +222,15 @@ int masr_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
 int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                        void* out, int64_t ldo, float* lse, int B, int H, int Lq, int Lk,
                        const int64_t* klens, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* The two forward calls with K / V that hold `kv_rows` >= Lk rows per utterance, of which the first Lk are attended to:
+ * incremental greedy decoding reads a key/value cache of fixed capacity in place (rows beyond Lk must be finite). */
+int masr_umma_attn_fwd_cached(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                              void* out, int64_t ldo, float* lse, int B, int H, int Lq, int Lk, int kv_rows,
+                              const int64_t* klens, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream);
+int masr_attn_fwd_cached(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                         void* out, int64_t ldo, float* lse, int dtype,
+                         int B, int H, int Lq, int Lk, int kv_rows, int hd, const int64_t* klens, int causal,
+                         float p_drop, uint64_t seed, uint32_t site, void* stream);
 int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                        const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
                        float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,

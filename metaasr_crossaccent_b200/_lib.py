@@ -66,6 +66,10 @@ SIGNATURES = {
                       c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],
     "masr_umma_attn_fwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p,
                            c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],
+    "masr_umma_attn_fwd_cached": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p,
+                                  c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],
+    "masr_attn_fwd_cached": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i,
+                             c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],
     "masr_umma_attn_bwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p,
                            c_p, c_i64, c_p, c_i64, c_p, c_i64,
                            c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_i, c_p, c_p],

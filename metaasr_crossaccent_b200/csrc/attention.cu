@@ -35,7 +35,7 @@ template <typename T>
 __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk,
                 const T* __restrict__ v, int64_t ldv, T* __restrict__ out, int64_t ldo,
-                float* __restrict__ lse, int B, int H, int Lq, int Lk, int hd,
+                float* __restrict__ lse, int B, int H, int Lq, int Lk, int kv_rows, int hd,
                 const int64_t* __restrict__ klens, int causal, float scale,
                 float p, float inv_keep, SeedArg seed_arg, uint32_t site) {
   const uint64_t seed = resolve_seed(seed_arg);
@@ -46,8 +46,8 @@ attn_fwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, i
   const int q0 = blockIdx.x * AT_QT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const T* qb = q + int64_t(b) * Lq * ldq + h * hd;
-  const T* kb = k + int64_t(b) * Lk * ldk + h * hd;
-  const T* vb = v + int64_t(b) * Lk * ldv + h * hd;
+  const T* kb = k + int64_t(b) * kv_rows * ldk + h * hd;      // kv_rows = rows per utterance in K / V (Lk, or a cache's capacity)
+  const T* vb = v + int64_t(b) * kv_rows * ldv + h * hd;
   int kmax = Lk;
   if (klens != nullptr) kmax = min(kmax, int(klens[b]));
   if (causal) kmax = min(kmax, q0 + AT_QT);
@@ -300,7 +300,16 @@ extern "C" int masr_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t 
                              void* out, int64_t ldo, float* lse, int dtype,
                              int B, int H, int Lq, int Lk, int hd, const int64_t* klens, int causal,
                              float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  return masr_attn_fwd_cached(q, ldq, k, ldk, v, ldv, out, ldo, lse, dtype, B, H, Lq, Lk, Lk, hd, klens, causal, p_drop, seed,
+                              site, stream);
+}
+
+extern "C" int masr_attn_fwd_cached(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                    void* out, int64_t ldo, float* lse, int dtype,
+                                    int B, int H, int Lq, int Lk, int kv_rows, int hd, const int64_t* klens, int causal,
+                                    float p_drop, uint64_t seed, uint32_t site, void* stream) {
   MASR_REQUIRE(hd > 0 && hd <= 64, "attention: head dim must be <= 64");
+  MASR_REQUIRE(kv_rows >= Lk, "attention: kv_rows (rows per utterance of K / V) must be >= Lk");
   if (B == 0 || H == 0 || Lq == 0) return MASR_OK;
   dim3 grid(unsigned(ceil_div64(Lq, AT_QT)), unsigned(B * H));
   const float scale = 1.0f / sqrtf(float(hd));
@@ -308,7 +317,7 @@ extern "C" int masr_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t 
   MASR_DISPATCH_DTYPE(dtype, T,
       attn_fwd_kernel<T><<<grid, AT_THREADS, 0, as_stream(stream)>>>(
           static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv,
-          static_cast<T*>(out), ldo, lse, B, H, Lq, Lk, hd, klens, causal, scale, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
+          static_cast<T*>(out), ldo, lse, B, H, Lq, Lk, kv_rows, hd, klens, causal, scale, p_drop, inv_keep, SeedArg{seed, g_seed_dev_ptr}, site));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -56,6 +56,7 @@ struct AttnFwdParams {
   float* lse;
   const uint64_t* seed_ptr;      // device-resident per-step seed offset (CUDA-graph replay), may be NULL
   int kv_stages;                 // K/V ring depth: 1 (Lk <= 128) or 2
+  int kv_rows;                   // rows per utterance in K / V: Lk, or the capacity of a decode cache
 };
 
 __global__ void __launch_bounds__(AU_THREADS, 2)
@@ -115,8 +116,8 @@ attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_wait(&kv_empty[s], ((kvst == 2 ? (t >> 1) : t) & 1) ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&kv_full[s], 2 * AU_T64);
-        tma_load_2d(sKV + s * 2 * AU_T64, &map_k, &kv_full[s], h * 64, b * p.Lk + t * AU_TILE);
-        tma_load_2d(sKV + s * 2 * AU_T64 + AU_T64, &map_v, &kv_full[s], h * 64, b * p.Lk + t * AU_TILE);
+        tma_load_2d(sKV + s * 2 * AU_T64, &map_k, &kv_full[s], h * 64, b * p.kv_rows + t * AU_TILE);
+        tma_load_2d(sKV + s * 2 * AU_T64 + AU_T64, &map_v, &kv_full[s], h * 64, b * p.kv_rows + t * AU_TILE);
       }
       __syncwarp();
     }
@@ -552,15 +553,23 @@ using namespace masr;
 extern "C" int masr_umma_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                   void* out, int64_t ldo, float* lse, int B, int H, int Lq, int Lk,
                                   const int64_t* klens, int causal, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  return masr_umma_attn_fwd_cached(q, ldq, k, ldk, v, ldv, out, ldo, lse, B, H, Lq, Lk, Lk, klens, causal, p_drop, seed, site, stream);
+}
+
+extern "C" int masr_umma_attn_fwd_cached(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                         void* out, int64_t ldo, float* lse, int B, int H, int Lq, int Lk, int kv_rows,
+                                         const int64_t* klens, int causal, float p_drop, uint64_t seed, uint32_t site,
+                                         void* stream) {
   if (B == 0 || H == 0 || Lq == 0) return MASR_OK;
+  MASR_REQUIRE(kv_rows >= Lk, "umma attention: kv_rows (rows per utterance of K / V) must be >= Lk");
   MASR_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "umma attention: out must be 16 B aligned");
   CUtensorMap mq, mk, mv;
   int rc = rows_map(&mq, q, ldq, int64_t(B) * Lq, H * 64); if (rc) return rc;
-  rc = rows_map(&mk, k, ldk, int64_t(B) * Lk, H * 64); if (rc) return rc;
-  rc = rows_map(&mv, v, ldv, int64_t(B) * Lk, H * 64); if (rc) return rc;
+  rc = rows_map(&mk, k, ldk, int64_t(B) * kv_rows, H * 64); if (rc) return rc;
+  rc = rows_map(&mv, v, ldv, int64_t(B) * kv_rows, H * 64); if (rc) return rc;
   const uint32_t thr16 = attn_drop_thr16(p_drop);
   AttnFwdParams p{B, H, Lq, Lk, klens, causal, 0.125f, p_drop, p_drop > 0.f ? attn_drop_inv_keep(thr16) : 1.f, thr16, seed, site,
-                  static_cast<__nv_bfloat16*>(out), ldo, lse, g_seed_dev_ptr, Lk <= AU_TILE ? 1 : 2};
+                  static_cast<__nv_bfloat16*>(out), ldo, lse, g_seed_dev_ptr, Lk <= AU_TILE ? 1 : 2, kv_rows};
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AU_FWD_SMEM))); attr = true; }
   dim3 grid(unsigned(ceil_div64(Lq, AU_TILE)), unsigned(B * H));

@@ -769,6 +769,72 @@ class TransformerEngine:
         be.conv1_wgrad(db["x"], g_a1, G["feat_extractor.0.weight"], G["feat_extractor.0.bias"])
         self._join()
 
+    # ------------------------------------------------------------------ greedy decoding with a key/value cache
+    @torch.no_grad()
+    def greedy_decode(self, xs_pad, ilens, n_steps):
+        """MyTransformer.recog (mono_transformer_torch.py:143-176) without its O(L^2) decoder re-runs.  The reference
+        feeds the growing prefix [sos, y_0 .. y_{j-1}] through the whole decoder at step j and re-decides EVERY position;
+        the decoder is causal, so positions < j reproduce their earlier decision and only position j is new.  Here step
+        0 is the ordinary forward on the prefix [sos] (conv front end, encoder, memory K/V projections of every layer);
+        every later step runs ONE decoder row per utterance against the cached self-attention keys / values (fixed
+        capacity, read in place by the attention kernel) and the memory K/V of step 0.  Returns ids [n_steps, B]."""
+        cfg, be = self.cfg, self.be
+        B = xs_pad.shape[0]
+        d, ff, H, C = cfg.d_model, cfg.d_inner, cfg.nheads, cfg.odim
+        dev, adt, f32 = self.device, self.act_dtype, torch.float32
+        was_training, self.training = self.training, False
+        self.weights_dirty = True
+        empty = [torch.zeros(0, dtype=torch.int64) for _ in range(B)]
+        db = self.to_device(self.prepare_batch(xs_pad, ilens, empty, None))
+        ws0 = self.forward(db, want_grad=False)
+        ids = [ws0["argmax"].view(B).clone()]
+        if n_steps > 1:
+            T4 = ws0["dims"][5]
+            cap = n_steps
+            P, W = self.P, self.W
+            kc = [torch.zeros(B * cap, d, dtype=adt, device=dev) for _ in range(cfg.dec_layers)]
+            vc = [torch.zeros(B * cap, d, dtype=adt, device=dev) for _ in range(cfg.dec_layers)]
+            for l in range(cfg.dec_layers):
+                qkv0 = ws0[f"d{l}.qkv"]
+                kc[l].view(B, cap, d)[:, 0].copy_(qkv0[:, d:2 * d])
+                vc[l].view(B, cap, d)[:, 0].copy_(qkv0[:, 2 * d:])
+            mk = lambda *shape, dt=adt: torch.empty(*shape, dtype=dt, device=dev)
+            x0, qkv, ctx, s, q2 = mk(B, d), mk(B, 3 * d), mk(B, d), mk(B, d), mk(B, d)
+            h1, h2, h3a, h3b, f1, dout = mk(B, d), mk(B, d), mk(B, d), mk(B, d), mk(B, ff), mk(B, d)
+            lse, mean, rstd = mk(B * H, dt=f32), mk(B, dt=f32), mk(B, dt=f32)
+            logits, argmax = mk(B, C, dt=f32), mk(B, dt=torch.int64)
+            gold = torch.full((B,), IGNORE_ID, dtype=torch.int64, device=dev)
+            self._bind_seed()
+            for j in range(1, n_steps):
+                be.embed_pe_fwd(ids[-1], P["pre_embed.weight"], self.pe2d[j:j + 1], x0, 1, 0.0, 0, 0)
+                x = x0
+                for l in range(cfg.dec_layers):
+                    pre = f"decoder.layers.{l}"
+                    be.linear_fwd(x, W[pre + ".self_attn.in_proj_weight"], P[pre + ".self_attn.in_proj_bias"], qkv)
+                    kc[l].view(B, cap, d)[:, j].copy_(qkv[:, d:2 * d])
+                    vc[l].view(B, cap, d)[:, j].copy_(qkv[:, 2 * d:])
+                    be.attn_fwd(qkv[:, :d], kc[l], vc[l], ctx, lse, B, H, 1, j + 1, None, False, kv_rows=cap)
+                    be.linear_fwd(ctx, W[pre + ".self_attn.out_proj.weight"], P[pre + ".self_attn.out_proj.bias"], s)
+                    be.add_layernorm_fwd(s, x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"], h1, mean, rstd, 0.0, 0, 0)
+                    Wc, bc = W[pre + ".multihead_attn.in_proj_weight"], P[pre + ".multihead_attn.in_proj_bias"]
+                    be.linear_fwd(h1, Wc[:d], bc[:d], q2)
+                    kv2 = ws0[f"d{l}.kv2"]
+                    be.attn_fwd(q2, kv2[:, :d], kv2[:, d:], ctx, lse, B, H, 1, T4, db["enc_lens"], False)
+                    be.linear_fwd(ctx, W[pre + ".multihead_attn.out_proj.weight"], P[pre + ".multihead_attn.out_proj.bias"], s)
+                    be.add_layernorm_fwd(s, h1, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"], h2, mean, rstd, 0.0, 0, 0)
+                    be.linear_fwd(h2, W[pre + ".linear1.weight"], P[pre + ".linear1.bias"], f1, relu=True)
+                    be.linear_fwd(f1, W[pre + ".linear2.weight"], P[pre + ".linear2.bias"], s)
+                    h3 = h3b if x is h3a else h3a               # the layer's input is still its first residual
+                    be.add_layernorm_fwd(s, h2, P[pre + ".norm3.weight"], P[pre + ".norm3.bias"], h3, mean, rstd, 0.0, 0, 0)
+                    x = h3
+                be.add_layernorm_fwd(x, None, P["decoder.norm.weight"], P["decoder.norm.bias"], dout, mean, rstd, 0.0, 0, 0)
+                be.linear_fwd(dout, W["char_trans.weight"], P["char_trans.bias"], logits)
+                be.zero_(self.stats)
+                be.ls_ce(logits, gold, self.eps_ls, 1.0, self.stats, argmax, None, None)
+                ids.append(argmax.clone())
+        self.training = was_training
+        return torch.stack(ids, 0)
+
     # ------------------------------------------------------------------ public step
     N_SEGMENTS = 3
 

@@ -97,8 +97,16 @@ class B200Transformer(nn.Module):
     # prefix for max(enc_lens) steps and EVERY position is re-decided each time; unlike the reference the conv
     # front end and the encoder run once (their output is cached and handed to the later steps).
     @torch.no_grad()
-    def recog(self, xs_pad, ilens):
+    def recog(self, xs_pad, ilens, kv_cache=True):
+        """Greedy ids [L, B].  kv_cache=True (default): engine.greedy_decode -- one decoder row per step against cached
+        keys / values; kv_cache=False: the reference's own schedule (decoder re-run on the growing prefix), kept as the
+        cross-check of the cached path."""
         eng = self.engine
+        if kv_cache:
+            n_steps = int(torch.floor(ilens.to(dtype=torch.float32) / 4).max())
+            if n_steps <= 0:
+                return torch.zeros((0, xs_pad.shape[0]), dtype=torch.int64)
+            return eng.greedy_decode(xs_pad, ilens, n_steps).cpu()
         eng.weights_dirty = True
         was_training, eng.training = eng.training, False
         B = xs_pad.shape[0]

@@ -335,14 +335,16 @@ class CudaBackend:
         return all(t.dtype == torch.bfloat16 and t.data_ptr() % 16 == 0 and t.stride(0) % 8 == 0 and t.stride(1) == 1
                    for t in ts)
 
-    def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
+    def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0, kv_rows=None):
+        """kv_rows: rows per utterance in k / v when they are a decode cache of fixed capacity (default Lk)."""
         hd = out.shape[1] // H
+        kv_rows = Lk if kv_rows is None else int(kv_rows)
         if self._attn_umma_ok(hd, q, k, v, out):
-            return self._timed_call(("attn_fwd", B * H, Lq, Lk), "masr_umma_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
-                              out.stride(0), _p(lse), B, H, Lq, Lk, _p(klens), int(causal), float(p), seed, site,
+            return self._timed_call(("attn_fwd", B * H, Lq, Lk), "masr_umma_attn_fwd_cached", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+                              out.stride(0), _p(lse), B, H, Lq, Lk, kv_rows, _p(klens), int(causal), float(p), seed, site,
                               self.stream)
-        self._call("masr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
-                   _p(lse), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site, self.stream)
+        self._call("masr_attn_fwd_cached", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                   _p(lse), _dt(q), B, H, Lq, Lk, kv_rows, hd, _p(klens), int(causal), float(p), seed, site, self.stream)
 
     def attn_bwd(self, q, k, v, out, dout, lse, dsum, dq, dk, dv, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0,
                  dsum_ready=False):

@@ -185,9 +185,35 @@ def test_greedy_decode_ids_vs_reference_golden(dev):
     s = make_solver("fomaml")
     load_tiny(s)
     x, ilens, _, _ = load_batch(z, "in.")
-    ids = s.asr_model.recog(x, ilens)
+    ids = s.asr_model.recog(x, ilens)                       # key/value-cached decode (engine.greedy_decode)
     assert ids.shape == z["greedy"].shape
     assert np.array_equal(ids.numpy(), z["greedy"])
+    ids2 = s.asr_model.recog(x, ilens, kv_cache=False)      # the reference's O(L^2) schedule on the same kernels
+    assert np.array_equal(ids2.numpy(), z["greedy"])
+
+
+@pytest.mark.parametrize("dtype,gemm", [("fp32", "simt"), ("bf16", "umma")])
+def test_kv_cached_greedy_decode_hkust_vs_oracle_and_recompute(dev, dtype, gemm):
+    """hkust-size network, ragged batch: ids of the key/value-cached decode against oracle/port.greedy_decode (the
+    reference's loop restated, fp32: bit-exact) and against the re-run schedule on the same kernels (bf16: positions may
+    differ only after the first near-tie flips a token, so the agreement is counted on the common prefix)."""
+    from tests.helpers import hkust_profile_batch
+    s = make_solver("fomaml", dtype=dtype, tiny=False, gemm=gemm)
+    cfg = port.NetCfg()
+    sd = port.init_state_dict(cfg, seed=7)
+    s.asr_model.load_state_dict(sd)
+    x, ilens, _, _ = hkust_profile_batch(5, "rag", B=4, T=96, L=4)
+    ids = s.asr_model.recog(x, ilens)
+    ids_rerun = s.asr_model.recog(x, ilens, kv_cache=False)
+    assert ids.shape == ids_rerun.shape == (int(ilens.max()) // 4, 4)
+    if dtype == "fp32":
+        with torch.no_grad():
+            ref = port.greedy_decode(sd, cfg, x, ilens)
+        assert torch.equal(ids, ref)
+        assert torch.equal(ids_rerun, ref)
+    else:
+        agree = float((ids == ids_rerun).float().mean())
+        assert agree >= 0.9, agree
 
 
 def test_multi_step_vs_reference_golden(dev):

@@ -266,8 +266,10 @@ def test_recog_greedy_ids_bit_exact_host_logic():
     z = np.load(GOLD / "run_batch_tiny.npz")
     s = make_solver("fomaml")
     x, ilens, _, _ = load_batch(z, "in.")
-    ids = s.asr_model.recog(x, ilens)
+    ids = s.asr_model.recog(x, ilens)                       # key/value-cached: one decoder row per step
     assert np.array_equal(ids.numpy(), z["greedy"])
+    ids_ref_schedule = s.asr_model.recog(x, ilens, kv_cache=False)      # the reference's O(L^2) re-run schedule
+    assert np.array_equal(ids_ref_schedule.numpy(), z["greedy"])
 
 
 # ---------------------------------------------------------------------------- fine-tune loop

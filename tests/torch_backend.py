@@ -118,8 +118,11 @@ class TorchBackend:
         s = qq @ kk.transpose(-1, -2) / (hd ** 0.5) + self._mask(B, Lq, Lk, klens, causal, q.device)
         return qq, kk, vv, s
 
-    def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0):
+    def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0, kv_rows=None):
         assert p == 0.0
+        if kv_rows is not None and kv_rows != Lk:        # decode cache of fixed capacity: the first Lk rows per utterance
+            k = k.reshape(B, kv_rows, -1)[:, :Lk].reshape(B * Lk, -1)
+            v = v.reshape(B, kv_rows, -1)[:, :Lk].reshape(B * Lk, -1)
         qq, kk, vv, s = self._attn(q, k, v, B, H, Lq, Lk, klens, causal)
         lse.copy_(torch.logsumexp(s, -1).reshape(-1))
         o = torch.softmax(s, -1) @ vv
