@@ -60,7 +60,8 @@ ACCENTS = ["af", "au", "ca", "en", "in", "ir", "nz", "us"]
 def hkust_config(dtype, gemm, dropout=0.1, graphs=True, lanes=1, meta=True, ctc_weight=0.0):
     am = {"idim": IDIM, "nheads": 8, "d_model": 512, "d_inner": 2048, "dropout": dropout, "tgt_share_weight": 1,
           "encoder": {"nlayers": 2}, "decoder": {"nlayers": 4}, "pos_dropout": dropout, "dtype": dtype, "gemm": gemm,
-          "cuda_graphs": graphs, "task_lanes": lanes, "ctc_weight": ctc_weight}
+          "cuda_graphs": graphs, "task_lanes": lanes, "ctc_weight": ctc_weight,
+          "strict_tcgen05": gemm == "umma"}        # the timed path must never drop to a CUDA-core kernel
     if meta:
         am.update({"inner_optimizer_cls": "SGD", "inner_optimizer_opt": {"momentum": 0.9, "nesterov": True},
                    "meta_opt_cls": "noam", "meta": {"optimizer_opt": {"k": 1.0, "warmup_steps": 25000}}})
@@ -255,7 +256,8 @@ def bench_meta(args, algo, meta_k, dtype, steps, warmup, detail, rank, world, de
     }
     if not detail:
         if graphs:                                # graph replays bypass the host-side launch counter: count one eager step
-            eng.use_graphs = False
+            eng.use_graphs = False                # (one lane: the other lanes' engines keep their graphs)
+            solver.config["asr_model"]["task_lanes"] = 1
             _, out["gpu_launches"], _, _ = timed(step_resident, 1, 0, dev, world, be)
         del solver, dev_tasks
         return out

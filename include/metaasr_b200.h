@@ -191,8 +191,8 @@ int masr_maxpool2x2_fwd(const void* x, void* y, int dtype, int B, int H, int W, 
 /* dx = scatter(dy) to the first arg-max of each window, times (x > 0) when relu_mask != 0 */
 int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int dtype, int relu_mask,
                         int B, int H, int W, int C, void* stream);
-/* dx *= (y > 0), elementwise */
-int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, void* stream);
+/* dx = (y > 0) ? dx * scale : 0, elementwise (scale = 1/(1-p): backward of ReLU followed by dropout(p) from the stored output) */
+int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, float scale, void* stream);
 
 /* ------------------------------------------------------------------ attention
  * softmax(Q K^T / sqrt(hd) + mask) V with the masks built from lengths inside the kernel:

@@ -297,11 +297,11 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
 }
 
 template <typename T>
-__global__ void relu_bwd_kernel(const T* __restrict__ y, T* __restrict__ dx, int64_t n) {
+__global__ void relu_bwd_kernel(const T* __restrict__ y, T* __restrict__ dx, int64_t n, float scale) {
   pdl_launch_dependents();
   pdl_wait();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
-    if (!(to_f<T>(y[i]) > 0.f)) dx[i] = from_f<T>(0.f);
+    dx[i] = (to_f<T>(y[i]) > 0.f) ? from_f<T>(to_f<T>(dx[i]) * scale) : from_f<T>(0.f);
 }
 
 // ------------------------------------------------------------------ vectorised pool kernels (C % 8 == 0)
@@ -616,10 +616,10 @@ extern "C" int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int 
   return MASR_OK;
 }
 
-extern "C" int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, void* stream) {
+extern "C" int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, float scale, void* stream) {
   if (n == 0) return MASR_OK;
   MASR_DISPATCH_DTYPE(dtype, T,
-      launch_pdl(relu_bwd_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), static_cast<const T*>(y), static_cast<T*>(dx), n));
+      launch_pdl(relu_bwd_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), static_cast<const T*>(y), static_cast<T*>(dx), n, scale));
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -359,18 +359,8 @@ static bool band_geometry(int H, int W, int ch, int BN, BandGeom* g) {
   return false;
 }
 
-static bool band_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MASR_CONV_BAND"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
-  return v != 0;
-}
-static int band_rows_per_box(int nr) {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MASR_CONV_BAND_RPB"); v = e != nullptr ? atoi(e) : 1; }
-  int r = v <= 0 ? nr : std::min(v, nr);
-  while (nr % r != 0) --r;          // equal boxes
-  return r;
-}
+// rows of the activation band per TMA box: one (measured best of 1 / 2 / all)
+static int band_rows_per_box(int nr) { (void)nr; return 1; }
 
 template <int CH, int BN, int MODE, int NM, bool RES>
 static int launch_band2(const CUtensorMap& ma, const CUtensorMap& mw, const BandParams& p, const BandGeom& g, cudaStream_t st) {
@@ -397,7 +387,6 @@ static int launch_band(const CUtensorMap& ma, const CUtensorMap& mw, const BandP
 // mode 0: forward (wp [Cout][tap][Cin]); 1: dgrad reading wp MN-major; 2: dgrad with wpt [Cin][tap][Cout]
 int conv_band_try(int mode, const void* act, const void* wp, void* out, const void* relu_src, const float* bias, int relu,
                   int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
-  if (!band_enabled()) return 1;
   const int Cred = mode == 0 ? Cin : Cout, Cn = mode == 0 ? Cout : Cin;
   BandGeom g;
   if (!band_geometry(H, W, Cred / 64, Cn, &g)) return 1;
@@ -416,8 +405,7 @@ int conv_band_try(int mode, const void* act, const void* wp, void* out, const vo
   rc = make_tmap_bf16(&mw, wp, 2, wd, ws, wb, true);
   if (rc != MASR_OK) return rc;
   const int kstride = mode == 2 ? Cout : Cin;              // columns per tap inside the weight rows
-  static int pf = -1;
-  if (pf < 0) { const char* e = getenv("MASR_CONV_BAND_PF"); pf = e != nullptr ? atoi(e) : 0; }   // measured: no effect
+  const int pf = 0;                                        // L2 prefetch of the next band: measured, no effect
   BandParams p{B, H, W, g.W2, kstride, g.tiles_per_img, B * g.tiles_per_img, g.nr, g.slot_bytes, g.sb, rpb, pf,
                static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(relu_src), bias, relu};
   const int key = (mode << 2) | ((Cred == 128 ? 1 : 0) << 1) | (Cn == 128 ? 1 : 0);

@@ -740,9 +740,7 @@ extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp
     const int wp = W + 4;
     const int r = std::max(1, std::min(H, 96 / wp));
     const int kr = (wp * r + 15) / 16 * 16;
-    static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("MASR_CONV_WGRAD2"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
-    if (enabled && kr <= 128 && wp <= 256) {
+    if (kr <= 128 && wp <= 256) {
       CUtensorMap mdy2, mx2;
       uint32_t box[4] = {64, uint32_t(wp), uint32_t(r), 1};
       uint64_t dd[4] = {uint64_t(Cout), uint64_t(W), uint64_t(H), uint64_t(B)};
@@ -757,9 +755,7 @@ extern "C" int masr_umma_conv3x3_wgrad(const void* x, const void* dy, float* dwp
       Wgrad2Params p2{B, H, W, Cin, Cout, wp, r, kr, B * tpi, tpi, dwp, db};
       cudaStream_t st2 = as_stream(stream);
       if (Cout == 64 && Cin == 64) {
-        static int w3 = -1;
-        if (w3 < 0) { const char* e = getenv("MASR_CONV_WGRAD3"); w3 = (e != nullptr && e[0] == '0') ? 0 : 1; }
-        if (w3 && wp <= 124) {
+        if (wp <= 124) {
           // tap-pair variant: one image row of dY and three of X per k-block
           CUtensorMap mdy3, mx3;
           uint32_t by[4] = {64, uint32_t(wp), 1, 1}, bx[4] = {64, uint32_t(wp), 3, 1};

@@ -658,9 +658,7 @@ extern "C" int masr_ctc_fwd_bwd_ex(const float* acts, int T, int B, int C, int64
     // tables in the workspace) whenever the extended label sequence fits 32 lanes x 12 states
     const int S = 2 * max_tgt_len + 1;
     const int spl = (S + 31) / 32;
-    static int ctc_ver = -1;
-    if (ctc_ver < 0) { const char* e = getenv("MASR_CTC_VERSION"); ctc_ver = e != nullptr ? atoi(e) : 3; }
-    if (ctc_ver >= 3) {
+    {
       const int rc3 = ctc3_try(acts, T, B, C, st_t, st_b, act_is_logprob, targets, tgt_offsets, in_lens, tgt_lens, max_tgt_len, blank,
                                zero_infinity, grad_scale, nll, loss, grad, g_ctc_dbg, st);
       if (rc3 != CTC3_NOT_APPLICABLE) return rc3;

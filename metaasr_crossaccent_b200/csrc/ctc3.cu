@@ -1,25 +1,25 @@
-// Kernel 1, v3: log-space CTC alpha-beta forward-backward, one CTA per utterance, ONE posterior table.
+// Kernel 1: log-space CTC alpha-beta forward-backward, one CTA per utterance, ONE posterior table, pipelined in the CTA.
 //
 // Same contract as ctc.cu (replaces F.log_softmax + nn.CTCLoss(blank, 'mean', zero_infinity) and its backward,
-// src/blstm_trainer.py:22,65-70).  v2 (ctc.cu) keeps alpha [T][S], beta [T][S] and the emissions in shared memory
-// (92 KB at T'=128, L=34: two CTAs per SM) and spends ~117 k warp instructions per utterance, most of them in the
-// gradient phase: at 2 048 utterances the SMs are issue-bound at 1.66 TB/s.  v3:
-//
-//   * ONE table.  The alpha warp walks t = 0 .. Tb-1, the beta warp t = Tb-1 .. 0, concurrently.  Until they meet
-//     in the middle each stores its own values; after ONE 64-thread named barrier every frame they reach already
-//     holds the other recursion's values, so they store the combined log2 posterior
-//         P[t][s] = alpha_t(s) + beta_t(s) - E_t(s)
-//     in place (one extra shared-memory load per state, off the dependent chain).  55 KB per CTA at the BASELINE
-//     shape -> four CTAs per SM; the recursion warps are warps {0,1} or {2,3} by a hash of the CTA index so that
-//     co-resident CTAs spread their MUFU-bound chains over all four SM sub-partitions;
+// src/blstm_trainer.py:22,65-70).
+//   * ONE table.  The alpha warp walks t = 0 .. Tb-1, the beta warp t = Tb-1 .. 0, concurrently.  Until they meet in the
+//     middle each stores its own values; afterwards every frame they reach already holds the other recursion's values,
+//     so they store the combined log2 posterior P[t][s] = alpha_t(s) + beta_t(s) - E_t(s) in place;
 //   * emissions and class posteriors are indexed by SLOT (= first position of the class in the target, L = blank,
-//     Lmax+1 = a dummy slot for classes that do not occur).  Every lane keeps the slot of its 12 classes in
-//     registers: phase 0 scatters x*log2e - logZ to E[t][slot] with unconditional shared stores (no scattered
-//     global gather), phase 3 reads the class posterior G[slot] with unconditional shared loads (the dummy slot
+//     Lmax+1 = a dummy slot for classes that do not occur).  Every lane keeps the slot of its 12 classes in registers:
+//     the emission workers scatter x*log2e - logZ to E[slot][t] with unconditional shared stores (no scattered global
+//     gather), the gradient workers read the class posterior G[slot] with unconditional shared loads (the dummy slot
 //     holds 0): no branches, no predicates, no shared-memory atomics in the streaming loops;
-//   * the lse of the three predecessors is 1 + 2^(lo1-m) + 2^(lo2-m): two MUFU.EX2 + one MUFU.LG2 per state;
-//   * gradient rows are written with streaming stores (evict-first) so they do not push the activation rows out
-//     of L2 before phase 3 re-reads them.
+//   * the lse of the three predecessors is 1 + 2^(lo1-m) + 2^(lo2-m): two MUFU.EX2 + one MUFU.LG2 per state.  (A
+//     linear-domain recursion with per-lane block exponents -- adds and multiplies on the dependent chain, logarithms off
+//     it -- was built and measured in round 2: same 252 us at 2 048 utterances.  With three co-resident CTAs the SM is
+//     bound by the issue slots of the streaming warps (2.2 IPC of 4, 35 % warp occupancy), not by the recursion chain,
+//     so the exact log-domain step stays);
+//   * six streaming warps produce emission frames from both ends towards the middle and announce them per frame; the two
+//     recursion warps poll eight frames ahead; the log-likelihood is taken at the meeting frame, so the streaming warps
+//     turn into gradient workers that follow the recursions outward from the middle;
+//   * gradient rows are written with streaming stores (evict-first) so they do not push the activation rows out of L2
+//     before the gradient workers re-read them.
 #include "common.cuh"
 
 namespace masr {
@@ -73,80 +73,6 @@ __device__ __forceinline__ void recur(float (&a)[SPL], const float (&e)[SPL], co
   }
 #pragma unroll
   for (int i = 0; i < SPL; ++i) a[i] = nw[i];
-}
-
-// One warp, one direction.  Returns (FWD only) log2 P(labels | x) from the final alpha row held in registers.
-// E2 is slot-major: E2[slot * TP + t].
-template <int SPL, bool FWD>
-__device__ __forceinline__ float chain(float* __restrict__ P, const float* __restrict__ E2, const int* __restrict__ tg,
-                                       const short* __restrict__ cmap, int lane, int L, int S, int Tb, int Sstride,
-                                       int TP, int blank) {
-  float a[SPL], e[SPL], skipadd[SPL], validadd[SPL];
-  bool valid[SPL];
-  const float* pe[SPL];             // emission of the state's class at the current frame
-  const int t0 = FWD ? 0 : Tb - 1;
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) {
-    const int s = lane * SPL + i;
-    const int j = s >> 1;
-    const bool odd = s & 1;
-    valid[i] = s < S;
-    pe[i] = E2 + ((odd && j < L) ? int(cmap[tg[j]]) : L) * TP + t0;
-    bool skip;
-    if (FWD) skip = odd && s > 1 && s < S && tg[j] != tg[j - 1];
-    else     skip = odd && s + 2 < S && tg[j] != tg[j + 1];
-    skipadd[i] = skip ? 0.f : NEG;
-    validadd[i] = valid[i] ? 0.f : NEG;
-  }
-  const int mid = Tb >> 1;
-  const int npre = FWD ? mid : Tb - mid;           // frames this warp reaches first
-  const int tstep = FWD ? 1 : -1, sstep = FWD ? Sstride : -Sstride;
-  float* dst = P + t0 * Sstride + lane * SPL;
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) {
-    const int s = lane * SPL + i;
-    e[i] = *pe[i];
-    const bool start = FWD ? (s <= 1) : (s >= S - 2);
-    a[i] = (start && valid[i]) ? e[i] : NEG;
-  }
-  int k = 0;
-  for (; k < npre; ++k) {                          // a[], e[] belong to frame t0 +- k
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) if (valid[i]) dst[i] = a[i];
-    if (k + 1 < Tb) {
-      dst += sstep;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) { pe[i] += tstep; e[i] = *pe[i]; }
-      recur<SPL, FWD>(a, e, skipadd, validadd, lane);
-    }
-  }
-  bar_sync_named(1, 64);                           // everything the other warp stored so far is visible from here on
-  for (; k < Tb; ++k) {
-    float o[SPL];
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) o[i] = valid[i] ? dst[i] : 0.f;
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) if (valid[i]) dst[i] = (a[i] - e[i]) + o[i];
-    if (k + 1 < Tb) {
-      dst += sstep;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) { pe[i] += tstep; e[i] = *pe[i]; }
-      recur<SPL, FWD>(a, e, skipadd, validadd, lane);
-    }
-  }
-  float ll2 = 0.f;
-  if (FWD) {
-    float m = NEG;
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) { const int s = lane * SPL + i; if (valid[i] && s >= S - 2) m = fmaxf(m, a[i]); }
-    m = warp_max(m);
-    float se = 0.f;
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) { const int s = lane * SPL + i; if (valid[i] && s >= S - 2) se += ex2f(a[i] - m); }
-    se = warp_sum(se);
-    ll2 = se > 0.f ? m + lg2f(se) : NEG;
-  }
-  return ll2;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -303,282 +229,6 @@ inline size_t smem_bytes(int T, int Lmax, int C, int spl_dispatched) {
   const size_t b = sizeof(float) * (size_t(T) + 4 + size_t(Lmax + 3) * ctc3_tp(T, F3) + size_t(T) * (2 * size_t(Lmax) + 2)) +
                    sizeof(int) * size_t(Lmax + 1) + sizeof(short) * (size_t(C) + 3 * npos + 2 * EXMAX);
   return (b + 15) / 16 * 16;
-}
-
-// F0 / F3: frames per warp iteration in the emission / gradient phase; MINB: CTAs per SM the register budget allows
-template <int SPL, int F0, int F3, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-ctc3_kernel(const float* __restrict__ acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob,
-            const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
-            const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
-            int Lmax, int blank, int zero_infinity, float grad_scale,
-            float* __restrict__ nll_out, float* __restrict__ loss_out, float* __restrict__ grad,
-            long long* __restrict__ dbg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // optional phase timestamps of CTA 0 (masr_ctc_debug_enable): [start, setup, phase0, chains, -, end]
-#define CTC_STAMP(i) do { if (dbg != nullptr && b == 0 && tid == 0) dbg[i] = clock64(); } while (0)
-  CTC_STAMP(0);
-  const int Sstride = 2 * Lmax + 2, NEGCOL = 2 * Lmax + 1;      // P rows end with a column that holds NEG (2^NEG = 0)
-  const int NSLOT = Lmax + 3, DUMMY = Lmax + 1, TRASH = Lmax + 2;     // slots: [positions | blank L | .. | 0 | trash]
-  const int TP = ctc3_tp(T, F3);               // odd pitch of a slot's row of emissions (bank-conflict-free)
-  constexpr int NJ = SPL / 2 + 1;              // label positions / even states per lane: L + 1 <= 16 SPL + 1
-
-  float* logZ2 = reinterpret_cast<float*>(smem_raw);             // [T]
-  float* red = logZ2 + T;                                        // [4]
-  float* E2 = red + 4;                                           // [NSLOT][TP] emissions (log2), slot-major; phase 3: G
-  float* P = E2 + size_t(NSLOT) * TP;                            // [T][Sstride] alpha / beta, then log2 posteriors
-  int* tg = reinterpret_cast<int*>(P + size_t(T) * Sstride);     // [Lmax]
-  int* nextra = tg + Lmax;                                       // [1]
-  short* cmap = reinterpret_cast<short*>(nextra + 1);            // [C] class -> slot (first position; L blank; DUMMY none)
-  short* colA = cmap + C;                      // [32 NJ] P column of a first position's own label state (else NEGCOL)
-  short* colB = colA + 32 * NJ;                // [32 NJ] P column of the class's second occurrence (else NEGCOL)
-  short* gslot = colB + 32 * NJ;               // [32 NJ] slot a position's posterior is stored to (else TRASH)
-  short* excol = gslot + 32 * NJ;              // [EXMAX] P column / slot of the label states not covered by colA / colB
-  short* exslot = excol + EXMAX;
-
-  const int L = int(tgt_lens[b]);
-  const int Tb = min(T, int(in_lens[b]));
-  const int S = 2 * L + 1;
-  const int64_t toff = tgt_offsets[b];
-
-  for (int j = tid; j < L; j += THREADS) tg[j] = int(targets[toff + j]);
-  for (int c = tid; c < C; c += THREADS) cmap[c] = short(c == blank ? L : DUMMY);
-  if (tid == 0) *nextra = 0;
-  __syncthreads();
-  for (int j = tid; j < 32 * NJ; j += THREADS) {
-    int ca = NEGCOL, cb = NEGCOL, gs = TRASH;
-    if (j < L) {
-      const int cls = tg[j];
-      int firstpos = j, rank = 0, nx = -1;                 // first position of the class, # earlier occurrences, next one
-      if (cls != blank) {
-        for (int i = j - 1; i >= 0; --i) if (tg[i] == cls) { firstpos = i; ++rank; }
-        if (rank == 0) {
-          for (int i = j + 1; i < L; ++i) if (tg[i] == cls) { nx = i; break; }
-          cmap[cls] = short(j);
-          ca = 2 * j + 1; gs = j;
-          if (nx >= 0) cb = 2 * nx + 1;
-        }
-      } else {
-        firstpos = L; rank = 2;                            // a label equal to the blank class (legal for ATen): blank slot
-      }
-      if (rank >= 2) {
-        const int e = atomicAdd(nextra, 1);
-        if (e < EXMAX) { excol[e] = short(2 * j + 1); exslot[e] = short(firstpos); }
-      }
-    }
-    colA[j] = short(ca); colB[j] = short(cb); gslot[j] = short(gs);
-  }
-  for (int t = tid; t < T; t += THREADS) P[t * Sstride + NEGCOL] = NEG;
-  __syncthreads();
-  const int nex = *nextra;
-  const bool fast_c = C >= 32 && C <= 32 * CPL;
-  const bool fast3 = fast_c && nex <= EXMAX;
-
-  CTC_STAMP(1);
-  // ---- phase 0: log2-domain normaliser and the emission table.  A warp handles F0 frames at a time and issues
-  // all their row loads before reducing; x * log2e - logZ goes to E2[slot(class)][t] with unconditional stores.
-  if (fast_c) {
-    float* ek[CPL];                 // E2 row of class lane + 32 k (classes that do not occur: the dummy slot)
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) { const int c = lane + 32 * k; ek[k] = E2 + (c < C ? int(cmap[c]) : DUMMY) * TP; }
-    for (int t0 = warp * F0; t0 < Tb; t0 += NW * F0) {
-      float x[F0][CPL];
-      // frames past Tb are clamped to Tb-1: they recompute and re-store the same values (idempotent)
-      const bool full = t0 + F0 <= Tb;
-#pragma unroll
-      for (int f = 0; f < F0; ++f) {
-        const float* row = acts + (int64_t(full ? t0 + f : min(t0 + f, Tb - 1)) * st_t + b * st_b) + lane;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldg(row + 32 * k) : NEG;
-      }
-      float z2[F0];
-#pragma unroll
-      for (int f = 0; f < F0; ++f) {
-        z2[f] = 0.f;
-        if (!is_logprob) {
-          float mx = x[f][0];
-#pragma unroll
-          for (int k = 1; k < CPL; ++k) mx = fmaxf(mx, x[f][k]);
-          mx = warp_max(mx) * LOG2E;
-          float se = 0.f;
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) se += ex2f(fmaf(x[f][k], LOG2E, -mx));
-          se = warp_sum(se);
-          z2[f] = mx + lg2f(se);
-        }
-      }
-      if (full) {
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float* d = ek[k] + t0;
-#pragma unroll
-          for (int f = 0; f < F0; ++f) d[f] = fmaf(x[f][k], LOG2E, -z2[f]);
-        }
-        if (lane < F0) {
-          float z = z2[0];
-#pragma unroll
-          for (int f = 1; f < F0; ++f) if (lane == f) z = z2[f];
-          logZ2[t0 + lane] = z;
-        }
-      } else {
-#pragma unroll
-        for (int f = 0; f < F0; ++f) {
-          const int tt = min(t0 + f, Tb - 1);
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) ek[k][tt] = fmaf(x[f][k], LOG2E, -z2[f]);
-          if (lane == 0) logZ2[tt] = z2[f];
-        }
-      }
-    }
-  } else {
-    for (int t = warp; t < Tb; t += NW) {
-      const float* row = acts + (int64_t(t) * st_t + b * st_b);
-      float z2 = 0.f;
-      if (!is_logprob) {
-        float mx = -INFINITY;
-        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int c = lane; c < C; c += 32) se += ex2f((row[c] - mx) * LOG2E);
-        se = warp_sum(se);
-        z2 = mx * LOG2E + lg2f(se);
-      }
-      if (lane == 0) logZ2[t] = z2;
-      for (int j = lane; j <= L; j += 32) {
-        const int cls = j < L ? tg[j] : blank;
-        if (j == L || int(cmap[cls]) == j) E2[j * TP + t] = row[cls] * LOG2E - z2;
-      }
-    }
-  }
-  __syncthreads();
-
-  CTC_STAMP(2);
-  // ---- phase 1: alpha and beta in two warps, meeting in the middle
-  const int cw = (__popc(unsigned(b)) & 1) * 2;         // recursion warps {0,1} or {2,3}
-  if (Tb > 0 && (warp == cw || warp == cw + 1)) {
-    if (warp == cw) {
-      const float v = chain<SPL, true>(P, E2, tg, cmap, lane, L, S, Tb, Sstride, TP, blank);
-      if (lane == 0) red[0] = v;
-    } else {
-      chain<SPL, false>(P, E2, tg, cmap, lane, L, S, Tb, Sstride, TP, blank);
-    }
-  } else if (Tb == 0 && tid == 0) {
-    red[0] = (S == 1) ? 0.f : NEG;
-  }
-  __syncthreads();
-  CTC_STAMP(3);
-
-  const float ll2 = red[0];
-  const bool feasible = (ll2 > 0.5f * NEG);
-  if (tid == 0) {
-    float nll = feasible ? -ll2 * LN2 : INFINITY;
-    if (!feasible && zero_infinity) nll = 0.f;
-    nll_out[b] = nll;
-    if (loss_out != nullptr) atomicAdd(loss_out, nll / float(max(L, 1)) / float(B));
-  }
-  if (grad == nullptr) return;
-  const float scale = grad_scale / (float(B) * float(max(L, 1)));
-
-  // ---- phase 3: gradient rows, F3 frames per warp iteration: grad[t][c] = softmax_t(c) * scale - G_t(slot(c)),
-  // G_t(slot) = scale * sum over the states of the slot's class of 2^(P[t][s] - ll2).  The emission table is dead
-  // now: each warp keeps its posteriors G[slot][f] there (dummy slot = 0).
-  float* Gw = E2 + warp * (F3 * NSLOT);
-  if (lane < F3) Gw[DUMMY * F3 + lane] = 0.f;
-  const float* gk[CPL];             // G row of class lane + 32 k
-#pragma unroll
-  for (int k = 0; k < CPL; ++k) { const int c = lane + 32 * k; gk[k] = Gw + ((fast_c && c < C) ? int(cmap[c]) : DUMMY) * F3; }
-  __syncwarp();
-  for (int t0 = warp * F3; t0 < T; t0 += NW * F3) {
-    if (fast3 && feasible && t0 + F3 <= Tb) {
-      // ---------------- fast path: F3 live frames, no per-frame predicates, no branches
-      float x[F3][CPL];
-#pragma unroll
-      for (int f = 0; f < F3; ++f) {
-        const float* row = acts + (int64_t(t0 + f) * st_t + b * st_b) + lane;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldcs(row + 32 * k) : 0.f;
-      }
-      const float* Pt = P + t0 * Sstride;
-      float bs[F3];
-#pragma unroll
-      for (int f = 0; f < F3; ++f) bs[f] = 0.f;
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) {
-        const int m = lane + 32 * i;
-        const int ca = colA[m], cb = colB[m], gs = gslot[m];
-        const int ce = m <= L ? 2 * m : NEGCOL;          // even (blank) state 2m
-#pragma unroll
-        for (int f = 0; f < F3; ++f) {
-          const float* Pf = Pt + f * Sstride;
-          Gw[gs * F3 + f] = (ex2f(Pf[ca] - ll2) + ex2f(Pf[cb] - ll2)) * scale;
-          bs[f] += ex2f(Pf[ce] - ll2);
-        }
-      }
-#pragma unroll
-      for (int f = 0; f < F3; ++f) bs[f] = warp_sum(bs[f]);
-      if (lane == 0) {
-#pragma unroll
-        for (int f = 0; f < F3; ++f) Gw[L * F3 + f] = bs[f] * scale;
-      }
-      __syncwarp();
-      if (nex > 0) {                         // third and later occurrences of a class, labels equal to the blank class
-        if (lane < F3) {
-          const float* Pf = Pt + lane * Sstride;
-          for (int e = 0; e < nex; ++e) Gw[int(exslot[e]) * F3 + lane] += ex2f(Pf[excol[e]] - ll2) * scale;
-        }
-        __syncwarp();
-      }
-      float z2[F3];
-#pragma unroll
-      for (int f = 0; f < F3; ++f) z2[f] = logZ2[t0 + f];
-      float* grow = grad + (int64_t(t0) * st_t + b * st_b) + lane;
-      const int64_t fstride = st_t;
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        if (lane + 32 * k < C) {
-#pragma unroll
-          for (int f = 0; f < F3; ++f) {
-            const float pr = ex2f(fmaf(x[f][k], LOG2E, -z2[f]));
-            __stcs(grow + f * fstride + 32 * k, fmaf(pr, scale, -gk[k][f]));
-          }
-        }
-      }
-      __syncwarp();                          // G is rewritten by the next iteration
-    } else {
-      // ---------------- generic path: ragged tail, padded frames, infeasible utterances, C outside [32, 384]
-#pragma unroll 1
-      for (int f = 0; f < F3; ++f) {
-        const int t = t0 + f;
-        if (t >= T) break;
-        float* grow = grad + (int64_t(t) * st_t + b * st_b);
-        if (!feasible || t >= Tb) {
-          // beyond the input length ATen writes zeros; an infeasible utterance under zero_infinity too (without
-          // zero_infinity the loss is inf and the gradient NaN, as in ATen)
-          const float fill = (!feasible && !zero_infinity && t < Tb) ? NAN : 0.f;
-          for (int c = lane; c < C; c += 32) grow[c] = fill;
-          continue;
-        }
-        const float* row = acts + (int64_t(t) * st_t + b * st_b);
-        const float* Pt = P + t * Sstride;
-        float bsum = 0.f;
-        for (int m = lane; m <= L; m += 32) bsum += ex2f(Pt[2 * m] - ll2);
-        for (int j = lane; j < L; j += 32) if (int(cmap[tg[j]]) == L) bsum += ex2f(Pt[2 * j + 1] - ll2);
-        bsum = warp_sum(bsum);
-        const float z2 = logZ2[t];
-        for (int c = lane; c < C; c += 32) {
-          const float pr = ex2f(row[c] * LOG2E - z2);
-          const int u = int(cmap[c]);
-          float occ = (u == L) ? bsum : 0.f;
-          if (u < L) for (int j = u; j < L; ++j) if (tg[j] == c) occ += ex2f(Pt[2 * j + 1] - ll2);
-          grow[c] = (pr - occ) * scale;
-        }
-      }
-    }
-  }
-  CTC_STAMP(5);
-#undef CTC_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -882,73 +532,25 @@ int launch_pipe(const float* acts, int T, int B, int C, int64_t st_t, int64_t st
   return MASR_OK;
 }
 
-template <int SPL, int F0, int F3, int MINB>
-int launch(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
-           const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
-           float* nll, float* loss, float* grad, long long* dbg, size_t smem, cudaStream_t st) {
-  auto kern = ctc3_kernel<SPL, F0, F3, MINB>;
-  static size_t attr_smem = 0;      // per instantiation: the attribute call costs more than the launch
-  if (smem > attr_smem) {
-    MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_smem = smem;
-  }
-  kern<<<B, THREADS, smem, st>>>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,
-                                 zero_infinity, grad_scale, nll, loss, grad, dbg);
-  MASR_LAUNCH_CHECK();
-  return MASR_OK;
-}
-
-template <int F0, int F3>
-static int dispatch(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
-                    const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
-                    float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
+static int dispatch(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets,
+                    const int64_t* tgt_offsets, const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank,
+                    int zero_infinity, float grad_scale, float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
   const int S = 2 * Lmax + 1;
   const int spl = (S + 31) / 32;
-  if (spl > 12) return CTC3_NOT_APPLICABLE;
+  if (spl > 12 || Lmax > 30000 || C > 32000) return CTC3_NOT_APPLICABLE;
   const int spld = spl <= 4 ? spl : (spl <= 6 ? 6 : (spl <= 8 ? 8 : 12));
-  size_t smem = smem_bytes<F3>(T, Lmax, C, spld);
-  if (smem > 227 * 1024 || Lmax > 30000 || C > 32000) return CTC3_NOT_APPLICABLE;
-  static int pipe = -1;             // MASR_CTC_PIPE=0: the block-barrier kernel instead of the pipelined one
-  if (pipe < 0) { const char* e = getenv("MASR_CTC_PIPE"); pipe = e != nullptr ? atoi(e) : 1; }
-  if (pipe && F0 == 2 && F3 == 2) {
-    const size_t smem_p = smem_bytes_pipe(T, Lmax, C, spld);
-    if (smem_p <= 227 * 1024) {
+  const size_t smem_p = smem_bytes_pipe(T, Lmax, C, spld);
+  if (smem_p > 227 * 1024) return CTC3_NOT_APPLICABLE;          // tables beyond shared memory: ctc.cu (global workspace)
 #define CTC3P_CASE(N) return launch_pipe<N, 3>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, \
                                                zero_infinity, grad_scale, nll, loss, grad, dbg, smem_p, st)
-      if (spl <= 1) CTC3P_CASE(1);
-      if (spl <= 2) CTC3P_CASE(2);
-      if (spl <= 3) CTC3P_CASE(3);
-      if (spl <= 4) CTC3P_CASE(4);
-      if (spl <= 6) CTC3P_CASE(6);
-      if (spl <= 8) CTC3P_CASE(8);
-      CTC3P_CASE(12);
+  if (spl <= 1) CTC3P_CASE(1);
+  if (spl <= 2) CTC3P_CASE(2);
+  if (spl <= 3) CTC3P_CASE(3);
+  if (spl <= 4) CTC3P_CASE(4);
+  if (spl <= 6) CTC3P_CASE(6);
+  if (spl <= 8) CTC3P_CASE(8);
+  CTC3P_CASE(12);
 #undef CTC3P_CASE
-    }
-  }
-  static int pad = -1;              // MASR_CTC_SMEM_PAD: extra bytes per CTA (occupancy experiments)
-  if (pad < 0) { const char* e = getenv("MASR_CTC_SMEM_PAD"); pad = e != nullptr ? atoi(e) : 0; }
-  if (smem + size_t(pad) <= 227 * 1024) smem += size_t(pad);
-  // 64-register build (four CTAs per SM) while the whole batch fits one wave of it, else the 80-register build
-  // (three CTAs per SM, no spills): equal at 2 048 utterances, 94 vs 111 us at 512.  MASR_CTC_MINB=3|4 overrides.
-  static int minb_env = -1;
-  if (minb_env < 0) { const char* e = getenv("MASR_CTC_MINB"); minb_env = e != nullptr ? atoi(e) : 0; }
-  const int minb = minb_env != 0 ? minb_env : (B <= 4 * sm_count() ? 4 : 3);
-#define CTC3_CASE(N)                                                                                                         \
-  do {                                                                                                                       \
-    if (minb == 4)                                                                                                           \
-      return launch<N, F0, F3, 4>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,         \
-                                  zero_infinity, grad_scale, nll, loss, grad, dbg, smem, st);                               \
-    return launch<N, F0, F3, 3>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,           \
-                                zero_infinity, grad_scale, nll, loss, grad, dbg, smem, st);                                 \
-  } while (0)
-  if (spl <= 1) CTC3_CASE(1);
-  if (spl <= 2) CTC3_CASE(2);
-  if (spl <= 3) CTC3_CASE(3);
-  if (spl <= 4) CTC3_CASE(4);
-  if (spl <= 6) CTC3_CASE(6);
-  if (spl <= 8) CTC3_CASE(8);
-  CTC3_CASE(12);
-#undef CTC3_CASE
 }
 
 }  // namespace
@@ -956,9 +558,8 @@ static int dispatch(const float* acts, int T, int B, int C, int64_t st_t, int64_
 int ctc3_try(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets, const int64_t* tgt_offsets,
              const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank, int zero_infinity, float grad_scale,
              float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
-  // frames per warp iteration (emission, gradient) = (2, 2): measured best of (2,2) / (3,3) / (4,2) at 80 registers
-  return dispatch<2, 2>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, zero_infinity,
-                        grad_scale, nll, loss, grad, dbg, st);
+  return dispatch(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, zero_infinity,
+                  grad_scale, nll, loss, grad, dbg, st);
 }
 
 }  // namespace masr

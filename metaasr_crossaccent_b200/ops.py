@@ -46,6 +46,11 @@ class CudaBackend:
         self.prof_tag = ""
         self._scratch = {}
         self.scratch_tag = ""         # set by the engine while it launches on its side stream
+        # gemm="umma" promises the tcgen05 kernels.  An operand that cannot take them (dtype / alignment / head dim /
+        # channel count) is never silent: the miss is counted in self.fallbacks, reported once per (op, reason) through
+        # `warnings`, and raises when strict_umma is set (asr_model.strict_tcgen05: bench.py and the hkust-size tests)
+        self.fallbacks = {}
+        self.strict_umma = False
         # one device-resident dropout seed offset per device, alive for the whole process (the library
         # keeps its address; kernels add it to every dropout seed so CUDA-graph replays get fresh masks)
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -92,13 +97,28 @@ class CudaBackend:
             self.lib.masr_gemm_set_stage_cap(int(stages))
             self._stage_cap = stages
 
-    def _umma_ok(self, *ts):
+    def _miss(self, op, reason):
+        """A launch in gemm='umma' mode that cannot use the tcgen05 kernel: count, warn once, raise if strict."""
+        key = (op, reason)
+        n = self.fallbacks.get(key, 0)
+        self.fallbacks[key] = n + 1
+        if self.strict_umma:
+            raise _lib.MetaASRLibraryError(f"{op}: tcgen05 path not applicable ({reason}) and strict_tcgen05 is set")
+        if n == 0:
+            import warnings
+            warnings.warn(f"metaasr_b200: {op} runs on the CUDA-core kernel ({reason}); further misses are only counted "
+                          f"in backend.fallbacks", RuntimeWarning, stacklevel=3)
+        return False
+
+    def _umma_ok(self, *ts, op="gemm"):
         """tcgen05 path: bf16 operands, 16 B aligned bases, leading dimensions multiple of 8."""
         if self.gemm_path != "umma":
             return False
         for t in ts:
-            if t.dtype != torch.bfloat16 or t.data_ptr() % 16 or t.stride(0) % 8 or t.stride(1) != 1:
-                return False
+            if t.dtype != torch.bfloat16:
+                return self._miss(op, f"operand dtype {t.dtype}")
+            if t.data_ptr() % 16 or t.stride(0) % 8 or t.stride(1) != 1:
+                return self._miss(op, f"operand alignment: stride {tuple(t.stride())}, base % 16 = {t.data_ptr() % 16}")
         return True
 
     def umma_gemm(self, A, a_mn, B, b_mn, C, bias, M, N, K, flags=0, splitk=1, rowsum=None, mask=None, mask_scale=1.0,
@@ -141,9 +161,9 @@ class CudaBackend:
             return False
         for t in ts:
             if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.data_ptr() % 16:
-                return False
+                return self._miss("conv3x3", f"operand dtype {t.dtype} / layout")
             if t.dim() == 4 and t.shape[3] not in (64, 128):
-                return False
+                return self._miss("conv3x3", f"{t.shape[3]} channels (64 or 128 supported)")
         return True
 
     def _timed_call(self, key, name, *args, n_kernels=1):
@@ -210,9 +230,7 @@ class CudaBackend:
             self.gemm(dy, dy.stride(0), 1, w, 1, w.stride(0), dx, dx.stride(0), None, M, K, N,
                       GEMM_ACCUM if accumulate else 0)
         if relu_drop_mask is not None:
-            self.relu_bwd(relu_drop_mask, dx)
-            if scale != 1.0:
-                self.scale_(dx, scale)
+            self.relu_bwd(relu_drop_mask, dx, scale)
 
     def linear_wgrad(self, x, dy, dw, db):
         """dw[N,K] += dy[M,N]^T @ x[M,K] (fp32); db[N] += column sums of dy."""
@@ -232,8 +250,11 @@ class CudaBackend:
 
     # -------------------------------------------------------------- conv front end
     def _conv1_umma_ok(self, x, act, Cout):
-        return (self.gemm_path == "umma" and Cout == 64 and act.dtype == torch.bfloat16 and act.is_contiguous()
-                and x.dtype == torch.float32 and x.is_contiguous() and act.data_ptr() % 16 == 0)
+        if self.gemm_path != "umma":
+            return False
+        ok = (Cout == 64 and act.dtype == torch.bfloat16 and act.is_contiguous()
+              and x.dtype == torch.float32 and x.is_contiguous() and act.data_ptr() % 16 == 0)
+        return ok or self._miss("conv1", f"Cout {Cout}, activation dtype {act.dtype}")
 
     def conv1_fwd(self, x, w, bias, y):
         B, H, W = x.shape
@@ -320,20 +341,19 @@ class CudaBackend:
         B, H, W, Cc = x.shape
         self._call("masr_maxpool2x2_bwd", _p(x), _p(dy), _p(dx), _dt(x), int(relu_mask), B, H, W, Cc, self.stream)
 
-    def scale_(self, x, a):
-        """x *= a (only used by the non-tensor-core fallback of the fused ReLU/dropout backward)."""
-        x.mul_(a)
-
-    def relu_bwd(self, y, dx):
-        self._call("masr_relu_bwd", _p(y), _p(dx), _dt(y), y.numel(), self.stream)
+    def relu_bwd(self, y, dx, scale=1.0):
+        self._call("masr_relu_bwd", _p(y), _p(dx), _dt(y), y.numel(), float(scale), self.stream)
 
     # -------------------------------------------------------------- attention
     def _attn_umma_ok(self, hd, *ts):
         """tcgen05 attention: bf16, head dim 64, 16 B aligned rows."""
-        if self.gemm_path != "umma" or hd != 64:
+        if self.gemm_path != "umma":
             return False
-        return all(t.dtype == torch.bfloat16 and t.data_ptr() % 16 == 0 and t.stride(0) % 8 == 0 and t.stride(1) == 1
-                   for t in ts)
+        if hd != 64:
+            return self._miss("attention", f"head dim {hd} (64 supported)")
+        ok = all(t.dtype == torch.bfloat16 and t.data_ptr() % 16 == 0 and t.stride(0) % 8 == 0 and t.stride(1) == 1
+                 for t in ts)
+        return ok or self._miss("attention", "operand dtype / alignment")
 
     def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0, kv_rows=None):
         """kv_rows: rows per utterance in k / v when they are a decode cache of fixed capacity (default Lk)."""

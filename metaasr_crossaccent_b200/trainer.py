@@ -26,7 +26,9 @@ def _make_backend(config, paras):
     if factory is not None:
         return factory(dtype)
     torch.cuda.set_device(dev)
-    return ops.CudaBackend(dev, dtype, gemm=am.get("gemm", "simt"))
+    be = ops.CudaBackend(dev, dtype, gemm=am.get("gemm", "simt"))
+    be.strict_umma = bool(am.get("strict_tcgen05", False))     # raise instead of warn when a tcgen05 kernel cannot be used
+    return be
 
 
 def get_trainer(cls, config, paras, id2accent):
