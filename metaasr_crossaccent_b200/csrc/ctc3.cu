@@ -532,6 +532,417 @@ int launch_pipe(const float* acts, int T, int B, int C, int64_t st_t, int64_t st
   return MASR_OK;
 }
 
+// ===============================================================================================================
+// Long utterances (ctc3l_kernel): the posterior table of ONE utterance no longer fits shared memory (T' = 375 / 750
+// frames x 2L+2 = 206 / 306 states: 0.3 / 0.9 MB; these are the reference's real lengths, max_ilen 1500 / 3000).
+// The frames are processed in CHUNKS of Tc frames whose table does fit, with recomputation instead of a table in HBM:
+//   sweep A (chunks 0 .. nc-2, forward):  emissions of the chunk -> alpha through the chunk, only the alpha row at the
+//           chunk's last frame is kept (Abound[c], nc x S floats);
+//   sweep B (chunks nc-1 .. 0, backward): emissions of the chunk again -> alpha from Abound[c-1] and beta from the carry
+//           of the later chunk run through the chunk from both ends, meet in the middle and leave the log2 posterior
+//           table of the chunk (same single-table scheme as above) -> gradient rows of the chunk.  The log-likelihood
+//           comes out of the alpha row of the last frame, i.e. of the FIRST chunk sweep B visits.
+// Activations are read twice from HBM (+ once more out of L2 by the gradient workers), gradients written once; alpha is
+// computed twice.  Phases inside a chunk are separated by block barriers (emission | recursions | gradient).
+constexpr int EXMAXL = 192;         // long targets repeat classes often: room for more third-and-later occurrences
+
+template <int SPL, bool FWD>
+__device__ __forceinline__ void lane_consts(const int* __restrict__ tg, const short* __restrict__ cmap, int lane, int L, int S,
+                                            int (&slot)[SPL], float (&skipadd)[SPL], float (&validadd)[SPL], bool (&valid)[SPL]) {
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    const int j = s >> 1;
+    const bool odd = s & 1;
+    valid[i] = s < S;
+    slot[i] = (odd && j < L) ? int(cmap[tg[j]]) : L;
+    bool skip;
+    if (FWD) skip = odd && s > 1 && s < S && tg[j] != tg[j - 1];
+    else     skip = odd && s + 2 < S && tg[j] != tg[j + 1];
+    skipadd[i] = skip ? 0.f : NEG;
+    validadd[i] = valid[i] ? 0.f : NEG;
+  }
+}
+
+// alpha through one chunk without a table (sweep A).  fresh: the chunk starts the utterance; else a[] = alpha of the
+// frame before the chunk.  On return a[] = alpha of the chunk's last frame.
+template <int SPL>
+__device__ __forceinline__ void chain_fwd_chunk(float (&a)[SPL], bool fresh, const float* __restrict__ E2, const int (&slot)[SPL],
+                                                const float (&skipadd)[SPL], const float (&validadd)[SPL], const bool (&valid)[SPL],
+                                                int lane, int Tn, int TPc) {
+  float e[SPL];
+  for (int k = 0; k < Tn; ++k) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) e[i] = E2[slot[i] * TPc + k];
+    if (fresh && k == 0) {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) a[i] = (lane * SPL + i <= 1 && valid[i]) ? e[i] : NEG;
+    } else {
+      recur<SPL, true>(a, e, skipadd, validadd, lane);
+    }
+  }
+}
+
+// One recursion warp over one chunk of sweep B (alpha forward from the chunk's first frame, beta backward from its
+// last), meeting the other warp in the middle; leaves the log2 posteriors of the chunk in P.  fresh: the chunk holds the
+// utterance's first (alpha) / last (beta) frame; else a[] = the values of the frame just outside the chunk.  On return
+// a[] = the values at the far end of the chunk (the beta warp's carry into the previous chunk).
+template <int SPL, bool FWD>
+__device__ __forceinline__ void chain_chunk(float (&a)[SPL], bool fresh, float* __restrict__ P, const float* __restrict__ E2,
+                                            const int (&slot)[SPL], const float (&skipadd)[SPL], const float (&validadd)[SPL],
+                                            const bool (&valid)[SPL], int lane, int S, int Tn, int Sstride, int TPc) {
+  float e[SPL];
+  const float* pe[SPL];
+  const int t0 = FWD ? 0 : Tn - 1;
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) { pe[i] = E2 + slot[i] * TPc + t0; e[i] = *pe[i]; }
+  if (fresh) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      const int s = lane * SPL + i;
+      const bool start = FWD ? (s <= 1) : (s >= S - 2);
+      a[i] = (start && valid[i]) ? e[i] : NEG;
+    }
+  } else {
+    recur<SPL, FWD>(a, e, skipadd, validadd, lane);
+  }
+  const int mid = Tn >> 1;
+  const int npre = FWD ? mid : Tn - mid;
+  const int tstep = FWD ? 1 : -1, sstep = FWD ? Sstride : -Sstride;
+  float* dst = P + t0 * Sstride + lane * SPL;
+  int k = 0;
+  for (; k < npre; ++k) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) if (valid[i]) dst[i] = a[i];
+    if (k + 1 < Tn) {
+      dst += sstep;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) { pe[i] += tstep; e[i] = *pe[i]; }
+      recur<SPL, FWD>(a, e, skipadd, validadd, lane);
+    }
+  }
+  bar_sync_named(1, 64);                           // everything the other warp stored so far is visible from here on
+  for (; k < Tn; ++k) {
+    float o[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) o[i] = valid[i] ? dst[i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) if (valid[i]) dst[i] = (a[i] - e[i]) + o[i];
+    if (k + 1 < Tn) {
+      dst += sstep;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) { pe[i] += tstep; e[i] = *pe[i]; }
+      recur<SPL, FWD>(a, e, skipadd, validadd, lane);
+    }
+  }
+}
+
+__host__ __device__ inline int ctc3l_nj(int spl) { return spl / 2 + 1; }
+inline size_t smem_bytes_long(int Tc, int T, int Lmax, int C, int spl_dispatched) {
+  const size_t nc = size_t((T + Tc - 1) / Tc), Sstride = 2 * size_t(Lmax) + 2, npos = 32 * size_t(ctc3l_nj(spl_dispatched));
+  const size_t b = sizeof(float) * (size_t(Tc) + 4 + size_t(Lmax + 3) * size_t(Tc | 1) + size_t(Tc) * Sstride + nc * Sstride) +
+                   sizeof(int) * size_t(Lmax + 1) + sizeof(short) * (size_t(C) + 3 * npos + 2 * EXMAXL);
+  return (b + 15) / 16 * 16;
+}
+
+template <int SPL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+ctc3l_kernel(const float* __restrict__ acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob,
+             const int64_t* __restrict__ targets, const int64_t* __restrict__ tgt_offsets,
+             const int64_t* __restrict__ in_lens, const int64_t* __restrict__ tgt_lens,
+             int Lmax, int blank, int zero_infinity, float grad_scale, int Tc,
+             float* __restrict__ nll_out, float* __restrict__ loss_out, float* __restrict__ grad) {
+  constexpr int F = 2;               // frames per warp iteration (emission and gradient)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Sstride = 2 * Lmax + 2, NEGCOL = 2 * Lmax + 1;
+  const int NSLOT = Lmax + 3, DUMMY = Lmax + 1, TRASH = Lmax + 2;
+  const int TPc = Tc | 1;
+  const int NCmax = (T + Tc - 1) / Tc;
+  constexpr int NJ = SPL / 2 + 1;
+
+  float* logZ2 = reinterpret_cast<float*>(smem_raw);             // [Tc]
+  float* red = logZ2 + Tc;                                       // [4]
+  float* E2 = red + 4;                                           // [NSLOT][TPc] emissions of the chunk; gradient phase: G
+  float* P = E2 + size_t(NSLOT) * TPc;                           // [Tc][Sstride]
+  float* Abound = P + size_t(Tc) * Sstride;                      // [NCmax][Sstride] alpha at the last frame of each chunk
+  int* tg = reinterpret_cast<int*>(Abound + size_t(NCmax) * Sstride);   // [Lmax]
+  int* nextra = tg + Lmax;
+  short* cmap = reinterpret_cast<short*>(nextra + 1);            // [C]
+  short* colA = cmap + C;
+  short* colB = colA + 32 * NJ;
+  short* gslot = colB + 32 * NJ;
+  short* excol = gslot + 32 * NJ;
+  short* exslot = excol + EXMAXL;
+
+  const int L = int(tgt_lens[b]);
+  const int Tb = min(T, int(in_lens[b]));
+  const int S = 2 * L + 1;
+  const int64_t toff = tgt_offsets[b];
+
+  for (int j = tid; j < L; j += THREADS) tg[j] = int(targets[toff + j]);
+  for (int c = tid; c < C; c += THREADS) cmap[c] = short(c == blank ? L : DUMMY);
+  if (tid == 0) *nextra = 0;
+  __syncthreads();
+  for (int j = tid; j < 32 * NJ; j += THREADS) {
+    int ca = NEGCOL, cb = NEGCOL, gs = TRASH;
+    if (j < L) {
+      const int cls = tg[j];
+      int firstpos = j, rank = 0, nx = -1;
+      if (cls != blank) {
+        for (int i = j - 1; i >= 0; --i) if (tg[i] == cls) { firstpos = i; ++rank; }
+        if (rank == 0) {
+          for (int i = j + 1; i < L; ++i) if (tg[i] == cls) { nx = i; break; }
+          cmap[cls] = short(j);
+          ca = 2 * j + 1; gs = j;
+          if (nx >= 0) cb = 2 * nx + 1;
+        }
+      } else {
+        firstpos = L; rank = 2;
+      }
+      if (rank >= 2) {
+        const int e = atomicAdd(nextra, 1);
+        if (e < EXMAXL) { excol[e] = short(2 * j + 1); exslot[e] = short(firstpos); }
+      }
+    }
+    colA[j] = short(ca); colB[j] = short(cb); gslot[j] = short(gs);
+  }
+  for (int t = tid; t < Tc; t += THREADS) P[t * Sstride + NEGCOL] = NEG;
+  __syncthreads();
+  const int nex = *nextra;
+  const bool fast3 = nex <= EXMAXL;
+  const float scale = grad_scale / (float(B) * float(max(L, 1)));
+  const int nc = (Tb + Tc - 1) / Tc;                             // chunks of THIS utterance
+
+  // ---- emissions of chunk c (frames c*Tc .. c*Tc+Tn-1), all warps, two frames per warp iteration (C in [32, 384])
+  auto emissions = [&](int c, int Tn) {
+    float* ek[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { const int cc = lane + 32 * k; ek[k] = E2 + (cc < C ? int(cmap[cc]) : DUMMY) * TPc; }
+    const int tbase = c * Tc;
+    for (int t0 = warp * F; t0 < Tn; t0 += NW * F) {
+      float x[F][CPL];
+      const bool full = t0 + F <= Tn;       // a last odd frame is computed twice (idempotent stores)
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const float* row = acts + (int64_t(tbase + (full ? t0 + f : min(t0 + f, Tn - 1))) * st_t + b * st_b) + lane;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldg(row + 32 * k) : NEG;
+      }
+      float z2[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        z2[f] = 0.f;
+        if (!is_logprob) {
+          float mx = x[f][0];
+#pragma unroll
+          for (int k = 1; k < CPL; ++k) mx = fmaxf(mx, x[f][k]);
+          mx = warp_max(mx) * LOG2E;
+          float se = 0.f;
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) se += ex2f(fmaf(x[f][k], LOG2E, -mx));
+          se = warp_sum(se);
+          z2[f] = mx + lg2f(se);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const int tt = full ? t0 + f : min(t0 + f, Tn - 1);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) ek[k][tt] = fmaf(x[f][k], LOG2E, -z2[f]);
+        if (lane == 0) logZ2[tt] = z2[f];
+      }
+    }
+  };
+
+  const int cw = (__popc(unsigned(b)) & 1) * 2;                  // recursion warps {0,1} or {2,3}
+  float a[SPL], skipadd[SPL], validadd[SPL];
+  int slot[SPL];
+  bool valid[SPL];
+  if (warp == cw) lane_consts<SPL, true>(tg, cmap, lane, L, S, slot, skipadd, validadd, valid);
+  else            lane_consts<SPL, false>(tg, cmap, lane, L, S, slot, skipadd, validadd, valid);
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) a[i] = NEG;
+
+  // ---- sweep A: alpha rows at the chunk boundaries
+  for (int c = 0; c + 1 < nc; ++c) {
+    emissions(c, Tc);
+    __syncthreads();
+    if (warp == cw) {
+      chain_fwd_chunk<SPL>(a, c == 0, E2, slot, skipadd, validadd, valid, lane, Tc, TPc);
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) if (valid[i]) Abound[c * Sstride + lane * SPL + i] = a[i];
+    }
+    __syncthreads();
+  }
+
+  // ---- sweep B: posteriors and gradient rows, last chunk first
+  float ll2 = (S == 1 && Tb == 0) ? 0.f : NEG;
+  bool feasible = Tb == 0 ? (S == 1) : true;
+  for (int c = nc - 1; c >= 0; --c) {
+    const int Tn = min(Tc, Tb - c * Tc);
+    emissions(c, Tn);
+    __syncthreads();
+    if (warp == cw) {
+      if (c > 0) {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) a[i] = valid[i] ? Abound[(c - 1) * Sstride + lane * SPL + i] : NEG;
+      }
+      chain_chunk<SPL, true>(a, c == 0, P, E2, slot, skipadd, validadd, valid, lane, S, Tn, Sstride, TPc);
+      if (c == nc - 1) {                      // alpha of the last frame: log2 P(labels | x)
+        float m = NEG;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) { const int s = lane * SPL + i; if (valid[i] && s >= S - 2) m = fmaxf(m, a[i]); }
+        m = warp_max(m);
+        float se = 0.f;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) { const int s = lane * SPL + i; if (valid[i] && s >= S - 2) se += ex2f(a[i] - m); }
+        se = warp_sum(se);
+        if (lane == 0) red[0] = se > 0.f ? fmaxf(m + lg2f(se), NEG) : NEG;
+      }
+    } else if (warp == cw + 1) {
+      chain_chunk<SPL, false>(a, c == nc - 1, P, E2, slot, skipadd, validadd, valid, lane, S, Tn, Sstride, TPc);
+    }
+    __syncthreads();
+    if (c == nc - 1) {
+      ll2 = red[0];
+      feasible = ll2 > 0.5f * NEG;
+    }
+    if (grad == nullptr || !feasible) break;
+
+    // gradient rows of the chunk: grad[t][c] = softmax_t(c) * scale - G_t(slot(c)); the emission table is dead now, each
+    // warp keeps its class posteriors G[slot][f] there (dummy slot = 0)
+    float* Gw = E2 + warp * (F * NSLOT);
+    if (lane < F) Gw[DUMMY * F + lane] = 0.f;
+    const float* gk[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { const int cc = lane + 32 * k; gk[k] = Gw + (cc < C ? int(cmap[cc]) : DUMMY) * F; }
+    __syncwarp();
+    const int tbase = c * Tc;
+    for (int t0 = warp * F; t0 < Tn; t0 += NW * F) {
+      if (fast3 && t0 + F <= Tn) {
+        float x[F][CPL];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float* row = acts + (int64_t(tbase + t0 + f) * st_t + b * st_b) + lane;
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) x[f][k] = (lane + 32 * k < C) ? __ldcs(row + 32 * k) : 0.f;
+        }
+        const float* Pt = P + t0 * Sstride;
+        float bs[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) bs[f] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) {
+          const int m = lane + 32 * i;
+          const int ca = colA[m], cb = colB[m], gs = gslot[m];
+          const int ce = m <= L ? 2 * m : NEGCOL;
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const float* Pf = Pt + f * Sstride;
+            Gw[gs * F + f] = (ex2f(Pf[ca] - ll2) + ex2f(Pf[cb] - ll2)) * scale;
+            bs[f] += ex2f(Pf[ce] - ll2);
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < F; ++f) bs[f] = warp_sum(bs[f]);
+        if (lane == 0) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) Gw[L * F + f] = bs[f] * scale;
+        }
+        __syncwarp();
+        if (nex > 0) {
+          if (lane < F) {
+            const float* Pf = Pt + lane * Sstride;
+            for (int e = 0; e < nex; ++e) Gw[int(exslot[e]) * F + lane] += ex2f(Pf[excol[e]] - ll2) * scale;
+          }
+          __syncwarp();
+        }
+        float z2[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) z2[f] = logZ2[t0 + f];
+        float* grow = grad + (int64_t(tbase + t0) * st_t + b * st_b) + lane;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          if (lane + 32 * k < C) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+              const float pr = ex2f(fmaf(x[f][k], LOG2E, -z2[f]));
+              __stcs(grow + f * st_t + 32 * k, fmaf(pr, scale, -gk[k][f]));
+            }
+          }
+        }
+        __syncwarp();
+      } else {
+        // odd last frame of a chunk / targets with very many repeats: one frame at a time, classes matched by search
+#pragma unroll 1
+        for (int f = 0; f < F; ++f) {
+          const int tl = t0 + f;
+          if (tl >= Tn) break;
+          const float* row = acts + (int64_t(tbase + tl) * st_t + b * st_b);
+          float* grow = grad + (int64_t(tbase + tl) * st_t + b * st_b);
+          const float* Pt = P + tl * Sstride;
+          float bsum = 0.f;
+          for (int m = lane; m <= L; m += 32) bsum += ex2f(Pt[2 * m] - ll2);
+          for (int j = lane; j < L; j += 32) if (int(cmap[tg[j]]) == L) bsum += ex2f(Pt[2 * j + 1] - ll2);
+          bsum = warp_sum(bsum);
+          const float z2 = logZ2[tl];
+          for (int cc = lane; cc < C; cc += 32) {
+            const float pr = ex2f(row[cc] * LOG2E - z2);
+            const int u = int(cmap[cc]);
+            float occ = (u == L) ? bsum : 0.f;
+            if (u < L) for (int j = u; j < L; ++j) if (tg[j] == cc) occ += ex2f(Pt[2 * j + 1] - ll2);
+            grow[cc] = (pr - occ) * scale;
+          }
+        }
+      }
+    }
+    __syncthreads();                          // the next chunk's emissions overwrite G and the table
+  }
+
+  if (tid == 0) {
+    float nll = feasible ? -ll2 * LN2 : INFINITY;
+    if (!feasible && zero_infinity) nll = 0.f;
+    nll_out[b] = nll;
+    if (loss_out != nullptr) atomicAdd(loss_out, nll / float(max(L, 1)) / float(B));
+  }
+  if (grad == nullptr) return;
+  // padded frames get zeros; an infeasible utterance zeros (zero_infinity) or NaN (as ATen) on its live frames
+  for (int t = (feasible ? Tb : 0) + warp; t < T; t += NW) {
+    float* grow = grad + (int64_t(t) * st_t + b * st_b);
+    const float fill = (!feasible && !zero_infinity && t < Tb) ? NAN : 0.f;
+    for (int cc = lane; cc < C; cc += 32) grow[cc] = fill;
+  }
+}
+
+template <int SPL>
+int launch_long(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets,
+                const int64_t* tgt_offsets, const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank,
+                int zero_infinity, float grad_scale, int Tc, float* nll, float* loss, float* grad, size_t smem, cudaStream_t st) {
+  auto kern = ctc3l_kernel<SPL, 2>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_smem = smem;
+  }
+  kern<<<B, THREADS, smem, st>>>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank,
+                                 zero_infinity, grad_scale, Tc, nll, loss, grad);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+// chunk length: the largest even Tc <= 128 that leaves room for two CTAs per SM, else for one
+static int pick_chunk(int T, int Lmax, int C, int spld, size_t* smem_out) {
+  for (size_t budget : {size_t(113) * 1024, size_t(227) * 1024}) {
+    for (int Tc = 128; Tc >= 16; Tc -= 2) {
+      const size_t sm = smem_bytes_long(Tc, T, Lmax, C, spld);
+      if (sm <= budget) { *smem_out = sm; return Tc; }
+    }
+  }
+  return 0;
+}
+
 static int dispatch(const float* acts, int T, int B, int C, int64_t st_t, int64_t st_b, int is_logprob, const int64_t* targets,
                     const int64_t* tgt_offsets, const int64_t* in_lens, const int64_t* tgt_lens, int Lmax, int blank,
                     int zero_infinity, float grad_scale, float* nll, float* loss, float* grad, long long* dbg, cudaStream_t st) {
@@ -540,7 +951,22 @@ static int dispatch(const float* acts, int T, int B, int C, int64_t st_t, int64_
   if (spl > 12 || Lmax > 30000 || C > 32000) return CTC3_NOT_APPLICABLE;
   const int spld = spl <= 4 ? spl : (spl <= 6 ? 6 : (spl <= 8 ? 8 : 12));
   const size_t smem_p = smem_bytes_pipe(T, Lmax, C, spld);
-  if (smem_p > 227 * 1024) return CTC3_NOT_APPLICABLE;          // tables beyond shared memory: ctc.cu (global workspace)
+  if (smem_p > 227 * 1024) {
+    // the table of an utterance does not fit shared memory: frame-chunked kernel (recomputation, no table in HBM)
+    size_t smem_l = 0;
+    const int Tc = (C >= 32 && C <= 32 * CPL && T >= 32) ? pick_chunk(T, Lmax, C, spld, &smem_l) : 0;
+    if (Tc == 0) return CTC3_NOT_APPLICABLE;                     // ctc.cu: tables in a global workspace
+#define CTC3L_CASE(N) return launch_long<N>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, \
+                                            zero_infinity, grad_scale, Tc, nll, loss, grad, smem_l, st)
+    if (spl <= 1) CTC3L_CASE(1);
+    if (spl <= 2) CTC3L_CASE(2);
+    if (spl <= 3) CTC3L_CASE(3);
+    if (spl <= 4) CTC3L_CASE(4);
+    if (spl <= 6) CTC3L_CASE(6);
+    if (spl <= 8) CTC3L_CASE(8);
+    CTC3L_CASE(12);
+#undef CTC3L_CASE
+  }
 #define CTC3P_CASE(N) return launch_pipe<N, 3>(acts, T, B, C, st_t, st_b, is_logprob, targets, tgt_offsets, in_lens, tgt_lens, Lmax, blank, \
                                                zero_infinity, grad_scale, nll, loss, grad, dbg, smem_p, st)
   if (spl <= 1) CTC3P_CASE(1);

@@ -104,6 +104,55 @@ def test_ctc_infeasible_and_large_workspace(dev):
     assert float((grad - lg.grad).abs().max()) <= gtol * float(lg.grad.abs().max())
 
 
+@pytest.mark.parametrize("case", ["ragged_mixed", "many_repeats", "logprob_input"])
+def test_ctc_long_utterances_frame_chunked_kernel(dev, case):
+    """Utterances whose posterior table exceeds shared memory (T' = 375 .. 750, the reference's max_ilen 1500 / 3000) run
+    on the frame-chunked kernel (alpha boundary rows in sweep A, chunk tables recomputed in sweep B): against float64
+    F.ctc_loss, with in one batch a full-length utterance, odd chunk remainders, an utterance shorter than one chunk, a
+    one-frame utterance, an empty target and an infeasible one; and targets with so many repeated classes that the
+    side list of third-and-later occurrences overflows (per-frame search path)."""
+    from metaasr_crossaccent_b200.ctc import ctc_fwd_bwd
+    g = torch.Generator().manual_seed(11)
+    C = 367
+    if case == "many_repeats":
+        T = 400
+        ys = [torch.randint(1, 6, (150,), generator=g), torch.randint(1, 4, (120,), generator=g)]   # ~5 classes over 150 positions
+        in_lens = torch.tensor([400, 391])
+    else:
+        T = 750 if case == "ragged_mixed" else 377
+        lens = [152, 140, 3, 1, 0, 120, 90]
+        ys = [torch.randint(1, C, (l,), generator=g) for l in lens]
+        in_lens = torch.tensor([T, T - 33, 50, 1, 5, 100, T - 1])        # utterance 5: 120 labels in 100 frames -> infeasible
+    B = len(ys)
+    logits = (torch.randn(T, B, C, generator=g) * 2).to(dev)
+    targets = torch.cat(ys)
+    tl = torch.tensor([len(y) for y in ys], dtype=torch.int64)
+    lg = logits.double().requires_grad_(True)
+    lp = F.log_softmax(lg, -1)
+    ref = F.ctc_loss(lp, targets.to(dev), in_lens, tl, blank=0, reduction='mean', zero_infinity=True)
+    ref.backward()
+    if case == "logprob_input":
+        lp32 = F.log_softmax(logits, -1).contiguous()
+        loss, nll, grad_lp = ctc_fwd_bwd(lp32, targets, in_lens, tl, is_logprob=True)
+        # ATen's gradient w.r.t. the log-probabilities, pushed through log_softmax = the gradient w.r.t. the logits
+        grad = grad_lp - torch.exp(lp32) * grad_lp.sum(-1, keepdim=True)
+    else:
+        loss, nll, grad = ctc_fwd_bwd(logits, targets, in_lens, tl)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    scale = float(lg.grad.abs().max())
+    gtol = max(2e-4, 8 * 1.2e-7 * float(nll.abs().max()))
+    assert float((grad - lg.grad).abs().max()) <= gtol * scale + 1e-9
+    for b in range(B):
+        if int(in_lens[b]) < T:
+            assert float(grad[int(in_lens[b]):, b].abs().max()) == 0.0
+    if case != "many_repeats":
+        assert float(nll[5]) == 0.0 and float(grad[:, 5].abs().max()) == 0.0       # infeasible under zero_infinity
+    # forward only (no gradient buffer) gives the same likelihoods
+    loss2, nll2, _ = ctc_fwd_bwd(logits if case != "logprob_input" else lp32, targets, in_lens, tl,
+                                 is_logprob=case == "logprob_input", want_grad=False)
+    assert torch.equal(nll2, nll)
+
+
 def _torch_ref(logits, targets, in_lens, tl, dev):
     lg = logits.double().requires_grad_(True)
     ref = F.ctc_loss(F.log_softmax(lg, -1), targets.to(dev), in_lens, tl, blank=0, reduction='mean', zero_infinity=True)
