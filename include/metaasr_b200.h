@@ -236,6 +236,10 @@ int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        float* dsum_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                        int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
                        float p_drop, uint64_t seed, uint32_t site, int dsum_ready, float* dq_ws, void* stream);
+/* Query sequences of at most max_lq rows (default and upper bound 64: the decoder's tgt length, mono_transformer_torch.py:200-203)
+ * are served inside masr_umma_attn_fwd* / masr_umma_attn_bwd by warp-level MMA kernels that keep S / P / dS in registers
+ * (one CTA per (batch, head)); longer ones take the 128-row tcgen05 tiles.  0 sends every problem to tcgen05 (tests). */
+int masr_attn_set_small_lq(int max_lq);
 /* dsum_ready != 0: dsum_ws already holds D[b,h,q] = dO . O (e.g. from masr_umma_gemm_ex's dot epilogue). */
 
 /* ------------------------------------------------------------------ kernel 3: fused elementwise
@@ -267,6 +271,13 @@ int masr_dropout(void* x, int dtype, int64_t n, float p_drop, uint64_t seed, uin
 int masr_colsum_add(const void* x, int dtype, int64_t ldx, float* out, int M, int N, void* stream);
 /* dst = cast(src) */
 int masr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* Every derived weight copy the engine needs before a run-batch, in ONE launch (the nn.Module weights the reference
+ * reads in place, src/model/transformer_pytorch/mono_transformer_torch.py:49-60,113-122, in the layouts the kernels
+ * want): shadow (may be NULL = already fresh) = cast(params[0:n]) to `dtype`; for every job wp = masr_conv_w_prep(w) and
+ * (wpt != NULL) wpt = masr_conv_w_prep_t(w); v2e_p (may be NULL) = masr_permute_cf(v2e). */
+typedef struct { const float* w; void* wp; void* wpt; int Cout, Cin; } masr_conv_prep_job;
+int masr_prep_weights(const float* params, void* shadow, int64_t n, const masr_conv_prep_job* jobs, int njobs,
+                      const float* v2e, void* v2e_p, int v2e_rows, int C, int F, int dtype, void* stream);
 /* dst[r, f*C + c] = src[r, c*F + f]   (vgg2enc column permutation, (c,f) -> (f,c)); with add != 0
  * and the roles swapped it un-permutes a gradient: dst[r, c*F+f] += src[r, f*C+c] (fp32 only) */
 int masr_permute_cf(const void* src, int src_dtype, void* dst, int dst_dtype, int rows, int C, int F,
@@ -311,6 +322,18 @@ int masr_mt_sumsq(const float* g, int64_t n, double* out, int zero_first, void* 
  * g is scaled in place by the clip coefficient (as clip_grad_norm_ does). first_step: buf = g. */
 int masr_mt_clip_sgd(float* p, float* g, float* buf, int64_t n, const double* sumsq, float max_norm,
                      float lr, float momentum, int nesterov, int first_step, void* stream);
+/* Same, and in the same pass: shadow_bf16 (may be NULL) = bf16(p) -- the compute-dtype copy of the arena that
+ * TransformerEngine.prep_weights would otherwise produce with a separate cast pass before the next run-batch
+ * (src/fo_meta_interface.py:229-240: the step is always followed by a forward on the new weights).
+ * flags & MASR_SGD_LAST_STEP: no further inner step of this task follows (meta_k reached, :229): the scaled gradient
+ * and the momentum buffer are dead and are not written back. */
+#define MASR_SGD_LAST_STEP 1
+int masr_mt_clip_sgd_ex(float* p, float* g, float* buf, int64_t n, const double* sumsq, float max_norm,
+                        float lr, float momentum, int nesterov, int first_step, void* shadow_bf16, int flags,
+                        void* stream);
+/* dst = src and shadow_bf16 = bf16(src) in one pass (either destination may be NULL):
+ * asr_model.load_state_dict(self._original) at the head of run_task (src/fo_meta_interface.py:226) on flat arenas */
+int masr_mt_copy_cast(float* dst, void* shadow_bf16, const float* src, int64_t n, void* stream);
 /* g *= min(1, max_norm / (sqrt(sumsq) + 1e-6)) */
 int masr_mt_clip(float* g, int64_t n, const double* sumsq, float max_norm, void* stream);
 /* FOMAML: upd += g * clipcoef(sumsq)   (fo_meta_interface.py:148-149,192-196); sumsq may be NULL */

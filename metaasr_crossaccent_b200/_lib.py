@@ -42,6 +42,7 @@ SIGNATURES = {
     "masr_umma_gemm_ex": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "masr_umma_gemm_pair": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "masr_gemm_set_pair_mode": [c_i],
+    "masr_attn_set_small_lq": [c_i],
     "masr_gemm_set_stage_cap": [c_i],
     "masr_umma_gemm_tn": [c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_umma_conv3x3_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -87,6 +88,9 @@ SIGNATURES = {
     "masr_seed_bump": [c_p, c_u64, c_p],
     "masr_mt_sumsq": [c_p, c_i64, c_p, c_i, c_p],
     "masr_mt_clip_sgd": [c_p, c_p, c_p, c_i64, c_p, c_f, c_f, c_f, c_i, c_i, c_p],
+    "masr_mt_clip_sgd_ex": [c_p, c_p, c_p, c_i64, c_p, c_f, c_f, c_f, c_i, c_i, c_p, c_i, c_p],
+    "masr_mt_copy_cast": [c_p, c_p, c_p, c_i64, c_p],
+    "masr_prep_weights": [c_p, c_p, c_i64, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "masr_mt_clip": [c_p, c_i64, c_p, c_f, c_p],
     "masr_mt_accumulate": [c_p, c_p, c_i64, c_p, c_f, c_p],
     "masr_mt_reptile_delta": [c_p, c_p, c_p, c_i64, c_p],
@@ -102,6 +106,11 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("rowsum", c_p), ("mask", c_p), ("ldmask", c_i64), ("mask_scale", c_f), ("p_drop", c_f),
                 ("seed", c_u64), ("site", c_u32), ("dot_src", c_p), ("lddot", c_i64), ("dot_out", c_p),
                 ("dot_L", c_i), ("dot_H", c_i)]
+
+
+class ConvPrepJob(C.Structure):
+    """masr_conv_prep_job of include/metaasr_b200.h."""
+    _fields_ = [("w", c_p), ("wp", c_p), ("wpt", c_p), ("Cout", c_i), ("Cin", c_i)]
 
 
 class MetaASRLibraryError(RuntimeError):

@@ -543,6 +543,16 @@ static int rows_map(CUtensorMap* out, const void* base, int64_t ld, int64_t nrow
   return make_tmap_bf16(out, base, 2, dims, strides, box, true);
 }
 
+// attn_small.cu: warp-MMA kernels for short query sequences (the decoder's 33-row problems)
+bool attn_small_applicable(int Lq);
+int attn_small_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo,
+                   float* lse, int B, int H, int Lq, int Lk, int kv_rows, const int64_t* klens, int causal, float p_drop,
+                   uint64_t seed, uint32_t site, cudaStream_t st);
+int attn_small_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out, int64_t ldo,
+                   const void* dout, int64_t lddo, const float* lse, const float* dsum, void* dq, int64_t lddq, void* dk,
+                   int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
+                   float p_drop, uint64_t seed, uint32_t site, cudaStream_t st);
+
 constexpr size_t AU_FWD_SMEM = AU_T64 + 4 * AU_T64 + AU_T128 + 256 + 2048 + 1024;
 constexpr size_t AU_BWD_SMEM = 2 * AU_T64 + 4 * AU_T64 + 2 * AU_T128 + 256 + 1024;
 
@@ -562,6 +572,9 @@ extern "C" int masr_umma_attn_fwd_cached(const void* q, int64_t ldq, const void*
                                          void* stream) {
   if (B == 0 || H == 0 || Lq == 0) return MASR_OK;
   MASR_REQUIRE(kv_rows >= Lk, "umma attention: kv_rows (rows per utterance of K / V) must be >= Lk");
+  if (attn_small_applicable(Lq))
+    return attn_small_fwd(q, ldq, k, ldk, v, ldv, out, ldo, lse, B, H, Lq, Lk, kv_rows, klens, causal, p_drop, seed, site,
+                          as_stream(stream));
   MASR_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "umma attention: out must be 16 B aligned");
   CUtensorMap mq, mk, mv;
   int rc = rows_map(&mq, q, ldq, int64_t(B) * Lq, H * 64); if (rc) return rc;
@@ -585,6 +598,9 @@ extern "C" int masr_umma_attn_bwd(const void* q, int64_t ldq, const void* k, int
                                   int B, int H, int Lq, int Lk, const int64_t* klens, int causal,
                                   float p_drop, uint64_t seed, uint32_t site, int dsum_ready, float* dq_ws, void* stream) {
   if (B == 0 || H == 0) return MASR_OK;
+  if (attn_small_applicable(Lq))
+    return attn_small_bwd(q, ldq, k, ldk, v, ldv, out, ldo, dout, lddo, lse, dsum_ready ? dsum_ws : nullptr, dq, lddq, dk, lddk,
+                          dv, lddv, B, H, Lq, Lk, klens, causal, p_drop, seed, site, as_stream(stream));
   const int nkt = int(ceil_div64(std::max(Lk, 1), AU_TILE));
   MASR_REQUIRE(nkt == 1 || dq_ws != nullptr, "umma attention backward: Lk > 128 needs the [B*Lq, H*64] fp32 dq workspace");
   MASR_REQUIRE(dsum_ws != nullptr, "attention backward needs a [B*H*Lq] fp32 workspace");

@@ -440,6 +440,68 @@ __global__ void permute_cf_kernel(const TS* __restrict__ src, TD* __restrict__ d
   }
 }
 
+// ------------------------------------------------------------------ every derived weight copy in ONE launch
+// engine.prep_weights: (a) the compute-dtype shadow of the parameter arena (skipped when an optimizer kernel wrote it
+// already), (b) the [Cout][tap][Cin] / [Cin][tap][Cout] layouts of the 3x3 conv weights, (c) the (c,f)->(f,c) column
+// permutation of vgg2enc.weight.  Eight dependent ~3 us launches in front of every batch before; block ranges now.
+struct PrepParams {
+  const float* params; void* shadow; int64_t n;       // (a)
+  masr_conv_prep_job jobs[4]; int njobs;              // (b)
+  const float* v2e; void* v2e_p; int v2e_rows, C, F;  // (c)
+  int blk_end[6];                                     // block range ends: cast | job 0..3 | permute
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) prep_weights_kernel(const __grid_constant__ PrepParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  int seg = 0;
+  while (seg < 5 && int(blockIdx.x) >= p.blk_end[seg]) ++seg;
+  const int b0 = seg == 0 ? 0 : p.blk_end[seg - 1];
+  const int64_t tid = int64_t(blockIdx.x - b0) * blockDim.x + threadIdx.x;
+  const int64_t nth = int64_t(p.blk_end[seg] - b0) * blockDim.x;
+  if (seg == 0) {
+    T* sh = static_cast<T*>(p.shadow);
+    const int64_t n4 = p.n / 4;
+    const float4* s4 = reinterpret_cast<const float4*>(p.params);
+    for (int64_t i = tid; i < n4; i += nth) {
+      const float4 v = s4[i];
+      if constexpr (sizeof(T) == 2) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(sh)[i] = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+      } else {
+        reinterpret_cast<float4*>(sh)[i] = v;
+      }
+    }
+    if (tid < (p.n & 3)) sh[n4 * 4 + tid] = from_f<T>(p.params[n4 * 4 + tid]);
+  } else if (seg <= 4) {
+    const masr_conv_prep_job& j = p.jobs[seg - 1];
+    const int Cout = j.Cout, Cin = j.Cin, total = Cout * Cin * 9;
+    T* wp = static_cast<T*>(j.wp);
+    T* wpt = static_cast<T*>(j.wpt);
+    for (int64_t idx = tid; idx < total; idx += nth) {
+      {
+        const int ci = int(idx % Cin), tap = int((idx / Cin) % 9), co = int(idx / (9 * Cin));
+        wp[idx] = from_f<T>(j.w[(co * Cin + ci) * 9 + tap]);
+      }
+      if (wpt != nullptr) {
+        const int co = int(idx % Cout), tap = int((idx / Cout) % 9), ci = int(idx / (9 * Cout));
+        wpt[idx] = from_f<T>(j.w[(co * Cin + ci) * 9 + tap]);
+      }
+    }
+  } else {
+    T* dst = static_cast<T*>(p.v2e_p);
+    const int CF = p.C * p.F;
+    const int64_t n = int64_t(p.v2e_rows) * CF;
+    for (int64_t i = tid; i < n; i += nth) {
+      const int64_t r = i / CF;
+      const int jj = int(i - r * CF);
+      const int f = jj / p.C, c = jj % p.C;
+      dst[i] = from_f<T>(p.v2e[r * CF + int64_t(c) * p.F + f]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ label-smoothed CE + accuracy + grad
 // src/transformer_torch_trainer.py:64-84.  One warp per row of C logits.
 //   q_c = (1-eps) for the gold class, eps/C otherwise (sums to 1 - eps/C)
@@ -685,6 +747,33 @@ extern "C" int masr_permute_cf(const void* src, int src_dtype, void* dst, int ds
   else if (src_dtype == MASR_F32 && dst_dtype == MASR_BF16 && !inverse_add)
     launch_pdl(permute_cf_kernel<float, __nv_bfloat16>, dim3(g), dim3(256), 0, st, static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), rows, C, F, 0);
   else { set_error("masr_permute_cf: unsupported dtype combination"); return MASR_E_INVALID; }
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
+extern "C" int masr_prep_weights(const float* params, void* shadow, int64_t n, const masr_conv_prep_job* jobs, int njobs,
+                                 const float* v2e, void* v2e_p, int v2e_rows, int C, int F, int dtype, void* stream) {
+  MASR_REQUIRE(njobs >= 0 && njobs <= 4, "masr_prep_weights: at most four conv jobs");
+  MASR_REQUIRE(shadow == nullptr || ((reinterpret_cast<uintptr_t>(params) & 15u) == 0 && (reinterpret_cast<uintptr_t>(shadow) & 15u) == 0),
+               "masr_prep_weights: arena alignment");
+  PrepParams p{};
+  p.params = params; p.shadow = shadow; p.n = shadow != nullptr ? n : 0;
+  p.njobs = njobs;
+  for (int i = 0; i < njobs; ++i) p.jobs[i] = jobs[i];
+  p.v2e = v2e; p.v2e_p = v2e_p; p.v2e_rows = v2e_p != nullptr ? v2e_rows : 0; p.C = C; p.F = F;
+  int b = 0;
+  if (p.n > 0) b += int(std::min<int64_t>(ceil_div64(p.n / 4 + 1, 256), int64_t(sm_count()) * 8));
+  p.blk_end[0] = b;
+  for (int i = 0; i < 4; ++i) {
+    if (i < njobs) b += int(std::min<int64_t>(ceil_div64(int64_t(jobs[i].Cout) * jobs[i].Cin * 9, 256 * 2), 148));
+    p.blk_end[1 + i] = b;
+  }
+  if (p.v2e_rows > 0) b += int(std::min<int64_t>(ceil_div64(int64_t(v2e_rows) * C * F, 256 * 4), int64_t(sm_count()) * 4));
+  p.blk_end[5] = b;
+  if (b == 0) return MASR_OK;
+  if (dtype == MASR_BF16) launch_pdl(prep_weights_kernel<__nv_bfloat16>, dim3(b), dim3(256), 0, as_stream(stream), p);
+  else if (dtype == MASR_F32) launch_pdl(prep_weights_kernel<float>, dim3(b), dim3(256), 0, as_stream(stream), p);
+  else { set_error("masr_prep_weights: bad dtype"); return MASR_E_INVALID; }
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

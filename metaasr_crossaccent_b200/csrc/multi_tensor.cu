@@ -55,7 +55,12 @@ __global__ void mt_zero_double_kernel(double* p) {
 
 __global__ void __launch_bounds__(MT_THREADS)
 mt_clip_sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, int64_t n,
-                   const double* __restrict__ sumsq, float max_norm, float lr, float mu, int nesterov, int first) {
+                   const double* __restrict__ sumsq, float max_norm, float lr, float mu, int nesterov, int first,
+                   __nv_bfloat16* __restrict__ shadow, int flags) {
+  // shadow (may be NULL): the bf16 copy of the parameter arena the GEMMs read, written in the same pass (the engine then
+  // skips its cast pass).  flags & MASR_SGD_LAST_STEP: the task takes no further inner step and nothing reads the
+  // scaled gradient or the momentum afterwards -- their write-backs (200 MB of the 500 MB this pass moves) are dropped.
+  const bool keep = !(flags & MASR_SGD_LAST_STEP);
   pdl_launch_dependents();
   pdl_wait();
   const double ss = *sumsq;
@@ -66,7 +71,16 @@ mt_clip_sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restri
   if (ss != ss) {                                  // NaN gradient norm: skip the step (:245-248)
     // a skipped FIRST step of a task leaves the momentum of the previous task behind while the host clears its
     // `first` flag: zero it, so that the next step's mu * buf + g is the fresh buffer torch.optim.SGD would create
-    if (first && mu != 0.f) {
+    if (shadow != nullptr) {                       // the parameters did not move, but the shadow must still mirror them
+      uint2* s2 = reinterpret_cast<uint2*>(shadow);
+      for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+        const float4 pv = p4[i];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+        s2[i] = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+      }
+      if (blockIdx.x == 0 && threadIdx.x < (n & 3)) shadow[n4 * 4 + threadIdx.x] = __float2bfloat16(p[n4 * 4 + threadIdx.x]);
+    }
+    if (first && mu != 0.f && keep) {
       for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x)
         b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (blockIdx.x == 0 && threadIdx.x < (n & 3)) buf[n4 * 4 + threadIdx.x] = 0.f;
@@ -86,13 +100,46 @@ mt_clip_sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restri
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
     float4 pv = p4[i], gv = g4[i], bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : b4[i];
     upd(pv.x, gv.x, bv.x); upd(pv.y, gv.y, bv.y); upd(pv.z, gv.z, bv.z); upd(pv.w, gv.w, bv.w);
-    p4[i] = pv; g4[i] = gv; b4[i] = bv;
+    p4[i] = pv;
+    if (keep) { g4[i] = gv; b4[i] = bv; }
+    if (shadow != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = n4 * 4 + threadIdx.x;
     float pv = p[i], gv = g[i], bv = first ? 0.f : buf[i];
     upd(pv, gv, bv);
-    p[i] = pv; g[i] = gv; buf[i] = bv;
+    p[i] = pv;
+    if (keep) { g[i] = gv; buf[i] = bv; }
+    if (shadow != nullptr) shadow[i] = __float2bfloat16(pv);
+  }
+}
+
+// dst = src (fp32) and shadow = bf16(src) in one pass: load_state_dict(_original) of run_task (fo_meta_interface.py:226)
+// plus the engine's compute-dtype copy of the fresh weights
+__global__ void __launch_bounds__(MT_THREADS)
+mt_copy_cast_kernel(float* __restrict__ dst, __nv_bfloat16* __restrict__ shadow, const float* __restrict__ src, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t n4 = n / 4;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  uint2* h2 = reinterpret_cast<uint2*>(shadow);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 v = s4[i];
+    if (dst != nullptr) d4[i] = v;
+    if (shadow != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      h2[i] = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    const float v = src[i];
+    if (dst != nullptr) dst[i] = v;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16(v);
   }
 }
 
@@ -215,11 +262,29 @@ extern "C" int masr_mt_sumsq(const float* g, int64_t n, double* out, int zero_fi
   return MASR_OK;
 }
 
+extern "C" int masr_mt_clip_sgd_ex(float* p, float* g, float* buf, int64_t n, const double* sumsq, float max_norm,
+                                   float lr, float momentum, int nesterov, int first_step, void* shadow_bf16, int flags,
+                                   void* stream) {
+  MT_ALIGN_CHECK(p, g, buf);
+  MASR_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7u) == 0, "masr_mt_clip_sgd_ex: shadow must be 8-byte aligned");
+  if (n == 0) return MASR_OK;
+  launch_pdl(mt_clip_sgd_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), p, g, buf, n, sumsq, max_norm, lr,
+             momentum, nesterov, first_step, static_cast<__nv_bfloat16*>(shadow_bf16), flags);
+  MASR_LAUNCH_CHECK();
+  return MASR_OK;
+}
+
 extern "C" int masr_mt_clip_sgd(float* p, float* g, float* buf, int64_t n, const double* sumsq, float max_norm,
                                 float lr, float momentum, int nesterov, int first_step, void* stream) {
-  MT_ALIGN_CHECK(p, g, buf);
+  return masr_mt_clip_sgd_ex(p, g, buf, n, sumsq, max_norm, lr, momentum, nesterov, first_step, nullptr, 0, stream);
+}
+
+extern "C" int masr_mt_copy_cast(float* dst, void* shadow_bf16, const float* src, int64_t n, void* stream) {
+  MT_ALIGN_CHECK(src);
+  MASR_REQUIRE(aligned16(dst) && (reinterpret_cast<uintptr_t>(shadow_bf16) & 7u) == 0, "masr_mt_copy_cast: alignment");
   if (n == 0) return MASR_OK;
-  launch_pdl(mt_clip_sgd_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), p, g, buf, n, sumsq, max_norm, lr, momentum, nesterov, first_step);
+  launch_pdl(mt_copy_cast_kernel, dim3(mt_grid(n / 4)), dim3(MT_THREADS), 0, as_stream(stream), dst,
+             static_cast<__nv_bfloat16*>(shadow_bf16), src, n);
   MASR_LAUNCH_CHECK();
   return MASR_OK;
 }

@@ -157,6 +157,8 @@ class TransformerEngine:
         if self.act_dtype != torch.float32:
             self.shadow = torch.zeros(n, dtype=self.act_dtype, device=self.device)
         self.W = OrderedDict()      # name -> compute-dtype weight used by GEMMs
+        self._shadow_views = None
+        self._shadow_fresh, self._shadow_version = False, -1
         self.wpt = {}               # conv idx -> [Cin, 9*Cout] compute dtype (dgrad operand), tensor-core path only
         self.wp = {}                # conv idx -> [Cout, 9*Cin] compute dtype
         self.dwp = {}               # conv idx -> fp32 gradient in the same layout
@@ -204,22 +206,52 @@ class TransformerEngine:
             out[name] = self.pe if name == "pos_encoder.pe" else self.P[name]
         return out
 
+    def mark_shadow_fresh(self):
+        """An optimizer kernel (masr_mt_clip_sgd_ex / masr_mt_copy_cast) just wrote the compute-dtype shadow together with
+        the master arena: the next prep_weights skips its cast pass.  Consumed by that one prep; anything else that
+        touches the parameters (load_state_dict, a foreign optimizer on the nn.Parameters) goes through the full prep."""
+        self.weights_dirty = True
+        self._shadow_fresh = True
+        self._shadow_version = self.params._version      # a torch-side in-place write to the arena (or a view) bumps it
+
     def prep_weights(self):
         """Refresh the derived weight copies after the fp32 master arena changed."""
         if not self.weights_dirty:
             return
         be = self.be
         src = self.P
+        fresh = self._shadow_fresh and self._shadow_version == self.params._version
+        self._shadow_fresh = False
         if self.shadow is not None:
-            be.cast(self.params, self.shadow)
-            src = OrderedDict((nm, self.layout.view(self.shadow, nm)) for nm in self.layout.offsets)
+            src = self._shadow_views
+            if src is None:
+                src = self._shadow_views = OrderedDict((nm, self.layout.view(self.shadow, nm)) for nm in self.layout.offsets)
         self.W = src
-        for i in (2, 5, 7):
-            be.conv_w_prep(self.P[f"feat_extractor.{i}.weight"], self.wp[i])
-            if i in self.wpt:
-                be.conv_w_prep_t(self.P[f"feat_extractor.{i}.weight"], self.wpt[i])
-        be.permute_cf(self.P["vgg2enc.weight"], self.vgg2enc_p, self.cfg.vgg_ch, self.cfg.f4, False)
+        if hasattr(be, "prep_weights"):            # one launch: cast (unless fresh) + conv re-layouts + vgg2enc permutation
+            jobs = [(self.P[f"feat_extractor.{i}.weight"], self.wp[i], self.wpt.get(i)) for i in (2, 5, 7)]
+            be.prep_weights(self.params, None if (self.shadow is None or fresh) else self.shadow, jobs,
+                            self.P["vgg2enc.weight"], self.vgg2enc_p, self.cfg.vgg_ch, self.cfg.f4, self.vgg2enc_p)
+        else:
+            if self.shadow is not None and not fresh:
+                be.cast(self.params, self.shadow)
+            for i in (2, 5, 7):
+                be.conv_w_prep(self.P[f"feat_extractor.{i}.weight"], self.wp[i])
+                if i in self.wpt:
+                    be.conv_w_prep_t(self.P[f"feat_extractor.{i}.weight"], self.wpt[i])
+            be.permute_cf(self.P["vgg2enc.weight"], self.vgg2enc_p, self.cfg.vgg_ch, self.cfg.f4, False)
         self.weights_dirty = False
+
+    def load_flat(self, flat):
+        """params <- flat (an arena of the same layout, e.g. the FOMAML meta weights): load_state_dict(_original) of
+        run_task (fo_meta_interface.py:226) as one pass that also refreshes the compute-dtype shadow."""
+        be = self.be
+        n = self.layout.total
+        if hasattr(be, "mt_copy_cast") and self.shadow is not None:
+            if be.mt_copy_cast(self.params[:n], self.shadow[:n], flat[:n]):
+                self.mark_shadow_fresh()
+                return
+        be.copy_(self.params, flat)
+        self.weights_dirty = True
 
     # ------------------------------------------------------------------ helpers
     def site(self, name):
@@ -857,6 +889,10 @@ class TransformerEngine:
             ent = self._graph_entry(db)
             graphs, sdb, ws = ent
             self._load_static(sdb, db)
+            # the derived weight copies are refreshed OUTSIDE the captured segments (one launch): what it has to do
+            # depends on who moved the weights (an optimizer kernel that wrote the shadow already, or anything else)
+            self.weights_dirty = True
+            self.prep_weights()
             return {"graphs": graphs, "db": sdb, "ws": ws}
         return {"graphs": None, "db": db, "ws": None}
 
@@ -873,9 +909,10 @@ class TransformerEngine:
         if hasattr(self.be, "set_seed_ptr"):
             self.be.set_seed_ptr(self.seed_t)  # kernels launched from here on read this engine's offset
 
-    def _segment_eager(self, db, i, join):
+    def _segment_eager(self, db, i, join, prep=True):
         if i == 0:
-            self.weights_dirty = True         # training: the master weights may have moved since the last batch
+            if prep:
+                self.weights_dirty = True     # training: the master weights may have moved since the last batch
             self._bind_seed()
             if hasattr(self.be, "seed_bump"):
                 self.be.seed_bump(1)          # fresh dropout masks: device-resident seed offset += 1
@@ -923,7 +960,7 @@ class TransformerEngine:
         for i in range(self.N_SEGMENTS):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._segment_eager(sdb, i, join=True)
+                self._segment_eager(sdb, i, join=True, prep=False)      # fb_begin preps eagerly before the replays
             graphs.append(g)
         ent = (graphs, sdb, self.workspace(B, T, L1))
         self._graphs[key] = ent

@@ -331,8 +331,7 @@ class FOMetaMixin:
         eng = lane.eng
         be = eng.be
         self._counter += 1
-        be.copy_(eng.params, self._original_flat)              # load_state_dict(_original): one flat copy
-        eng.weights_dirty = True
+        eng.load_flat(self._original_flat)                     # load_state_dict(_original): one flat pass (+ bf16 shadow)
         if lane.stream is None:
             self.asr_model.train()
         eng.training = True
@@ -500,8 +499,7 @@ class FOMetaMixin:
             for lane, st, slot, task in assign:                 # run_task prologue: load_state_dict(_original), fresh SGD
                 with torch.cuda.stream(st):
                     self._counter += 1
-                    lane.eng.be.copy_(lane.eng.params, self._original_flat)
-                    lane.eng.weights_dirty = True
+                    lane.eng.load_flat(self._original_flat)
                     lane.eng.training = True
                     lane.sgd.reset()
             n_train = max(len(t[0]) for _, _, _, t in assign)
@@ -522,7 +520,6 @@ class FOMetaMixin:
                         else:
                             hb = eng.prepare_batch(x, ilens, ys, olens)
                             db = hb if eng.use_graphs else eng.to_device(hb)
-                        eng.weights_dirty = True
                         h = eng.fb_begin(db)
                         ev = torch.cuda.Event()
                         ev.record(st)
@@ -563,7 +560,8 @@ class FOMetaMixin:
                             self._stats_ring[slot].copy_(eng.stats)
                             self._partial_meta_update(lane)
                         else:
-                            lane.sgd.step(lane.gnorm, GRAD_CLIP)
+                            # the task's last inner step: nothing reads its scaled gradient / momentum afterwards
+                            lane.sgd.step(lane.gnorm, GRAD_CLIP, last=(rnd == n_train - 1))
         for st in streams + [conv]:
             main.wait_stream(st)
         for l in lanes[1:]:                      # combine the lanes' accumulators (then clear them)

@@ -355,6 +355,13 @@ class CudaBackend:
                  for t in ts)
         return ok or self._miss("attention", "operand dtype / alignment")
 
+    attn_small_lq = 64        # query sequences up to this length run on the warp-MMA attention kernels (attn_small.cu)
+
+    def set_attn_small_lq(self, max_lq):
+        """Process-wide (library global): 0 sends every bf16 attention problem to the tcgen05 kernels."""
+        self.lib.masr_attn_set_small_lq(int(max_lq))
+        CudaBackend.attn_small_lq = max(0, min(64, int(max_lq)))
+
     def attn_fwd(self, q, k, v, out, lse, B, H, Lq, Lk, klens, causal, p=0.0, seed=0, site=0, kv_rows=None):
         """kv_rows: rows per utterance in k / v when they are a decode cache of fixed capacity (default Lk)."""
         hd = out.shape[1] // H
@@ -376,7 +383,7 @@ class CudaBackend:
                               out.stride(0), _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0),
                               _p(dk), dk.stride(0), _p(dv), dv.stride(0), B, H, Lq, Lk, _p(klens), int(causal),
                               float(p), seed, site, int(dsum_ready), _p(dq_ws), self.stream,
-                              n_kernels=(1 if dsum_ready else 2) + (2 if Lk > 128 else 0))
+                              n_kernels=1 if Lq <= self.attn_small_lq else (1 if dsum_ready else 2) + (2 if Lk > 128 else 0))
         self._call("masr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
                    _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                    _p(dv), dv.stride(0), _dt(q), B, H, Lq, Lk, hd, _p(klens), int(causal), float(p), seed, site,
@@ -465,6 +472,32 @@ class CudaBackend:
     def mt_clip_sgd(self, p, g, buf, sumsq, max_norm, lr, momentum, nesterov, first_step):
         self._call("masr_mt_clip_sgd", _p(p), _p(g), _p(buf), p.numel(), _p(sumsq), float(max_norm), float(lr),
                    float(momentum), int(nesterov), int(first_step), self.stream)
+
+    def mt_clip_sgd_ex(self, p, g, buf, sumsq, max_norm, lr, momentum, nesterov, first_step, shadow=None, last_step=False):
+        """clip + SGD that also writes the bf16 shadow of the arena (and, on a task's last inner step, skips the dead
+        write-backs of the scaled gradient and the momentum)."""
+        if shadow is not None and shadow.dtype != torch.bfloat16:
+            shadow = None
+        self._call("masr_mt_clip_sgd_ex", _p(p), _p(g), _p(buf), p.numel(), _p(sumsq), float(max_norm), float(lr),
+                   float(momentum), int(nesterov), int(first_step), _p(shadow), 1 if last_step else 0, self.stream)
+        return shadow is not None
+
+    def mt_copy_cast(self, dst, shadow, src):
+        """dst = src (fp32 arenas) and shadow = bf16(src) in one pass; returns True when the shadow was written."""
+        if shadow is not None and shadow.dtype != torch.bfloat16:
+            shadow = None
+        self._call("masr_mt_copy_cast", _p(dst), _p(shadow), _p(src), src.numel(), self.stream)
+        return shadow is not None
+
+    def prep_weights(self, params, shadow, jobs, v2e, v2e_p, Cc, Fq, dtype_of):
+        """All derived weight copies in one launch (masr_prep_weights).  jobs: [(w fp32 [Cout,Cin,3,3], wp, wpt or None)];
+        shadow None = the arena's compute-dtype copy is fresh already."""
+        arr = (_lib.ConvPrepJob * max(len(jobs), 1))()
+        for i, (w, wp, wpt) in enumerate(jobs):
+            arr[i].w, arr[i].wp, arr[i].wpt = _p(w), _p(wp), _p(wpt)
+            arr[i].Cout, arr[i].Cin = w.shape[0], w.shape[1]
+        self._call("masr_prep_weights", _p(params), _p(shadow), params.numel(), arr, len(jobs), _p(v2e), _p(v2e_p),
+                   v2e.shape[0], int(Cc), int(Fq), _dt(dtype_of), self.stream)
 
     def mt_clip(self, g, sumsq, max_norm):
         self._call("masr_mt_clip", _p(g), g.numel(), _p(sumsq), float(max_norm), self.stream)

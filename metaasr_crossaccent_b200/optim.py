@@ -108,8 +108,21 @@ class FlatInnerSGD:
     def zero_grad(self):
         pass
 
-    def step(self, gnorm_sumsq, max_norm):
+    def step(self, gnorm_sumsq, max_norm, last=False):
+        """last: no further step of this task follows and the caller reads neither .grad nor the momentum again (the
+        lock-step meta-step scheduler): the kernel skips those write-backs.  On the CUDA path the same pass writes the
+        engine's bf16 shadow of the new weights."""
         e = self.engine
+        if hasattr(e.be, "mt_clip_sgd_ex"):
+            n = e.layout.total
+            wrote = e.be.mt_clip_sgd_ex(e.params[:n], e.grads[:n], self.buf[:n], gnorm_sumsq, max_norm, self.lr, self.momentum,
+                                        self.nesterov, self.first, None if e.shadow is None else e.shadow[:n], last)
+            self.first = False
+            if wrote:
+                e.mark_shadow_fresh()
+            else:
+                e.weights_dirty = True
+            return
         e.be.mt_clip_sgd(e.params, e.grads, self.buf, gnorm_sumsq, max_norm, self.lr, self.momentum,
                          self.nesterov, self.first)
         self.first = False

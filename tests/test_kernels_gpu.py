@@ -364,6 +364,62 @@ def test_flat_multi_tensor_ops(dev):
     assert bool(torch.isnan(gg).all())
 
 
+def test_fused_weight_refresh_kernels(dev):
+    """masr_mt_clip_sgd_ex / masr_mt_copy_cast write the bf16 shadow in the same pass as the fp32 arena, and
+    masr_prep_weights does every derived weight copy in one launch: each must equal the separate kernels bit for bit."""
+    from metaasr_crossaccent_b200.ops import CudaBackend
+    cb = CudaBackend(dev, torch.bfloat16)
+    n = 1_000_003
+    p, g, buf = rnd((n,), dev, seed=1), rnd((n,), dev, seed=2), rnd((n,), dev, seed=3)
+    ss = torch.zeros(1, dtype=torch.float64, device=dev)
+    cb.mt_sumsq(g, ss)
+    for first in (True, False):
+        for last in (False, True):
+            a = [t.clone() for t in (p, g, buf)]
+            b = [t.clone() for t in (p, g, buf)]
+            sh = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+            cb.mt_clip_sgd(a[0], a[1], a[2], ss, 5.0, 0.01, 0.9, True, first)
+            assert cb.mt_clip_sgd_ex(b[0], b[1], b[2], ss, 5.0, 0.01, 0.9, True, first, sh, last)
+            assert torch.equal(a[0], b[0]) and torch.equal(sh, a[0].to(torch.bfloat16))
+            if last:      # the dead write-backs are skipped: gradient and momentum keep their old contents
+                assert torch.equal(b[1], g) and torch.equal(b[2], buf)
+            else:
+                assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    nan = torch.full((1,), float("nan"), dtype=torch.float64, device=dev)
+    sh = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+    p0 = p.clone()
+    cb.mt_clip_sgd_ex(p0, g.clone(), buf.clone(), nan, 5.0, 0.01, 0.9, True, True, sh, False)
+    assert torch.equal(p0, p) and torch.equal(sh, p.to(torch.bfloat16))          # skipped step: the shadow still mirrors p
+    dst, sh = torch.zeros_like(p), torch.zeros(n, dtype=torch.bfloat16, device=dev)
+    assert cb.mt_copy_cast(dst, sh, p)
+    assert torch.equal(dst, p) and torch.equal(sh, p.to(torch.bfloat16))
+    # prep_weights: cast + three conv re-layouts (both orientations) + the vgg2enc permutation
+    for dt in (torch.bfloat16, torch.float32):
+        cbd = CudaBackend(dev, dt)
+        ws = [rnd((co, ci, 3, 3), dev, seed=10 + i) for i, (co, ci) in enumerate(((64, 64), (128, 64), (128, 128)))]
+        jobs, ref = [], []
+        for w in ws:
+            co, ci = w.shape[:2]
+            wp, wpt = torch.zeros(co, 9 * ci, dtype=dt, device=dev), torch.zeros(ci, 9 * co, dtype=dt, device=dev)
+            rp, rpt = torch.zeros_like(wp), torch.zeros_like(wpt)
+            cbd.conv_w_prep(w, rp); cbd.conv_w_prep_t(w, rpt)
+            jobs.append((w, wp, wpt)); ref.append((rp, rpt))
+        jobs[1] = (jobs[1][0], jobs[1][1], None)                                  # a job without the transposed layout
+        v2e = rnd((512, 2560), dev, seed=20)
+        v2e_p, v2e_r = torch.zeros(512, 2560, dtype=dt, device=dev), torch.zeros(512, 2560, dtype=dt, device=dev)
+        cbd.permute_cf(v2e, v2e_r, 128, 20, False)
+        sh = torch.zeros(n, dtype=dt, device=dev)
+        cbd.prep_weights(p, sh, jobs, v2e, v2e_p, 128, 20, v2e_p)
+        assert torch.equal(sh, p.to(dt)) and torch.equal(v2e_p, v2e_r)
+        for i, ((w, wp, wpt), (rp, rpt)) in enumerate(zip(jobs, ref)):
+            assert torch.equal(wp, rp), i
+            if wpt is not None:
+                assert torch.equal(wpt, rpt), i
+        sh.zero_()
+        cbd.prep_weights(p, None, jobs, v2e, v2e_p, 128, 20, v2e_p)               # fresh shadow: the cast is skipped
+        assert float(sh.float().abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (4096, 1536, 512), (1056, 512, 2048), (200, 96, 72),
                                    (130, 367, 512), (64, 576, 5000)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
