@@ -227,8 +227,14 @@ def bench_meta(args, algo, meta_k, dtype, steps, warmup, detail, rank, world, de
 
     last_info = {}
 
+    nxt = {}
+
     def step_e2e():
-        solver.meta_step_on_tasks([clone_host(t) for t in host_tasks], global_task_count=N_ACCENTS)
+        # like a prefetching loader: the NEXT step's host batches are handed over with the current ones, so their
+        # host->device copies (copy stream) run under this step's compute; every step still copies all of its inputs
+        cur = nxt.pop("t", None) or [clone_host(t) for t in host_tasks]
+        nxt["t"] = [clone_host(t) for t in host_tasks]
+        solver.meta_step_on_tasks(cur, global_task_count=N_ACCENTS, next_tasks=nxt["t"])
         last_info["i"] = solver.flush_train_info()           # device->host read of the step's losses
         return last_info["i"]
 

@@ -390,6 +390,8 @@ class TransformerEngine:
         """Runs the network on a device batch; fills ws['logits'] [B*L1, C] fp32 and the loss
         statistics; with want_grad also d(mean loss)/d logits.  `mem` (greedy decode): an encoder memory
         [B*T', d] computed by an earlier call on the same x -- the conv front end and the encoder are skipped."""
+        if db.get("ready") is not None:       # a batch staged on a copy stream (interfaces.stage_tasks)
+            torch.cuda.current_stream(self.device).wait_event(db["ready"])
         if mem is None:
             self.forward_conv(db)
         return self.forward_rest(db, want_grad, mem)
@@ -885,6 +887,8 @@ class TransformerEngine:
 
     def fb_begin(self, db):
         """Stages the inputs of a batch on the CURRENT stream and returns the handle fb_segment takes."""
+        if db.get("ready") is not None:       # staged ahead of time on a copy stream (interfaces.stage_tasks)
+            torch.cuda.current_stream(self.device).wait_event(db["ready"])
         if self.use_graphs and self.device.type == "cuda":
             ent = self._graph_entry(db)
             graphs, sdb, ws = ent

@@ -411,9 +411,62 @@ class FOMetaMixin:
 
     _global_task_count = 0       # tasks of the meta-batch over ALL ranks (0: read it from the all-reduce)
 
-    def meta_step_on_tasks(self, tasks, global_task_count=None):
+    # -- host batches: staged on a copy stream, ahead of the compute that consumes them
+    def stage_tasks(self, tasks, _prefetch=False):
+        """Host batches of a meta-step -> device-resident prepared batches, copied on a private copy stream; every batch
+        carries the event its consumer waits on, so the copy of the inner-test batch overlaps the inner-train batch and
+        (through meta_step_on_tasks(next_tasks=)) the copies of step k+1 overlap step k.  Batches that are already
+        prepared device dicts pass through."""
+        eng = self.asr_model.engine
+        if eng.device.type != 'cuda':
+            return tasks
+        if not any(not isinstance(b[1][0], dict) for tr, te in tasks for b in list(tr) + [te]):
+            return tasks
+        if '_copy_stream' not in self.__dict__:
+            self._copy_stream = torch.cuda.Stream(eng.device)
+            self._step_done = []               # end-of-step events of the last two meta-steps
+        cs = self._copy_stream
+        # staging blocks the allocator hands back may still be read by the kernels of the step that owned them: the copies
+        # wait for the end of that step.  Staged at the head of a step: the previous step's buffers were just released.
+        # Prefetched behind a step's launches: that step's buffers are still referenced, the ones released belong to the
+        # step before it -- so these copies run under the compute of the step in flight.
+        k = 2 if _prefetch else 1
+        if len(self._step_done) >= k:
+            cs.wait_event(self._step_done[-k])
+
+        def stage(batch):
+            idx, (x, ilens, ys, olens) = batch
+            if isinstance(x, dict):
+                return batch
+            hb = eng.prepare_batch(x, ilens, ys, olens)
+            db = eng.to_device(hb)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            db["ready"] = ev
+            return idx, (db, None, [None] * hb["B"], None)
+
+        with torch.cuda.stream(cs):
+            return [([stage(b) for b in tr], stage(te)) for tr, te in tasks]
+
+    def meta_step_on_tasks(self, tasks, global_task_count=None, next_tasks=None):
         """One meta-step given this rank's tasks = [(train_batches, test_batch), ...]; batches are
-        (accent_idx, (x, ilens, ys, olens)) tuples as DataContainer.get_item yields them."""
+        (accent_idx, (x, ilens, ys, olens)) tuples as DataContainer.get_item yields them.  next_tasks: the NEXT step's
+        tasks, if the caller has them already (a prefetching loader): their host->device copies are issued behind this
+        step's launches and run under its compute; pass the same list object as `tasks` of the next call."""
+        pre = self.__dict__.pop('_prefetched', None)
+        if pre is not None and pre[0] is tasks:
+            tasks = pre[1]
+        else:
+            tasks = self.stage_tasks(tasks)
+        self._meta_step_staged(tasks, global_task_count)
+        if self.asr_model.engine.device.type == 'cuda' and '_copy_stream' in self.__dict__:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.asr_model.engine.device))
+            self._step_done = (self._step_done + [ev])[-2:]
+        if next_tasks is not None:
+            self._prefetched = (next_tasks, self.stage_tasks(next_tasks, _prefetch=True))
+
+    def _meta_step_staged(self, tasks, global_task_count=None):
         if global_task_count is not None:
             self._global_task_count = global_task_count
         self._ring_sizes = []

@@ -114,6 +114,41 @@ def test_fomaml_meta_step_vs_reference_golden(dev):
         check_adam_weights(z, "s0.w.", ["s0.mg."], n, s._original[n], s.meta_opt.lr)
 
 
+def test_prefetched_host_batches_equal_unstaged(dev):
+    """meta_step_on_tasks(next_tasks=) issues the NEXT step's host->device copies on a copy stream behind the current step's
+    launches: two meta-steps with prefetch must give the inner-test losses and meta weights of two plain steps (fp32
+    mode, no dropout in the tiny config), and the prepared batches must carry the `olens += 1` side effect."""
+    z = np.load(GOLD / "fomaml_tiny.npz")
+
+    def tasks_of():
+        out = []
+        for acc in range(2):
+            tr = [(acc, load_batch(z, f"s0.a{acc}.tr{j}.")) for j in range(2)]
+            out.append((tr, (acc, load_batch(z, f"s0.a{acc}.te."))))
+        return out
+    res = []
+    for prefetch in (False, True):
+        s = make_solver("fomaml")
+        load_tiny(s)
+        t1, t2 = tasks_of(), tasks_of()
+        ol = t2[0][0][0][1][3]
+        before = ol.clone()
+        s.meta_step_on_tasks(t1, next_tasks=t2 if prefetch else None)
+        if prefetch:
+            assert torch.equal(ol, before + 1)          # staged already: prepare_batch ran
+            assert s.__dict__.get('_prefetched') is not None
+        s.meta_step_on_tasks(t2)
+        assert s.__dict__.get('_prefetched') is None
+        assert torch.equal(ol, before + 1)
+        losses = [i["loss"] for i in s.flush_train_info()]
+        res.append((s._original_flat.clone(), losses))
+    # (not bit-equal even between two plain runs: the split-K weight gradients reduce with fp32 atomics, and Adam with
+    # eps 1e-9 turns a noise-level gradient into a +-lr move)
+    for a, b in zip(res[0][1], res[1][1]):
+        assert abs(a - b) <= 1e-5 * abs(a), (res[0][1], res[1][1])
+    assert float((res[0][0] - res[1][0]).norm()) <= 1e-3 * float(res[0][0].norm())
+
+
 def test_reptile_meta_step_vs_definition(dev):
     """Reptile (no reference implementation, `fo_meta_interface.py:195-198` raises; parity unpinned):
     `_updates += theta - phi` after meta_k inner steps, then the same noam-Adam -- through the CUDA path
