@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "epilogue.cuh"
+#include "epilogue_tma.cuh"
 
 namespace masr {
 
@@ -21,22 +22,38 @@ __device__ __forceinline__ uint32_t kmajor_off(int t, int j) {
   return uint32_t(t >> 3) * 1024u + uint32_t(t & 7) * 128u + (uint32_t((j >> 3) ^ (t & 7)) << 4) + uint32_t(j & 7) * 2u;
 }
 
-// 3x3 neighbourhood of pixel p (flattened b, h, w) of x [B, H, W] fp32, zero outside the image
-__device__ __forceinline__ void load_taps(const float* __restrict__ x, int64_t p, int64_t P, int H, int W, float* tap) {
+// Position of a builder thread's pixel, advanced by a constant stride from tile to tile without divisions (the 64-bit
+// div / mod of the flattened index was ~100 instructions per tile, and the tap loads that depended on it sat on the
+// thread's critical path).
+struct PixCursor {
+  int64_t pix, row;        // flattened pixel, image row b * H + h
+  int h, w;
+  int d_w, d_h; int64_t d_row, d_pix;
+  __device__ __forceinline__ void init(int64_t p0, int64_t stride, int H, int W) {
+    pix = p0; row = p0 / W; w = int(p0 - row * W); h = int(row % H);
+    d_pix = stride; d_row = stride / W; d_w = int(stride - d_row * W); d_h = int(d_row % H);
+  }
+  __device__ __forceinline__ void advance(int H, int W) {
+    pix += d_pix; row += d_row; w += d_w; h += d_h;
+    if (w >= W) { w -= W; ++row; ++h; }
+    if (h >= H) h -= H;
+    if (h >= H) h -= H;
+  }
+};
+
+// 3x3 neighbourhood of the cursor's pixel of x [B, H, W] fp32, zero outside the image / past the last pixel
+__device__ __forceinline__ void load_taps(const float* __restrict__ x, const PixCursor& c, int64_t P, int H, int W, float* tap) {
 #pragma unroll
   for (int t = 0; t < 9; ++t) tap[t] = 0.f;
-  if (p >= P) return;
-  const int w = int(p % W);
-  const int64_t row = p / W;               // b * H + h
-  const int h = int(row % H);
+  if (c.pix >= P) return;
 #pragma unroll
   for (int dh = -1; dh <= 1; ++dh) {
-    const int hh = h + dh;
+    const int hh = c.h + dh;
     if (hh < 0 || hh >= H) continue;
-    const float* xr = x + (row + dh) * W;
+    const float* xr = x + (c.row + dh) * W;
 #pragma unroll
     for (int dw = -1; dw <= 1; ++dw) {
-      const int ww = w + dw;
+      const int ww = c.w + dw;
       if (ww >= 0 && ww < W) tap[(dh + 1) * 3 + (dw + 1)] = __ldg(xr + ww);
     }
   }
@@ -45,6 +62,7 @@ __device__ __forceinline__ void load_taps(const float* __restrict__ x, int64_t p
 // ================================================================================================ forward
 constexpr int C1F_THREADS = 320;          // warp 0 -, warp 1 MMA, warps 2-5 patch builders, warps 6-9 epilogue
 constexpr int C1F_STAGES = 3;
+constexpr int C1_AHEAD = 2;              // tiles of input taps a builder thread keeps in flight
 
 struct C1FwdParams {
   const float* x; const float* w; const float* bias; __nv_bfloat16* y;
@@ -52,14 +70,14 @@ struct C1FwdParams {
 };
 
 __global__ void __launch_bounds__(C1F_THREADS, 2)
-conv1_fwd_umma_kernel(C1FwdParams p) {
+conv1_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_y, C1FwdParams p) {
   using namespace umma;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* sA = smem;                                      // C1F_STAGES x [128 rows x 128 B] (K = 16 used)
   unsigned char* sW = sA + C1F_STAGES * 16384;                   // [64 co x 128 B]
-  unsigned char* sStage = sW + 8192;                             // epilogue staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + EpiLayout<64, __nv_bfloat16>::BYTES);
+  unsigned char* sStage = sW + 8192;                             // epilogue boxes (epilogue_tma.cuh), 1024 B aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + EPT_CTA_BYTES);
   uint64_t* a_full = bars;                    // [STAGES] count 4 (builder warps)
   uint64_t* a_empty = bars + C1F_STAGES;      // [STAGES] count 1 (MMA commit)
   uint64_t* t_full = bars + 2 * C1F_STAGES;   // [2]
@@ -70,6 +88,7 @@ conv1_fwd_umma_kernel(C1FwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
+    prefetch_tmap(&map_y);
     for (int s = 0; s < C1F_STAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
     fence_barrier_init();
@@ -98,26 +117,41 @@ conv1_fwd_umma_kernel(C1FwdParams p) {
   const int first = int(blockIdx.x), step = int(gridDim.x);
 
   if (warp >= 2 && warp <= 5) {
-    // ===== patch builders: thread = pixel row of the tile =====
+    // ===== patch builders: thread = pixel row of the tile; the taps of the next two tiles are in flight while the
+    // current one is packed (the loads were the builders' -- and the kernel's -- critical path) =====
     const int r = (warp - 2) * 32 + lane;
     int s = 0; uint32_t ph = 0;
-    for (int tile = first; tile < p.ntiles; tile += step) {
-      float tap[9];
-      load_taps(p.x, int64_t(tile) * 128 + r, p.P, p.H, p.W, tap);
-      uint32_t pk[8];
+    PixCursor cur;
+    cur.init(int64_t(first) * 128 + r, int64_t(step) * 128, p.H, p.W);
+    // C1_AHEAD tiles of taps in flight per thread, in a register ring indexed statically (the loop is unrolled by the
+    // ring size: a register-to-register hand-over would wait on the pending loads).  x is re-fetched from HBM under the
+    // streaming output (5 MB of input against 174 MB written), so the load latency is microseconds, not an L2 hit.
+    float tp[C1_AHEAD][9];
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(j < 9 ? tap[j] : 0.f, j + 1 < 9 ? tap[j + 1] : 0.f);
-        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+    for (int d = 0; d < C1_AHEAD; ++d) { load_taps(p.x, cur, p.P, p.H, p.W, tp[d]); cur.advance(p.H, p.W); }
+    for (int tile = first; tile < p.ntiles; tile += step * C1_AHEAD) {
+#pragma unroll
+      for (int d = 0; d < C1_AHEAD; ++d) {
+        if (tile + d * step >= p.ntiles) break;
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(j < 9 ? tp[d][j] : 0.f, j + 1 < 9 ? tp[d][j + 1] : 0.f);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        mbar_wait(&a_empty[s], ph ^ 1);
+        unsigned char* a = sA + s * 16384;
+        *reinterpret_cast<uint4*>(a + kmajor_off(r, 0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(a + kmajor_off(r, 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[s]);
+        if (++s == C1F_STAGES) { s = 0; ph ^= 1; }
+        // C1_AHEAD tiles ahead (zeros past the last pixel); issued behind the fences above, so that the pack of the next
+        // slot never shares a scoreboard with these younger loads
+        load_taps(p.x, cur, p.P, p.H, p.W, tp[d]);
+        cur.advance(p.H, p.W);
       }
-      mbar_wait(&a_empty[s], ph ^ 1);
-      unsigned char* a = sA + s * 16384;
-      *reinterpret_cast<uint4*>(a + kmajor_off(r, 0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(a + kmajor_off(r, 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[s]);
-      if (++s == C1F_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (converged warp, elected lane issues) =====
@@ -139,23 +173,24 @@ conv1_fwd_umma_kernel(C1FwdParams p) {
       if (++s == C1F_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp >= 6) {
-    // ===== epilogue: bias + ReLU -> bf16 NHWC (a tile's 128 pixels are 16 KB of contiguous output) =====
+    // ===== epilogue: bias + ReLU -> bf16 -> swizzled box -> one bulk tensor store per warp and tile (rows past the last
+    // pixel are clipped by the TMA) =====
     const int q = warp & 3;
-    int it = 0;
+    int it = 0, boxsel = 0;
+    EptOpts o;
+    o.sbias = sbias;
+    o.relu = true;
     for (int tile = first; tile < p.ntiles; tile += step, ++it) {
       const int ab = it & 1;
       mbar_wait(&t_full[ab], (it >> 1) & 1);
       tc_fence_after();
-      const int64_t pix = int64_t(tile) * 128 + q * 32 + lane;
-      __nv_bfloat16* orow = pix < p.P ? p.y + pix * 64 : nullptr;
-      EpiOpts o;
-      o.sbias = sbias;
-      o.relu = true;
-      epilogue_tile<64, __nv_bfloat16>(tmem_base + uint32_t(ab * 64), q, lane, sStage, orow, 64, true, EPI_STORE, o);
+      epilogue_tma_bf16<false>(&map_y, tmem_base + uint32_t(ab * 64), q, lane, tile * 128 + q * 32, 0, 1, 64, true,
+                               sStage + q * EPT_WARP_BYTES, boxsel, o);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[ab]);
     }
+    epilogue_tma_drain(lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -239,22 +274,31 @@ conv1_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, C1WgradParam
     const int r = (warp - 2) * 32 + lane;            // pixel within the 128-pixel block
     const int kbk = r >> 6, j = r & 63;
     int s = 0; uint32_t ph = 0;
-    for (int i = 0; i < my_blocks; ++i) {
-      const int blk = first + i * step;
-      const int64_t pix = int64_t(blk) * 128 + r;
-      float tap[9];
-      load_taps(p.x, pix, p.P, p.H, p.W, tap);
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      unsigned char* sb = smem + s * C1W_STAGE + C1W_A + kbk * 2048;
+    PixCursor cur;
+    cur.init(int64_t(first) * 128 + r, int64_t(step) * 128, p.H, p.W);
+    float tp[C1_AHEAD][9];                             // taps of the next C1_AHEAD blocks (see the forward kernel)
+    bool tv[C1_AHEAD];
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const float v = t < 9 ? tap[t] : ((t == 9 && pix < p.P) ? 1.f : 0.f);      // row 9 = ones: bias gradient
-        *reinterpret_cast<__nv_bfloat16*>(sb + kmajor_off(t, j)) = __float2bfloat16_rn(v);
+    for (int d = 0; d < C1_AHEAD; ++d) { tv[d] = cur.pix < p.P; load_taps(p.x, cur, p.P, p.H, p.W, tp[d]); cur.advance(p.H, p.W); }
+    for (int i = 0; i < my_blocks; i += C1_AHEAD) {
+#pragma unroll
+      for (int d = 0; d < C1_AHEAD; ++d) {
+        if (i + d >= my_blocks) break;
+        __nv_bfloat16 bv[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) bv[t] = __float2bfloat16_rn(t < 9 ? tp[d][t] : ((t == 9 && tv[d]) ? 1.f : 0.f));   // row 9 = ones: bias gradient
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* sb = smem + s * C1W_STAGE + C1W_A + kbk * 2048;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) *reinterpret_cast<__nv_bfloat16*>(sb + kmajor_off(t, j)) = bv[t];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (++s == C1W_STAGES) { s = 0; ph ^= 1; }
+        tv[d] = cur.pix < p.P;
+        load_taps(p.x, cur, p.P, p.H, p.W, tp[d]);
+        cur.advance(p.H, p.W);
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-      if (++s == C1W_STAGES) { s = 0; ph ^= 1; }
     }
     // ===== final epilogue: an M = 64 accumulator occupies 16 lanes of each 32-lane TMEM quadrant =====
     if (my_blocks > 0) {
@@ -288,13 +332,21 @@ extern "C" int masr_umma_conv1_fwd(const float* x, const float* w, const float* 
   MASR_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "umma conv1: y must be 16 B aligned");
   const int64_t P = int64_t(B) * H * W;
   if (P == 0) return MASR_OK;
-  MASR_REQUIRE(P < (int64_t(1) << 37), "umma conv1: too many pixels");
+  MASR_REQUIRE(P < (int64_t(1) << 31) - 256, "umma conv1: too many pixels");
   C1FwdParams p{x, w, bias, static_cast<__nv_bfloat16*>(y), H, W, P, int(ceil_div64(P, 128))};
-  const size_t smem = C1F_STAGES * 16384 + 8192 + EpiLayout<64, __nv_bfloat16>::BYTES + 256 + 64 * 4 + 1024;
+  CUtensorMap my;
+  {
+    uint64_t dims[2] = {64, uint64_t(P)};
+    uint64_t strides[1] = {128};
+    uint32_t box[2] = {64, 32};
+    const int rc = make_tmap_bf16(&my, y, 2, dims, strides, box, true);
+    if (rc != MASR_OK) return rc;
+  }
+  const size_t smem = C1F_STAGES * 16384 + 8192 + EPT_CTA_BYTES + 256 + 64 * 4 + 1024;
   static bool attr = false;
   if (!attr) { MASR_CHECK_CUDA(cudaFuncSetAttribute(conv1_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
   const unsigned grid = unsigned(std::min(p.ntiles, 2 * sm_count()));
-  MASR_CHECK_CUDA(launch_pdl(conv1_fwd_umma_kernel, dim3(grid), dim3(C1F_THREADS), smem, as_stream(stream), p));
+  MASR_CHECK_CUDA(launch_pdl(conv1_fwd_umma_kernel, dim3(grid), dim3(C1F_THREADS), smem, as_stream(stream), my, p));
   return MASR_OK;
 }
 
