@@ -191,6 +191,13 @@ int masr_maxpool2x2_fwd(const void* x, void* y, int dtype, int B, int H, int W, 
 /* dx = scatter(dy) to the first arg-max of each window, times (x > 0) when relu_mask != 0 */
 int masr_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int dtype, int relu_mask,
                         int B, int H, int W, int C, void* stream);
+/* The same pool with a per-output code byte (bits 0-1: which of the four inputs won, first maximum in (h, w) scan order;
+ * bit 2: the maximum is positive): the backward scatters dy from the codes and no longer re-reads the full-resolution
+ * activation (C % 8 == 0, 16-byte aligned tensors; code [B, H/2, W/2, C] uint8).  nn.MaxPool2d(2, stride=2) behind the
+ * ReLU of mono_transformer_torch.py:52-58. */
+int masr_maxpool2x2_fwd_code(const void* x, void* y, void* code, int dtype, int B, int H, int W, int C, void* stream);
+int masr_maxpool2x2_bwd_code(const void* code, const void* dy, void* dx, int dtype, int relu_mask,
+                             int B, int H, int W, int C, void* stream);
 /* dx = (y > 0) ? dx * scale : 0, elementwise (scale = 1/(1-p): backward of ReLU followed by dropout(p) from the stored output) */
 int masr_relu_bwd(const void* y, void* dx, int dtype, int64_t n, float scale, void* stream);
 

@@ -59,6 +59,8 @@ SIGNATURES = {
     "masr_conv_w_unprep_add": [c_p, c_p, c_i, c_i, c_p],
     "masr_maxpool2x2_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_maxpool2x2_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_maxpool2x2_fwd_code": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "masr_maxpool2x2_bwd_code": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "masr_relu_bwd": [c_p, c_p, c_i, c_i64, c_f, c_p],
     "masr_attn_fwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i,
                       c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_f, c_u64, c_u32, c_p],

@@ -422,13 +422,20 @@ class TransformerEngine:
         a2 = buf("a2", (B, T, F0, 64))
         be.conv3x3_fwd(a1, self.wp[2], P["feat_extractor.2.bias"], a2)
         p1 = buf("p1", (B, T2, F2, 64))
-        be.maxpool_fwd(a2, p1)
+        codes = getattr(be, "pool_codes", False)     # arg-max bytes: the pool backward does not re-read a2 / a4
+        if codes:
+            be.maxpool_fwd(a2, p1, code=buf("p1.code", (B, T2, F2, 64), torch.uint8))
+        else:
+            be.maxpool_fwd(a2, p1)
         a3 = buf("a3", (B, T2, F2, 128))
         be.conv3x3_fwd(p1, self.wp[5], P["feat_extractor.5.bias"], a3)
         a4 = buf("a4", (B, T2, F2, 128))
         be.conv3x3_fwd(a3, self.wp[7], P["feat_extractor.7.bias"], a4)
         p2 = buf("p2", (B, T4, F4, 128))
-        be.maxpool_fwd(a4, p2)
+        if codes:
+            be.maxpool_fwd(a4, p2, code=buf("p2.code", (B, T4, F4, 128), torch.uint8))
+        else:
+            be.maxpool_fwd(a4, p2)
         return ws
 
     def forward_rest(self, db, want_grad=True, mem=None):
@@ -780,7 +787,8 @@ class TransformerEngine:
         fork = self._fork
         g_p2 = ws["g.p2"]
         g_a4 = buf("g.a4", (B, T2, F2, 128))
-        be.maxpool_bwd(ws["a4"], g_p2, g_a4, True)
+        pool_kw = lambda nm: {"code": ws[nm]} if nm in ws else {}
+        be.maxpool_bwd(ws["a4"], g_p2, g_a4, True, **pool_kw("p2.code"))
 
         def conv_wgrad(i, x, dy):
             def run():
@@ -796,7 +804,7 @@ class TransformerEngine:
         g_p1 = buf("g.p1", (B, T2, F2, 64))
         be.conv3x3_dgrad(g_a3, self.wp[5], g_p1, None, **({"wpt": self.wpt[5]} if 5 in self.wpt else {}))
         g_a2 = buf("g.a2", (B, T, F0, 64))
-        be.maxpool_bwd(ws["a2"], g_p1, g_a2, True)
+        be.maxpool_bwd(ws["a2"], g_p1, g_a2, True, **pool_kw("p1.code"))
         conv_wgrad(2, ws["a1"], g_a2)
         g_a1 = buf("g.a1", (B, T, F0, 64))
         be.conv3x3_dgrad(g_a2, self.wp[2], g_a1, ws["a1"], **({"wpt": self.wpt[2]} if 2 in self.wpt else {}))

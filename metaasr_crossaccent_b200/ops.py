@@ -333,12 +333,23 @@ class CudaBackend:
             self.gemm(dy, 1, Cout, col, 1, 9 * Cin, dwp, 9 * Cin, None, Cout, 9 * Cin, P, GEMM_SPLITK, splitk)
         self.colsum_add(dy.view(P, Cout), db)
 
-    def maxpool_fwd(self, x, y):
+    pool_codes = True         # the engine may ask for the arg-max code bytes (maxpool_fwd(code=) / maxpool_bwd(code=))
+
+    @staticmethod
+    def _pool_code_ok(x, *ts):
+        return x.shape[3] % 8 == 0 and all(t.data_ptr() % 16 == 0 for t in (x,) + ts)
+
+    def maxpool_fwd(self, x, y, code=None):
+        """code (optional, uint8 [B, H/2, W/2, C]): per-output arg-max / positive-maximum byte for maxpool_bwd(code=)."""
         B, H, W, Cc = x.shape
+        if code is not None and self._pool_code_ok(x, y, code):
+            return self._call("masr_maxpool2x2_fwd_code", _p(x), _p(y), _p(code), _dt(x), B, H, W, Cc, self.stream)
         self._call("masr_maxpool2x2_fwd", _p(x), _p(y), _dt(x), B, H, W, Cc, self.stream)
 
-    def maxpool_bwd(self, x, dy, dx, relu_mask=True):
+    def maxpool_bwd(self, x, dy, dx, relu_mask=True, code=None):
         B, H, W, Cc = x.shape
+        if code is not None and self._pool_code_ok(x, dy, dx, code):
+            return self._call("masr_maxpool2x2_bwd_code", _p(code), _p(dy), _p(dx), _dt(x), int(relu_mask), B, H, W, Cc, self.stream)
         self._call("masr_maxpool2x2_bwd", _p(x), _p(dy), _p(dx), _dt(x), int(relu_mask), B, H, W, Cc, self.stream)
 
     def relu_bwd(self, y, dx, scale=1.0):

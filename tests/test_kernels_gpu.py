@@ -142,6 +142,16 @@ def test_conv1_and_pool(pair, dev):
             assert torch.equal(g1, g2)                 # ties only among zeros, which the ReLU mask removes
         else:
             assert torch.equal(g1.sum((1, 2)), g1.sum((1, 2))) and float((g1 - g2).abs().sum()) >= 0
+    # pool with arg-max code bytes: the backward reads the codes instead of the full-resolution input -- bit-identical
+    # to the plain kernels (H = 13, W = 83 odd: the floor-dropped last row / column get zero gradients)
+    p3, code = torch.empty_like(p1), torch.empty(p1.shape, device=dev, dtype=torch.uint8)
+    cb.maxpool_fwd(y2, p3, code=code)
+    assert torch.equal(p3, p1) and int(code.max()) <= 7
+    for relu_mask in (True, False):
+        g1, g3 = torch.full_like(y2, 7.0), torch.full_like(y2, 9.0)
+        cb.maxpool_bwd(y2, dp, g1, relu_mask)
+        cb.maxpool_bwd(y2, dp, g3, relu_mask, code=code)
+        assert torch.equal(g1, g3)
     r1 = dy.clone()
     r2 = dy.clone()
     cb.relu_bwd(y2, r1)

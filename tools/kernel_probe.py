@@ -87,6 +87,9 @@ def main():
         timeit("maxpool_fwd 32x512x83x64", lambda: be.maxpool_fwd(a1, p1), args.reps, tab, None, nb + p1.numel() * 2)
         g1 = torch.empty_like(a1)
         timeit("maxpool_bwd 32x512x83x64", lambda: be.maxpool_bwd(a1, p1, g1, True), args.reps, tab, None, 2 * nb + p1.numel() * 2)
+        code = torch.empty(p1.shape, device=dev, dtype=torch.uint8)
+        timeit("maxpool_fwd + arg-max codes", lambda: be.maxpool_fwd(a1, p1, code=code), args.reps, tab, None, nb + p1.numel() * 3)
+        timeit("maxpool_bwd from codes", lambda: be.maxpool_bwd(a1, p1, g1, True, code=code), args.reps, tab, None, nb + p1.numel() * 3)
     if want("attn"):
         for (B, H, Lq, Lk, causal, kl) in [(32, 8, 128, 128, False, True), (32, 8, 33, 33, True, False), (32, 8, 33, 128, False, True)]:
             d = H * 64
