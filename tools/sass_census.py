@@ -2,7 +2,7 @@
 """Instruction census of the shipped library: `cuobjdump -sass libmetaasr_b200.so`, per kernel the counts of the SASS
 mnemonics that prove the Blackwell paths (tcgen05.mma = UTCHMMA / UTCQMMA..., TMEM loads = LDTM, TMEM alloc = UTCALLOC...,
 TMA = UTMALDG / UTMASTG / UTMAREDG / UBLKCP, mbarrier = SYNCS, tcgen05.commit = UTCBAR) next to the CUDA-core work
-(FFMA, MUFU, HMMA = legacy mma.sync: must be 0).  Usage: python tools/sass_census.py [out.md]"""
+(FFMA, MUFU; HMMA = warp-level mma.sync: only the short-query attention kernels of attn_small.cu, on purpose).  Usage: python tools/sass_census.py [out.md]"""
 import collections
 import re
 import subprocess
