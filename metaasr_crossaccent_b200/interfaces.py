@@ -396,33 +396,9 @@ class FOMetaMixin:
             ev.record()
             self._phase_log.append((tag, ev))
 
-    def _reduce_and_adam_chunked(self, n_chunks):
-        """Several ranks, task count known up front: the update arena is all-reduced in n_chunks slices (NCCL's stream) and
-        the average + Adam kernel of slice i runs on the compute stream while slice i+1 is still on the wire -- the
-        0.14 ms Adam pass disappears behind the all-reduce.  Same arithmetic per element as the one-shot path, so the
-        replicas stay bit-identical."""
-        import torch.distributed as tdist
-        eng = self.asr_model.engine
-        n = eng.layout.total
-        step = -(-n // n_chunks)
-        step = -(-step // 1024) * 1024                      # slices start on 4 KB boundaries (128-bit kernel accesses)
-        ranges = [(a, min(a + step, n)) for a in range(0, n, step)]
-        self._mark('reduce0')
-        works = [tdist.all_reduce(self._upd_flat[a:b], op=tdist.ReduceOp.SUM, async_op=True) for a, b in ranges]
-        self.meta_opt.step(self._upd_flat[:n], max(float(self._global_task_count), 1.0), ranges=ranges, waits=works)
-        self._mark('reduce1')
-
     def _final_meta_update(self):
         eng = self.asr_model.engine
         n = eng.layout.total
-        n_chunks = int(self.config['asr_model'].get('reduce_chunks', 4))
-        if (D.is_dist() and self._global_task_count and n_chunks > 1
-                and not (self.paras.algo == 'reptile' and self.reptile_outer == 'interp')):
-            self._reduce_and_adam_chunked(n_chunks)
-            eng.be.zero_(self._upd_flat)
-            self._counter, self._updates = 0, None
-            self._mark('adam1')
-            return
         count = self._reduce_updates()
         if self.paras.algo == 'reptile' and self.reptile_outer == 'interp':
             eng.be.mt_axpy(self._original_flat[:n], self._upd_flat[:n], -self.reptile_eps / max(count, 1.0))
@@ -712,20 +688,14 @@ class _MetaNoamAdam:
         self.state = FlatAdamState(backend, original_flat)
         self.step_num, self.lr = 0, d_model ** (-0.5)
 
-    def step(self, upd_flat, count, ranges=None, waits=None):
-        """ranges / waits: apply the step slice by slice, each after its (asynchronous) all-reduce has completed."""
+    def step(self, upd_flat, count):
         self.step_num += 1
         self.lr = noam_lr(self.step_num, self.k, self.d_model, self.warmup_steps)
         n = upd_flat.numel()
         st = self.state
         st.t += 1
         bc1, bc2 = 1.0 - st.b1 ** st.t, 1.0 - st.b2 ** st.t
-        if ranges is None:
-            st.be.mt_adam(st.p[:n], st.m[:n], st.v[:n], upd_flat, count, self.lr, st.b1, st.b2, st.eps, bc1, bc2)
-            return
-        for (a, b), w in zip(ranges, waits):
-            w.wait()                                   # the compute stream waits for this slice (no host block on NCCL)
-            st.be.mt_adam(st.p[a:b], st.m[a:b], st.v[a:b], upd_flat[a:b], count, self.lr, st.b1, st.b2, st.eps, bc1, bc2)
+        st.be.mt_adam(st.p[:n], st.m[:n], st.v[:n], upd_flat, count, self.lr, st.b1, st.b2, st.eps, bc1, bc2)
 
     def zero_grad(self):
         pass
