@@ -43,12 +43,12 @@ def main():
              f"`cuobjdump -sass {LIB.relative_to(ROOT)}` -> static instruction counts per kernel ({len(rows)} kernels).",
              "UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, UTCATOMSWS = tcgen05.alloc / dealloc, UTMALDG /",
              "UTMASTG / UTMAREDG = TMA tensor load / store / reduce-add, SYNCS = mbarrier ops, ELECT = elect.sync (converged-warp",
-             "issue), UCGABAR = cluster barrier (CTA-pair GEMM), HMMA = legacy mma.sync (none).", "",
+             "issue), UCGABAR = cluster barrier (CTA-pair GEMM), HMMA = warp-level mma.sync (only attn_small_*: the 33-row decoder attention problems, latency-bound, DESIGN.md 2c').", "",
              "| kernel | total | " + " | ".join(COLS) + " |", "|---|---|" + "---|" * len(COLS)]
     for short, cnt in rows:
         lines.append(f"| `{short}` | {cnt['_total']} | " + " | ".join(str(sum(v for k, v in cnt.items() if k.startswith(c))) for c in COLS) + " |")
     tot_tc = sum(1 for _, c in rows if c["UTCHMMA"] > 0)
-    lines += ["", f"{tot_tc} kernels issue tcgen05.mma; {sum(1 for _, c in rows if any(k.startswith('HMMA') for k in c))} use legacy HMMA."]
+    lines += ["", f"{tot_tc} kernels issue tcgen05.mma; {sum(1 for _, c in rows if any(k.startswith('HMMA') for k in c))} use warp-level HMMA (attn_small_fwd / attn_small_bwd)."]
     text = "\n".join(lines) + "\n"
     if len(sys.argv) > 1:
         Path(sys.argv[1]).write_text(text)
