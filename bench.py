@@ -398,24 +398,54 @@ def replica_check(solver, eng, rank, world, dev, meta_k):
 
     _, mine_tasks = host_tasks_of(rank, world, meta_k, pin=False)
     accumulate([clone_host(t) for t in mine_tasks])
+    u_own = solver._upd_flat[:n].clone()                 # this rank's share before the collective
     solver._reduce_updates()
     u_dist = solver._upd_flat[:n].clone()
-    every = []
+    every, owner = [], []
     for r in range(world):
-        every += host_tasks_of(r, world, meta_k, pin=False)[1]
-    accumulate([clone_host(t) for t in every])
+        ts = host_tasks_of(r, world, meta_k, pin=False)[1]
+        every += ts
+        owner += [r] * len(ts)
+    # sequential replay on THIS rank, keeping the share of every rank apart: which rank's share differs, and where
+    shares = [torch.zeros(n, device=dev) for _ in range(world)] if world <= 8 else None
+    solver._upd_flat.zero_()
+    solver._counter = 0
+    prev = torch.zeros(n, device=dev)
+    for t, r in zip(every, owner):
+        tr, te = clone_host(t)
+        solver.run_task(tr)
+        solver.inner_test(te)
+        cur = solver._upd_flat[:n].clone()
+        if shares is not None:
+            shares[r] += cur - prev
+        prev = cur
+    solver._ring_sizes = []
     u_seq = solver._upd_flat[:n].clone()
     solver._upd_flat.zero_()
     solver._counter = 0
     rel = float((u_dist - u_seq).norm() / u_seq.norm().clamp_min(1e-30))
+    per_rank, worst_tensor = None, None
+    if shares is not None:
+        mine_seq = shares[rank]
+        own_rel = torch.tensor([float((u_own - mine_seq).norm() / mine_seq.norm().clamp_min(1e-30))], device=dev)
+        allr = [torch.zeros_like(own_rel) for _ in range(world)]
+        torch.distributed.all_gather(allr, own_rel)
+        per_rank = [round(float(v), 10) for v in allr]
+        worst = max(((float((eng.layout.view(u_own, nm) - eng.layout.view(mine_seq, nm)).norm() /
+                             eng.layout.view(mine_seq, nm).norm().clamp_min(1e-30)), nm) for nm in eng.layout.offsets))
+        wl = [None] * world
+        torch.distributed.all_gather_object(wl, (round(worst[0], 8), worst[1]))
+        worst_tensor = max(wl)
     cfg.dropout, cfg.pos_dropout, eng.use_graphs = pd, ppd, g_cfg
     solver.config["asr_model"]["task_lanes"] = lanes_cfg
     torch.cuda.synchronize(); D.barrier()
     return {"meta_weight_checksum_spread_over_ranks": spread,
             "meta_grad_rel_l2_vs_sequential_replay": rel,
+            "own_share_rel_l2_vs_its_replay_on_this_rank_by_rank": per_rank, "worst_tensor_of_any_rank": worst_tensor,
             "note": "checksum = (sum, sum of squares) of _original_flat in float64 after the timed steps, max - min over ranks; "
                     "replay = all 8 accents run on this rank alone (dropout 0), bf16 split-K reductions use fp32 atomics "
-                    "(run-to-run order noise)"}
+                    "(run-to-run order noise ~1e-7); own_share...: every rank's own share against the same accents inside "
+                    "its sequential replay (same GPU: detects state leaking between tasks)"}
 
 
 # ================================================================================================= multi-task (config 4)
