@@ -444,8 +444,11 @@ def replica_check(solver, eng, rank, world, dev, meta_k):
             "own_share_rel_l2_vs_its_replay_on_this_rank_by_rank": per_rank, "worst_tensor_of_any_rank": worst_tensor,
             "note": "checksum = (sum, sum of squares) of _original_flat in float64 after the timed steps, max - min over ranks; "
                     "replay = all 8 accents run on this rank alone (dropout 0), bf16 split-K reductions use fp32 atomics "
-                    "(run-to-run order noise ~1e-7); own_share...: every rank's own share against the same accents inside "
-                    "its sequential replay (same GPU: detects state leaking between tasks)"}
+                    "(run-to-run order noise ~1e-7 when the reduction order repeats; when it does not, the last-bit "
+                    "difference of the inner-train step flips bf16 roundings of the inner-test forward and the two bf16 "
+                    "realisations of an accent's share differ at the bf16 level, 1e-3..1e-2 -- tools/flaky_probe.py shows the "
+                    "chain element by element); own_share...: every rank's own share against the same accents inside its "
+                    "sequential replay on the same GPU"}
 
 
 # ================================================================================================= multi-task (config 4)

@@ -354,6 +354,21 @@ int masr_mt_reptile_delta(float* upd, const float* theta, const float* phi, int6
 int masr_mt_adam(float* p, float* m, float* v, const float* upd, int64_t n, float count,
                  float lr, float beta1, float beta2, float eps, double bc1, double bc2,
                  const double* skip_if_nan, const double* clip_sumsq, float max_norm, void* stream);
+/* The one collective of the path (src/fo_meta_interface.py:200-221 has none: the reference is single-process) done in the
+ * NVSwitch: multicast_ptr = the multicast mapping of a symmetric allocation holding every rank's flat update arena; this
+ * rank sums elements [begin, end) over all ranks (multimem.ld_reduce, addition inside the switch) and writes the sums
+ * into every rank's copy (multimem.st).  The caller orders it against the arena's producers / consumers on the other GPUs
+ * with a cross-GPU barrier before and after. */
+int masr_nvls_allreduce_f32(void* multicast_ptr, int64_t begin, int64_t end, void* stream);
+/* The outer update of a multi-GPU meta-step in one kernel (src/fo_meta_interface.py:200-221: `_updates /= counter`, noam-Adam
+ * step on the meta weights; plus the collective the reference does not have).  mc_upd / mc_theta: multicast mappings of
+ * the symmetric allocations holding every rank's update arena / meta weights; theta, m, v: this rank's local arenas (the
+ * moments are maintained only for the owned slice [begin, end)).  g = (sum over ranks of upd)[i] / count, Adam, new theta
+ * written into every rank's meta weights, upd[begin, end) cleared on every rank.  Elements >= n are only cleared.
+ * Cross-GPU barriers before and after are the caller's. */
+int masr_nvls_reduce_adam(void* mc_upd, void* mc_theta, const float* theta, float* m, float* v,
+                          int64_t begin, int64_t end, int64_t n, float count, float lr, float beta1, float beta2,
+                          float eps, double bc1, double bc2, void* stream);
 /* Reptile interpolation outer update: theta -= eps * upd * inv_count */
 int masr_mt_axpy(float* y, const float* x, float a, int64_t n, void* stream);
 

@@ -98,6 +98,8 @@ SIGNATURES = {
     "masr_mt_reptile_delta": [c_p, c_p, c_p, c_i64, c_p],
     "masr_mt_adam": [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_f, c_d, c_d, c_p, c_p, c_f, c_p],
     "masr_mt_axpy": [c_p, c_p, c_f, c_i64, c_p],
+    "masr_nvls_allreduce_f32": [c_p, c_i64, c_i64, c_p],
+    "masr_nvls_reduce_adam": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_f, c_f, c_f, c_f, c_f, c_d, c_d, c_p],
 }
 SPECIAL_RESTYPE = {"masr_last_error": C.c_char_p, "masr_ctc_workspace_bytes": c_sz}
 EXTRA = {"masr_last_error": [], "masr_ctc_workspace_bytes": [c_i, c_i, c_i, c_i]}

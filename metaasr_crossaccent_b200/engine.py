@@ -348,12 +348,24 @@ class TransformerEngine:
     def to_device(self, hb):
         """H2D of one prepared batch: x and the packed int64 block (two asynchronous copies)."""
         x = hb["x"]
+        pinned_tmp = None
         if self.device.type == "cuda" and x.device.type == "cpu" and not x.is_pinned():
-            x = x.pin_memory()        # (a loader with device= hands over features that are already resident)
+            x = pinned_tmp = x.pin_memory()        # (a loader with device= hands over features that are already resident)
         B, L1 = hb["B"], hb["L1"]
         meta = hb["meta"].to(self.device, non_blocking=True)
         self._meta_copied(hb)
         dev = {"x": x.to(self.device, non_blocking=True), "meta": meta}
+        if pinned_tmp is not None:
+            # the temporary pinned copy must outlive the asynchronous H2D copy that reads it: keep a reference until an
+            # event recorded behind the copy has completed (belt and braces on top of torch's caching host allocator)
+            held = self.__dict__.setdefault("_held_host", [])
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            held.append((ev, pinned_tmp))
+            while len(held) > 64 or (held and held[0][0].query()):
+                if not held[0][0].query():
+                    held[0][0].synchronize()
+                held.pop(0)
         dev.update(self._meta_views(meta, B, L1))
         dev.update({k: hb[k] for k in ("n_total", "B", "T", "L1")})
         return dev

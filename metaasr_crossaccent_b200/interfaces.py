@@ -208,6 +208,7 @@ class PretrainHost:
     def save_per_steps(self):
         """snapshot.latest / snapshot.step.N / info_dict.latest / global_step, rank 0 only
         (fo_meta_interface.py:70-88); what is saved is asr_model = last task's fast weights."""
+        osd = self.optimizer_state()          # (a collective when the meta-Adam moments are sharded: before the rank filter)
         if self.log_dir is None:
             return
         sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in self.asr_model.state_dict().items())
@@ -217,7 +218,6 @@ class PretrainHost:
         with open(self.log_dir.joinpath("global_step"), 'w') as f:
             print(self.global_step, file=f)
         torch.save(sd, self.log_dir.joinpath(f"snapshot.step.{self.global_step}"))
-        osd = self.optimizer_state()
         if osd is not None:
             torch.save(osd, self.log_dir.joinpath("optimizer.latest"))
 
@@ -260,6 +260,10 @@ class FOMetaMixin:
         # tensors that receive identical gradients and identical Adam states, i.e. stay bit-identical
         # forever -> one copy is exact.
         self._original_flat = eng.params.clone()
+        self._nvls = self._setup_nvls(eng)               # several NVSwitch-connected ranks: symmetric arenas + multicast
+        if self._nvls is not None:
+            self._nvls['theta'][:eng.layout.total].copy_(self._original_flat)
+            self._original_flat = self._nvls['theta'][:eng.layout.total]
         self._original = OrderedDict()
         for name in eng.layout.shapes:
             if name == "pos_encoder.pe":
@@ -276,7 +280,11 @@ class FOMetaMixin:
             st.m.copy_(osd['m']); st.v.copy_(osd['v'])
             st.t, self.meta_opt.step_num = int(osd['t']), int(osd['step_num'])
         # update arena: [n params | 1 slot for the task counter] -> a single all-reduce carries both
-        self._upd_flat = torch.zeros(eng.layout.total + 64, dtype=torch.float32, device=eng.device)
+        if self._nvls is not None:
+            self._upd_flat = self._nvls['upd'][:eng.layout.total + 64]
+            self._upd_flat.zero_()
+        else:
+            self._upd_flat = torch.zeros(eng.layout.total + 64, dtype=torch.float32, device=eng.device)
         self._gnorm = torch.zeros(1, dtype=torch.float64, device=eng.device)
         io = am.get('inner_optimizer_opt', {})
         if am.get('inner_optimizer_cls', 'SGD') != 'SGD':
@@ -286,9 +294,60 @@ class FOMetaMixin:
         self._ring_sizes = []
 
     def optimizer_state(self):
+        """A collective when the Adam moments are sharded over the ranks (NVLS meta-update): every rank must call it."""
         st = self.meta_opt.state
-        return {'original': self._original_flat.detach().cpu().clone(), 'm': st.m.detach().cpu().clone(),
-                'v': st.v.detach().cpu().clone(), 't': st.t, 'step_num': self.meta_opt.step_num}
+        m, v = st.m, st.v
+        nv = getattr(self, '_nvls', None)
+        if nv is not None and nv['sharded']:
+            import torch.distributed as tdist
+            n, per, w, r = m.numel(), nv['per'], D.world_size(), D.rank()
+            full = []
+            for t in (m, v):
+                mine = torch.zeros(per, dtype=t.dtype, device=t.device)
+                a, b = r * per, min((r + 1) * per, n)
+                if b > a:
+                    mine[:b - a].copy_(t[a:b])
+                allt = torch.empty(per * w, dtype=t.dtype, device=t.device)
+                tdist.all_gather_into_tensor(allt, mine)
+                full.append(allt[:n])
+            m, v = full
+        return {'original': self._original_flat.detach().cpu().clone(), 'm': m.detach().cpu().clone(),
+                'v': v.detach().cpu().clone(), 't': st.t, 'step_num': self.meta_opt.step_num}
+
+    def _setup_nvls(self, eng):
+        """Symmetric (peer-mapped, NVSwitch-multicast) allocations for the meta weights and the update arena, so that the
+        outer update -- sum over ranks, average, Adam, new weights to every rank -- is ONE kernel over the multicast
+        mappings (masr_nvls_reduce_adam) instead of NCCL all-reduce + Adam + memset.  None (the NCCL path stays) unless
+        there are several CUDA ranks under NCCL whose allocations get a multicast mapping; `asr_model.nvls_meta_update:
+        false` switches it off."""
+        if not (D.is_dist() and eng.device.type == 'cuda' and hasattr(eng.be, 'lib')):
+            return None
+        if not bool(self.config['asr_model'].get('nvls_meta_update', True)):
+            return None
+        import torch.distributed as tdist
+        if tdist.get_backend() != 'nccl':
+            return None
+        ok = torch.ones(1, device=eng.device)
+        out = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            w = D.world_size()
+            n = eng.layout.total
+            per = -(-(n + 64) // w)
+            per = -(-per // 1024) * 1024                 # slice per rank, 4 KB granular
+            theta = symm_mem.empty(per * w, dtype=torch.float32, device=eng.device)
+            upd = symm_mem.empty(per * w, dtype=torch.float32, device=eng.device)
+            ht = symm_mem.rendezvous(theta, tdist.group.WORLD)
+            hu = symm_mem.rendezvous(upd, tdist.group.WORLD)
+            if not (ht.multicast_ptr and hu.multicast_ptr):
+                raise RuntimeError("no multicast mapping")
+            theta.zero_(); upd.zero_()
+            out = {'theta': theta, 'upd': upd, 'ht': ht, 'hu': hu, 'per': per, 'sharded': False}
+        except Exception as e:                                # no NVLS on this box: keep NCCL
+            ok.zero_()
+            self._nvls_error = repr(e)
+        tdist.all_reduce(ok, op=tdist.ReduceOp.MIN)           # all ranks take the same path
+        return out if float(ok) > 0 else None
 
     # -- lanes: independent accents of a meta-batch may run CONCURRENTLY on one GPU (asr_model.task_lanes > 1)
     def _lane(self, i):
@@ -396,9 +455,43 @@ class FOMetaMixin:
             ev.record()
             self._phase_log.append((tag, ev))
 
+    def _nvls_meta_update(self):
+        """reduce + average + Adam + broadcast of the new meta weights + clearing of the update arena in one kernel."""
+        eng, nv = self.asr_model.engine, self._nvls
+        n, per, r = eng.layout.total, nv['per'], D.rank()
+        opt = self.meta_opt
+        opt.step_num += 1
+        opt.lr = noam_lr(opt.step_num, opt.k, opt.d_model, opt.warmup_steps)
+        st = opt.state
+        st.t += 1
+        bc1, bc2 = 1.0 - st.b1 ** st.t, 1.0 - st.b2 ** st.t
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        self._mark('reduce0')
+        nv['hu'].barrier(channel=0)               # every rank's update arena is final, nobody still reads the old weights
+        rc = eng.be.lib.masr_nvls_reduce_adam(nv['hu'].multicast_ptr, nv['ht'].multicast_ptr, self._original_flat.data_ptr(),
+                                              st.m.data_ptr(), st.v.data_ptr(), r * per, (r + 1) * per, n,
+                                              float(max(self._global_task_count, 1)), float(opt.lr), st.b1, st.b2, st.eps,
+                                              bc1, bc2, stream)
+        if rc != 0:
+            from . import _lib
+            _lib.check(rc, "masr_nvls_reduce_adam")
+        eng.be.launches += 1
+        nv['hu'].barrier(channel=1)               # every slice of the new weights has landed everywhere
+        nv['sharded'] = True
+        self._mark('reduce1')
+
     def _final_meta_update(self):
         eng = self.asr_model.engine
         n = eng.layout.total
+        if (getattr(self, '_nvls', None) is not None and self._global_task_count
+                and not (self.paras.algo == 'reptile' and self.reptile_outer == 'interp')):
+            self._nvls_meta_update()
+            self._counter, self._updates = 0, None
+            self._mark('adam1')
+            return
+        if getattr(self, '_nvls', None) is not None and self._nvls['sharded'] and self.paras.algo != 'reptile':
+            raise RuntimeError("the meta-Adam moments are sharded over the ranks (NVLS meta-update): every meta-step needs "
+                               "the global task count (meta_step_on_tasks(global_task_count=...))")
         count = self._reduce_updates()
         if self.paras.algo == 'reptile' and self.reptile_outer == 'interp':
             eng.be.mt_axpy(self._original_flat[:n], self._upd_flat[:n], -self.reptile_eps / max(count, 1.0))

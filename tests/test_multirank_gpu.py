@@ -41,7 +41,10 @@ def _fomaml_worker(rank, world, port_no, out):
         tr = [(acc, load_batch(z, f"s0.a{acc}.tr{j}.")) for j in range(2)]
         tasks.append((tr, (acc, load_batch(z, f"s0.a{acc}.te."))))
     s.meta_step_on_tasks(tasks, global_task_count=2)
-    torch.save({"w": s._original_flat.cpu(), "cs": s.replica_checksum().cpu()}, f"{out}/w{rank}.pt")
+    osd = s.optimizer_state()                  # (a collective when the Adam moments are sharded: NVLS meta-update)
+    torch.save({"w": s._original_flat.cpu(), "cs": s.replica_checksum().cpu(), "m": osd["m"], "v": osd["v"],
+                "nvls": getattr(s, "_nvls", None) is not None, "upd_absmax": float(s._upd_flat.abs().max())},
+               f"{out}/w{rank}.pt")
     torch.distributed.destroy_process_group()
 
 
@@ -72,6 +75,17 @@ def test_two_rank_fomaml_meta_step_on_cuda_equals_sequential_and_golden(tmp_path
     d = (w0 - s._original_flat.cpu()).abs()
     assert float(d.max()) <= 2.0 * lr + 1e-12
     assert float((d > 3e-2 * lr).float().mean()) < 0.02
+    # two GPUs under NCCL on an NVSwitch box: the outer update ran as ONE kernel over the multicast mappings
+    # (masr_nvls_reduce_adam) with the Adam moments sharded over the ranks; gathered, they equal the 1-rank moments, and
+    # the kernel left every rank's update arena cleared
+    if torch.cuda.device_count() >= 2:
+        print("NVLS meta-update:", r0["nvls"], r1["nvls"])
+    assert r0["nvls"] == r1["nvls"]
+    assert r0["upd_absmax"] == 0.0 and r1["upd_absmax"] == 0.0
+    st = s.meta_opt.state
+    for key, ref in (("m", st.m.cpu()), ("v", st.v.cpu())):
+        assert torch.equal(r0[key], r1[key])
+        assert float((r0[key] - ref).norm()) <= 1e-4 * float(ref.norm()) + 1e-12, key
 
 
 def _multi_worker(rank, world, port_no, out):
