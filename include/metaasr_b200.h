@@ -139,6 +139,14 @@ int masr_umma_gemm_pair(const void* A, int64_t lda, int a_mn, const void* B, int
 /* Upper bound of the TMA operand ring depth of masr_umma_gemm* (0 = default policy: the whole shared memory when the
  * grid fits one wave).  The lock-step meta-step sets 3 while several task lanes run their small GEMMs concurrently, so
  * that two CTAs of different lanes fit one SM. */
+/* Grouped launch of small GEMMs.  Between _begin and _end every masr_umma_gemm / masr_umma_gemm_ex call that resolves to
+ * the one-tile tcgen05 kernel is recorded instead of launched (its operands must stay valid and unchanged until _end);
+ * _end launches the recorded problems, all those of one kernel instantiation in ONE grid (up to 24 per launch).  Made for
+ * the weight gradients of a batch (the implied backward of every nn.Linear of the decoder, mono_transformer_torch.py:
+ * 74-98): ~26 independent 16-64 CTA problems that otherwise cost a launch each.  Calls that resolve to other kernels
+ * (CTA-pair GEMM, CUDA-core GEMM) launch immediately.  Not re-entrant; per host thread. */
+int masr_gemm_group_begin(void);
+int masr_gemm_group_end(void* stream);
 int masr_gemm_set_stage_cap(int stages);
 /* mode 0: masr_umma_gemm* never use the CTA-pair kernel; 1 (default): by problem size (A/B measurements). */
 int masr_gemm_set_pair_mode(int mode);

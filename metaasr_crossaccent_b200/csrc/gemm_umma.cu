@@ -12,6 +12,7 @@
 // descriptor (LBO/SBO) and two bits of the instruction descriptor, the data are never transposed in memory.
 #include <type_traits>
 #include "gemm_common.cuh"
+#include <vector>
 
 namespace masr {
 
@@ -64,10 +65,12 @@ static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void*
 // ------------------------------------------------------------------ kernel
 constexpr int UG_THREADS = 192;
 
+// One CTA of the one-tile GEMM: tile (bx, by) of k-slice bz of the problem described by (maps, p).  Shared by the
+// plain kernel (one problem per launch) and the grouped kernel (many small problems -- the decoder's weight gradients --
+// in one launch).
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(UG_THREADS, 2)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, UmmaGemmParams p) {
+__device__ __forceinline__ void umma_gemm_cta(const CUtensorMap* pmap_a, const CUtensorMap* pmap_b, const CUtensorMap* pmap_c,
+                                              const UmmaGemmParams& p, const int bx, const int by, const int bz) {
   using namespace umma;
   constexpr uint32_t A_BYTES = UG_BM * UG_BK * 2;          // 16 KB
   constexpr uint32_t B_BYTES = BN * UG_BK * 2;
@@ -87,20 +90,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   pdl_launch_dependents();          // the next kernel's prologue may overlap this kernel (see common.cuh)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
+  const int m0 = by * UG_BM, n0 = bx * BN;
   const int total_kb = (p.K + UG_BK - 1) / UG_BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_begin = bz * p.kb_per_split;
   const int num_kb = min(total_kb - kb_begin, p.kb_per_split);      // >= 1 by construction of the grid
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&map_a);
-    prefetch_tmap(&map_b);
-    if (EPI != GEPI_LEGACY) prefetch_tmap(&map_c);
+    prefetch_tmap(pmap_a);
+    prefetch_tmap(pmap_b);
+    if (EPI != GEPI_LEGACY) prefetch_tmap(pmap_c);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  const bool rowsum = p.rowsum != nullptr && blockIdx.x == 0;          // the n-tile-0 CTAs also sum A's rows
+  const bool rowsum = p.rowsum != nullptr && bx == 0;          // the n-tile-0 CTAs also sum A's rows
   const uint32_t tmem_cols = p.rowsum != nullptr ? 2 * BN : BN;
   if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   if (rowsum && threadIdx.x >= 64) {
@@ -125,18 +128,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (elect_one_sync()) {
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         if (!A_MN) {
-          tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);               // box {64 k, 128 m}
+          tma_load_2d(sa, pmap_a, &full_bar[s], k0, m0);               // box {64 k, 128 m}
         } else {
 #pragma unroll
           for (int c = 0; c < UG_BM / 64; ++c)                          // box {64 m, 64 k} per 64-wide chunk
-            tma_load_2d(sa + c * (64 * UG_BK * 2), &map_a, &full_bar[s], m0 + c * 64, k0);
+            tma_load_2d(sa + c * (64 * UG_BK * 2), pmap_a, &full_bar[s], m0 + c * 64, k0);
         }
         if (!B_MN) {
-          tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+          tma_load_2d(sb, pmap_b, &full_bar[s], k0, n0);
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 64; ++c)
-            tma_load_2d(sb + c * (64 * UG_BK * 2), &map_b, &full_bar[s], n0 + c * 64, k0);
+            tma_load_2d(sb + c * (64 * UG_BK * 2), pmap_b, &full_bar[s], n0 + c * 64, k0);
         }
         }
         __syncwarp();
@@ -187,7 +190,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = warp & 3;
     const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
     const bool splitk = p.flags & MASR_GEMM_SPLITK;
-    const bool use_bias = p.bias != nullptr && (!splitk || blockIdx.z == 0);
+    const bool use_bias = p.bias != nullptr && (!splitk || bz == 0);
     if (use_bias) {
       for (int i = et; i < BN; i += 128) sbias[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
     }
@@ -200,7 +203,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else {
       // the accumulator is complete, i.e. every MMA has read its operands: the pipeline stages are free for the boxes
       int boxsel = 0;
-      gemm_epilogue_tma_piece<EPI>(p, &map_c, tmem_base, q, lane, m0 + q * 32, n0, BN, smem + q * EPT_WARP_BYTES, sbias,
+      gemm_epilogue_tma_piece<EPI>(p, pmap_c, tmem_base, q, lane, m0 + q * 32, n0, BN, smem + q * EPT_WARP_BYTES, sbias,
                                    use_bias, boxsel);
       epilogue_tma_drain(lane);
     }
@@ -216,15 +219,83 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+
+template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(UG_THREADS, 2)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ UmmaGemmParams p) {
+  umma_gemm_cta<BN, MIN_STAGES, A_MN, B_MN, EPI>(&map_a, &map_b, &map_c, p, int(blockIdx.x), int(blockIdx.y), int(blockIdx.z));
+}
+
+// ---- grouped launch: up to GG_MAX independent problems of the same kernel instantiation in ONE grid.  The ~26
+// weight-gradient GEMMs of the decoder (M, N <= 2048, K = 1 056 rows) are 16-64 CTAs each: launched one by one on the
+// side stream they fill a fraction of the machine and pay a launch each; together they are one ~1 500-CTA wave.
+constexpr int GG_MAX = 24;
+struct alignas(64) GemmGroupEntry {
+  CUtensorMap ma, mb, mc;
+  UmmaGemmParams p;
+  int cta_begin, nx, ny, nz;
+};
+struct GemmGroupTable {
+  GemmGroupEntry e[GG_MAX];
+  int n, total;
+};
+
+template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(UG_THREADS, 2)
+umma_gemm_group_kernel(const __grid_constant__ GemmGroupTable t) {
+  int i = 0;
+  while (i + 1 < t.n && int(blockIdx.x) >= t.e[i + 1].cta_begin) ++i;
+  const GemmGroupEntry& e = t.e[i];
+  const int local = int(blockIdx.x) - e.cta_begin;
+  const int bx = local % e.nx, by = (local / e.nx) % e.ny, bz = local / (e.nx * e.ny);
+  umma_gemm_cta<BN, MIN_STAGES, A_MN, B_MN, EPI>(&e.ma, &e.mb, &e.mc, e.p, bx, by, bz);
+}
+
 // masr_gemm_set_stage_cap: upper bound of the operand ring depth.  A lone CTA per SM wants the whole shared memory as a
 // deep ring; when several task lanes run their small GEMMs concurrently (lock-step meta-step) a 192 KB CTA would keep
 // every other lane off its SM -- three stages (96 KB) leave room for a second CTA.
 static int g_stage_cap = 0;
 
+// masr_gemm_group_begin / _end: between the two, problems that resolve to the one-tile kernel are recorded (tensor maps,
+// parameters, grid) instead of launched; _end launches them grouped by kernel instantiation.
+struct GroupRec {
+  int (*launch)(const GemmGroupTable&, cudaStream_t);
+  GemmGroupEntry e;
+};
+static thread_local bool g_group_on = false;
+static thread_local std::vector<GroupRec>* g_group = nullptr;
+
+template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
+static int launch_group(const GemmGroupTable& t, cudaStream_t st) {
+  constexpr size_t STAGE = size_t(UG_BM * UG_BK * 2 + BN * UG_BK * 2);
+  auto kern = umma_gemm_group_kernel<BN, MIN_STAGES, A_MN, B_MN, EPI>;
+  const size_t smem = size_t(MIN_STAGES) * STAGE + 2048 + 1024 + 512 + BN * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_set = true;
+  }
+  MASR_CHECK_CUDA(launch_pdl(kern, dim3(unsigned(t.total)), dim3(UG_THREADS), smem, st, t));
+  return MASR_OK;
+}
+
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
 static int launch_umma(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, UmmaGemmParams p, cudaStream_t st) {
   constexpr size_t STAGE = size_t(UG_BM * UG_BK * 2 + BN * UG_BK * 2);
   constexpr int MAX_STAGES = int((198 * 1024) / STAGE);
+  if (g_group_on) {                     // recorded: many problems share the launch, every CTA gets the shallow ring
+    const int total_kb = int(ceil_div64(p.K, UG_BK));
+    GroupRec r;
+    r.launch = &launch_group<BN, MIN_STAGES, A_MN, B_MN, EPI>;
+    r.e.ma = ma; r.e.mb = mb; r.e.mc = mc;
+    p.stages = MIN_STAGES;
+    r.e.p = p;
+    r.e.nx = int(ceil_div64(p.N, BN)); r.e.ny = int(ceil_div64(p.M, UG_BM)); r.e.nz = int(ceil_div64(total_kb, p.kb_per_split));
+    r.e.cta_begin = 0;
+    g_group->push_back(r);
+    return MASR_OK;
+  }
   auto kern = umma_gemm_kernel<BN, MIN_STAGES, A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -403,6 +474,46 @@ extern "C" int masr_umma_gemm_pair(const void* A, int64_t lda, int a_mn, const v
     }
   }
   return launch_umma_pair(A, lda, a_mn, B, ldb, b_mn, p, splitk, bn, as_stream(stream));
+}
+
+extern "C" int masr_gemm_group_begin(void) {
+  MASR_REQUIRE(!g_group_on, "masr_gemm_group_begin: a group is already open");
+  if (g_group == nullptr) g_group = new std::vector<GroupRec>();
+  g_group->clear();
+  g_group_on = true;
+  return MASR_OK;
+}
+
+extern "C" int masr_gemm_group_end(void* stream) {
+  MASR_REQUIRE(g_group_on, "masr_gemm_group_end: no open group");
+  g_group_on = false;
+  cudaStream_t st = as_stream(stream);
+  std::vector<GroupRec>& recs = *g_group;
+  std::vector<char> done(recs.size(), 0);
+  for (size_t i = 0; i < recs.size(); ++i) {
+    if (done[i]) continue;
+    GemmGroupTable t;
+    t.n = 0; t.total = 0;
+    for (size_t j = i; j < recs.size(); ++j) {
+      if (done[j] || recs[j].launch != recs[i].launch) continue;
+      if (t.n == GG_MAX) {              // table full: launch it and start the next one of the same instantiation
+        const int rc = recs[i].launch(t, st);
+        if (rc != MASR_OK) { recs.clear(); return rc; }
+        t.n = 0; t.total = 0;
+      }
+      GemmGroupEntry& e = t.e[t.n++];
+      e = recs[j].e;
+      e.cta_begin = t.total;
+      t.total += e.nx * e.ny * e.nz;
+      done[j] = 1;
+    }
+    if (t.n > 0) {
+      const int rc = recs[i].launch(t, st);
+      if (rc != MASR_OK) { recs.clear(); return rc; }
+    }
+  }
+  recs.clear();
+  return MASR_OK;
 }
 
 extern "C" int masr_gemm_set_stage_cap(int stages) {

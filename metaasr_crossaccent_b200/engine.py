@@ -186,6 +186,7 @@ class TransformerEngine:
         # weight-gradient GEMMs (and bias sums) never feed the back-propagation chain: they run on a
         # second stream, concurrently with the dgrad chain (small launches fill only part of the 148 SMs)
         self.multi_stream = self.device.type == "cuda"
+        self.group_wgrads = True          # grouped launch of the weight-gradient GEMMs (backward_rest)
         self._side = None
         self._side_busy = False
 
@@ -648,8 +649,25 @@ class TransformerEngine:
 
         fork = self._fork
 
+        # Weight gradients never feed the dgrad chain.  Where the backend can group launches (tcgen05 path) they are
+        # collected and issued as ONE grouped launch per stretch (decoder, encoder) on the side stream: ~26 problems of
+        # 16-64 CTAs each otherwise.  Every operand of a deferred problem is a forward activation or a gradient buffer
+        # private to its (layer, sub-layer), so nothing overwrites it before the flush.
+        grouped = self.group_wgrads and hasattr(be, "gemm_group") and getattr(be, "gemm_path", "") == "umma" and \
+            self.act_dtype != torch.float32
+        pending = []
+
         def wgrad(x, dy, dw, db):
-            fork(lambda: be.linear_wgrad(x, dy, dw, db))
+            if grouped:
+                pending.append(lambda: be.linear_wgrad(x, dy, dw, db))
+            else:
+                fork(lambda: be.linear_wgrad(x, dy, dw, db))
+
+        def flush_wgrads():
+            if pending:
+                calls = list(pending)
+                pending.clear()
+                fork(lambda: be.gemm_group(calls))
 
         def ffn_bwd(pre, g_s, f1, h_in, g_res, Mrows, tag):
             """g_s: grad wrt linear2 output; accumulates the FFN input gradient into g_res."""
@@ -732,6 +750,7 @@ class TransformerEngine:
             self_attn_bwd(pre, g_br, ws[f"d{l}.qkv"], ws[f"d{l}.ctx1"], ws[f"d{l}.lse1"], ws[f"d{l}.in"], gd[nxt],
                           Md, L1, None, True, tag, self.site(pre + ".sa"))
             cur = nxt
+        flush_wgrads()                 # the decoder's weight gradients: one grouped launch under the encoder's dgrad chain
         # the scatter-add into the tied embedding matrix shares its target with the char_trans wgrad: keep
         # both on the side stream (ordered); nothing on the main stream touches gd[] after this point
         g_emb = gd[cur]
@@ -772,6 +791,7 @@ class TransformerEngine:
             self_attn_bwd(pre, g_ebr, ws[f"e{l}.qkv"], ws[f"e{l}.ctx"], ws[f"e{l}.lse"], x_in, ge[nxt],
                           Me, T4, db["enc_lens"], False, tag, self.site(pre + ".sa"))
             cur = nxt
+        flush_wgrads()                 # the encoder's
         g_h0 = ge[cur]
         be.dropout(g_h0, ppd, seed, self.site("enc.pe"))
 

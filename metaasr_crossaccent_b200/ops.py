@@ -232,6 +232,22 @@ class CudaBackend:
         if relu_drop_mask is not None:
             self.relu_bwd(relu_drop_mask, dx, scale)
 
+    def gemm_group(self, calls):
+        """Run the callables (each issuing linear_wgrad-style GEMMs) as ONE grouped launch per kernel instantiation
+        (masr_gemm_group_begin / _end): the operands of every recorded problem must stay untouched until this returns."""
+        rc = self.lib.masr_gemm_group_begin()
+        if rc != 0:
+            _lib.check(rc, "masr_gemm_group_begin")
+        before = self.launches
+        try:
+            for fn in calls:
+                fn()
+        finally:
+            rc = self.lib.masr_gemm_group_end(self.stream)
+        if rc != 0:
+            _lib.check(rc, "masr_gemm_group_end")
+        self.group_calls = getattr(self, "group_calls", 0) + (self.launches - before)
+
     def linear_wgrad(self, x, dy, dw, db):
         """dw[N,K] += dy[M,N]^T @ x[M,K] (fp32); db[N] += column sums of dy."""
         M, K = x.shape

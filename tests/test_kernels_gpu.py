@@ -430,6 +430,39 @@ def test_fused_weight_refresh_kernels(dev):
         assert float(sh.float().abs().max()) == 0.0
 
 
+def test_grouped_weight_gradient_launch(dev):
+    """masr_gemm_group_begin / _end: the weight-gradient GEMMs of a batch recorded and launched as one grid per kernel
+    instantiation (30 problems of four shapes: two tables of the 128-wide kernel, one of the 64-wide one, one problem that
+    resolves to the CTA-pair kernel and launches at once) equal the same problems launched one by one."""
+    from metaasr_crossaccent_b200.ops import CudaBackend
+    bf = torch.bfloat16
+    cb = CudaBackend(dev, bf, gemm="umma")
+    shapes = [(1056, 512, 512)] * 14 + [(1056, 512, 2048)] * 6 + [(1056, 2048, 512)] * 6 + [(1056, 64, 512)] * 3 + [(4096, 512, 2048)]
+    probs = []
+    for i, (M, K, N) in enumerate(shapes):             # x [M, K], dy [M, N] -> dw [N, K], db [N]
+        probs.append((rnd((M, K), dev, bf, 100 + i), rnd((M, N), dev, bf, 200 + i, 0.1)))
+    ref = []
+    for x, dy in probs:
+        dw, db = torch.full((dy.shape[1], x.shape[1]), 0.5, device=dev), torch.full((dy.shape[1],), 0.25, device=dev)
+        cb.linear_wgrad(x, dy, dw, db)
+        ref.append((dw, db))
+    got = [(torch.full_like(dw, 0.5), torch.full_like(db, 0.25)) for dw, db in ref]
+    before = cb.launches
+    cb.gemm_group([(lambda x=x, dy=dy, dw=dw, db=db: cb.linear_wgrad(x, dy, dw, db)) for (x, dy), (dw, db) in zip(probs, got)])
+    torch.cuda.synchronize()
+    assert cb.launches - before == len(probs)
+    for i, ((dw, db), (rw, rb)) in enumerate(zip(got, ref)):
+        close(dw, rw, torch.float32, 1e-5, f"grouped wgrad {i} {shapes[i]}")
+        close(db, rb, torch.float32, 1e-5, f"grouped bias grad {i}")
+    # and against the fp32 definition for one of them
+    x, dy = probs[0]
+    close(got[0][0], 0.5 + dy.float().t() @ x.float(), torch.float32, 2e-3, "grouped wgrad vs definition")
+    # a group left open is an error, an empty group is not
+    cb.gemm_group([])
+    assert cb.lib.masr_gemm_group_begin() == 0 and cb.lib.masr_gemm_group_begin() != 0
+    assert cb.lib.masr_gemm_group_end(cb.stream) == 0
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (4096, 1536, 512), (1056, 512, 2048), (200, 96, 72),
                                    (130, 367, 512), (64, 576, 5000)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
