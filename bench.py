@@ -260,6 +260,10 @@ def bench_meta(args, algo, meta_k, dtype, steps, warmup, detail, rank, world, de
         "gpu_launches": int(launches), "clocks": clocks,
         "last_inner_test_loss": [round(i["loss"], 4) for i in last_info.get("i", [])][:2],
     }
+    if world > 1:
+        out["config"]["meta_update"] = ("one kernel over NVSwitch multicast memory (masr_nvls_reduce_adam: sum in the switch, "
+                                        "sharded Adam, new weights multicast)" if getattr(solver, "_nvls", None) is not None
+                                        else "NCCL all-reduce + replicated Adam")
     if not detail:
         if graphs:                                # graph replays bypass the host-side launch counter: count one eager step
             eng.use_graphs = False                # (one lane: the other lanes' engines keep their graphs)

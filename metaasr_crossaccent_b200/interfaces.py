@@ -327,27 +327,35 @@ class FOMetaMixin:
         import torch.distributed as tdist
         if tdist.get_backend() != 'nccl':
             return None
-        ok = torch.ones(1, device=eng.device)
-        out = None
+        # Two agreement points, so that a rank on which a step fails never leaves the others inside a collective: (1) every
+        # rank could allocate the symmetric arenas, (2) every rank got a multicast mapping out of the rendezvous.
+        def agreed(flag):
+            t = torch.tensor([1.0 if flag else 0.0], device=eng.device)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
+            return float(t) > 0
+        w = D.world_size()
+        n = eng.layout.total
+        per = -(-(n + 64) // w)
+        per = -(-per // 1024) * 1024                 # slice per rank, 4 KB granular
+        theta = upd = None
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            w = D.world_size()
-            n = eng.layout.total
-            per = -(-(n + 64) // w)
-            per = -(-per // 1024) * 1024                 # slice per rank, 4 KB granular
             theta = symm_mem.empty(per * w, dtype=torch.float32, device=eng.device)
             upd = symm_mem.empty(per * w, dtype=torch.float32, device=eng.device)
+        except Exception as e:                                # no symmetric memory in this build / on this box: keep NCCL
+            self._nvls_error = repr(e)
+        if not agreed(theta is not None and upd is not None):
+            return None
+        ht = hu = None
+        try:
             ht = symm_mem.rendezvous(theta, tdist.group.WORLD)
             hu = symm_mem.rendezvous(upd, tdist.group.WORLD)
-            if not (ht.multicast_ptr and hu.multicast_ptr):
-                raise RuntimeError("no multicast mapping")
-            theta.zero_(); upd.zero_()
-            out = {'theta': theta, 'upd': upd, 'ht': ht, 'hu': hu, 'per': per, 'sharded': False}
-        except Exception as e:                                # no NVLS on this box: keep NCCL
-            ok.zero_()
+        except Exception as e:
             self._nvls_error = repr(e)
-        tdist.all_reduce(ok, op=tdist.ReduceOp.MIN)           # all ranks take the same path
-        return out if float(ok) > 0 else None
+        if not agreed(ht is not None and hu is not None and bool(ht.multicast_ptr) and bool(hu.multicast_ptr)):
+            return None
+        theta.zero_(); upd.zero_()
+        return {'theta': theta, 'upd': upd, 'ht': ht, 'hu': hu, 'per': per, 'sharded': False}
 
     # -- lanes: independent accents of a meta-batch may run CONCURRENTLY on one GPU (asr_model.task_lanes > 1)
     def _lane(self, i):
