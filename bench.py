@@ -57,10 +57,10 @@ WORKLOADS = {
 ACCENTS = ["af", "au", "ca", "en", "in", "ir", "nz", "us"]
 
 
-def hkust_config(dtype, gemm, dropout=0.1, graphs=True, lanes=1, meta=True, ctc_weight=0.0):
+def hkust_config(dtype, gemm, dropout=0.1, graphs=True, lanes=1, meta=True, ctc_weight=0.0, nvls=True):
     am = {"idim": IDIM, "nheads": 8, "d_model": 512, "d_inner": 2048, "dropout": dropout, "tgt_share_weight": 1,
           "encoder": {"nlayers": 2}, "decoder": {"nlayers": 4}, "pos_dropout": dropout, "dtype": dtype, "gemm": gemm,
-          "cuda_graphs": graphs, "task_lanes": lanes, "ctc_weight": ctc_weight,
+          "cuda_graphs": graphs, "task_lanes": lanes, "ctc_weight": ctc_weight, "nvls_meta_update": nvls,
           "strict_tcgen05": gemm == "umma"}        # the timed path must never drop to a CUDA-core kernel
     if meta:
         am.update({"inner_optimizer_cls": "SGD", "inner_optimizer_opt": {"momentum": 0.9, "nesterov": True},
@@ -163,7 +163,7 @@ def timed(fn, steps, warmup, dev, world, be=None, profile=False):
 
 
 # ================================================================================================= FOMAML / Reptile
-def make_meta_solver(algo, meta_k, dtype, graphs, lanes):
+def make_meta_solver(algo, meta_k, dtype, graphs, lanes, nvls=True):
     from metaasr_crossaccent_b200 import interfaces as I
     from metaasr_crossaccent_b200.trainer import get_trainer
     import random
@@ -173,7 +173,7 @@ def make_meta_solver(algo, meta_k, dtype, graphs, lanes):
                                meta_k=meta_k, meta_batch_size=N_ACCENTS, max_step=0, resume=False, algo=algo,
                                pretrain_suffix="bench", log_root=None)
     random.seed(531); torch.manual_seed(531)
-    solver = get_trainer(I.FOMetaASRInterface, hkust_config(dtype, gemm, graphs=graphs, lanes=lanes), paras, id2accent)
+    solver = get_trainer(I.FOMetaASRInterface, hkust_config(dtype, gemm, graphs=graphs, lanes=lanes, nvls=nvls), paras, id2accent)
     solver.set_model()
     return solver, gemm
 
@@ -211,7 +211,9 @@ def bench_meta(args, algo, meta_k, dtype, steps, warmup, detail, rank, world, de
     """One line for a FOMAML / Reptile meta-step configuration."""
     from metaasr_crossaccent_b200 import dist as D
     graphs = not args.no_graphs
-    solver, gemm = make_meta_solver(algo, meta_k, dtype, graphs, args.lanes)
+    # the headline run takes the NVSwitch-multicast meta-update when there are several ranks; the short runs of the other
+    # configurations (several solvers in one process) stay on the NCCL all-reduce
+    solver, gemm = make_meta_solver(algo, meta_k, dtype, graphs, args.lanes, nvls=detail)
     eng, be = solver.asr_model.engine, solver.backend
     mine, host_tasks = host_tasks_of(rank, world, meta_k)
     frames = N_ACCENTS * (meta_k + 1) * INNER_B * T_FRAMES
