@@ -139,7 +139,9 @@ def timed(fn, steps, warmup, dev, world, be=None, profile=False):
     from metaasr_crossaccent_b200 import dist as D
     for _ in range(warmup):
         fn()
-    torch.cuda.synchronize(); D.barrier()
+    torch.cuda.synchronize()
+    if world > 1:           # (world = 1 also for legs that only rank 0 runs inside a multi-rank job: no collective there)
+        D.barrier()
     if be is not None:
         be.launches = 0
         be.prof = {} if profile else None
@@ -149,7 +151,9 @@ def timed(fn, steps, warmup, dev, world, be=None, profile=False):
     for _ in range(steps):
         fn()
     e1.record()
-    torch.cuda.synchronize(); D.barrier()
+    torch.cuda.synchronize()
+    if world > 1:
+        D.barrier()
     t1 = time.time()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
