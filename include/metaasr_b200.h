@@ -147,6 +147,8 @@ int masr_umma_gemm_pair(const void* A, int64_t lda, int a_mn, const void* B, int
  * (CTA-pair GEMM, CUDA-core GEMM) launch immediately.  Not re-entrant; per host thread. */
 int masr_gemm_group_begin(void);
 int masr_gemm_group_end(void* stream);
+/* how many problems the last masr_gemm_group_end of this thread had recorded and how many kernels it launched for them */
+int masr_gemm_group_last(int* recorded, int* launched);
 int masr_gemm_set_stage_cap(int stages);
 /* mode 0: masr_umma_gemm* never use the CTA-pair kernel; 1 (default): by problem size (A/B measurements). */
 int masr_gemm_set_pair_mode(int mode);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "masr_gemm_set_pair_mode": [c_i],
     "masr_gemm_group_begin": [],
     "masr_gemm_group_end": [c_p],
+    "masr_gemm_group_last": [c_p, c_p],
     "masr_attn_set_small_lq": [c_i],
     "masr_gemm_set_stage_cap": [c_i],
     "masr_umma_gemm_tn": [c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_p, c_i, c_i, c_i, c_i, c_p],

@@ -264,6 +264,7 @@ struct GroupRec {
   GemmGroupEntry e;
 };
 static thread_local bool g_group_on = false;
+static thread_local int g_group_recorded = 0, g_group_launched = 0;      // of the last masr_gemm_group_end
 static thread_local std::vector<GroupRec>* g_group = nullptr;
 
 template <int BN, int MIN_STAGES, bool A_MN, bool B_MN, int EPI>
@@ -490,6 +491,8 @@ extern "C" int masr_gemm_group_end(void* stream) {
   cudaStream_t st = as_stream(stream);
   std::vector<GroupRec>& recs = *g_group;
   std::vector<char> done(recs.size(), 0);
+  g_group_recorded = int(recs.size());
+  g_group_launched = 0;
   for (size_t i = 0; i < recs.size(); ++i) {
     if (done[i]) continue;
     GemmGroupTable t;
@@ -499,6 +502,7 @@ extern "C" int masr_gemm_group_end(void* stream) {
       if (t.n == GG_MAX) {              // table full: launch it and start the next one of the same instantiation
         const int rc = recs[i].launch(t, st);
         if (rc != MASR_OK) { recs.clear(); return rc; }
+        ++g_group_launched;
         t.n = 0; t.total = 0;
       }
       GemmGroupEntry& e = t.e[t.n++];
@@ -510,9 +514,17 @@ extern "C" int masr_gemm_group_end(void* stream) {
     if (t.n > 0) {
       const int rc = recs[i].launch(t, st);
       if (rc != MASR_OK) { recs.clear(); return rc; }
+      ++g_group_launched;
     }
   }
   recs.clear();
+  return MASR_OK;
+}
+
+/* problems recorded by / kernels launched by the last masr_gemm_group_end of this thread (launch accounting) */
+extern "C" int masr_gemm_group_last(int* recorded, int* launched) {
+  if (recorded != nullptr) *recorded = g_group_recorded;
+  if (launched != nullptr) *launched = g_group_launched;
   return MASR_OK;
 }
 

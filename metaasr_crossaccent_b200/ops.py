@@ -246,7 +246,10 @@ class CudaBackend:
             rc = self.lib.masr_gemm_group_end(self.stream)
         if rc != 0:
             _lib.check(rc, "masr_gemm_group_end")
-        self.group_calls = getattr(self, "group_calls", 0) + (self.launches - before)
+        # launch accounting: the recorded problems were counted one launch each by _call; replace by what was launched
+        rec, lau = _lib.C.c_int(0), _lib.C.c_int(0)
+        self.lib.masr_gemm_group_last(_lib.C.byref(rec), _lib.C.byref(lau))
+        self.launches += lau.value - rec.value
 
     def linear_wgrad(self, x, dy, dw, db):
         """dw[N,K] += dy[M,N]^T @ x[M,K] (fp32); db[N] += column sums of dy."""

@@ -450,7 +450,8 @@ def test_grouped_weight_gradient_launch(dev):
     before = cb.launches
     cb.gemm_group([(lambda x=x, dy=dy, dw=dw, db=db: cb.linear_wgrad(x, dy, dw, db)) for (x, dy), (dw, db) in zip(probs, got)])
     torch.cuda.synchronize()
-    assert cb.launches - before == len(probs)
+    assert 2 <= cb.launches - before <= 8     # 30 problems -> a handful of grouped grids (one per kernel instantiation and
+                                              # 24 problems) + whatever resolved to the CTA-pair kernel
     for i, ((dw, db), (rw, rb)) in enumerate(zip(got, ref)):
         close(dw, rw, torch.float32, 1e-5, f"grouped wgrad {i} {shapes[i]}")
         close(db, rb, torch.float32, 1e-5, f"grouped bias grad {i}")
