@@ -186,7 +186,11 @@ class TransformerEngine:
         # weight-gradient GEMMs (and bias sums) never feed the back-propagation chain: they run on a
         # second stream, concurrently with the dgrad chain (small launches fill only part of the 148 SMs)
         self.multi_stream = self.device.type == "cuda"
-        self.group_wgrads = True          # grouped launch of the weight-gradient GEMMs (backward_rest)
+        # grouped launch of the weight-gradient GEMMs (backward_rest).  Pays when several task lanes share the GPU (one
+        # ~1 500-CTA grid instead of 26 small launches per lane: 31.9 -> 31.6 ms at four lanes); on a single lane the small
+        # launches hide under the latency-bound dgrad chain and deferring them costs 0.05 ms per batch, so the meta-step
+        # scheduler switches it on only for multi-lane steps
+        self.group_wgrads = False
         self._side = None
         self._side_busy = False
 
@@ -976,7 +980,7 @@ class TransformerEngine:
 
     def _graph_entry(self, db):
         B, T, L1 = db["B"], db["T"], db["L1"]
-        key = (B, T, L1, self.training)
+        key = (B, T, L1, self.training, bool(self.group_wgrads))
         ent = self._graphs.get(key)
         if ent is not None:
             self._graphs.move_to_end(key)
@@ -985,7 +989,8 @@ class TransformerEngine:
         # captured graph pins its workspaces (hundreds of MB at full size), so keep only the most recent shapes
         while len(self._graphs) >= self.max_graphs:
             old_key, _ = self._graphs.popitem(last=False)
-            self._ws.pop(old_key[:3], None)
+            if not any(k[:3] == old_key[:3] for k in self._graphs):      # (another variant of the shape may still use it)
+                self._ws.pop(old_key[:3], None)
         dev = self.device
         smeta = torch.empty(B * (1 + 2 * L1) + (2 * B if self.cfg.ctc_weight > 0.0 else 0), dtype=torch.int64, device=dev)
         sdb = {"x": torch.empty(B, T, self.cfg.idim, dtype=torch.float32, device=dev), "meta": smeta,

@@ -575,6 +575,7 @@ class FOMetaMixin:
         be0 = self.asr_model.engine.be
         if hasattr(be0, 'gemm_stage_cap'):         # concurrent lanes share SMs: shallower operand rings (two CTAs per SM)
             be0.gemm_stage_cap(3 if n_lanes > 1 else 0)
+        self.asr_model.engine.group_wgrads = False
         if n_lanes <= 1 or self.asr_model.engine.device.type != 'cuda':
             self._mark('step0')
             for tr_batches, val_batch in tasks:
@@ -637,6 +638,8 @@ class FOMetaMixin:
             self._lane0_stream = torch.cuda.Stream(dev)
         conv = self._conv_stream
         lanes = [self._lane(i) for i in range(n_lanes)]
+        for l in lanes:
+            l.eng.group_wgrads = True          # several lanes share the GPU: one grouped weight-gradient launch per stretch
         streams = [self._lane0_stream] + [l.stream for l in lanes[1:]]
         for st in streams + [conv]:
             st.wait_stream(main)
