@@ -312,3 +312,28 @@ def test_mono_finetune_filter_freeze_steps_match_reference(tmp_path):
     for (n, a), (_, b) in zip(r.asr_model.state_dict().items(), s.asr_model.state_dict().items()):
         assert torch.equal(a, b), n
     assert torch.equal(r.asr_opt.state.m, s.asr_opt.state.m) and torch.equal(r.asr_opt.state.v, s.asr_opt.state.v)
+
+
+def test_next_tasks_handover_is_a_no_op_on_the_host_double():
+    """meta_step_on_tasks(next_tasks=) (copy-stream prefetch on the CUDA path) must not change the schedule: on the CPU double
+    staging passes batches through, the handed-over list is picked up by identity at the next call, and two steps with the
+    hand-over equal two plain steps bit for bit; optimizer_state() stays a local (non-collective) call."""
+    z = np.load(GOLD / "fomaml_tiny.npz")
+
+    def tasks_of():
+        out = []
+        for acc in range(int(z["n_accents"])):
+            tr = [(acc, load_batch(z, f"s0.a{acc}.tr{j}.")) for j in range(int(z["meta_k"]))]
+            out.append((tr, (acc, load_batch(z, f"s0.a{acc}.te."))))
+        return out
+    res = []
+    for handover in (False, True):
+        s = make_solver("fomaml")
+        t1, t2 = tasks_of(), tasks_of()
+        s.meta_step_on_tasks(t1, next_tasks=t2 if handover else None)
+        assert (s.__dict__.get("_prefetched") is not None) == handover
+        s.meta_step_on_tasks(t2)
+        assert s.__dict__.get("_prefetched") is None and getattr(s, "_nvls", None) is None
+        osd = s.optimizer_state()
+        res.append((s._original_flat.clone(), osd["m"].clone(), [i["loss"] for i in s.flush_train_info()]))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
