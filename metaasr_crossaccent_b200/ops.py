@@ -356,7 +356,8 @@ class CudaBackend:
 
     @staticmethod
     def _pool_code_ok(x, *ts):
-        return x.shape[3] % 8 == 0 and all(t.data_ptr() % 16 == 0 for t in (x,) + ts)
+        return (x.shape[3] % 8 == 0 and x.shape[1] >= 2 and x.shape[2] >= 2 and x.shape[0] > 0
+                and all(t.data_ptr() % 16 == 0 for t in (x,) + ts))
 
     def maxpool_fwd(self, x, y, code=None):
         """code (optional, uint8 [B, H/2, W/2, C]): per-output arg-max / positive-maximum byte for maxpool_bwd(code=)."""
