@@ -225,3 +225,38 @@ def port_flat(s):
     st.m.zero_(); st.v.zero_(); st.t = 0
     s.meta_opt.step_num = 0
     return s._flat0
+
+
+def test_mixed_shapes_lanes_graphs_prefetch_match_sequential(dev):
+    """Real loaders give every accent its own (B, T, L): three accents with different shapes (equal-length and ragged, T = 512 /
+    384 / 256, B = 32 / 16 / 8) through the full bench schedule -- 3 task lanes in lock step, CUDA-graph replay per shape,
+    grouped weight-gradient launches, host batches staged on the copy stream with the next step's batches handed over --
+    against the plain sequential eager schedule: inner-test losses and the meta-gradient of two consecutive meta-steps."""
+    shapes = [dict(B=32, T=512, L=32, profile="eq"), dict(B=16, T=384, L=20, profile="rag"), dict(B=8, T=256, L=12, profile="eq")]
+    batches = [(hkust_profile_batch(400 + 2 * a, sh["profile"], B=sh["B"], T=sh["T"], L=sh["L"]),
+                hkust_profile_batch(401 + 2 * a, sh["profile"], B=sh["B"], T=sh["T"], L=sh["L"])) for a, sh in enumerate(shapes)]
+    tasks_of = lambda: [([(a, clone_batch(batches[a][0]))], (a, clone_batch(batches[a][1]))) for a in range(len(shapes))]
+    res = []
+    for lanes, graphs, prefetch in ((1, False, False), (3, True, True)):
+        s, _ = make_solver("bf16", "umma", lanes=lanes, graphs=graphs)
+        s.paras.num_pretrain = s.num_pretrain = 3
+        s._stats_ring = torch.zeros(3, 8, dtype=torch.float64, device=s.asr_model.engine.device)
+        s.asr_model.engine.use_graphs = graphs
+        grads = []
+        orig = s.meta_opt.step
+
+        def spy(upd, count, orig=orig, grads=grads):
+            grads.append((upd / count).clone())
+            return orig(upd, count)
+        s.meta_opt.step = spy
+        t1, t2 = tasks_of(), tasks_of()
+        s.meta_step_on_tasks(t1, next_tasks=t2 if prefetch else None)
+        l1 = [i["loss"] for i in s.flush_train_info()]
+        s.meta_step_on_tasks(t2)
+        l2 = [i["loss"] for i in s.flush_train_info()]
+        torch.cuda.synchronize()
+        res.append((l1 + l2, grads))
+    (la, ga), (lb, gb) = res
+    assert len(la) == 6 and all(abs(a - b) <= 2e-4 * abs(a) for a, b in zip(la, lb)), (la, lb)
+    for x, y in zip(ga, gb):
+        assert float((x - y).norm()) <= 3e-2 * float(x.norm())
